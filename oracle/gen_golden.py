@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED
+reference (/root/reference) on CPU in the build container.
+
+TEST INFRASTRUCTURE ONLY (see oracle/oracle.py header).  The reference cannot
+travel to the GPU box, so its outputs are committed as small fixtures together
+with this script.  Re-run with:
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+Shims (test-side only, reference files untouched):
+  * ``CpuRank('cpu')``: a str that compares equal to 0, so ``.to(rank)`` /
+    ``device=rank`` resolve to the CPU while ``if rank == 0`` still fires;
+  * ``queue.Queue`` for the eviction fifo, eviction_manager body
+    (cache_manager.py:58-62) applied inline after every window (sequential
+    schedule);
+  * ``torch.set_num_threads(1)`` so duplicate ``index_put_`` is last-wins;
+  * for the 2-rank aggregation fixture: gloo + lambdas for the removed
+    ``dist.*_multigpu`` calls.
+"""
+import hashlib
+import json
+import os
+import queue
+import sys
+
+import numpy as np
+
+REF = os.environ.get("CDLRM_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+
+import torch  # noqa: E402
+
+torch.set_num_threads(1)
+
+import cache_manager as C  # noqa: E402  (reference)
+import main_no_ddp as R  # noqa: E402  (reference)
+import model_no_ddp as M  # noqa: E402  (reference)
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+class CpuRank(str):
+    def __eq__(self, o):
+        return o == 0 or str.__eq__(self, o)
+
+    __hash__ = str.__hash__
+
+
+def digest(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def make_ids(cfg):
+    """Synthetic index stream; the same function lives in tests/util.py."""
+    rng = np.random.default_rng(cfg["data_seed"])
+    T = len(cfg["ln_emb"])
+    N = cfg["n_windows"] * cfg["lookahead"] * cfg["batch"]
+    ids = np.empty((T, N), dtype=np.int64)
+    for k, n in enumerate(cfg["ln_emb"]):
+        if cfg["dist"] == "uniform":
+            ids[k] = rng.integers(0, n, size=N)
+        else:  # bounded power law over a permuted id space
+            r = rng.zipf(cfg["zipf_a"], size=N) - 1
+            perm_mul = 2654435761 % n if n > 1 else 0
+            ids[k] = (r * max(perm_mul, 1) + k) % n
+    return ids
+
+
+def run_trace(cfg, full):
+    """Drive the reference for n_windows windows with a synthetic upstream
+    gradient G (so that the MLPs are not needed): L = sum_k <ly_k, G[step,k]>."""
+    seed = cfg["seed"]
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    ln_emb = np.asarray(cfg["ln_emb"])
+    d, B, L = cfg["dim"], cfg["batch"], cfg["lookahead"]
+    T = len(ln_emb)
+    master = M.Embedding_Table_Group(d, ln_emb)
+    cg = M.Embedding_Table_Cache_Group(d, ln_emb, max_cache_size=cfg["cache_size"],
+                                       aux_table_size=B, num_ways=cfg["num_ways"])
+    for e in cg.emb_l:
+        e.weight.data.zero_()
+    opt = torch.optim.SGD(cg.parameters(), lr=cfg["lr_embeds"])
+    rank = CpuRank("cpu")
+    evq = queue.Queue()
+    ids = make_ids(cfg)
+    grng = np.random.default_rng(cfg["data_seed"] + 1)
+    out = {"master_init_digest": np.array([digest(e.weight.data.numpy()) for e in master.emb_l]),
+           "cache_sizes": np.asarray(cg.cache_sizes, dtype=np.int64)}
+    if full == "all":
+        for k, e in enumerate(master.emb_l):
+            out[f"master_init_{k}"] = e.weight.data.numpy().copy()
+    lS_o = torch.arange(B).reshape(1, -1).repeat(T, 1)
+    # the seed for the victim RNG is re-armed right before the first window, as
+    # Run does (main_no_ddp.py:337) -- master init above consumed numpy only.
+    torch.manual_seed(seed)
+    step = 0
+    for w in range(cfg["n_windows"]):
+        win = torch.from_numpy(ids[:, w * L * B:(w + 1) * L * B])
+        rows, uniq, maps = C.Prefetcher.process_batch_slice(win, master)
+        R.CacheEmbeddings(rows, uniq, maps, cg, evq, rank)
+        ev = evq.get()
+        for k, (ix, emb) in enumerate(ev):                      # cache_manager.py:58-62
+            master.emb_l[k].weight.data[ix] = (
+                (master.emb_l[k].weight.data[ix] + emb) / 2 if cfg.get("avg_wb", False) else emb)
+        out[f"w{w}_uniq_len"] = np.asarray([u.numel() for u in uniq], dtype=np.int64)
+        out[f"w{w}_tags_digest"] = np.array([digest(t.numpy()) for t in cg.occupancy_tables])
+        out[f"w{w}_evict_len"] = np.asarray([e[0].numel() for e in ev], dtype=np.int64)
+        out[f"w{w}_evict_ids"] = np.concatenate([e[0].numpy() for e in ev])
+        out[f"w{w}_evict_rows_sum"] = np.asarray([e[1].double().sum().item() for e in ev])
+        out[f"w{w}_rng_digest"] = np.array(digest(torch.get_rng_state().numpy()))
+        if full:
+            out[f"w{w}_tags"] = np.concatenate([t.numpy().ravel() for t in cg.occupancy_tables])
+            out[f"w{w}_evict_rows"] = np.concatenate([e[1].numpy() for e in ev], axis=0)
+        for b in range(L):
+            lS_i = win[:, b * B:(b + 1) * B]
+            ly, slots = cg(lS_o, lS_i, master, rank)
+            G = grng.standard_normal((T, B, d)).astype(np.float32)
+            loss = sum((ly[k] * torch.from_numpy(G[k])).sum() for k in range(T))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            sl = torch.stack(slots).numpy()
+            nm = np.asarray([cg.victim_cache_entries[k][0].numel() for k in range(T)], dtype=np.int64)
+            out[f"s{step}_n_miss"] = nm
+            out[f"s{step}_slots_digest"] = np.array(digest(sl))
+            out[f"s{step}_out_sum"] = np.asarray([v.detach().double().sum().item() for v in ly])
+            if full:
+                out[f"s{step}_slots"] = sl
+            if full == "all" or b < 2:
+                out[f"s{step}_out"] = torch.stack([v.detach() for v in ly]).numpy()
+            step += 1
+        out[f"w{w}_weight_sum"] = np.asarray([e.weight.data.double().sum().item() for e in cg.emb_l])
+    for k in range(T):
+        if full:
+            out[f"final_weight_{k}"] = cg.emb_l[k].weight.data.numpy().copy()
+        if full == "all":
+            out[f"final_master_{k}"] = master.emb_l[k].weight.data.numpy().copy()
+        else:  # sampled rows: every 97th row
+            out[f"final_master_s_{k}"] = master.emb_l[k].weight.data.numpy()[::97].copy()
+        if not full:
+            out[f"final_weight_s_{k}"] = cg.emb_l[k].weight.data.numpy()[::97].copy()
+        out[f"final_master_sum_{k}"] = np.asarray(master.emb_l[k].weight.data.double().sum().item())
+    out["cfg_json"] = np.array(json.dumps(cfg))
+    return out
+
+
+TINY = dict(name="tiny", ln_emb=[1000, 37, 5000, 3], dim=8, cache_size=64, num_ways=4, batch=32,
+            lookahead=4, n_windows=3, lr_embeds=0.3, seed=123, data_seed=7, dist="zipf", zipf_a=1.2)
+PRESSURE = dict(name="pressure", ln_emb=[20000, 500, 6000], dim=16, cache_size=300, num_ways=8,
+                batch=256, lookahead=8, n_windows=4, lr_embeds=0.8, seed=123, data_seed=11,
+                dist="zipf", zipf_a=1.05)
+PRESSURE_AVG = dict(PRESSURE, name="pressure_avgwb", avg_wb=True, dist="uniform", n_windows=3,
+                    ln_emb=[3000, 700, 40], data_seed=13)
+CFG0 = dict(name="cfg0_small", ln_emb=[100000] * 8, dim=16, cache_size=10000, num_ways=16, batch=128,
+            lookahead=100, n_windows=2, lr_embeds=0.3, seed=123, data_seed=17, dist="zipf",
+            zipf_a=1.05)
+
+
+def gen_geometry():
+    sizes = [1, 2, 3, 4, 10, 64, 100, 300, 1000, 10000, 10240, 50000, 100000, 150000, 300000, 600000]
+    cg = M.Embedding_Table_Cache_Group.__new__(M.Embedding_Table_Cache_Group)
+    res = {str(s): cg.find_next_prime(s) for s in sizes}
+    isp = {str(n): bool(M.isPrime(n)) for n in list(range(1, 200)) + [10006, 150001, 300002, 600011]}
+    with open(os.path.join(OUT, "geometry.json"), "w") as f:
+        json.dump({"find_next_prime": res, "isPrime": isp}, f, indent=0, sort_keys=True)
+
+
+def gen_rng():
+    out = {}
+    for seed in (123, 7):
+        torch.manual_seed(seed)
+        out[f"q_{seed}"] = torch.empty(257, 16).exponential_(1).numpy()
+        out[f"q2_{seed}"] = torch.empty(5, 4).exponential_(1).numpy()   # stream continues
+        out[f"state_{seed}"] = np.array(digest(torch.get_rng_state().numpy()))
+    g = np.random.default_rng(0)
+    for ways in (4, 16, 5):
+        avail = g.random((3000, ways)) < 0.5
+        avail[avail.sum(1) == 0, ways - 1] = True
+        torch.manual_seed(99)
+        s = torch.distributions.Categorical(torch.from_numpy(avail).float()).sample().numpy()
+        out[f"avail_{ways}"] = avail
+        out[f"sample_{ways}"] = s
+    np.savez_compressed(os.path.join(OUT, "rng.npz"), **out)
+
+
+def gen_interact():
+    out = {}
+    g = np.random.default_rng(5)
+    for name, (B, nf, d, itself) in {"a": (9, 27, 128, False), "b": (17, 9, 16, False),
+                                     "c": (9, 5, 8, True), "d": (5, 4, 6, False)}.items():
+        net = M.DLRM_Net.__new__(M.DLRM_Net)
+        torch.nn.Module.__init__(net)
+        net.arch_interaction_op = "dot"
+        net.arch_interaction_itself = itself
+        x = torch.from_numpy(g.standard_normal((B, d)).astype(np.float32)).requires_grad_()
+        ly = [torch.from_numpy(g.standard_normal((B, d)).astype(np.float32)).requires_grad_()
+              for _ in range(nf - 1)]
+        Rr = net.interact_features(x, ly)
+        dR = torch.from_numpy(g.standard_normal(tuple(Rr.shape)).astype(np.float32))
+        Rr.backward(dR)
+        out[f"{name}_x"] = x.detach().numpy()
+        out[f"{name}_ly"] = torch.stack([t.detach() for t in ly]).numpy()
+        out[f"{name}_R"] = Rr.detach().numpy()
+        out[f"{name}_dR"] = dR.numpy()
+        out[f"{name}_dx"] = x.grad.numpy()
+        out[f"{name}_dly"] = torch.stack([t.grad for t in ly]).numpy()
+        out[f"{name}_itself"] = np.array(itself)
+    np.savez_compressed(os.path.join(OUT, "interact.npz"), **out)
+
+
+def _agg_worker(rank, world, op, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.all_reduce_multigpu = lambda ts, op=dist.ReduceOp.SUM, async_op=False: dist.all_reduce(
+        ts[0], op=op, async_op=async_op)
+    _el = torch.empty_like
+    torch.empty_like = lambda t, device=None, **kw: _el(t, **kw)
+    torch.set_num_threads(1)
+    ln_emb = np.asarray([50, 7, 300])
+    cg = M.Embedding_Table_Cache_Group(4, ln_emb, max_cache_size=10, aux_table_size=6, num_ways=2)
+    g = np.random.default_rng(100 + rank)
+    for e in cg.emb_l:
+        e.weight.data = torch.from_numpy(g.standard_normal(tuple(e.weight.shape)).astype(np.float32))
+    rows = min(e.weight.shape[0] for e in cg.emb_l)
+    idxs = torch.from_numpy(g.integers(0, rows, size=(3, 9)).astype(np.int32))
+    before = [e.weight.data.numpy().copy() for e in cg.emb_l]
+    R.broadcast_and_aggregate(cg, idxs, rank, op)
+    ret.put((rank, before, idxs.numpy(), [e.weight.data.numpy().copy() for e in cg.emb_l]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def gen_aggregate():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = {}
+    for i, op in enumerate(("mean", "sum", "max")):
+        ret = ctx.Queue()
+        ps = [ctx.Process(target=_agg_worker, args=(r, 2, op, 29611 + i, ret)) for r in range(2)]
+        [p.start() for p in ps]
+        got = sorted([ret.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+        [p.join() for p in ps]
+        for r, before, idxs, after in got:
+            out[f"{op}_r{r}_idxs"] = idxs
+            for k in range(3):
+                out[f"{op}_r{r}_before_{k}"] = before[k]
+                out[f"{op}_r{r}_after_{k}"] = after[k]
+    np.savez_compressed(os.path.join(OUT, "aggregate.npz"), **out)
+
+
+def gen_dlrm_tiny():
+    """End-to-end losses of the reference model on the TINY stream (MLPs,
+    interaction, BCE loss, both SGD optimizers) -- pins the loss-parity test."""
+    cfg = dict(TINY, name="dlrm_tiny")
+    seed = cfg["seed"]
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    ln_emb = np.asarray(cfg["ln_emb"])
+    d, B, L = cfg["dim"], cfg["batch"], cfg["lookahead"]
+    T = len(ln_emb)
+    ln_bot = np.asarray([13, 16, d])
+    nf = T + 1
+    ln_top = np.asarray([d + nf * (nf - 1) // 2, 16, 1])
+    master = M.Embedding_Table_Group(d, ln_emb)          # numpy RNG order: master first (main :621)
+    cg = M.Embedding_Table_Cache_Group(d, ln_emb, max_cache_size=cfg["cache_size"],
+                                       aux_table_size=B, num_ways=cfg["num_ways"])
+    for e in cg.emb_l:
+        e.weight.data.zero_()
+    np.random.seed(seed)                                 # Run re-seeds (main :335)
+    torch.manual_seed(seed)
+    dlrm = M.DLRM_Net(ln_bot, ln_top, arch_interaction_op="dot", arch_interaction_itself=False,
+                      sigmoid_bot=-1, sigmoid_top=ln_top.size - 2)
+    loss_fn = torch.nn.BCELoss(reduction="mean")
+    opt_m = torch.optim.SGD(dlrm.parameters(), lr=0.1)
+    opt_e = torch.optim.SGD(cg.parameters(), lr=cfg["lr_embeds"])
+    rank = CpuRank("cpu")
+    evq = queue.Queue()
+    ids = make_ids(cfg)
+    drng = np.random.default_rng(cfg["data_seed"] + 2)
+    nsteps = cfg["n_windows"] * L
+    X = np.log1p(drng.integers(0, 100, size=(nsteps, B, 13))).astype(np.float32)
+    Y = (drng.random((nsteps, B, 1)) < 0.25).astype(np.float32)
+    out = {"X": X, "Y": Y, "cfg_json": np.array(json.dumps(cfg)),
+           "ln_bot": ln_bot, "ln_top": ln_top}
+    for i, p in enumerate(dlrm.parameters()):
+        out[f"mlp_init_{i}"] = p.detach().numpy().copy()
+    lS_o = torch.arange(B).reshape(1, -1).repeat(T, 1)
+    losses = []
+    step = 0
+    for w in range(cfg["n_windows"]):
+        win = torch.from_numpy(ids[:, w * L * B:(w + 1) * L * B])
+        rows, uniq, maps = C.Prefetcher.process_batch_slice(win, master)
+        R.CacheEmbeddings(rows, uniq, maps, cg, evq, rank)
+        for k, (ix, emb) in enumerate(evq.get()):
+            master.emb_l[k].weight.data[ix] = emb
+        for b in range(L):
+            lS_i = win[:, b * B:(b + 1) * B]
+            ly, _ = cg(lS_o, lS_i, master, rank)
+            Z = dlrm(torch.from_numpy(X[step]), ly)
+            E = loss_fn(Z, torch.from_numpy(Y[step]))
+            opt_m.zero_grad()
+            opt_e.zero_grad()
+            E.backward()
+            opt_e.step()
+            opt_m.step()
+            losses.append(E.item())
+            step += 1
+    out["losses"] = np.asarray(losses, dtype=np.float64)
+    for i, p in enumerate(dlrm.parameters()):
+        out[f"mlp_final_{i}"] = p.detach().numpy().copy()
+    for k in range(T):
+        out[f"final_weight_{k}"] = cg.emb_l[k].weight.data.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "dlrm_tiny.npz"), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    gen_geometry()
+    gen_rng()
+    gen_interact()
+    for cfg, full in ((TINY, "all"), (PRESSURE, "ints"), (PRESSURE_AVG, "ints"), (CFG0, False)):
+        res = run_trace(cfg, full)
+        np.savez_compressed(os.path.join(OUT, f"trace_{cfg['name']}.npz"), **res)
+        print(cfg["name"], "done",
+              {k: res[k].tolist() for k in res if k.endswith("evict_len") or k.endswith("uniq_len")})
+    gen_dlrm_tiny()
+    gen_aggregate()
+    print("golden vectors written to", os.path.abspath(OUT))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,358 @@
+"""B200-native mirror of the reference's ``cache_manager.py`` (lkp411/cDLRM) plus the
+GPU-resident look-ahead planner/mover that replaces its CPU worker pool.
+
+Reference API kept: ``Prefetcher(args, emb_tables_cpu, batch_fifo, eviction_fifo,
+finish_event, cache_ld)`` with ``start/join/run`` and the statics
+``process_batch_slice``, ``eviction_manager``, ``pin_pool`` (cache_manager.py:8-115).
+
+New (B200-first): ``WindowPlanner`` -- plans window w+1 on a side stream while window w
+trains (tags in HBM, bitmap-unique, ballot probe, bit-exact victim choice from the
+torch-compatible mt19937 stream) and installs it at the boundary with zero-copy evict /
+fill kernels over the pinned master tables.  All arithmetic is in libcdlrm_b200.so.
+"""
+import ctypes
+import math
+import os
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_vp = ctypes.c_void_p
+
+
+def _sp(stream):
+    return _vp(stream.cuda_stream)
+
+
+# ------------------------------------------------------------------------------------
+# victim-way random stream (main_no_ddp.py:183-185)
+# ------------------------------------------------------------------------------------
+
+
+class VictimRng:
+    """Host mt19937 stream bit-identical to ``torch.manual_seed(seed)`` followed by
+    ``torch.empty(n).exponential_(1)`` (what Categorical.sample() consumes), produced by
+    cdlrm_rng_exponential with a multi-threaded log1p transform."""
+
+    def __init__(self, seed, threads=None):
+        self._h = _vp()
+        check(lib.cdlrm_rng_create(ctypes.byref(self._h), int(seed)))
+        self.threads = threads or max(1, min(16, (os.cpu_count() or 2) - 1))
+
+    def exponential(self, n, pin=True):
+        out = torch.empty(max(int(n), 1), dtype=torch.float32, pin_memory=pin and torch.cuda.is_available())
+        if n:
+            check(lib.cdlrm_rng_exponential(self._h, _vp(out.data_ptr()), int(n), self.threads))
+        return out[:n]
+
+    @property
+    def draws(self):
+        return int(lib.cdlrm_rng_draws(self._h))
+
+    def __del__(self):
+        try:
+            lib.cdlrm_rng_destroy(self._h)
+        except Exception:
+            pass
+
+
+class TorchGlobalRng:
+    """Draws from torch's global CPU generator -- literally what the reference's
+    ``Categorical(...).sample()`` does, so interleaving with any other consumer of the
+    global generator stays identical.  Used by the drop-in ``CacheEmbeddings``."""
+
+    def exponential(self, n, pin=True):
+        q = torch.empty(int(n), dtype=torch.float32).exponential_(1) if n else torch.empty(0)
+        return q.pin_memory() if (pin and n and torch.cuda.is_available()) else q
+
+
+# ------------------------------------------------------------------------------------
+# planner + mover
+# ------------------------------------------------------------------------------------
+
+
+class PlanRecord:
+    """Decisions for one window (all device tensors are concatenated over tables; the
+    lists of table k start at ``off[k]``)."""
+    __slots__ = ("uniq", "hits", "dropped", "rows", "E", "F", "off", "evict_ids", "evict_slots",
+                 "evict_primary", "fill_ids", "fill_slots", "event")
+
+    def evict_list(self, k):
+        o, e = self.off[k], self.E[k]
+        return self.evict_ids[o:o + e], self.evict_slots[o:o + e], self.evict_primary[o:o + e]
+
+    def fill_list(self, k):
+        o, f = self.off[k], self.F[k]
+        return self.fill_ids[o:o + f], self.fill_slots[o:o + f]
+
+
+class WindowPlanner:
+    def __init__(self, cache_group, emb_tables, window_len, rng=None, stream=None, lookahead_tags=False):
+        self.cg = cache_group
+        self.emb_tables = emb_tables
+        self.ctx = cache_group._ensure_ctx(emb_tables)
+        self.dev = cache_group.device
+        self.T = len(cache_group.emb_l)
+        self.ways = cache_group.num_ways
+        self.dim = cache_group.dim
+        self.rng = rng if rng is not None else TorchGlobalRng()
+        self.stream = stream or torch.cuda.current_stream(self.dev)
+        self.window_len = int(window_len)
+        nbytes = lib.cdlrm_plan_workspace_bytes(self.ctx, self.window_len)
+        if nbytes < 0:
+            raise _lib.CdlrmError("cdlrm_plan_workspace_bytes failed")
+        self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.dev)
+        base = (self._ws.data_ptr() + 255) // 256 * 256
+        check(lib.cdlrm_plan_bind_workspace(self.ctx, _vp(base), nbytes, self.window_len))
+        self._h_counts = torch.zeros(self.T * 4, dtype=torch.int64).pin_memory()
+        self._h_counts2 = torch.zeros(self.T * 2, dtype=torch.int64).pin_memory()
+        self.plan_tags = None
+        if lookahead_tags:
+            self.enable_lookahead_tags()
+
+    def enable_lookahead_tags(self):
+        """Give the planner its own evolving copy of the tags so that it can run one or more
+        windows ahead of the live tags (which are patched by ``install``)."""
+        self.plan_tags = [t.clone() for t in self.cg.occupancy_tables]
+        check(lib.cdlrm_ctx_bind_plan_tags(self.ctx, _lib.ptr_array([t.data_ptr() for t in self.plan_tags])))
+
+    def unique_ptr(self, k):
+        return lib.cdlrm_plan_unique_ptr(self.ctx, k)
+
+    def unique_tensor(self, k, n):
+        """Copy of the ascending unique ids of table k found by the last plan (device)."""
+        out = torch.empty(n, dtype=torch.int64, device=self.dev)
+        check(lib.cdlrm_plan_copy_unique(self.ctx, k, _vp(out.data_ptr()), n,
+                                         _sp(torch.cuda.current_stream(self.dev))))
+        return out
+
+    # -- plan -----------------------------------------------------------------------------
+    def plan(self, win_ids=None, uniq_lists=None):
+        """win_ids: int64 device tensor [T, n] (raw window ids), or uniq_lists: list of T
+        ascending-unique int64 tensors (the reference-API path)."""
+        s = self.stream
+        rec = PlanRecord()
+        with torch.cuda.stream(s):
+            if uniq_lists is not None:
+                lens = [int(u.numel()) for u in uniq_lists]
+                ld = max(max(lens), 1)
+                if ld > self.window_len:
+                    raise _lib.CdlrmError("unique list longer than the planner workspace window")
+                buf = torch.zeros(self.T, ld, dtype=torch.int64, device=self.dev)
+                for k, u in enumerate(uniq_lists):
+                    if lens[k]:
+                        buf[k, :lens[k]].copy_(u.to(self.dev, non_blocking=True))
+                check(lib.cdlrm_plan_phase_a(self.ctx, _vp(buf.data_ptr()), buf.stride(0), ld,
+                                             _lib.i64_array(lens), _vp(self._h_counts.data_ptr()), _sp(s)))
+            else:
+                assert win_ids.is_cuda and win_ids.dtype == torch.int64 and win_ids.stride(1) == 1
+                check(lib.cdlrm_plan_phase_a(self.ctx, _vp(win_ids.data_ptr()), win_ids.stride(0),
+                                             win_ids.shape[1], None, _vp(self._h_counts.data_ptr()), _sp(s)))
+            s.synchronize()
+            cnt = self._h_counts.view(self.T, 4).clone()
+            rec.uniq = cnt[:, 0].tolist()
+            rec.hits = cnt[:, 1].tolist()
+            rec.dropped = cnt[:, 2].tolist()
+            rec.rows = cnt[:, 3].tolist()
+            total = int(sum(rec.rows))
+            rec.off = [0] * self.T
+            for k in range(1, self.T):
+                rec.off[k] = rec.off[k - 1] + rec.rows[k - 1]
+            # q for table 0..T-1 in one draw: the stream is split-invariant
+            q_host = self.rng.exponential(total * self.ways)
+            q = q_host.to(self.dev, non_blocking=True) if total else torch.empty(0, device=self.dev)
+            n = max(total, 1)
+            rec.evict_ids = torch.empty(n, dtype=torch.int64, device=self.dev)
+            rec.evict_slots = torch.empty(n, dtype=torch.int32, device=self.dev)
+            rec.evict_primary = torch.empty(n, dtype=torch.uint8, device=self.dev)
+            rec.fill_ids = torch.empty(n, dtype=torch.int64, device=self.dev)
+            rec.fill_slots = torch.empty(n, dtype=torch.int32, device=self.dev)
+            check(lib.cdlrm_plan_phase_b(self.ctx, _vp(q.data_ptr()) if total else None, _lib.i64_array(rec.rows),
+                                         _vp(rec.evict_ids.data_ptr()), _vp(rec.evict_slots.data_ptr()),
+                                         _vp(rec.evict_primary.data_ptr()), _vp(rec.fill_ids.data_ptr()),
+                                         _vp(rec.fill_slots.data_ptr()), _vp(self._h_counts2.data_ptr()), _sp(s)))
+            s.synchronize()
+            c2 = self._h_counts2.view(self.T, 2).clone()
+            rec.E = c2[:, 0].tolist()
+            rec.F = c2[:, 1].tolist()
+            del q_host
+        rec.event = None
+        return rec
+
+    # -- install ---------------------------------------------------------------------------
+    def install(self, rec, write_master=True, average_on_writeback=False, collect_evictions=False,
+                fill_rows=None, stream=None):
+        """Apply a plan at the window boundary on ``stream`` (default: current stream):
+        evicted rows are read BEFORE any fill writes; with ``write_master`` they go straight
+        back to the pinned master (zero-copy); ``collect_evictions`` additionally returns the
+        reference's ``eviction_data`` list [(ids, rows)] as device tensors.
+        ``fill_rows``: optional list of (rows_k, src_index_k) device tensors -- rows provided
+        by the caller (reference API: ``table_cache[map[ids]]``); default reads the master."""
+        s = stream or torch.cuda.current_stream(self.dev)
+        out = []
+        with torch.cuda.stream(s):
+            for k in range(self.T):
+                ids, slots, prim = rec.evict_list(k)
+                rows = None
+                if collect_evictions:
+                    rows = torch.empty(rec.E[k], self.dim, dtype=torch.float32, device=self.dev)
+                if rec.E[k]:
+                    check(lib.cdlrm_move_evict(self.ctx, k, _vp(ids.data_ptr()), _vp(slots.data_ptr()),
+                                               _vp(prim.data_ptr()), rec.E[k],
+                                               _vp(rows.data_ptr()) if rows is not None else None,
+                                               int(write_master), int(average_on_writeback), _sp(s)))
+                if collect_evictions:
+                    out.append((ids, rows))
+            for k in range(self.T):
+                ids, slots = rec.fill_list(k)
+                if not rec.F[k]:
+                    continue
+                r, si = (None, None) if fill_rows is None else fill_rows[k]
+                check(lib.cdlrm_move_fill(self.ctx, k, _vp(ids.data_ptr()), _vp(slots.data_ptr()), rec.F[k],
+                                          _vp(r.data_ptr()) if r is not None else None,
+                                          _vp(si.data_ptr()) if si is not None else None, _sp(s)))
+        return out
+
+
+# ------------------------------------------------------------------------------------
+# Prefetcher -- cache_manager.py:8-115
+# ------------------------------------------------------------------------------------
+
+_UTIL = {}
+
+
+def _util_planner(emb_tables_cpu, device, window_len):
+    """A planner-only context per (master tables, device) used by the static
+    ``process_batch_slice`` (it needs the unique + master-gather kernels, no cache)."""
+    from .model_no_ddp import Embedding_Table_Cache_Group
+    key = (id(emb_tables_cpu), device.index)
+    ent = _UTIL.get(key)
+    if ent is None or ent[1].window_len < window_len:
+        ln = np.asarray([E.weight.shape[0] for E in emb_tables_cpu.emb_l])
+        dim = emb_tables_cpu.emb_l[0].weight.shape[1]
+        cg = Embedding_Table_Cache_Group(dim, ln, max_cache_size=2, aux_table_size=0, num_ways=1, device=device)
+        ent = (cg, WindowPlanner(cg, emb_tables_cpu, window_len))
+        _UTIL[key] = ent
+    return ent
+
+
+class Prefetcher(threading.Thread):
+    """Look-ahead scanner.  The reference runs it as a separate process with a CPU worker
+    pool (cache_manager.py:66-115); here the scan is a handful of kernels, so ``run`` is a
+    light host thread that only slices the loader's batches into windows of
+    ``lookahead * mini_batch_size`` samples (:75,85-110) and hands the raw window ids to the
+    trainer, whose ``WindowPlanner`` does the rest on a side stream."""
+
+    def __init__(self, args, emb_tables_cpu, batch_fifo, eviction_fifo, finish_event, cache_ld):
+        super().__init__(daemon=True)
+        self.args = args
+        self.emb_tables_cpu = emb_tables_cpu
+        self.batch_fifo = batch_fifo
+        self.eviction_fifo = eviction_fifo
+        self.finish_event = finish_event
+        self.cache_ld = cache_ld
+
+    @staticmethod
+    def pin_pool(p, core):
+        """cache_manager.py:20-25 (CPU affinity of pool worker p)."""
+        try:
+            os.sched_setaffinity(0, {core + 3 + p})
+        except (OSError, ValueError):
+            pass
+        return 1
+
+    @staticmethod
+    def process_batch_slice(slice, emb_tables_cpu):
+        """cache_manager.py:27-46: per table the ascending unique ids of the window, the
+        dense id->position map and the unique rows of the master table.  Unique and the row
+        gather run on the GPU (bitmap compaction + zero-copy gather); results come back on
+        the device of ``slice`` (CPU in the reference's multi-process hand-off)."""
+        if not torch.cuda.is_available():
+            raise _lib.CdlrmError("process_batch_slice needs a CUDA device: no CPU fallback")
+        src_dev = slice.device
+        dev = slice.device if slice.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        ids = slice.to(dev, dtype=torch.int64).contiguous()
+        cg, pl = _util_planner(emb_tables_cpu, dev, int(ids.shape[1]))
+        s = torch.cuda.current_stream(dev)
+        check(lib.cdlrm_plan_unique(pl.ctx, _vp(ids.data_ptr()), ids.stride(0), ids.shape[1],
+                                    _vp(pl._h_counts.data_ptr()), _sp(s)))
+        s.synchronize()
+        cg.check_device_flags()
+        U = pl._h_counts.view(-1, 4)[:, 0].tolist()
+        rows_l, uniq_l, maps_l = [], [], []
+        for k in range(len(emb_tables_cpu.emb_l)):
+            u = pl.unique_tensor(k, U[k])
+            rows = torch.empty(U[k], cg.dim, dtype=torch.float32, device=dev)
+            check(lib.cdlrm_move_gather_master(pl.ctx, k, _vp(u.data_ptr()), U[k], _vp(rows.data_ptr()), _sp(s)))
+            m = torch.full((int(u.max().item()) + 1 if U[k] else 1, 1), -1, dtype=torch.long, device=dev)
+            if U[k]:
+                m[u, 0] = torch.arange(U[k], device=dev)
+            uniq_l.append(u.to(src_dev))
+            rows_l.append(rows.to(src_dev))
+            maps_l.append(m.to(src_dev))
+        return rows_l, uniq_l, maps_l
+
+    @staticmethod
+    def apply_eviction_data(emb_tables, eviction_data, average_on_writeback=False):
+        """Body of the eviction loop (cache_manager.py:58-62): ``W[idxs] = emb`` or
+        ``(W[idxs] + emb) / 2`` through cdlrm_move_scatter_master (zero-copy writes into the
+        pinned master)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        _cg, pl = _util_planner(emb_tables, dev, 1)
+        s = torch.cuda.current_stream(dev)
+        for k, (idxs, embeddings) in enumerate(eviction_data):
+            n = int(idxs.numel())
+            if n == 0:
+                continue
+            if average_on_writeback:
+                # duplicates carry identical rows; keep one so the average is applied once
+                idxs_u, inv = torch.unique(idxs, return_inverse=True)
+                rep = torch.empty(idxs_u.numel(), dtype=torch.long, device=idxs.device)
+                rep[inv] = torch.arange(n, device=idxs.device)
+                idxs, embeddings, n = idxs_u, embeddings[rep], int(idxs_u.numel())
+            i_d = idxs.to(dev, dtype=torch.int64).contiguous()
+            e_d = embeddings.to(dev, dtype=torch.float32).contiguous()
+            check(lib.cdlrm_move_scatter_master(pl.ctx, k, _vp(i_d.data_ptr()), n, _vp(e_d.data_ptr()),
+                                                int(bool(average_on_writeback)), _sp(s)))
+        s.synchronize()
+
+    @staticmethod
+    def eviction_manager(emb_tables, eviction_fifo, average_on_writeback, core, timeout):
+        """cache_manager.py:48-64: pop eviction_data and write the rows back into the master
+        tables.  (With ``WindowPlanner.install(write_master=True)`` the write-back already
+        happened on the GPU and nothing is queued.)"""
+        try:
+            os.sched_setaffinity(0, {core})
+        except (OSError, ValueError):
+            pass
+        try:
+            while True:
+                eviction_data = eviction_fifo.get(timeout=timeout) if timeout > 0 else eviction_fifo.get()
+                Prefetcher.apply_eviction_data(emb_tables, eviction_data, average_on_writeback)
+        except Exception:
+            print('Eviction queue empty longer than expected. Exiting eviction manager...')
+
+    def windows(self):
+        """Generator of raw window id tensors [T, <= lookahead*mini_batch_size] in training
+        order: entry w covers steps [w*lookahead, (w+1)*lookahead) (SURVEY 3.4 invariant)."""
+        per = self.args.lookahead
+        for _epoch in range(self.args.nepochs):
+            acc = []
+            for _j, batch in enumerate(self.cache_ld):
+                acc.append(batch[2])
+                if len(acc) == per:
+                    yield torch.cat(acc, dim=1)
+                    acc = []
+            if acc:
+                yield torch.cat(acc, dim=1)
+
+    def run(self):
+        for win in self.windows():
+            self.batch_fifo.put(win)
+        self.batch_fifo.put(None)
+        if self.finish_event is not None:
+            self.finish_event.wait()

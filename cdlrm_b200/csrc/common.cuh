@@ -1,0 +1,95 @@
+// common.cuh -- shared declarations of libcdlrm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cdlrm_b200.h"
+
+#define CDLRM_OK 0
+#define CDLRM_ERR_ARG -1
+#define CDLRM_ERR_CUDA -2
+#define CDLRM_ERR_STATE -3
+
+void cdlrm_set_error(const char* fmt, ...);
+
+#define CU_CHECK(call)                                                                    \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            cdlrm_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return CDLRM_ERR_CUDA;                                                        \
+        }                                                                                 \
+    } while (0)
+
+#define ARG_CHECK(cond)                                                                   \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            cdlrm_set_error("%s:%d bad argument: %s", __FILE__, __LINE__, #cond);         \
+            return CDLRM_ERR_ARG;                                                         \
+        }                                                                                 \
+    } while (0)
+
+// One per table; lives in device memory (ctx->d_tabs) and on the host (ctx->tabs).
+struct TableDesc {
+    float* weight;        // [cache_rows, dim]
+    int64_t* tags;        // live tags [num_sets, ways]
+    int64_t* plan_tags;   // planner's look-ahead copy (may alias tags)
+    const float* master;  // device-visible master table [n_rows, dim]
+    uint32_t* dirty;      // bitmap over cache_rows (may be null)
+    int64_t num_sets;
+    int64_t n_rows;
+    int64_t cache_rows;
+    int64_t dirty_word_off;  // offset of this table's bitmap in the concatenated bitmap
+};
+
+// Planner workspace carve-up (device pointers into the caller's buffer).
+struct PlanTable {
+    uint32_t* bitmap;   // n_rows bits
+    int64_t* uniq;      // [umax]
+    int32_t* surv;      // [umax] survivor r -> index into uniq
+    int64_t umax;
+};
+
+struct cdlrm_ctx {
+    int device = 0;
+    int T = 0, dim = 0, ways = 0;
+    int64_t aux = 0;
+    int64_t max_cache_size = 0;  // after find_next_prime
+    std::vector<TableDesc> tabs;
+    TableDesc* d_tabs = nullptr;
+    bool tabs_dirty = true;
+    // forward/backward scratch
+    int32_t* d_miss_cnt = nullptr;  // [T][max_chunks]
+    int64_t scratch_max_idx = 0;
+    uint32_t* d_flags = nullptr;    // sticky error flags
+    // planner
+    std::vector<PlanTable> ptabs;
+    PlanTable* d_ptabs = nullptr;
+    int64_t plan_window_len = 0;
+    uint8_t* p_state = nullptr;     // [umax_max] per-unique state (way or miss)
+    std::vector<unsigned long long*> pins;  // per table [num_sets] pin masks of the window being planned
+    int32_t* p_blocksum2 = nullptr; // second tile-sum array
+    int32_t* p_blocksum = nullptr;  // [nblk_max + 1]
+    int32_t* p_claim = nullptr;     // [cache_rows_max], kept at -1 between uses
+    int32_t* p_slot = nullptr;      // [umax_max] slot chosen per survivor
+    int64_t* p_old = nullptr;       // [umax_max] old tag per survivor
+    uint8_t* p_flag = nullptr;      // [umax_max] bit0 evict, bit1 winner
+    int64_t* p_counts = nullptr;    // device counters [T*8]
+    std::vector<int64_t> last_uniq; // U_k of the last phase A (host, after sync by caller)
+    int64_t umax_max = 0, sets_max = 0, rows_max = 0;
+};
+
+int cdlrm_sync_tabs(cdlrm_ctx* ctx, cudaStream_t s);
+
+static inline int ceil_div_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ int64_t set_index(int64_t id, int64_t S) {
+    // torch.remainder semantics (non-negative result for S > 0)
+    if ((uint64_t)id < 0x100000000ull && (uint64_t)S < 0x100000000ull)
+        return (int64_t)((uint32_t)id % (uint32_t)S);
+    int64_t r = id % S;
+    return r < 0 ? r + S : r;
+}

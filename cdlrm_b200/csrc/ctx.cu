@@ -1,0 +1,205 @@
+// ctx.cu -- context, geometry and bindings of libcdlrm_b200.
+// Replaces Embedding_Table_Cache_Group.__init__ and helpers (model_no_ddp.py:102-147,
+// :319-331 of the reference).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void cdlrm_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* cdlrm_last_error(void) { return g_err; }
+extern "C" int cdlrm_abi_version(void) { return CDLRM_ABI_VERSION; }
+
+// model_no_ddp.py:319-331 -- deliberately NOT a correct primality test: divisors
+// start at 3 (so even n pass) and stop at i*i < n (so squares of primes pass).
+extern "C" int cdlrm_is_prime_ref(int64_t n) {
+    if (n == 1 || n == 2) return 0;
+    for (int64_t i = 3; i * i < n; ++i)
+        if (n % i == 0) return 0;
+    return 1;
+}
+
+// model_no_ddp.py:122-125
+extern "C" int64_t cdlrm_find_next_prime(int64_t c) {
+    for (int64_t i = c; i < 2 * c; ++i)
+        if (cdlrm_is_prime_ref(i)) return i;
+    return -1;
+}
+
+extern "C" int cdlrm_ctx_create(cdlrm_ctx** out, int device, int T, int dim, int ways, int64_t aux,
+                                const int64_t* n_rows, int64_t max_cache_size) {
+    ARG_CHECK(out && n_rows);
+    ARG_CHECK(T > 0 && dim > 0 && aux >= 0);
+    ARG_CHECK(ways > 0 && ways <= CDLRM_MAX_WAYS);
+    int64_t mcs = cdlrm_find_next_prime(max_cache_size);
+    if (mcs < 0) {
+        cdlrm_set_error("find_next_prime(%lld) found nothing in [c, 2c)", (long long)max_cache_size);
+        return CDLRM_ERR_ARG;
+    }
+    int ndev = 0;
+    CU_CHECK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        cdlrm_set_error("device %d not available (%d CUDA devices); there is no CPU fallback", device, ndev);
+        return CDLRM_ERR_CUDA;
+    }
+    CU_CHECK(cudaSetDevice(device));
+    cdlrm_ctx* c = new cdlrm_ctx();
+    c->device = device;
+    c->T = T;
+    c->dim = dim;
+    c->ways = ways;
+    c->aux = aux;
+    c->max_cache_size = mcs;
+    c->tabs.resize(T);
+    int64_t word_off = 0;
+    for (int k = 0; k < T; ++k) {
+        TableDesc& t = c->tabs[k];
+        memset(&t, 0, sizeof(t));
+        ARG_CHECK(n_rows[k] > 0);
+        t.n_rows = n_rows[k];
+        t.num_sets = n_rows[k] < mcs ? n_rows[k] : mcs;     // model_no_ddp.py:136
+        t.cache_rows = (int64_t)ways * t.num_sets + aux;    // :138
+        if (t.cache_rows >= (int64_t)1 << 31) {
+            cdlrm_set_error("table %d: %lld cache rows do not fit int32 slots", k, (long long)t.cache_rows);
+            delete c;
+            return CDLRM_ERR_ARG;
+        }
+        t.dirty_word_off = word_off;
+        word_off += (t.cache_rows + 31) / 32;
+    }
+    CU_CHECK(cudaMalloc(&c->d_tabs, sizeof(TableDesc) * T));
+    CU_CHECK(cudaMalloc(&c->d_flags, sizeof(uint32_t)));
+    CU_CHECK(cudaMemset(c->d_flags, 0, sizeof(uint32_t)));
+    CU_CHECK(cudaMalloc(&c->p_counts, sizeof(int64_t) * T * 8));
+    c->last_uniq.assign(T, 0);
+    c->tabs_dirty = true;
+    *out = c;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_ctx_destroy(cdlrm_ctx* c) {
+    if (!c) return CDLRM_OK;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_tabs);
+    cudaFree(c->d_flags);
+    cudaFree(c->d_miss_cnt);
+    cudaFree(c->p_counts);
+    cudaFree(c->d_ptabs);
+    delete c;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_ctx_geometry(const cdlrm_ctx* c, int64_t* num_sets, int64_t* cache_rows) {
+    ARG_CHECK(c);
+    for (int k = 0; k < c->T; ++k) {
+        if (num_sets) num_sets[k] = c->tabs[k].num_sets;
+        if (cache_rows) cache_rows[k] = c->tabs[k].cache_rows;
+    }
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_ctx_bind_cache(cdlrm_ctx* c, float* const* w, int64_t* const* tags) {
+    ARG_CHECK(c && w && tags);
+    for (int k = 0; k < c->T; ++k) {
+        ARG_CHECK(w[k] && tags[k]);
+        ARG_CHECK(((uintptr_t)w[k] & 15) == 0);
+        c->tabs[k].weight = w[k];
+        c->tabs[k].tags = tags[k];
+        if (!c->tabs[k].plan_tags) c->tabs[k].plan_tags = tags[k];
+    }
+    c->tabs_dirty = true;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_ctx_bind_plan_tags(cdlrm_ctx* c, int64_t* const* pt) {
+    ARG_CHECK(c && pt);
+    for (int k = 0; k < c->T; ++k) {
+        ARG_CHECK(pt[k]);
+        c->tabs[k].plan_tags = pt[k];
+    }
+    c->tabs_dirty = true;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_ctx_bind_master(cdlrm_ctx* c, float* const* m) {
+    ARG_CHECK(c && m);
+    for (int k = 0; k < c->T; ++k) {
+        ARG_CHECK(m[k]);
+        ARG_CHECK(((uintptr_t)m[k] & 15) == 0 || (c->dim & 3) != 0);
+        c->tabs[k].master = m[k];
+    }
+    c->tabs_dirty = true;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_ctx_bind_dirty(cdlrm_ctx* c, uint32_t* const* d) {
+    ARG_CHECK(c && d);
+    for (int k = 0; k < c->T; ++k) c->tabs[k].dirty = d[k];
+    c->tabs_dirty = true;
+    return CDLRM_OK;
+}
+
+int cdlrm_sync_tabs(cdlrm_ctx* c, cudaStream_t s) {
+    if (!c->tabs_dirty) return CDLRM_OK;
+    // Synchronous copy on purpose: bindings change only at set-up time, and a
+    // pageable-source async copy would not be legal inside graph capture anyway.
+    CU_CHECK(cudaStreamSynchronize(s));
+    CU_CHECK(cudaMemcpy(c->d_tabs, c->tabs.data(), sizeof(TableDesc) * c->T, cudaMemcpyHostToDevice));
+    c->tabs_dirty = false;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_ctx_reserve(cdlrm_ctx* c, int64_t max_idx) {
+    ARG_CHECK(c && max_idx >= 0);
+    CU_CHECK(cudaSetDevice(c->device));
+    if (max_idx <= c->scratch_max_idx && c->d_miss_cnt) return CDLRM_OK;
+    if (c->d_miss_cnt) {
+        CU_CHECK(cudaDeviceSynchronize());
+        CU_CHECK(cudaFree(c->d_miss_cnt));
+        c->d_miss_cnt = nullptr;
+    }
+    int64_t chunks = (max_idx + 255) / 256 + 1;
+    CU_CHECK(cudaMalloc(&c->d_miss_cnt, sizeof(int32_t) * c->T * chunks));
+    c->scratch_max_idx = max_idx;
+    return CDLRM_OK;
+}
+
+__global__ void fill_i64_kernel(int64_t* p, int64_t n, int64_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+extern "C" int cdlrm_tags_reset(cdlrm_ctx* c, cdlrm_stream stream) {
+    ARG_CHECK(c);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(c->device));
+    for (int k = 0; k < c->T; ++k) {
+        const TableDesc& t = c->tabs[k];
+        ARG_CHECK(t.tags);
+        int64_t n = t.num_sets * c->ways;
+        int grid = (int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368);
+        fill_i64_kernel<<<grid, 256, 0, s>>>(t.tags, n, -1);
+        if (t.plan_tags && t.plan_tags != t.tags) fill_i64_kernel<<<grid, 256, 0, s>>>(t.plan_tags, n, -1);
+    }
+    CU_CHECK(cudaGetLastError());
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_ctx_check(cdlrm_ctx* c, cdlrm_stream stream, uint32_t* h_flags) {
+    ARG_CHECK(c && h_flags);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(c->device));
+    CU_CHECK(cudaMemcpyAsync(h_flags, c->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU_CHECK(cudaMemsetAsync(c->d_flags, 0, sizeof(uint32_t), s));
+    CU_CHECK(cudaStreamSynchronize(s));
+    return CDLRM_OK;
+}

@@ -1,0 +1,327 @@
+// move.cu -- data movers of the window install and the table aggregation.
+//   evict / fill / master gather: data part of CacheEmbeddings (main_no_ddp.py:190-199,
+//   :205-206), Prefetcher.eviction_manager (cache_manager.py:48-64) and
+//   Embedding_Table_Group.fetch_unique_idx_slices (model_no_ddp.py:80-87).
+//   collect / pack / unpack: broadcast_and_aggregate (main_no_ddp.py:250-292) around one
+//   NCCL all-reduce issued by the host side.
+// The master pointers are device-visible addresses of pinned host memory: the gathers
+// and the write-back are zero-copy PCIe reads/writes issued by the SMs, so scattered
+// 512-byte rows move without any host-side staging or CPU work.
+#include "common.cuh"
+#include "compact.cuh"
+
+namespace {
+
+template <int VEC> struct VT;
+template <> struct VT<4> { using type = float4; };
+template <> struct VT<2> { using type = float2; };
+template <> struct VT<1> { using type = float; };
+
+__device__ __forceinline__ float4 avg2(float4 a, float4 b) { return make_float4((a.x + b.x) / 2, (a.y + b.y) / 2, (a.z + b.z) / 2, (a.w + b.w) / 2); }
+__device__ __forceinline__ float2 avg2(float2 a, float2 b) { return make_float2((a.x + b.x) / 2, (a.y + b.y) / 2); }
+__device__ __forceinline__ float avg2(float a, float b) { return (a + b) / 2; }
+__device__ __forceinline__ float4 vdiv(float4 a, float d) { return make_float4(a.x / d, a.y / d, a.z / d, a.w / d); }
+__device__ __forceinline__ float2 vdiv(float2 a, float d) { return make_float2(a.x / d, a.y / d); }
+__device__ __forceinline__ float vdiv(float a, float d) { return a / d; }
+
+// mode 0: evict   rows_out[e] = weight[slot[e]]; master[id[e]] = row (or average)
+// mode 1: gather  rows_out[i] = master[id[i]]
+// mode 2: fill    weight[slot[i]] = rows ? rows[src?src[i]:i] : master[id[i]]; tags updated
+// mode 3: pack    buf[i] = weight[slot[i]] / divisor
+// mode 4: unpack  weight[slot[i]] = buf[i]
+// mode 5: scatter master[id[i]] = rows[i] (or average)
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(256) rows_kernel(TableDesc T, const int64_t* __restrict__ ids,
+                                                   const int32_t* __restrict__ slots,
+                                                   const uint8_t* __restrict__ primary, int64_t n,
+                                                   float* __restrict__ rows, const int64_t* __restrict__ src_index,
+                                                   int write_master, int average, float divisor, int dim, int ways,
+                                                   int G) {
+    using V = typename VT<VEC>::type;
+    const int gl = threadIdx.x % G, group = threadIdx.x / G, NG = 256 / G;
+    const int cpr = dim / VEC;
+    float* master = const_cast<float*>(T.master);
+    constexpr int U = 4;
+    for (int64_t i0 = (int64_t)blockIdx.x * NG * U + group; i0 < n; i0 += (int64_t)gridDim.x * NG * U) {
+        for (int c = gl; c < cpr; c += G) {
+            V v[U];
+            const float* src[U];
+            float* dst[U];
+            float* dst2[U];
+            bool valid[U], avg[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * NG;
+                valid[u] = i < n;
+                src[u] = nullptr; dst[u] = nullptr; dst2[u] = nullptr; avg[u] = false;
+                if (!valid[u]) continue;
+                if (MODE == 0) {
+                    src[u] = T.weight + (int64_t)slots[i] * dim;
+                    dst[u] = rows ? rows + i * dim : nullptr;
+                    if (write_master && (!average || primary[i])) {
+                        dst2[u] = master + ids[i] * dim;
+                        avg[u] = average != 0;
+                    }
+                } else if (MODE == 1) {
+                    src[u] = master + ids[i] * dim;
+                    dst[u] = rows + i * dim;
+                } else if (MODE == 2) {
+                    src[u] = rows ? rows + (src_index ? src_index[i] : i) * dim : master + ids[i] * dim;
+                    dst[u] = T.weight + (int64_t)slots[i] * dim;
+                } else if (MODE == 3) {
+                    src[u] = T.weight + (int64_t)slots[i] * dim;
+                    dst[u] = rows + i * dim;
+                } else if (MODE == 4) {
+                    src[u] = rows + i * dim;
+                    dst[u] = T.weight + (int64_t)slots[i] * dim;
+                } else {
+                    src[u] = rows + i * dim;
+                    dst2[u] = master + ids[i] * dim;
+                    avg[u] = average != 0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (valid[u]) v[u] = reinterpret_cast<const V*>(src[u])[c];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!valid[u]) continue;
+                if (MODE == 3 && divisor != 1.0f) v[u] = vdiv(v[u], divisor);
+                if (dst[u]) reinterpret_cast<V*>(dst[u])[c] = v[u];
+                if ((MODE == 0 || MODE == 5) && dst2[u]) {
+                    V* m = reinterpret_cast<V*>(dst2[u]) + c;
+                    *m = avg[u] ? avg2(*m, v[u]) : v[u];
+                }
+            }
+        }
+        if (MODE == 2 && gl == 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * NG;
+                if (i < n) {
+                    const int64_t sl = slots[i];
+                    const int64_t way = sl / T.num_sets, s = sl - way * T.num_sets;
+                    T.tags[s * ways + way] = ids[i];
+                }
+            }
+        }
+    }
+}
+
+__global__ void or_bitmaps_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ gathered, int world,
+                                  int64_t words) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < words; i += stride) {
+        uint32_t v = 0;
+        for (int r = 0; r < world; ++r) v |= gathered[(int64_t)r * words + i];
+        dst[i] = v;
+    }
+}
+
+inline int pow2_ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+inline int vec_for(int dim, const void* a, const void* b) {
+    auto al = [](const void* p, int n) { return p == nullptr || ((uintptr_t)p % n) == 0; };
+    if (dim % 4 == 0 && al(a, 16) && al(b, 16)) return 4;
+    if (dim % 2 == 0 && al(a, 8) && al(b, 8)) return 2;
+    return 1;
+}
+
+template <int MODE>
+int launch_rows(cdlrm_ctx* c, int k, const int64_t* ids, const int32_t* slots, const uint8_t* primary, int64_t n,
+                float* rows, const int64_t* src_index, int write_master, int average, float divisor,
+                bool uses_master, cudaStream_t s) {
+    if (n <= 0) return CDLRM_OK;
+    const TableDesc& T = c->tabs[k];
+    const int vec = vec_for(c->dim, rows, uses_master ? T.master : nullptr);
+    const int cpr = c->dim / vec;
+    const int G = pow2_ceil(cpr) > 32 ? 32 : pow2_ceil(cpr);
+    const int NG = 256 / G;
+    int64_t blocks = (n + NG * 4 - 1) / (NG * 4);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (vec == 4) rows_kernel<4, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G);
+    else if (vec == 2) rows_kernel<2, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G);
+    else rows_kernel<1, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G);
+    CU_CHECK(cudaGetLastError());
+    return CDLRM_OK;
+}
+
+}  // namespace
+
+extern "C" int cdlrm_move_evict(cdlrm_ctx* c, int k, const int64_t* evict_ids, const int32_t* evict_slots,
+                                const uint8_t* evict_primary, int64_t n, float* rows_out, int write_master,
+                                int average, cdlrm_stream stream) {
+    ARG_CHECK(c && k >= 0 && k < c->T && n >= 0);
+    if (n == 0) return CDLRM_OK;
+    ARG_CHECK(evict_ids && evict_slots);
+    ARG_CHECK(!(write_master && average) || evict_primary);
+    ARG_CHECK(c->tabs[k].weight && (!write_master || c->tabs[k].master));
+    CU_CHECK(cudaSetDevice(c->device));
+    return launch_rows<0>(c, k, evict_ids, evict_slots, evict_primary, n, rows_out, nullptr, write_master, average,
+                          1.0f, write_master != 0, (cudaStream_t)stream);
+}
+
+extern "C" int cdlrm_move_gather_master(cdlrm_ctx* c, int k, const int64_t* ids, int64_t n, float* rows_out,
+                                        cdlrm_stream stream) {
+    ARG_CHECK(c && k >= 0 && k < c->T && n >= 0);
+    if (n == 0) return CDLRM_OK;
+    ARG_CHECK(ids && rows_out && c->tabs[k].master);
+    CU_CHECK(cudaSetDevice(c->device));
+    return launch_rows<1>(c, k, ids, nullptr, nullptr, n, rows_out, nullptr, 0, 0, 1.0f, true, (cudaStream_t)stream);
+}
+
+extern "C" int cdlrm_move_fill(cdlrm_ctx* c, int k, const int64_t* fill_ids, const int32_t* fill_slots, int64_t n,
+                               const float* rows, const int64_t* src_index, cdlrm_stream stream) {
+    ARG_CHECK(c && k >= 0 && k < c->T && n >= 0);
+    if (n == 0) return CDLRM_OK;
+    ARG_CHECK(fill_ids && fill_slots && c->tabs[k].weight && c->tabs[k].tags);
+    ARG_CHECK(rows || c->tabs[k].master);
+    CU_CHECK(cudaSetDevice(c->device));
+    return launch_rows<2>(c, k, fill_ids, fill_slots, nullptr, n, const_cast<float*>(rows), src_index, 0, 0, 1.0f,
+                          rows == nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int cdlrm_move_scatter_master(cdlrm_ctx* c, int k, const int64_t* ids, int64_t n, const float* rows,
+                                         int average, cdlrm_stream stream) {
+    ARG_CHECK(c && k >= 0 && k < c->T && n >= 0);
+    if (n == 0) return CDLRM_OK;
+    ARG_CHECK(ids && rows && c->tabs[k].master);
+    CU_CHECK(cudaSetDevice(c->device));
+    return launch_rows<5>(c, k, ids, nullptr, nullptr, n, const_cast<float*>(rows), nullptr, 1, average, 1.0f, true,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int cdlrm_host_register(int device, void* h_ptr, int64_t bytes, void** dev_ptr) {
+    ARG_CHECK(h_ptr && bytes > 0 && dev_ptr);
+    CU_CHECK(cudaSetDevice(device));
+    CU_CHECK(cudaHostRegister(h_ptr, (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    CU_CHECK(cudaHostGetDevicePointer(dev_ptr, h_ptr, 0));
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_host_unregister(void* h_ptr) {
+    ARG_CHECK(h_ptr);
+    CU_CHECK(cudaHostUnregister(h_ptr));
+    return CDLRM_OK;
+}
+
+// ---- aggregation ---------------------------------------------------------------------------------
+
+__global__ void mark_kernel(TableDesc T, const int32_t* __restrict__ idxs, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int32_t sl = idxs[i];
+        if (sl >= 0 && sl < T.cache_rows) atomicOr(T.dirty + (sl >> 5), 1u << (sl & 31));
+    }
+}
+
+extern "C" int cdlrm_agg_mark(cdlrm_ctx* c, const int32_t* idxs, int64_t ld, int64_t n, cdlrm_stream stream) {
+    ARG_CHECK(c && n >= 0);
+    if (n == 0) return CDLRM_OK;
+    ARG_CHECK(idxs);
+    CU_CHECK(cudaSetDevice(c->device));
+    for (int k = 0; k < c->T; ++k) {
+        ARG_CHECK(c->tabs[k].dirty);
+        int64_t blocks = (n + 255) / 256;
+        if (blocks > 1184) blocks = 1184;
+        mark_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(c->tabs[k], idxs + k * ld, n);
+    }
+    CU_CHECK(cudaGetLastError());
+    return CDLRM_OK;
+}
+
+static int dirty_is_concatenated(const cdlrm_ctx* c) {
+    for (int k = 0; k < c->T; ++k)
+        if (!c->tabs[k].dirty || c->tabs[k].dirty != c->tabs[0].dirty + c->tabs[k].dirty_word_off) return 0;
+    return 1;
+}
+
+extern "C" int cdlrm_agg_or_bitmaps(cdlrm_ctx* c, const uint32_t* gathered, int world, int64_t words_total,
+                                    cdlrm_stream stream) {
+    ARG_CHECK(c && gathered && world >= 1);
+    const TableDesc& last = c->tabs[c->T - 1];
+    ARG_CHECK(words_total == last.dirty_word_off + (last.cache_rows + 31) / 32);
+    if (!dirty_is_concatenated(c)) {
+        cdlrm_set_error("dirty bitmaps must be bound as one concatenated buffer");
+        return CDLRM_ERR_STATE;
+    }
+    CU_CHECK(cudaSetDevice(c->device));
+    or_bitmaps_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(c->tabs[0].dirty, gathered, world, words_total);
+    CU_CHECK(cudaGetLastError());
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_agg_collect(cdlrm_ctx* c, int32_t* slot_list, int64_t* d_counts, int64_t* h_counts,
+                                 cdlrm_stream stream) {
+    ARG_CHECK(c && slot_list && d_counts);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(c->device));
+    int64_t words_max = 0;
+    for (int k = 0; k < c->T; ++k) {
+        ARG_CHECK(c->tabs[k].dirty);
+        int64_t w = (c->tabs[k].cache_rows + 31) / 32;
+        words_max = w > words_max ? w : words_max;
+    }
+    static thread_local int32_t* bs = nullptr;
+    static thread_local int64_t bs_cap = 0;
+    const int64_t need = (words_max + TILE - 1) / TILE + 1;
+    if (need > bs_cap) {
+        if (bs) cudaFree(bs);
+        CU_CHECK(cudaMalloc(&bs, sizeof(int32_t) * need));
+        bs_cap = need;
+    }
+    int64_t cap_off = 0;
+    for (int k = 0; k < c->T; ++k) {
+        const TableDesc& t = c->tabs[k];
+        const int64_t nwords = (t.cache_rows + 31) / 32;
+        const int nblk = (int)((nwords + TILE - 1) / TILE);
+        bitmap_count_kernel<<<nblk, 256, 0, s>>>(t.dirty, nwords, bs);
+        scan_tiles_kernel<<<1, 1024, 0, s>>>(bs, nblk, reinterpret_cast<unsigned long long*>(d_counts + k));
+        bitmap_emit_kernel<int32_t, false><<<nblk, 256, 0, s>>>(t.dirty, nwords, bs, slot_list + cap_off);
+        cap_off += t.cache_rows;
+    }
+    CU_CHECK(cudaGetLastError());
+    if (h_counts) CU_CHECK(cudaMemcpyAsync(h_counts, d_counts, sizeof(int64_t) * c->T, cudaMemcpyDeviceToHost, s));
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_agg_pack(cdlrm_ctx* c, const int32_t* slot_list, const int64_t* h_counts, float divisor,
+                              float* buf, cdlrm_stream stream) {
+    ARG_CHECK(c && slot_list && h_counts && buf && divisor != 0.0f);
+    CU_CHECK(cudaSetDevice(c->device));
+    int64_t cap_off = 0, boff = 0;
+    for (int k = 0; k < c->T; ++k) {
+        ARG_CHECK(h_counts[k] >= 0 && h_counts[k] <= c->tabs[k].cache_rows);
+        int rc = launch_rows<3>(c, k, nullptr, slot_list + cap_off, nullptr, h_counts[k], buf + boff * c->dim, nullptr,
+                                0, 0, divisor, false, (cudaStream_t)stream);
+        if (rc) return rc;
+        cap_off += c->tabs[k].cache_rows;
+        boff += h_counts[k];
+    }
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_agg_unpack(cdlrm_ctx* c, const int32_t* slot_list, const int64_t* h_counts, const float* buf,
+                                int clear_dirty, cdlrm_stream stream) {
+    ARG_CHECK(c && slot_list && h_counts && buf);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(c->device));
+    int64_t cap_off = 0, boff = 0;
+    for (int k = 0; k < c->T; ++k) {
+        ARG_CHECK(h_counts[k] >= 0 && h_counts[k] <= c->tabs[k].cache_rows);
+        int rc = launch_rows<4>(c, k, nullptr, slot_list + cap_off, nullptr, h_counts[k],
+                                const_cast<float*>(buf) + boff * c->dim, nullptr, 0, 0, 1.0f, false, s);
+        if (rc) return rc;
+        if (clear_dirty && c->tabs[k].dirty)
+            CU_CHECK(cudaMemsetAsync(c->tabs[k].dirty, 0, sizeof(uint32_t) * ((c->tabs[k].cache_rows + 31) / 32), s));
+        cap_off += c->tabs[k].cache_rows;
+        boff += h_counts[k];
+    }
+    return CDLRM_OK;
+}

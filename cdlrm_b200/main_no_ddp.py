@@ -1,0 +1,429 @@
+"""B200-native mirror of the reference's ``main_no_ddp.py`` (lkp411/cDLRM): same function
+names, argument order and CLI flags, hot path in libcdlrm_b200.so.
+
+Kept verbatim as an interface (reference file:line): ``ProcessArgs`` (:34-145),
+``CacheEmbeddings`` (:148-209), ``loss_fn_wrap`` (:212-221), ``time_wrap`` (:224-226),
+``wait_wrap`` (:229-231), ``aggregate_gradients`` (:234-247), ``broadcast_and_aggregate``
+(:250-292), ``share_occupancy_tables`` (:295-306), ``load_caches_and_broadcast``
+(:309-321), ``Run`` (:324-502).
+"""
+import argparse
+import ctypes
+import math
+import os
+import queue
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, lib
+from .cache_manager import Prefetcher, TorchGlobalRng, VictimRng, WindowPlanner
+from .model_no_ddp import DLRM_Net, Embedding_Table_Cache_Group, Embedding_Table_Group
+
+_vp = ctypes.c_void_p
+
+# (flag, type or "flag", default) -- spelling and defaults of main_no_ddp.py:34-145
+_FLAGS = [
+    ("arch-sparse-feature-size", int, 2), ("arch-embedding-size", str, "4-3-2"), ("arch-mlp-bot", str, "4-3-2"),
+    ("arch-mlp-top", str, "4-2-1"), ("arch-interaction-op", str, "dot"), ("arch-interaction-itself", "flag", False),
+    ("activation-function", str, "relu"), ("loss-function", str, "mse"), ("loss-weights", str, "1.0-1.0"),
+    ("loss-threshold", float, 0.0), ("round-targets", bool, False),
+    ("data-size", int, 1), ("num-batches", int, 0), ("data-generation", str, "random"),
+    ("data-trace-file", str, "./input/dist_emb_j.log"), ("data-set", str, "kaggle"), ("raw-data-file", str, ""),
+    ("processed-data-file", str, ""), ("data-randomize", str, "total"), ("data-trace-enable-padding", bool, False),
+    ("max-ind-range", int, -1), ("data-sub-sample-rate", float, 0.0), ("num-indices-per-lookup", int, 10),
+    ("num-indices-per-lookup-fixed", bool, False), ("num-workers", int, 0), ("memory-map", "flag", False),
+    ("md-flag", "flag", False), ("md-threshold", int, 200), ("md-temperature", float, 0.3),
+    ("md-round-dims", "flag", False), ("qr-flag", "flag", False), ("qr-threshold", int, 200),
+    ("qr-operation", str, "mult"), ("qr-collisions", int, 4),
+    ("mini-batch-size", int, 1), ("nepochs", int, 1), ("learning-rate", float, 0.1), ("lr-embeds", float, 0.3),
+    ("print-precision", int, 5), ("numpy-rand-seed", int, 123), ("sync-dense-params", bool, True),
+    ("lookahead", int, 2), ("cache-workers", int, 2), ("cache-size", int, 10240), ("num-ways", int, 4),
+    ("average-on-writeback", "flag", False), ("evict-victim-cache", "flag", False),
+    ("print-freq", int, 1), ("test-freq", int, -1), ("test-mini-batch-size", int, -1), ("test-num-workers", int, -1),
+    ("print-time", "flag", False), ("debug-mode", "flag", False), ("enable-profiling", "flag", False),
+    ("plot-compute-graph", "flag", False), ("save-model", str, ""), ("load-model", str, ""),
+    ("mlperf-logging", "flag", False), ("mlperf-acc-threshold", float, 0.0), ("mlperf-auc-threshold", float, 0.0),
+    ("mlperf-bin-loader", "flag", False), ("mlperf-bin-shuffle", "flag", False), ("large-batch", "flag", False),
+    ("world-size", int, 2), ("master-port", int, 12345), ("trainer-start-core", int, 7), ("main-start-core", int, 0),
+    ("dense-threshold", int, 1000), ("table-agg-op", str, "mean"), ("table-agg-freq", int, 1),
+    ("batch-fifo-size", int, 8), ("eviction-fifo-size", int, 8), ("eviction-fifo-timeout", int, 300),
+    ("inference-only", "flag", False), ("save-onnx", "flag", False), ("use-gpu", "flag", False),
+]
+# additions of this implementation (not in the reference)
+_EXTRA_FLAGS = [
+    ("strict-reference", "flag", False),   # reproduce rank-0 install + overwrite of the other ranks
+    ("synthetic-dist", str, "zipf"), ("synthetic-zipf-a", float, 1.05), ("synthetic-steps", int, 0),
+]
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description="Train Deep Learning Recommendation Model (DLRM)")
+    for name, typ, default in _FLAGS + _EXTRA_FLAGS:
+        if typ == "flag":
+            parser.add_argument("--" + name, action="store_true", default=default)
+        else:
+            parser.add_argument("--" + name, type=typ, default=default)
+    return parser
+
+
+def ProcessArgs(argv=None):
+    return build_parser().parse_args(argv)
+
+
+# ------------------------------------------------------------------------------------
+# window install -- main_no_ddp.py:148-209
+# ------------------------------------------------------------------------------------
+
+
+def _planner_of(cache_group, emb_tables, need_len):
+    pl = getattr(cache_group, "_compat_planner", None)
+    if pl is None or pl.window_len < need_len:
+        pl = WindowPlanner(cache_group, emb_tables, max(need_len, 1), rng=TorchGlobalRng())
+        cache_group._compat_planner = pl
+    return pl
+
+
+def CacheEmbeddings(cached_entries_per_table, lists_of_unique_idxs, unique_indices_maps, cache_group, eviction_fifo,
+                    rank):
+    """Window install (main_no_ddp.py:148-209).  Decisions (hit / pinned / dropped / sampled
+    way / evicted / last-wins duplicates) come from cdlrm_plan_phase_a/_b and are bit-exact
+    with the reference; the victim way uses the global torch CPU generator exactly as
+    ``Categorical.sample()`` does (:183-185).  Evicted (id, row) pairs are put on
+    ``eviction_fifo`` as CPU tensors when ``rank == 0`` (:208-209)."""
+    cg = cache_group
+    dev = cg.device
+    need = max(int(u.numel()) for u in lists_of_unique_idxs)
+    cg._ensure_ctx(None)
+    pl = _planner_of(cg, None, need)
+    rec = pl.plan(uniq_lists=lists_of_unique_idxs)
+    fill_rows = []
+    for k in range(len(cached_entries_per_table)):
+        ids, _slots = rec.fill_list(k)
+        rows_k, map_k = cached_entries_per_table[k], unique_indices_maps[k]
+        if rec.F[k] == 0:
+            fill_rows.append((None, None))
+        elif rows_k.is_cuda:
+            src = map_k.to(dev)[ids].flatten().contiguous()              # :205
+            fill_rows.append((rows_k.contiguous(), src))
+        else:
+            src = map_k[ids.cpu()].flatten()
+            fill_rows.append((rows_k[src].to(dev, non_blocking=False).contiguous(), None))
+    ev = pl.install(rec, write_master=False, collect_evictions=True, fill_rows=fill_rows)
+    cg.last_plan = rec
+    if rank == 0:
+        eviction_fifo.put([(i.cpu(), r.cpu()) for i, r in ev])
+
+
+def loss_fn_wrap(Z, T, loss_fn, args, loss_ws=None):
+    if args.loss_function == "mse" or args.loss_function == "bce":
+        return loss_fn(Z, T)
+    elif args.loss_function == "wbce":
+        loss_ws_ = loss_ws[T.data.view(-1).long()].view_as(T)
+        loss_fn_ = loss_fn(Z, T)
+    loss_sc_ = loss_ws_ * loss_fn_
+    return loss_sc_.mean()
+
+
+def time_wrap(rank):
+    torch.cuda.synchronize(rank)
+    return time.time()
+
+
+def wait_wrap(req_objs):
+    for obj in req_objs:
+        obj.wait()
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def aggregate_gradients(dlrm, include_bias=False):
+    """main_no_ddp.py:234-247: average the Linear WEIGHT grads over ranks (the reference never
+    reduces the biases; ``include_bias=True`` fixes that).  One flat bucket, one all-reduce."""
+    W = _world()
+    grads = []
+    for seq in (dlrm.bot_l, dlrm.top_l):
+        for layer in seq:
+            if isinstance(layer, nn.modules.linear.Linear):
+                grads.append(layer.weight.grad)
+                if include_bias:
+                    grads.append(layer.bias.grad)
+    if W == 1:
+        return []
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    flat /= W
+    work = dist.all_reduce(flat, async_op=True)
+
+    class _Unflatten:
+        def wait(self_inner):
+            work.wait()
+            o = 0
+            for g in grads:
+                g.copy_(flat[o:o + g.numel()].view_as(g))
+                o += g.numel()
+
+    return [_Unflatten()]
+
+
+# ------------------------------------------------------------------------------------
+# table aggregation -- main_no_ddp.py:250-292
+# ------------------------------------------------------------------------------------
+
+
+@torch.no_grad()
+def broadcast_and_aggregate(cache_group, cache_group_idxs, rank, reduce_op="mean"):
+    """Every ``table_agg_freq`` steps: union over ranks of the touched slots per table,
+    ``weight[u] = sum_r weight_r[u] / W`` (mean) or sum / max.  ``cache_group_idxs`` is the
+    reference's int32 ``[T, n]`` slot tensor; pass ``None`` to use the dirty bitmaps that the
+    fused backward maintains.  dirty bits -> all-gather + OR -> ascending slot lists ->
+    pack (pre-divided by W, :277) -> ONE all-reduce on a contiguous buffer -> unpack."""
+    cg = cache_group
+    ctx = cg._ensure_ctx(None)
+    dev = cg.device
+    s = _vp(torch.cuda.current_stream(dev).cuda_stream)
+    W = _world()
+    if cache_group_idxs is not None:
+        idx = cache_group_idxs.to(dev, dtype=torch.int32)
+        if idx.stride(1) != 1:
+            idx = idx.contiguous()
+        check(lib.cdlrm_agg_mark(ctx, _vp(idx.data_ptr()), idx.stride(0), idx.shape[1], s))
+    dirty = cg.dirty_bitmap()
+    if W > 1:
+        gathered = torch.empty(W, dirty.numel(), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(gathered.view(-1), dirty)
+        check(lib.cdlrm_agg_or_bitmaps(ctx, _vp(gathered.data_ptr()), W, dirty.numel(), s))
+    T = len(cg.emb_l)
+    bufs = getattr(cg, "_agg_bufs", None)
+    if bufs is None:
+        cap = int(sum(cg._cache_rows))
+        bufs = (torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(T, dtype=torch.int64, device=dev),
+                torch.zeros(T, dtype=torch.int64).pin_memory())
+        cg._agg_bufs = bufs
+    slot_list, d_counts, h_counts = bufs
+    check(lib.cdlrm_agg_collect(ctx, _vp(slot_list.data_ptr()), _vp(d_counts.data_ptr()), _vp(h_counts.data_ptr()), s))
+    torch.cuda.current_stream(dev).synchronize()
+    counts = h_counts.tolist()
+    total = int(sum(counts))
+    carr = _lib.i64_array(counts)
+    if total == 0:
+        return
+    buf = torch.empty(total, cg.dim, dtype=torch.float32, device=dev)
+    if reduce_op == "mean":
+        div, op = float(W), dist.ReduceOp.SUM
+    elif reduce_op == "sum":
+        div, op = 1.0, dist.ReduceOp.SUM
+    elif reduce_op == "max":
+        div, op = 1.0, dist.ReduceOp.MAX
+    else:
+        raise ValueError(reduce_op)
+    check(lib.cdlrm_agg_pack(ctx, _vp(slot_list.data_ptr()), carr, div, _vp(buf.data_ptr()), s))
+    if W > 1:
+        dist.all_reduce(buf, op=op)
+    check(lib.cdlrm_agg_unpack(ctx, _vp(slot_list.data_ptr()), carr, _vp(buf.data_ptr()), 1, s))
+
+
+def share_occupancy_tables(cache_group, occupancy_tables_fifos, rank):
+    """main_no_ddp.py:295-306 shares rank 0's CPU tag tensors through host shared memory.  Here
+    every rank keeps the tags in its own HBM and evolves them with the same deterministic
+    plan, so there is nothing to ship; the initial state (-1) is already identical."""
+    cache_group._ensure_ctx(None)
+
+
+@torch.no_grad()
+def load_caches_and_broadcast(cache_group, batch_fifo, eviction_fifo, rank):
+    """main_no_ddp.py:309-321, reference semantics: rank 0 installs the window, then every
+    table's full cache weight (and, here, the HBM tags) is broadcast from rank 0."""
+    dist_req_objs = []
+    if rank == 0:
+        cached_entries_per_table, lists_of_unique_idxs, unique_indices_maps = batch_fifo.get()
+        CacheEmbeddings(cached_entries_per_table, lists_of_unique_idxs, unique_indices_maps, cache_group,
+                        eviction_fifo, rank)
+    if _world() > 1:
+        cache_group._ensure_ctx(None)
+        for E, tags in zip(cache_group.emb_l, cache_group.occupancy_tables):
+            dist_req_objs.append(dist.broadcast(E.weight.data, src=0, async_op=True))
+            dist_req_objs.append(dist.broadcast(tags, src=0, async_op=True))
+    return dist_req_objs
+
+
+# ------------------------------------------------------------------------------------
+# trainer -- the body of Run (main_no_ddp.py:324-502) around the new path
+# ------------------------------------------------------------------------------------
+
+
+class Trainer:
+    """One rank of data-parallel training against a replicated look-ahead cache.
+
+    Per step (main_no_ddp.py:401-425): cache forward -> DLRM (stock PyTorch MLPs + the
+    interaction kernel) -> loss -> backward (interaction bwd, fused de-duplicated sparse
+    SGD on the cache) -> MLP grad all-reduce -> SGD.  Every ``lookahead`` steps the next
+    window's plan (computed ahead on a side stream by a background thread) is installed;
+    every ``table_agg_freq`` steps touched cache rows are averaged over ranks.
+
+    Differences from the reference, on purpose: every rank runs the same deterministic plan
+    on the global window (same ids, same seeded victim stream, tags replicated in HBM), so
+    the 1.2 GB-per-table full-cache broadcast (:318-319) disappears; at a window boundary the
+    touched rows are averaged first, so rank 0 writes back the cross-rank mean.
+    """
+
+    def __init__(self, args, m_spa, ln_emb, ln_bot, ln_top, emb_tables, rank=0, world=1, device=None):
+        self.args = args
+        self.rank, self.world = rank, world
+        self.dev = device if device is not None else torch.device("cuda", rank)
+        torch.cuda.set_device(self.dev)
+        np.random.seed(args.numpy_rand_seed)                       # :335-337
+        torch.cuda.manual_seed(args.numpy_rand_seed)
+        torch.manual_seed(args.numpy_rand_seed)
+        self.local_batch = math.ceil(args.mini_batch_size / world)  # :344
+        self.emb_tables = emb_tables
+        self.cache_group = Embedding_Table_Cache_Group(m_spa, ln_emb, max_cache_size=args.cache_size,
+                                                       aux_table_size=args.mini_batch_size,
+                                                       num_ways=args.num_ways, device=self.dev)
+        self.dlrm = DLRM_Net(ln_bot, ln_top, arch_interaction_op=args.arch_interaction_op,
+                             arch_interaction_itself=args.arch_interaction_itself,
+                             sync_dense_params=args.sync_dense_params, sigmoid_bot=-1,
+                             sigmoid_top=ln_top.size - 2, loss_threshold=args.loss_threshold).to(self.dev)
+        if args.loss_function == "mse":
+            self.loss_fn, self.loss_ws = torch.nn.MSELoss(reduction="mean"), None
+        elif args.loss_function == "bce":
+            self.loss_fn, self.loss_ws = torch.nn.BCELoss(reduction="mean"), None
+        elif args.loss_function == "wbce":
+            self.loss_ws = torch.tensor(np.fromstring(args.loss_weights, dtype=float, sep="-")).to(self.dev)
+            self.loss_fn = torch.nn.BCELoss(reduction="none")
+        else:
+            sys.exit("ERROR: --loss-function=" + args.loss_function + " is not supported")
+        self.optimizer_mlps = torch.optim.SGD(self.dlrm.parameters(), lr=args.learning_rate)
+        self.optimizer_embeds = torch.optim.SGD(self.cache_group.parameters(), lr=args.lr_embeds)   # :376
+        self.cache_group._ensure_ctx(emb_tables)
+        self.cache_group.assume_one_id_per_bag = True              # Criteo batches (:390)
+        self.side = torch.cuda.Stream(self.dev)
+        self.planner = WindowPlanner(self.cache_group, emb_tables, args.lookahead * args.mini_batch_size,
+                                     rng=VictimRng(args.numpy_rand_seed), stream=self.side, lookahead_tags=True)
+        self._plan_q = queue.Queue()
+        self._plan_thread = None
+        self.steps_since_agg = 0
+        self.caching_overhead = []
+
+    # -- look-ahead -------------------------------------------------------------------------
+    def submit_window(self, win_ids):
+        """Start planning a window (int64 [T, n] device tensor of the GLOBAL batch ids) in the
+        background; windows must be submitted in training order."""
+        import threading
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        prev = self._plan_thread
+
+        def work():
+            if prev is not None:
+                prev.join()
+            torch.cuda.set_device(self.dev)
+            self.side.wait_event(ev)
+            try:
+                self._plan_q.put(self.planner.plan(win_ids=win_ids))
+            except Exception as e:  # surfaced by install_window
+                self._plan_q.put(e)
+
+        self._plan_thread = threading.Thread(target=work, daemon=True)
+        self._plan_thread.start()
+
+    def install_window(self):
+        """Window boundary (main_no_ddp.py:393-399): wait for the plan, average touched rows
+        over ranks, evict (rank 0 writes the master back), fill."""
+        t0 = time.perf_counter()
+        rec = self._plan_q.get()
+        if isinstance(rec, Exception):
+            raise rec
+        if self.world > 1:
+            broadcast_and_aggregate(self.cache_group, None, self.rank, self.args.table_agg_op)
+            self.steps_since_agg = 0
+        self.planner.install(rec, write_master=(self.rank == 0),
+                             average_on_writeback=self.args.average_on_writeback)
+        if self.world > 1:
+            # rank 0's write-back must be visible to every rank's next master reads
+            torch.cuda.current_stream(self.dev).synchronize()
+            dist.barrier()
+        self.caching_overhead.append(time.perf_counter() - t0)
+        return rec
+
+    # -- one training step -------------------------------------------------------------------
+    def step(self, X, lS_o, lS_i, T):
+        lookups, _idxs = self.cache_group(lS_o, lS_i, self.emb_tables, self.dev.index)
+        Z = self.dlrm(X, lookups)
+        E = loss_fn_wrap(Z, T, self.loss_fn, self.args, self.loss_ws)
+        self.optimizer_mlps.zero_grad(set_to_none=True)
+        E.backward()
+        reqs = aggregate_gradients(self.dlrm)
+        self.optimizer_embeds.step()          # applies the fused sparse update (pre-step hook)
+        wait_wrap(reqs)
+        self.optimizer_mlps.step()
+        self.steps_since_agg += 1
+        return E, Z
+
+    def maybe_aggregate(self, j):
+        if self.world > 1 and j > 0 and j % self.args.table_agg_freq == 0:     # :418-420
+            broadcast_and_aggregate(self.cache_group, None, self.rank, self.args.table_agg_op)
+            self.steps_since_agg = 0
+
+
+def Run(rank, m_spa, ln_emb, ln_bot, ln_top, train_ld, test_ld, batch_fifo, eviction_fifo, occupancy_tables_fifos,
+        emb_tables, args):
+    """main_no_ddp.py:324-502.  ``batch_fifo`` carries raw window id tensors [T, n] in training
+    order (what this package's ``Prefetcher.run`` produces)."""
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", str(args.master_port))
+    if args.world_size > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", rank=rank, world_size=args.world_size)
+    tr = Trainer(args, m_spa, ln_emb, ln_bot, ln_top, emb_tables, rank=rank, world=args.world_size)
+    dev, lb = tr.dev, tr.local_batch
+    share_occupancy_tables(tr.cache_group, occupancy_tables_fifos, rank)
+    total_time = total_loss = total_accu = 0.0
+    total_iter = total_samp = 0
+    first = batch_fifo.get()
+    if first is not None:
+        tr.submit_window(first.to(dev, non_blocking=True))
+    for epoch in range(args.nepochs):
+        for j, (X, lS_o, lS_i, T) in enumerate(train_ld):
+            X = X[rank * lb:(rank + 1) * lb, :].to(dev, non_blocking=True)          # :388-391
+            lS_i = lS_i[:, rank * lb:(rank + 1) * lb].to(dev, non_blocking=True)
+            lS_o = lS_o[:, :lb]
+            T = T[rank * lb:(rank + 1) * lb, :].to(dev, non_blocking=True)
+            if j % args.lookahead == 0:
+                tr.install_window()
+                nxt = batch_fifo.get()
+                if nxt is not None:
+                    tr.submit_window(nxt.to(dev, non_blocking=True))
+            t1 = time.perf_counter()
+            E, Z = tr.step(X, lS_o, lS_i, T)
+            tr.maybe_aggregate(j)
+            if rank == 0 and j > 0 and j % args.print_freq == 0:
+                torch.cuda.synchronize(dev)
+                total_time += time.perf_counter() - t1
+                L = E.item()
+                A = float(((Z.detach().round() == T).sum()).item())
+                mbs = T.shape[0]
+                total_iter += 1
+                gT = 1000.0 * total_time / max(total_iter, 1)
+                ovh = 1000 * (np.mean(tr.caching_overhead) / args.lookahead) if tr.caching_overhead else 0.0
+                tr.caching_overhead = []
+                print('Epoch {}: Finished {}/{} in {} ms/it. Caching overhead = {}. Loss = {}, Train Acc = {}'.format(
+                    epoch, j, len(train_ld), gT, ovh, L, A / mbs))
+                total_time, total_iter = 0.0, 0
+            if rank == 0 and test_ld is not None and ((args.test_freq > 0 and j > 0 and j % args.test_freq == 0)
+                                                      or j == len(train_ld) - 1):
+                print('Testing at {}/{}....'.format(j, len(train_ld)))
+                test_samp = total_test_acc = 0
+                with torch.no_grad():
+                    for _i, (Xt, lS_ot, lS_it, Tt) in enumerate(test_ld):
+                        lookups, _ = tr.cache_group(lS_ot, lS_it.to(dev), emb_tables, rank)
+                        Zt = tr.dlrm(Xt.to(dev), lookups)
+                        total_test_acc += int((Zt.round().cpu() == Tt).sum())
+                        test_samp += Tt.shape[0]
+                print('Test accuracy = {}%'.format(100 * (total_test_acc / max(test_samp, 1))))
+    return tr

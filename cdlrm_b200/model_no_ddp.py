@@ -1,0 +1,535 @@
+"""B200-native mirror of the reference's ``model_no_ddp.py`` (lkp411/cDLRM).
+
+Same class names, constructor arguments, attribute names and error behaviour as the
+reference so that ``main_no_ddp.py`` can import it unchanged; the cache hot path runs in
+hand-written sm_100a CUDA kernels behind the C ABI of ``libcdlrm_b200.so``
+(``include/cdlrm_b200.h``).  There is no CPU / eager-PyTorch fallback: using the cache
+group or the dot interaction without a CUDA device raises.
+
+Reference citations are ``file:line`` in the reference tree.
+"""
+import ctypes
+import sys
+import weakref
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, lib
+
+_vp = ctypes.c_void_p
+
+
+def _stream_ptr(device):
+    return _vp(torch.cuda.current_stream(device).cuda_stream)
+
+
+def isPrime(n):
+    """model_no_ddp.py:319-331 (quirky on purpose: see cdlrm_is_prime_ref)."""
+    return bool(lib.cdlrm_is_prime_ref(int(n)))
+
+
+# ------------------------------------------------------------------------------------
+# master tables (host) -- model_no_ddp.py:21-98
+# ------------------------------------------------------------------------------------
+
+
+class Embedding_Table_Group(nn.Module):
+    """CPU master embedding tables (model_no_ddp.py:21-98).  ``emb_l[k].weight`` is an
+    ``nn.EmbeddingBag`` weight initialised U(+-sqrt(1/n)) from the numpy global RNG
+    exactly as the reference does (:66-74).  ``device_pointers(device)`` pins the tables
+    (cudaHostRegister, mapped) and returns the device-visible addresses the kernels read
+    (zero-copy) and write back to."""
+
+    def __init__(self, m_spa=None, ln_emb=None, qr_flag=False, qr_operation="mult", qr_collisions=0,
+                 qr_threshold=200, md_flag=False, md_threshold=200, init="reference"):
+        super().__init__()
+        self._registered = {}
+        if (m_spa is not None) and (ln_emb is not None):
+            if qr_flag or md_flag:
+                # unreachable in the reference as well (main_no_ddp.py:621 never passes them)
+                raise NotImplementedError("QR / mixed-dimension embeddings are outside the cache hot path")
+            self.qr_flag = qr_flag
+            self.md_flag = md_flag
+            self.emb_l = self.create_emb(m_spa, np.asarray(ln_emb), init)
+
+    def create_emb(self, m, ln, init="reference"):
+        emb_l = nn.ModuleList()
+        for i in range(0, ln.size):
+            n = int(ln[i])
+            if init == "reference":
+                W = np.random.uniform(low=-np.sqrt(1 / n), high=np.sqrt(1 / n), size=(n, m)).astype(np.float32)
+                wt = torch.from_numpy(W)
+            else:  # "fast": same distribution, chunked float32 generation for 40M-row tables
+                wt = torch.empty(n, m, dtype=torch.float32)
+                bound = float(np.sqrt(1 / n))
+                g = torch.Generator().manual_seed(1000 + i)
+                step = 1 << 20
+                for lo in range(0, n, step):
+                    wt[lo:lo + step].uniform_(-bound, bound, generator=g)
+            EE = nn.EmbeddingBag(n, m, mode="sum", sparse=True, _weight=wt)
+            EE.weight.requires_grad = False
+            emb_l.append(EE)
+        return emb_l
+
+    def fetch_unique_idx_slices(self, lists_of_unique_indices):
+        """model_no_ddp.py:80-87.  CUDA id lists are gathered by the zero-copy kernel
+        (cdlrm_move_gather_master) by callers that own a context; host id lists index
+        the host table directly (pure addressing, no arithmetic)."""
+        return [self.emb_l[k].weight.data[u.to(self.emb_l[k].weight.device)]
+                for k, u in enumerate(lists_of_unique_indices)]
+
+    def forward(self, lS_o, lS_i):
+        return [self.emb_l[k](lS_i[k], lS_o[k]) for k in range(len(lS_i))]
+
+    # -- pinning ---------------------------------------------------------------------
+    def device_pointers(self, device):
+        """Device-visible addresses of every table for ``device`` (int)."""
+        ptrs = []
+        for k, E in enumerate(self.emb_l):
+            w = E.weight.data
+            if w.is_cuda:                       # master kept in HBM (optional mode)
+                ptrs.append(w.data_ptr())
+                continue
+            key = (w.data_ptr(), device)
+            if key not in self._registered:
+                if w.is_pinned():
+                    # torch-pinned memory is mapped and portable; under UVA the device
+                    # address equals the host address
+                    self._registered[key] = w.data_ptr()
+                else:
+                    dev = _vp()
+                    check(lib.cdlrm_host_register(int(device), _vp(w.data_ptr()), w.numel() * 4,
+                                                  ctypes.byref(dev)))
+                    self._registered[key] = dev.value
+            ptrs.append(self._registered[key])
+        return ptrs
+
+    def unpin(self):
+        pinned = {E.weight.data_ptr() for E in self.emb_l if E.weight.data.is_pinned()}
+        for (hptr, _), _dev in list(self._registered.items()):
+            if hptr not in pinned:
+                lib.cdlrm_host_unregister(_vp(hptr))
+        self._registered.clear()
+
+
+# ------------------------------------------------------------------------------------
+# cache group -- model_no_ddp.py:101-212
+# ------------------------------------------------------------------------------------
+
+_GROUPS = weakref.WeakSet()      # cache groups with a pending fused update (optimizer hook)
+
+
+class _LookupFn(torch.autograd.Function):
+    """Autograd bridge: forward = cdlrm_embed_fwd, backward = de-duplicated sparse SGD
+    (cdlrm_embed_bwd_plan + cdlrm_embed_bwd_sgd).  The update is applied when
+    ``optimizer_embeds.step()`` runs (see ``_install_optimizer_hook``), or immediately
+    when ``group.fused_lr`` is set."""
+
+    @staticmethod
+    def forward(ctx, anchor, group, ids, offsets, n_idx, n_bags, tb):
+        out, slots, bag_ids = group._launch_forward(ids, offsets, n_idx, n_bags, tb)
+        ctx.group = group
+        ctx.tb = tb
+        ctx.slots = slots
+        ctx.bag_ids = bag_ids
+        ctx.n_idx = n_idx
+        ctx.mark_non_differentiable(slots)
+        return (slots,) + tuple(out.unbind(0))
+
+    @staticmethod
+    def backward(ctx, _gslots, *grads):
+        group = ctx.group
+        T = len(grads)
+        g0 = next((g for g in grads if g is not None), None)
+        if g0 is None:
+            return (None,) * 7
+        d = group.dim
+        # fast path: the T grads are planes of one buffer (what the interaction backward makes)
+        uniform = all(g is not None and g.stride(1) == 1 for g in grads)
+        if uniform:
+            rs = grads[0].stride(0)
+            ld = (grads[1].data_ptr() - grads[0].data_ptr()) // 4 if T > 1 else 0
+            uniform = all(g.stride(0) == rs and g.data_ptr() - grads[0].data_ptr() == 4 * ld * k
+                          for k, g in enumerate(grads)) and (T == 1 or ld > 0)
+        if uniform:
+            base, keep = grads[0], grads
+        else:
+            zero = torch.zeros_like(g0)
+            keep = torch.stack([g if g is not None else zero for g in grads]).contiguous()
+            base, rs, ld = keep, d, keep.stride(0)
+        group._queue_update(ctx.tb, ctx.slots, ctx.bag_ids, ctx.n_idx, base, ld, rs, keep)
+        return (None,) * 7
+
+
+class Embedding_Table_Cache_Group(nn.Module):
+    """Set-associative GPU cache of embedding rows (model_no_ddp.py:101-212).
+
+    Attributes kept from the reference: ``ln_emb, num_ways, max_cache_size, emb_l``
+    (``nn.EmbeddingBag(num_ways*num_sets + aux, dim)`` per table), ``cache_sizes``,
+    ``occupancy_tables`` (int64 ``[num_sets, num_ways]``, -1 = empty; moved to the GPU
+    with the module), ``victim_cache_entries``.
+    """
+
+    def __init__(self, m_spa, ln_emb, max_cache_size, aux_table_size, num_ways, device=None):
+        super().__init__()
+        self.ln_emb = np.asarray(ln_emb)
+        self.dim = int(m_spa)
+        self.num_ways = int(num_ways)
+        self.aux_table_size = int(aux_table_size)
+        self.raw_cache_size = int(max_cache_size)
+        self.max_cache_size = self.find_next_prime(int(max_cache_size))
+        self.emb_l, self.cache_sizes = self.create_emb(m_spa, self.ln_emb, self.max_cache_size, num_ways,
+                                                       aux_table_size, device)
+        self.occupancy_tables = self.create_occupancy_tables(self.cache_sizes, num_ways, device)
+        self.victim_cache_entries = [None] * len(self.emb_l)
+        self.record_victims = False        # True: fill victim_cache_entries (costs a device sync)
+        self.assume_one_id_per_bag = None  # None: check lS_o on the host when it is a CPU tensor
+        self.fused_lr = None               # set to apply the SGD update inside backward
+        self.last_n_miss = None
+        self._ctx = None
+        self._bound_key = None
+        self._anchor = None
+        self._pending = []
+        self._plan_buf = None
+        self._dirty = None
+        _install_optimizer_hook()
+
+    # -- geometry (model_no_ddp.py:122-147) -----------------------------------------------
+    def find_next_prime(self, max_cache_size):
+        r = lib.cdlrm_find_next_prime(int(max_cache_size))
+        return None if r < 0 else int(r)
+
+    def compute_set_indices(self, table_idx, lookup_idxs):
+        return torch.remainder(lookup_idxs, self.cache_sizes[table_idx])
+
+    def create_emb(self, m, ln, max_cache_size, num_ways, aux_table_size, device=None):
+        emb_l = nn.ModuleList()
+        cache_sizes = []
+        for i in range(0, ln.size):
+            n = int(ln[i])
+            num_rows = n if n < max_cache_size else max_cache_size
+            cache_sizes.append(num_rows)
+            # rows are only ever read after a fill: skip the N(0,1) init of nn.EmbeddingBag
+            w = torch.zeros(num_ways * num_rows + aux_table_size, m, dtype=torch.float32, device=device)
+            emb_l.append(nn.EmbeddingBag(num_ways * num_rows + aux_table_size, m, mode="sum", sparse=True,
+                                         _weight=w))
+        return emb_l, cache_sizes
+
+    def create_occupancy_tables(self, cache_sizes, num_ways, device=None):
+        return [torch.full((cache_sizes[i], num_ways), -1, dtype=torch.int64, device=device)
+                for i in range(len(cache_sizes))]
+
+    def _apply(self, fn, *a, **kw):
+        super()._apply(fn, *a, **kw)
+        self.occupancy_tables = [fn(t) for t in self.occupancy_tables]
+        self._bound_key = None
+        return self
+
+    # -- context / binding -------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.emb_l[0].weight.device
+
+    def _ensure_ctx(self, emb_tables=None):
+        dev = self.device
+        if dev.type != "cuda":
+            raise _lib.CdlrmError("Embedding_Table_Cache_Group needs a CUDA device: the cache hot path has no "
+                                  "CPU fallback (move the module with .to(rank) first)")
+        if self._ctx is None:
+            h = _vp()
+            n_rows = _lib.i64_array([int(n) for n in self.ln_emb])
+            check(lib.cdlrm_ctx_create(ctypes.byref(h), dev.index, len(self.emb_l), self.dim, self.num_ways,
+                                       self.aux_table_size, n_rows, self.raw_cache_size))
+            self._ctx = h
+            T = len(self.emb_l)
+            sets = (ctypes.c_int64 * T)()
+            rows = (ctypes.c_int64 * T)()
+            check(lib.cdlrm_ctx_geometry(self._ctx, sets, rows))
+            assert list(sets) == [int(s) for s in self.cache_sizes]
+            self._cache_rows = list(rows)
+            self._anchor = torch.zeros(1, device=dev, requires_grad=True)
+        self.occupancy_tables = [t if t.device == dev else t.to(dev) for t in self.occupancy_tables]
+        key = tuple(e.weight.data_ptr() for e in self.emb_l) + tuple(t.data_ptr() for t in self.occupancy_tables)
+        if key != self._bound_key:
+            check(lib.cdlrm_ctx_bind_cache(self._ctx, _lib.ptr_array([e.weight.data_ptr() for e in self.emb_l]),
+                                           _lib.ptr_array([t.data_ptr() for t in self.occupancy_tables])))
+            check(lib.cdlrm_ctx_bind_plan_tags(self._ctx, _lib.ptr_array([t.data_ptr() for t in self.occupancy_tables])))
+            words = [(r + 31) // 32 for r in self._cache_rows]
+            self._dirty = torch.zeros(sum(words), dtype=torch.int32, device=dev)
+            offs = np.concatenate([[0], np.cumsum(words)[:-1]])
+            check(lib.cdlrm_ctx_bind_dirty(self._ctx, _lib.ptr_array(
+                [self._dirty.data_ptr() + 4 * int(o) for o in offs])))
+            self._bound_key = key
+        if emb_tables is not None:
+            mkey = (id(emb_tables), tuple(E.weight.data_ptr() for E in emb_tables.emb_l))
+            if getattr(self, "_master_key", None) != mkey:
+                check(lib.cdlrm_ctx_bind_master(self._ctx, _lib.ptr_array(emb_tables.device_pointers(dev.index))))
+                self._master_key = mkey
+        return self._ctx
+
+    def __del__(self):
+        try:
+            if self._ctx is not None:
+                lib.cdlrm_ctx_destroy(self._ctx)
+        except Exception:
+            pass
+
+    # -- forward (model_no_ddp.py:149-212) --------------------------------------------------------
+    def _launch_forward(self, ids, offsets, n_idx, n_bags, tb=0):
+        dev = self.device
+        T = ids.shape[0]
+        out = torch.empty(T, n_bags, self.dim, dtype=torch.float32, device=dev)
+        slots = torch.empty(T, max(n_idx, 1), dtype=torch.int32, device=dev)
+        n_miss = torch.empty(T, dtype=torch.int32, device=dev)
+        bag_ids = None
+        if offsets is not None:
+            bag_ids = torch.empty(T, max(n_idx, 1), dtype=torch.int32, device=dev)
+        check(lib.cdlrm_embed_fwd(
+            self._ctx, tb, T, _vp(ids.data_ptr()), ids.stride(0),
+            _vp(offsets.data_ptr()) if offsets is not None else None,
+            offsets.stride(0) if offsets is not None else 0,
+            n_idx, n_bags, _vp(out.data_ptr()), out.stride(0), _vp(slots.data_ptr()), slots.stride(0),
+            _vp(n_miss.data_ptr()), _vp(bag_ids.data_ptr()) if bag_ids is not None else None,
+            bag_ids.stride(0) if bag_ids is not None else 0, _stream_ptr(dev)))
+        if tb == 0 and T == len(self.emb_l):
+            self.last_n_miss = n_miss
+        else:
+            if self.last_n_miss is None or self.last_n_miss.numel() != len(self.emb_l):
+                self.last_n_miss = torch.zeros(len(self.emb_l), dtype=torch.int32, device=dev)
+            self.last_n_miss[tb:tb + T] = n_miss
+        return out, slots, bag_ids
+
+    def _one_id_per_bag(self, lS_o, n_idx, n_bags):
+        if n_idx != n_bags:
+            return False
+        if self.assume_one_id_per_bag is not None:
+            return bool(self.assume_one_id_per_bag)
+        if isinstance(lS_o, torch.Tensor) and not lS_o.is_cuda:
+            ar = torch.arange(n_bags, dtype=lS_o.dtype)
+            return bool((lS_o == ar).all()) if lS_o.dim() == 2 else bool(torch.equal(lS_o, ar))
+        return False   # device offsets: cannot be inspected without a sync -> general pooling path
+
+    def forward(self, lS_o, lS_i, emb_tables, rank):
+        if (len(self.emb_l) != len(lS_o)) or (len(self.emb_l) != len(lS_i)):
+            sys.exit("ERROR: corrupted model input detected in parallel_forward call")
+        self._ensure_ctx(emb_tables)
+        dev = self.device
+        if isinstance(rank, int) and rank != dev.index:
+            raise _lib.CdlrmError(f"cache group lives on {dev}, forward called with rank={rank}")
+        uniform = isinstance(lS_i, torch.Tensor) and lS_i.dim() == 2 and isinstance(lS_o, torch.Tensor) \
+            and lS_o.dim() == 2
+        if not uniform:   # ragged lists: one table per call
+            lens_i = {int(t.numel()) for t in lS_i}
+            lens_o = {int(t.numel()) for t in lS_o}
+            if len(lens_i) == 1 and len(lens_o) == 1:
+                lS_i, lS_o, uniform = torch.stack(list(lS_i)), torch.stack(list(lS_o)), True
+        if uniform:
+            outs, slots = self._forward_uniform(lS_o, lS_i)
+            slots = [slots[k] for k in range(slots.shape[0])]
+        else:             # ragged: tables with different numbers of ids / bags, one launch set per table
+            outs, slots = [], []
+            for k in range(len(self.emb_l)):
+                o, s_ = self._forward_uniform(lS_o[k].reshape(1, -1), lS_i[k].reshape(1, -1), tb=k)
+                outs.append(o[0])
+                slots.append(s_[0])
+        if len(self.emb_l) != len(outs):
+            sys.exit("ERROR: corrupted intermediate result in parallel_forward call")
+        if self.record_victims:
+            nm = self.last_n_miss.tolist()
+            for k in range(len(self.emb_l)):
+                base = self.cache_sizes[k] * self.num_ways
+                aux = torch.arange(base, base + nm[k], device=dev)
+                sl = slots[k].long()
+                miss_pos = (sl >= base).nonzero().flatten()
+                self.victim_cache_entries[k] = (aux, lS_i[k].to(dev)[miss_pos])
+        return list(outs), slots
+
+    def _forward_uniform(self, lS_o, lS_i, tb=0):
+        dev = self.device
+        n_idx, n_bags = int(lS_i.shape[1]), int(lS_o.shape[1])
+        p1 = self._one_id_per_bag(lS_o, n_idx, n_bags)
+        ids = lS_i.to(dev, dtype=torch.int64, non_blocking=True)
+        if ids.stride(1) != 1:
+            ids = ids.contiguous()
+        offsets = None
+        if not p1:
+            offsets = lS_o.to(dev, dtype=torch.int64, non_blocking=True).contiguous()
+        # (overflow of the aux region is detected on the device: check_device_flags)
+        if torch.is_grad_enabled():
+            res = _LookupFn.apply(self._anchor, self, ids, offsets, n_idx, n_bags, tb)
+            slots, outs = res[0], res[1:]
+        else:
+            out, slots, _ = self._launch_forward(ids, offsets, n_idx, n_bags, tb)
+            outs = out.unbind(0)
+        return outs, slots[:, :n_idx]
+
+    def check_device_flags(self):
+        """Raise what the reference would have raised on the host (IndexError) for
+        conditions detected on the device.  Synchronises."""
+        f = ctypes.c_uint32(0)
+        check(lib.cdlrm_ctx_check(self._ctx, _stream_ptr(self.device), ctypes.byref(f)))
+        if f.value & 1:
+            raise IndexError("aux (victim) region overflow: more misses than aux_table_size "
+                             "(model_no_ddp.py:177-179)")
+        if f.value & 2:
+            raise IndexError("sparse index outside its embedding table")
+        return f.value
+
+    # -- backward + SGD (main_no_ddp.py:376,409,413) ----------------------------------------------
+    def _queue_update(self, tb, slots, bag_ids, n_idx, dbase, ld, rs, keep):
+        item = (tb, slots, bag_ids, n_idx, dbase, ld, rs, keep)
+        if self.fused_lr is not None:
+            self._apply_update(item, float(self.fused_lr))
+        else:
+            self._pending.append(item)
+            _GROUPS.add(self)
+
+    def _apply_update(self, item, lr):
+        tb, slots, bag_ids, n_idx, dbase, ld, rs, _keep = item
+        if n_idx == 0:
+            return
+        dev = self.device
+        T = slots.shape[0]
+        nbytes = lib.cdlrm_embed_bwd_plan_bytes(T, n_idx)
+        if self._plan_buf is None or self._plan_buf.numel() < nbytes:
+            self._plan_buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        s = _stream_ptr(dev)
+        check(lib.cdlrm_embed_bwd_plan(self._ctx, tb, T, _vp(slots.data_ptr()), slots.stride(0), n_idx,
+                                       _vp(self._plan_buf.data_ptr()), s))
+        check(lib.cdlrm_embed_bwd_sgd(self._ctx, tb, T, _vp(self._plan_buf.data_ptr()), n_idx,
+                                      _vp(bag_ids.data_ptr()) if bag_ids is not None else None,
+                                      bag_ids.stride(0) if bag_ids is not None else 0,
+                                      _vp(dbase.data_ptr()), ld, rs, lr, s))
+
+    def apply_pending_updates(self, lr):
+        """Apply the sparse SGD updates queued by backward (called by the optimizer hook
+        with the learning rate of the param group that holds this module's weights)."""
+        pend, self._pending = self._pending, []
+        for item in pend:
+            self._apply_update(item, lr)
+
+    def dirty_bitmap(self):
+        return self._dirty
+
+
+def _optimizer_pre_step(optimizer, args, kwargs):
+    if not _GROUPS:
+        return
+    for group in list(_GROUPS):
+        if not group._pending:
+            continue
+        mine = {id(e.weight) for e in group.emb_l}
+        for pg in optimizer.param_groups:
+            if any(id(p) in mine for p in pg["params"]):
+                group.apply_pending_updates(float(pg["lr"]))
+                break
+
+
+_HOOK = []
+
+
+def _install_optimizer_hook():
+    """``torch.optim.SGD(cache_group.parameters(), lr=args.lr_embeds)`` (main_no_ddp.py:376)
+    keeps working unmodified: the weights never get a ``.grad`` (so the stock step is a
+    no-op for them) and this global pre-step hook applies the fused update with the
+    optimizer's own learning rate at the moment ``optimizer_embeds.step()`` is called."""
+    if not _HOOK:
+        from torch.optim.optimizer import register_optimizer_step_pre_hook
+        _HOOK.append(register_optimizer_step_pre_hook(_optimizer_pre_step))
+
+
+# ------------------------------------------------------------------------------------
+# DLRM_Net -- model_no_ddp.py:215-316
+# ------------------------------------------------------------------------------------
+
+
+class _InteractFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, itself, x, *ly):
+        feats = (x,) + ly
+        B, d = x.shape
+        dev = x.device
+        rs = feats[0].stride(0)
+        ok = all(f.is_cuda and f.dtype == torch.float32 and f.shape == x.shape and f.stride(1) == 1 and
+                 f.stride(0) == rs for f in feats)
+        if not ok:
+            feats = tuple(f.contiguous().float() for f in feats)
+            rs = d
+        nf = len(feats)
+        npair = nf * (nf + 1) // 2 if itself else nf * (nf - 1) // 2
+        out = torch.empty(B, d + npair, dtype=torch.float32, device=dev)
+        check(lib.cdlrm_interact_fwd(dev.index, _lib.ptr_array([f.data_ptr() for f in feats]), nf, rs, B, d,
+                                     int(itself), _vp(out.data_ptr()), out.stride(0), _stream_ptr(dev)))
+        ctx.feats = feats
+        ctx.itself = itself
+        ctx.rs = rs
+        return out
+
+    @staticmethod
+    def backward(ctx, dR):
+        feats = ctx.feats
+        B, d = feats[0].shape
+        dev = dR.device
+        if dR.stride(1) != 1:
+            dR = dR.contiguous()
+        nf = len(feats)
+        dfeat = torch.empty(nf, B, d, dtype=torch.float32, device=dev)
+        check(lib.cdlrm_interact_bwd(dev.index, _lib.ptr_array([f.data_ptr() for f in feats]), nf, ctx.rs, B, d,
+                                     int(ctx.itself), _vp(dR.data_ptr()), dR.stride(0), _vp(dfeat.data_ptr()),
+                                     dfeat.stride(0), _stream_ptr(dev)))
+        return (None,) + tuple(dfeat.unbind(0))
+
+
+class DLRM_Net(nn.Module):
+    """model_no_ddp.py:215-316.  MLPs and loss stay stock PyTorch (cuBLAS); the pairwise-dot
+    interaction (:272-293) runs in cdlrm_interact_fwd/_bwd."""
+
+    def __init__(self, ln_bot=None, ln_top=None, arch_interaction_op=None, arch_interaction_itself=False,
+                 sync_dense_params=True, sigmoid_bot=-1, sigmoid_top=-1, loss_threshold=0.0):
+        super().__init__()
+        if (ln_bot is not None) and (ln_top is not None) and (arch_interaction_op is not None):
+            self.output_d = 0
+            self.parallel_model_batch_size = -1
+            self.parallel_model_is_not_prepared = True
+            self.arch_interaction_op = arch_interaction_op
+            self.arch_interaction_itself = arch_interaction_itself
+            self.sync_dense_params = sync_dense_params
+            self.loss_threshold = loss_threshold
+            self.cpu = torch.device("cpu")
+            self.bot_l = self.create_mlp(ln_bot, sigmoid_bot)
+            self.top_l = self.create_mlp(ln_top, sigmoid_top)
+
+    def create_mlp(self, ln, sigmoid_layer):
+        """:244-270 -- numpy-RNG initialisation in the reference's draw order."""
+        layers = nn.ModuleList()
+        for i in range(0, ln.size - 1):
+            n, m = int(ln[i]), int(ln[i + 1])
+            LL = nn.Linear(n, m, bias=True)
+            W = np.random.normal(0.0, np.sqrt(2 / (m + n)), size=(m, n)).astype(np.float32)
+            bt = np.random.normal(0.0, np.sqrt(1 / m), size=m).astype(np.float32)
+            LL.weight.data = torch.tensor(W, requires_grad=True)
+            LL.bias.data = torch.tensor(bt, requires_grad=True)
+            layers.append(LL)
+            layers.append(nn.Sigmoid() if i == sigmoid_layer else nn.ReLU())
+        return torch.nn.Sequential(*layers)
+
+    def interact_features(self, x, ly):
+        if self.arch_interaction_op == "dot":
+            if not x.is_cuda:
+                raise _lib.CdlrmError("interact_features('dot') needs CUDA tensors: no CPU fallback")
+            return _InteractFn.apply(bool(self.arch_interaction_itself), x, *ly)
+        elif self.arch_interaction_op == "cat":
+            return torch.cat([x] + list(ly), dim=1)
+        else:
+            sys.exit("ERROR: --arch-interaction-op=" + self.arch_interaction_op + " is not supported")
+
+    def forward(self, dense_x, ly):
+        x = self.bot_l(dense_x)
+        z = self.interact_features(x, ly)
+        p = self.top_l(z)
+        if 0.0 < self.loss_threshold < 1.0:
+            return torch.clamp(p, min=self.loss_threshold, max=(1.0 - self.loss_threshold))
+        return p

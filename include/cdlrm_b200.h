@@ -1,0 +1,221 @@
+/* cdlrm_b200.h -- C ABI of libcdlrm_b200.so: the B200-native (sm_100a) look-ahead
+ * embedding-cache hot path of cDLRM.
+ *
+ * The reference (lkp411/cDLRM) is pure Python on PyTorch and has no FFI layer; its
+ * boundary for this path is the Python API of cache_manager.py / model_no_ddp.py /
+ * main_no_ddp.py.  The same-named Python modules in cdlrm_b200/ keep that API and
+ * call the entry points below through ctypes.  Every entry
+ * point cites the reference code it replaces as file:line in the reference tree.
+ *
+ * Conventions
+ *  - plain C types only; pointers are DEVICE pointers unless the name starts with
+ *    h_ (host).  "master" pointers are device-visible addresses of the host-pinned
+ *    (cudaHostRegister/cudaHostAlloc mapped) master embedding tables, or plain
+ *    device pointers when the master is kept in HBM.
+ *  - every compute call enqueues work on `stream` (a cudaStream_t) and returns
+ *    without synchronising unless stated.  Return value 0 = OK, <0 = error; the
+ *    message is available from cdlrm_last_error() (thread-local).
+ *  - one cdlrm_ctx per (process, device); a ctx is not thread-safe.
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *  - table-range calls take (table_begin, table_count) and strided per-table
+ *    operands: operand of table k lives at base + (k - table_begin) * ld.
+ *  - cache slot numbering is the reference's: slot = num_sets * way + set
+ *    (model_no_ddp.py:174), aux (victim) slots start at num_sets * num_ways
+ *    (model_no_ddp.py:177); tags are int64, -1 = empty (model_no_ddp.py:144-147).
+ */
+#ifndef CDLRM_B200_H
+#define CDLRM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDLRM_ABI_VERSION 1
+#define CDLRM_MAX_WAYS 64          /* pin masks are 64-bit */
+#define CDLRM_SORT_MAX 16384       /* ids per table sorted by one CTA in the backward plan */
+
+typedef struct cdlrm_ctx cdlrm_ctx;
+typedef struct cdlrm_rng cdlrm_rng;
+typedef void* cdlrm_stream;        /* cudaStream_t */
+
+/* ---- status -------------------------------------------------------------------- */
+int cdlrm_abi_version(void);
+const char* cdlrm_last_error(void);
+
+/* ---- geometry: model_no_ddp.py:122-125 (find_next_prime), :319-331 (isPrime) ---- */
+int cdlrm_is_prime_ref(int64_t n);
+int64_t cdlrm_find_next_prime(int64_t max_cache_size);   /* -1 if none in [c, 2c) */
+
+/* ---- context: Embedding_Table_Cache_Group.__init__/create_emb/
+ *      create_occupancy_tables, model_no_ddp.py:102-147 -------------------------- */
+int cdlrm_ctx_create(cdlrm_ctx** out, int device, int num_tables, int dim, int num_ways,
+                     int64_t aux_rows, const int64_t* h_n_rows, int64_t max_cache_size);
+int cdlrm_ctx_destroy(cdlrm_ctx* ctx);
+/* h_num_sets[k] = min(n_rows[k], find_next_prime(max_cache_size)) (:113,136);
+ * h_cache_rows[k] = num_ways * num_sets[k] + aux_rows (:138) */
+int cdlrm_ctx_geometry(const cdlrm_ctx* ctx, int64_t* h_num_sets, int64_t* h_cache_rows);
+/* storage is owned by the caller (PyTorch): weight[k] float32 [cache_rows[k], dim],
+ * tags[k] int64 [num_sets[k], num_ways]; h_* are host arrays of device pointers */
+int cdlrm_ctx_bind_cache(cdlrm_ctx* ctx, float* const* h_weight, int64_t* const* h_tags);
+/* the planner's look-ahead copy of the tags (may equal the live tags) */
+int cdlrm_ctx_bind_plan_tags(cdlrm_ctx* ctx, int64_t* const* h_plan_tags);
+/* master tables: Embedding_Table_Group.emb_l[k].weight, model_no_ddp.py:21-98 */
+int cdlrm_ctx_bind_master(cdlrm_ctx* ctx, float* const* h_master);
+/* dirty-slot bitmaps for the table aggregation: ceil(cache_rows[k]/32) uint32 words */
+int cdlrm_ctx_bind_dirty(cdlrm_ctx* ctx, uint32_t* const* h_dirty);
+/* pre-size internal scratch for batches of up to max_idx ids per table (optional;
+ * scratch otherwise grows on demand, which is not allowed during graph capture) */
+int cdlrm_ctx_reserve(cdlrm_ctx* ctx, int64_t max_idx);
+/* tags[k][:] = -1 for all tables (live and plan copies) */
+int cdlrm_tags_reset(cdlrm_ctx* ctx, cdlrm_stream stream);
+/* sticky device-side error flags (bit0: aux region overflow, model_no_ddp.py:177-179
+ * would raise IndexError); synchronises `stream`; clears the flags */
+int cdlrm_ctx_check(cdlrm_ctx* ctx, cdlrm_stream stream, uint32_t* h_flags);
+
+/* ---- forward: Embedding_Table_Cache_Group.forward, model_no_ddp.py:149-212 ------
+ * per table k and id j: set = id mod num_sets; probe the tag line; hit ->
+ * slot = num_sets*way+set; miss -> slot = num_sets*num_ways + ordinal (batch order),
+ * weight[slot] = master[id]; out[b] = sum_{j in bag b} weight[slot_j].
+ * offsets == NULL means one id per bag (Criteo, data_loader_terabyte.py:85).
+ * out: float32 [n_bags, dim]; slots: int32 [n_idx]; n_miss: int32 [table_count];
+ * bag_ids (optional, may be NULL): int32 [n_idx] bag index of every id (needed by
+ * the backward when offsets != NULL). */
+int cdlrm_embed_fwd(cdlrm_ctx* ctx, int table_begin, int table_count,
+                    const int64_t* ids, int64_t ld_ids,
+                    const int64_t* offsets, int64_t ld_off,
+                    int32_t n_idx, int32_t n_bags,
+                    float* out, int64_t ld_out,
+                    int32_t* slots, int64_t ld_slots,
+                    int32_t* n_miss,
+                    int32_t* bag_ids, int64_t ld_bag,
+                    cdlrm_stream stream);
+
+/* ---- backward + SGD: autograd of EmbeddingBag(sparse=True) followed by
+ *      optimizer_embeds.step(), main_no_ddp.py:376,409,413 -------------------------
+ * weight[slot] -= lr * sum_{j: slot_j == slot} d_out[bag(j)], duplicates merged by a
+ * per-table sort (no atomics unless one slot has more than 32 contributions).
+ * d_out row of bag b of table k: d_out + (k-table_begin)*ld_dout + b*dout_row_stride.
+ * Marks touched slots in the dirty bitmaps when bound.  */
+int64_t cdlrm_embed_bwd_plan_bytes(int table_count, int32_t n_idx);
+int cdlrm_embed_bwd_plan(cdlrm_ctx* ctx, int table_begin, int table_count,
+                         const int32_t* slots, int64_t ld_slots, int32_t n_idx,
+                         void* plan, cdlrm_stream stream);
+int cdlrm_embed_bwd_sgd(cdlrm_ctx* ctx, int table_begin, int table_count,
+                        const void* plan, int32_t n_idx,
+                        const int32_t* bag_ids, int64_t ld_bag,
+                        const float* d_out, int64_t ld_dout, int64_t dout_row_stride,
+                        float lr, cdlrm_stream stream);
+
+/* ---- interaction: DLRM_Net.interact_features ("dot"), model_no_ddp.py:272-293 ---
+ * feat[0] = x, feat[1..] = ly; h_feat is a host array of n_feat device pointers to
+ * float32 [B, dim] matrices with row stride feat_row_stride (elements).
+ * out[b] = [x[b], <T_i, T_j> for i in 0..n_feat-1 for j in 0..i-1 (+ j == i if itself)]
+ * out row stride ld_out >= dim + n_pairs. */
+int cdlrm_interact_fwd(int device, const float* const* h_feat, int n_feat, int64_t feat_row_stride,
+                       int32_t batch, int dim, int itself, float* out, int64_t ld_out,
+                       cdlrm_stream stream);
+/* d_feat plane i (float32 [B, dim], contiguous) at d_feat + i*ld_dfeat receives the
+ * gradient of feat[i] (plane 0 also receives d_out[:, :dim]). */
+int cdlrm_interact_bwd(int device, const float* const* h_feat, int n_feat, int64_t feat_row_stride,
+                       int32_t batch, int dim, int itself, const float* d_out, int64_t ld_dout,
+                       float* d_feat, int64_t ld_dfeat, cdlrm_stream stream);
+
+/* ---- window planner: Prefetcher.process_batch_slice (cache_manager.py:27-46, the
+ *      torch.unique at :32) + the decision part of CacheEmbeddings
+ *      (main_no_ddp.py:155-204) ---------------------------------------------------- */
+/* bytes of planner workspace needed for windows of up to window_len ids per table */
+int64_t cdlrm_plan_workspace_bytes(const cdlrm_ctx* ctx, int64_t window_len);
+int cdlrm_plan_bind_workspace(cdlrm_ctx* ctx, void* workspace, int64_t bytes, int64_t window_len);
+/* unique only (all tables): the torch.unique of cache_manager.py:32.  Writes
+ * h_counts[k*4] = number of unique ids of table k (other three entries 0). */
+int cdlrm_plan_unique(cdlrm_ctx* ctx, const int64_t* win_ids, int64_t ld, int64_t n,
+                      int64_t* h_counts, cdlrm_stream stream);
+/* phase A, all tables: unique ids of the window (ascending), probe against the plan
+ * tags, pin hit ways, drop misses whose set is fully pinned, rank the survivors.
+ * win_ids of table k at win_ids + k*ld (int64 [n]).  If h_uniq != NULL ids are taken
+ * as already-unique ascending lists of length h_uniq_len[k] (the reference-API path).
+ * Writes h_counts[k*4 + {0,1,2,3}] = {unique, hits, dropped, survivor rows}
+ * (pinned host memory, valid after the stream is synchronised). */
+int cdlrm_plan_phase_a(cdlrm_ctx* ctx, const int64_t* win_ids, int64_t ld, int64_t n,
+                       const int64_t* h_uniq_len, int64_t* h_counts, cdlrm_stream stream);
+/* phase B, all tables: q is the concatenation over tables of float32 [rows_k, num_ways]
+ * exponential draws (main_no_ddp.py:183-185, see cdlrm_rng_*).  Chooses the way
+ * argmax(probs/q) among un-pinned ways, resolves duplicate (set, way) claims
+ * (last survivor wins), updates the plan tags and emits per table:
+ *   evict_ids / evict_slots / evict_primary [E_k]  (survivor order, duplicates kept;
+ *       primary = 1 for exactly one entry per distinct slot)
+ *   fill_ids / fill_slots [F_k]                     (winners only, survivor order)
+ * lists of table k start at element list_off[k] = sum_{j<k} rows_j of each output
+ * array (rows_j from phase A).  h_counts2[k*2+{0,1}] = {E_k, F_k}. */
+int cdlrm_plan_phase_b(cdlrm_ctx* ctx, const float* q, const int64_t* h_rows,
+                       int64_t* evict_ids, int32_t* evict_slots, uint8_t* evict_primary,
+                       int64_t* fill_ids, int32_t* fill_slots,
+                       int64_t* h_counts2, cdlrm_stream stream);
+/* unique ids of table k found by the last phase A (device pointer into the
+ * workspace, ascending, h_counts[k*4] entries) */
+const int64_t* cdlrm_plan_unique_ptr(const cdlrm_ctx* ctx, int table);
+/* out[0..n) = first n unique ids of table k found by the last unique / phase A */
+int cdlrm_plan_copy_unique(cdlrm_ctx* ctx, int table, int64_t* out, int64_t n, cdlrm_stream stream);
+
+/* ---- mover: the data part of CacheEmbeddings (main_no_ddp.py:190-199,205-206) and
+ *      Prefetcher.eviction_manager (cache_manager.py:48-64) ------------------------- */
+/* rows_out[e] = weight[k][evict_slots[e]] (if rows_out != NULL); if write_master:
+ * master[k][id] = row, or (master[k][id] + row)/2 when average_on_writeback
+ * (primary entries only) */
+int cdlrm_move_evict(cdlrm_ctx* ctx, int table, const int64_t* evict_ids, const int32_t* evict_slots,
+                     const uint8_t* evict_primary, int64_t n, float* rows_out,
+                     int write_master, int average_on_writeback, cdlrm_stream stream);
+/* eviction_manager body for rows that are already packed (cache_manager.py:58-62):
+ * master[k][ids[i]] = rows[i], or (master + rows[i]) / 2; ids must be distinct when
+ * averaging */
+int cdlrm_move_scatter_master(cdlrm_ctx* ctx, int table, const int64_t* ids, int64_t n, const float* rows,
+                              int average_on_writeback, cdlrm_stream stream);
+/* rows_out[i] = master[k][ids[i]]: Embedding_Table_Group.fetch_unique_idx_slices,
+ * model_no_ddp.py:80-87 (zero-copy gather over PCIe when the master is host-pinned) */
+int cdlrm_move_gather_master(cdlrm_ctx* ctx, int table, const int64_t* ids, int64_t n,
+                             float* rows_out, cdlrm_stream stream);
+/* weight[k][fill_slots[i]] = rows[src_index ? src_index[i] : i] (rows == NULL: read
+ * master[k][fill_ids[i]] directly); live tags[k][slot % S][slot / S] = fill_ids[i] */
+int cdlrm_move_fill(cdlrm_ctx* ctx, int table, const int64_t* fill_ids, const int32_t* fill_slots,
+                    int64_t n, const float* rows, const int64_t* src_index, cdlrm_stream stream);
+
+/* ---- table aggregation: broadcast_and_aggregate, main_no_ddp.py:250-292 ---------
+ * collect: ascending list of dirty slots per table (torch.unique(sorted=True) :270);
+ *          slot_list int32 [sum cache_rows] capacity, d_counts int64 [num_tables]
+ *          (device) and h_counts (pinned host, may be NULL).
+ * pack:    buf[i] = weight[k][slot_i] / divisor (:273-281); unpack: weight[k][slot_i] = buf[i]
+ *          (:292) and clears the dirty bits.  List of table k starts at h_list_off[k]. */
+/* mark: set the dirty bit of every slot in idxs (int32 [table_count][n], table k at
+ * idxs + k*ld) -- the reference's cache_group_idxs argument (main_no_ddp.py:251,268) */
+int cdlrm_agg_mark(cdlrm_ctx* ctx, const int32_t* idxs, int64_t ld, int64_t n, cdlrm_stream stream);
+int cdlrm_agg_or_bitmaps(cdlrm_ctx* ctx, const uint32_t* gathered, int world, int64_t words_total,
+                         cdlrm_stream stream);
+int cdlrm_agg_collect(cdlrm_ctx* ctx, int32_t* slot_list, int64_t* d_counts, int64_t* h_counts,
+                      cdlrm_stream stream);
+int cdlrm_agg_pack(cdlrm_ctx* ctx, const int32_t* slot_list, const int64_t* h_counts,
+                   float divisor, float* buf, cdlrm_stream stream);
+int cdlrm_agg_unpack(cdlrm_ctx* ctx, const int32_t* slot_list, const int64_t* h_counts,
+                     const float* buf, int clear_dirty, cdlrm_stream stream);
+
+/* ---- host memory: pin (cudaHostRegister, mapped + portable) a master table that lives
+ *      in ordinary or shared host memory (emb_tables.share_memory(), main_no_ddp.py:621-622)
+ *      and return its device-visible address ---------------------------------------- */
+int cdlrm_host_register(int device, void* h_ptr, int64_t bytes, void** dev_ptr);
+int cdlrm_host_unregister(void* h_ptr);
+
+/* ---- victim-way RNG (host): the torch CPU mt19937 stream consumed by
+ *      torch.distributions.Categorical(...).sample(), main_no_ddp.py:183-185 -------
+ * out[i] = float32(-log1p(-u_i)), u_i = (r64 & (2^53-1)) * 2^-53,
+ * r64 = (mt32() << 32) | mt32(), mt19937 seeded by init_genrand(seed)
+ * == torch.manual_seed(seed); torch.empty(n).exponential_(1). */
+int cdlrm_rng_create(cdlrm_rng** out, uint64_t seed);
+int cdlrm_rng_destroy(cdlrm_rng* rng);
+int cdlrm_rng_exponential(cdlrm_rng* rng, float* h_out, int64_t n, int threads);
+uint64_t cdlrm_rng_draws(const cdlrm_rng* rng);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDLRM_B200_H */

@@ -164,8 +164,13 @@ def gen_geometry():
     cg = M.Embedding_Table_Cache_Group.__new__(M.Embedding_Table_Cache_Group)
     res = {str(s): cg.find_next_prime(s) for s in sizes}
     isp = {str(n): bool(M.isPrime(n)) for n in list(range(1, 200)) + [10006, 150001, 300002, 600011]}
+    argv, sys.argv = sys.argv, [sys.argv[0]]
+    try:
+        defaults = {k: v for k, v in vars(R.ProcessArgs()).items()}
+    finally:
+        sys.argv = argv
     with open(os.path.join(OUT, "geometry.json"), "w") as f:
-        json.dump({"find_next_prime": res, "isPrime": isp}, f, indent=0, sort_keys=True)
+        json.dump({"find_next_prime": res, "isPrime": isp, "cli_defaults": defaults}, f, indent=0, sort_keys=True)
 
 
 def gen_rng():

@@ -1,0 +1,217 @@
+"""GPU parity tests: the CUDA path (through the Python mirror -> ctypes -> C ABI) against the
+golden vectors produced by the unmodified reference and against the numpy oracle.
+
+Integer / index / decision results: bit-exact.  Floating point: 1e-5 relative (north_star),
+see util.assert_close_fp32."""
+import queue
+
+import numpy as np
+import pytest
+import torch
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _mods():
+    from cdlrm_b200 import cache_manager as C
+    from cdlrm_b200 import main_no_ddp as R
+    from cdlrm_b200 import model_no_ddp as M
+    return C, R, M
+
+
+def _run_cuda_trace(cfg, mode):
+    """mode 'api': the reference-shaped calls (process_batch_slice -> CacheEmbeddings ->
+    eviction data applied to the master -> forward/backward/SGD.step).
+    mode 'fast': WindowPlanner on raw window ids with the C++ victim RNG and zero-copy
+    evict/fill against the pinned master."""
+    C, R, M = _mods()
+    seed = cfg["seed"]
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    ln_emb = np.asarray(cfg["ln_emb"])
+    d, B, L = cfg["dim"], cfg["batch"], cfg["lookahead"]
+    T = len(ln_emb)
+    master = M.Embedding_Table_Group(d, ln_emb)
+    cg = M.Embedding_Table_Cache_Group(d, ln_emb, max_cache_size=cfg["cache_size"], aux_table_size=B,
+                                       num_ways=cfg["num_ways"]).to(DEV)
+    opt = torch.optim.SGD(cg.parameters(), lr=cfg["lr_embeds"])
+    evq = queue.Queue()
+    ids = util.make_ids(cfg)
+    grads = util.upstream_grads(cfg)
+    rec = util.TraceRecorder()
+    lS_o = torch.arange(B).reshape(1, -1).repeat(T, 1)
+    torch.manual_seed(seed)
+    planner = None
+    if mode == "fast":
+        cg._ensure_ctx(master)
+        planner = C.WindowPlanner(cg, master, L * B, rng=C.VictimRng(seed), lookahead_tags=True)
+    step = 0
+    for w in range(cfg["n_windows"]):
+        win = torch.from_numpy(ids[:, w * L * B:(w + 1) * L * B])
+        if mode == "api":
+            rows, uniq, maps = C.Prefetcher.process_batch_slice(win, master)
+            R.CacheEmbeddings(rows, uniq, maps, cg, evq, 0)
+            ev = evq.get()
+            C.Prefetcher.apply_eviction_data(master, ev, cfg.get("avg_wb", False))
+            uniq_len = [int(u.numel()) for u in uniq]
+            ev_ids = [e[0].numpy() for e in ev]
+            ev_rows = [e[1].numpy() for e in ev]
+            rng_digest = util.digest(torch.get_rng_state().numpy())
+        else:
+            pr = planner.plan(win_ids=win.to(DEV))
+            ev = planner.install(pr, write_master=True, average_on_writeback=cfg.get("avg_wb", False),
+                                 collect_evictions=True)
+            torch.cuda.synchronize()
+            uniq_len = pr.uniq
+            ev_ids = [e[0].cpu().numpy() for e in ev]
+            ev_rows = [e[1].cpu().numpy() for e in ev]
+            rng_digest = None
+            for k in range(T):   # the planner's tags and the live tags agree after install
+                assert torch.equal(planner.plan_tags[k], cg.occupancy_tables[k])
+        rec.window(w, uniq_len, [t.cpu().numpy() for t in cg.occupancy_tables], ev_ids, ev_rows, rng_digest)
+        for b in range(L):
+            lS_i = win[:, b * B:(b + 1) * B]
+            ly, slots = cg(lS_o, lS_i, master, 0)
+            G = torch.from_numpy(next(grads)).to(DEV)
+            loss = sum((ly[k] * G[k]).sum() for k in range(T))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            rec.step(step, torch.stack(slots).cpu().numpy(), cg.last_n_miss.cpu().numpy(),
+                     torch.stack([v.detach() for v in ly]).cpu().numpy())
+            step += 1
+        rec.window_end(w, [e.weight.data.cpu().numpy() for e in cg.emb_l])
+    cg.check_device_flags()
+    rec.final([e.weight.data.cpu().numpy() for e in cg.emb_l], [e.weight.data.numpy() for e in master.emb_l])
+    rec.out["cache_sizes"] = np.asarray(cg.cache_sizes, dtype=np.int64)
+    return rec.out
+
+
+@pytest.mark.parametrize("name", ["trace_tiny.npz", "trace_pressure.npz", "trace_pressure_avgwb.npz",
+                                  "trace_cfg0_small.npz"])
+@pytest.mark.parametrize("mode", ["api", "fast"])
+def test_trace_matches_reference_golden(name, mode):
+    g = util.load_golden(name)
+    cfg = util.golden_cfg(g)
+    got = _run_cuda_trace(cfg, mode)
+    n = util.compare_trace(g, got, check_rng=(mode == "api"))
+    assert n > 20
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
+def test_interaction_matches_reference_golden(case):
+    _, _, M = _mods()
+    g = util.load_golden("interact.npz")
+    net = M.DLRM_Net.__new__(M.DLRM_Net)
+    torch.nn.Module.__init__(net)
+    net.arch_interaction_op = "dot"
+    net.arch_interaction_itself = bool(g[f"{case}_itself"])
+    x = torch.from_numpy(g[f"{case}_x"]).to(DEV).requires_grad_()
+    ly = [torch.from_numpy(a).to(DEV).requires_grad_() for a in g[f"{case}_ly"]]
+    R = net.interact_features(x, ly)
+    util.assert_close_fp32(R.detach().cpu().numpy(), g[f"{case}_R"])
+    R.backward(torch.from_numpy(g[f"{case}_dR"]).to(DEV))
+    util.assert_close_fp32(x.grad.cpu().numpy(), g[f"{case}_dx"])
+    util.assert_close_fp32(torch.stack([t.grad for t in ly]).cpu().numpy(), g[f"{case}_dly"])
+
+
+@pytest.mark.parametrize("shape", [(2048, 27, 128), (4099, 27, 16), (777, 9, 16), (513, 27, 64), (100, 3, 2)])
+def test_interaction_matches_oracle_at_size(shape):
+    from oracle import oracle as O
+    _, _, M = _mods()
+    B, nf, d = shape
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((B, d)).astype(np.float32)
+    ly = [rng.standard_normal((B, d)).astype(np.float32) for _ in range(nf - 1)]
+    net = M.DLRM_Net.__new__(M.DLRM_Net)
+    torch.nn.Module.__init__(net)
+    net.arch_interaction_op, net.arch_interaction_itself = "dot", False
+    xt = torch.from_numpy(x).to(DEV).requires_grad_()
+    lyt = [torch.from_numpy(a).to(DEV).requires_grad_() for a in ly]
+    R = net.interact_features(xt, lyt)
+    util.assert_close_fp32(R.detach().cpu().numpy(), O.interact_fwd(x, ly))
+    dR = rng.standard_normal(tuple(R.shape)).astype(np.float32)
+    R.backward(torch.from_numpy(dR).to(DEV))
+    dx, dly = O.interact_bwd(x, ly, dR)
+    util.assert_close_fp32(xt.grad.cpu().numpy(), dx)
+    util.assert_close_fp32(torch.stack([t.grad for t in lyt]).cpu().numpy(), np.stack(dly))
+
+
+def test_dlrm_tiny_loss_matches_reference_golden():
+    """End to end: cache + interaction kernels + stock MLPs, BCE loss, both optimizers."""
+    C, R, M = _mods()
+    g = util.load_golden("dlrm_tiny.npz")
+    cfg = util.golden_cfg(g)
+    seed = cfg["seed"]
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    ln_emb = np.asarray(cfg["ln_emb"])
+    d, B, L = cfg["dim"], cfg["batch"], cfg["lookahead"]
+    T = len(ln_emb)
+    master = M.Embedding_Table_Group(d, ln_emb)
+    cg = M.Embedding_Table_Cache_Group(d, ln_emb, max_cache_size=cfg["cache_size"], aux_table_size=B,
+                                       num_ways=cfg["num_ways"]).to(DEV)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    dlrm = M.DLRM_Net(g["ln_bot"], g["ln_top"], arch_interaction_op="dot", arch_interaction_itself=False,
+                      sigmoid_bot=-1, sigmoid_top=g["ln_top"].size - 2)
+    for i, p in enumerate(dlrm.parameters()):
+        assert np.array_equal(p.detach().numpy(), g[f"mlp_init_{i}"])   # same numpy-RNG init order
+    dlrm = dlrm.to(DEV)
+    loss_fn = torch.nn.BCELoss(reduction="mean")
+    opt_m = torch.optim.SGD(dlrm.parameters(), lr=0.1)
+    opt_e = torch.optim.SGD(cg.parameters(), lr=cfg["lr_embeds"])
+    evq = queue.Queue()
+    ids = util.make_ids(cfg)
+    lS_o = torch.arange(B).reshape(1, -1).repeat(T, 1)
+    losses = []
+    step = 0
+    for w in range(cfg["n_windows"]):
+        win = torch.from_numpy(ids[:, w * L * B:(w + 1) * L * B])
+        rows, uniq, maps = C.Prefetcher.process_batch_slice(win, master)
+        R.CacheEmbeddings(rows, uniq, maps, cg, evq, 0)
+        C.Prefetcher.apply_eviction_data(master, evq.get(), False)
+        for b in range(L):
+            ly, _ = cg(lS_o, win[:, b * B:(b + 1) * B], master, 0)
+            Z = dlrm(torch.from_numpy(g["X"][step]).to(DEV), ly)
+            E = loss_fn(Z, torch.from_numpy(g["Y"][step]).to(DEV))
+            opt_m.zero_grad()
+            opt_e.zero_grad()
+            E.backward()
+            opt_e.step()
+            opt_m.step()
+            losses.append(E.item())
+            step += 1
+    np.testing.assert_allclose(np.asarray(losses), g["losses"], rtol=1e-5)
+    for i, p in enumerate(dlrm.parameters()):
+        util.assert_close_fp32(p.detach().cpu().numpy(), g[f"mlp_final_{i}"], rtol=2e-5)
+    for k in range(T):
+        util.assert_close_fp32(cg.emb_l[k].weight.data.cpu().numpy(), g[f"final_weight_{k}"])
+
+
+def test_aggregate_single_rank_matches_reference_golden():
+    """W = 1: mean/sum/max of one rank leave the weights unchanged and clear the dirty bits;
+    the slot collection equals torch.unique of the idxs (golden rank-0 inputs)."""
+    _, R, M = _mods()
+    g = util.load_golden("aggregate.npz")
+    for op in ("mean", "sum", "max"):
+        cg = M.Embedding_Table_Cache_Group(4, np.asarray([50, 7, 300]), max_cache_size=10, aux_table_size=6,
+                                           num_ways=2).to(DEV)
+        for k, e in enumerate(cg.emb_l):
+            e.weight.data.copy_(torch.from_numpy(g[f"{op}_r0_before_{k}"]))
+        idx = torch.from_numpy(g[f"{op}_r0_idxs"]).to(DEV)
+        R.broadcast_and_aggregate(cg, idx, 0, op)
+        torch.cuda.synchronize()
+        counts = cg._agg_bufs[2].tolist()
+        assert counts == [len(np.unique(g[f"{op}_r0_idxs"][k])) for k in range(3)]
+        off = 0
+        for k in range(3):
+            got = cg._agg_bufs[0][off:off + counts[k]].cpu().numpy()
+            assert np.array_equal(got, np.unique(g[f"{op}_r0_idxs"][k]))
+            off += cg._cache_rows[k]
+            assert np.array_equal(cg.emb_l[k].weight.data.cpu().numpy(), g[f"{op}_r0_before_{k}"])
+        assert int(cg.dirty_bitmap().abs().sum()) == 0

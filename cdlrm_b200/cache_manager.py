@@ -222,21 +222,20 @@ class WindowPlanner:
 # Prefetcher -- cache_manager.py:8-115
 # ------------------------------------------------------------------------------------
 
-_UTIL = {}
-
-
 def _util_planner(emb_tables_cpu, device, window_len):
     """A planner-only context per (master tables, device) used by the static
-    ``process_batch_slice`` (it needs the unique + master-gather kernels, no cache)."""
+    ``process_batch_slice`` (it needs the unique + master-gather kernels, no cache).  Kept
+    on the master-table object so that it dies with it."""
     from .model_no_ddp import Embedding_Table_Cache_Group
-    key = (id(emb_tables_cpu), device.index)
-    ent = _UTIL.get(key)
+    reg = emb_tables_cpu.__dict__.setdefault("_cdlrm_util", {})
+    key = device.index
+    ent = reg.get(key)
     if ent is None or ent[1].window_len < window_len:
         ln = np.asarray([E.weight.shape[0] for E in emb_tables_cpu.emb_l])
         dim = emb_tables_cpu.emb_l[0].weight.shape[1]
         cg = Embedding_Table_Cache_Group(dim, ln, max_cache_size=2, aux_table_size=0, num_ways=1, device=device)
         ent = (cg, WindowPlanner(cg, emb_tables_cpu, window_len))
-        _UTIL[key] = ent
+        reg[key] = ent
     return ent
 
 

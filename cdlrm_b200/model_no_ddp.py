@@ -93,6 +93,12 @@ class Embedding_Table_Group(nn.Module):
             if w.is_cuda:                       # master kept in HBM (optional mode)
                 ptrs.append(w.data_ptr())
                 continue
+            if not w.is_pinned() and not w.is_shared():
+                # ordinary heap memory shares pages with its neighbours; registering it would
+                # leave those neighbours "partially pinned" and break their later copies.
+                # Re-home the table in page-locked memory of its own (one copy, at bind time).
+                E.weight.data = w.pin_memory()
+                w = E.weight.data
             key = (w.data_ptr(), device)
             if key not in self._registered:
                 if w.is_pinned():
@@ -106,6 +112,12 @@ class Embedding_Table_Group(nn.Module):
                     self._registered[key] = dev.value
             ptrs.append(self._registered[key])
         return ptrs
+
+    def __del__(self):
+        try:
+            self.unpin()
+        except Exception:
+            pass
 
     def unpin(self):
         pinned = {E.weight.data_ptr() for E in self.emb_l if E.weight.data.is_pinned()}

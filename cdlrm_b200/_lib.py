@@ -58,6 +58,11 @@ SIGNATURES = {
     "cdlrm_agg_collect": (C.c_int, [vp, vp, vp, vp, vp]),
     "cdlrm_agg_pack": (C.c_int, [vp, vp, c_i64p, C.c_float, vp, vp]),
     "cdlrm_agg_unpack": (C.c_int, [vp, vp, c_i64p, vp, C.c_int, vp]),
+    "cdlrm_prof_enable": (C.c_int, [C.c_int]),
+    "cdlrm_prof_launches": (C.c_int64, [C.c_int]),
+    "cdlrm_prof_num_kernels": (C.c_int, []),
+    "cdlrm_prof_kernel_name": (C.c_char_p, [C.c_int]),
+    "cdlrm_prof_report": (C.c_int, [C.POINTER(C.c_double), c_i64p, C.c_int]),
     "cdlrm_rng_create": (C.c_int, [C.POINTER(vp), C.c_uint64]),
     "cdlrm_rng_destroy": (C.c_int, [vp]),
     "cdlrm_rng_exponential": (C.c_int, [vp, vp, C.c_int64, C.c_int]),

@@ -194,6 +194,12 @@ class WindowPlanner:
         by the caller (reference API: ``table_cache[map[ids]]``); default reads the master."""
         s = stream or torch.cuda.current_stream(self.dev)
         out = []
+        if s != self.stream:
+            # the lists were allocated on the planner's stream: tell the caching allocator that
+            # `s` reads them, so that freeing the record cannot hand the memory to the next plan
+            # while the install kernels are still in flight
+            for t in (rec.evict_ids, rec.evict_slots, rec.evict_primary, rec.fill_ids, rec.fill_slots):
+                t.record_stream(s)
         with torch.cuda.stream(s):
             for k in range(self.T):
                 ids, slots, prim = rec.evict_list(k)

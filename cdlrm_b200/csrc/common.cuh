@@ -84,6 +84,22 @@ struct cdlrm_ctx {
 
 int cdlrm_sync_tabs(cdlrm_ctx* ctx, cudaStream_t s);
 
+// ---- launch accounting / optional per-kernel event timing (see cdlrm_prof_* in the header) ----
+enum KernelId {
+    K_PROBE = 0, K_GATHER, K_POOL, K_BWD_PLAN, K_BWD_SGD, K_INT_FWD, K_INT_BWD,
+    K_PLAN_BITMAP_SET, K_PLAN_COMPACT, K_PLAN_PROBE, K_PLAN_SURV, K_PLAN_SELECT, K_PLAN_LISTS,
+    K_MOVE_EVICT, K_MOVE_GATHER, K_MOVE_FILL, K_MOVE_SCATTER, K_AGG_MARK, K_AGG_OR, K_AGG_COLLECT,
+    K_AGG_PACK, K_AGG_UNPACK, K_MISC, K_COUNT
+};
+void cdlrm_prof_mark(int id, cudaStream_t s, int end);
+// wraps one kernel launch statement
+#define LAUNCH(id, stream, ...)              \
+    do {                                     \
+        cdlrm_prof_mark((id), (stream), 0);  \
+        __VA_ARGS__;                         \
+        cdlrm_prof_mark((id), (stream), 1);  \
+    } while (0)
+
 static inline int ceil_div_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ int64_t set_index(int64_t id, int64_t S) {

@@ -203,3 +203,71 @@ extern "C" int cdlrm_ctx_check(cdlrm_ctx* c, cdlrm_stream stream, uint32_t* h_fl
     CU_CHECK(cudaStreamSynchronize(s));
     return CDLRM_OK;
 }
+
+// ---- launch accounting / per-kernel timing -----------------------------------------------------
+#include <atomic>
+#include <mutex>
+
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+struct ProfRec { int id; cudaEvent_t b, e; };
+static std::vector<ProfRec> g_prof;
+static const char* const g_knames[K_COUNT] = {
+    "probe", "gather", "pool", "bwd_plan", "bwd_sgd", "interact_fwd", "interact_bwd",
+    "plan_bitmap_set", "plan_compact", "plan_probe", "plan_surv", "plan_select", "plan_lists",
+    "move_evict", "move_gather", "move_fill", "move_scatter", "agg_mark", "agg_or", "agg_collect",
+    "agg_pack", "agg_unpack", "misc"};
+
+void cdlrm_prof_mark(int id, cudaStream_t s, int end) {
+    if (!end) g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!end) {
+        ProfRec r{id, nullptr, nullptr};
+        cudaEventCreate(&r.b);
+        cudaEventCreate(&r.e);
+        cudaEventRecord(r.b, s);
+        g_prof.push_back(r);
+    } else {
+        for (size_t i = g_prof.size(); i-- > 0;)
+            if (g_prof[i].id == id) {
+                cudaEventRecord(g_prof[i].e, s);
+                break;
+            }
+    }
+}
+
+extern "C" int cdlrm_prof_enable(int on) {
+    g_prof_on.store(on ? 1 : 0);
+    return CDLRM_OK;
+}
+
+extern "C" int64_t cdlrm_prof_launches(int reset) {
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+extern "C" int cdlrm_prof_num_kernels(void) { return K_COUNT; }
+
+extern "C" const char* cdlrm_prof_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? g_knames[id] : ""; }
+
+extern "C" int cdlrm_prof_report(double* h_ms, int64_t* h_calls, int n) {
+    ARG_CHECK(h_ms && h_calls && n >= K_COUNT);
+    CU_CHECK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < n; ++i) { h_ms[i] = 0.0; h_calls[i] = 0; }
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.b, r.e) == cudaSuccess) {
+            h_ms[r.id] += ms;
+            h_calls[r.id] += 1;
+        }
+        cudaEventDestroy(r.b);
+        cudaEventDestroy(r.e);
+    }
+    cudaGetLastError();
+    g_prof.clear();
+    return CDLRM_OK;
+}

@@ -51,14 +51,17 @@ __device__ __forceinline__ int warp_sum(int v) {
 // model_no_ddp.py:166-174.
 // ------------------------------------------------------------------------------
 template <int GW>
-__global__ void __launch_bounds__(256) probe_kernel(const TableDesc* __restrict__ tabs, int tb,
+struct ProbeCfg { static constexpr int NT = GW >= 4 ? 1024 : 256; };   // 4 ids per group -> one batch in flight
+
+template <int GW>
+__global__ void __launch_bounds__(ProbeCfg<GW>::NT) probe_kernel(const TableDesc* __restrict__ tabs, int tb,
                                                     const int64_t* __restrict__ ids, int64_t ld_ids, int n_idx,
                                                     int32_t* __restrict__ slots, int64_t ld_slots,
                                                     int32_t* __restrict__ miss_cnt, int chunks, int ways) {
-    constexpr int GPW = 32 / GW;       // groups per warp
-    constexpr int NG = 8 * GPW;        // groups per CTA
-    constexpr int IPG = FWD_CHUNK / NG;  // ids per group (== GW)
-    static_assert(IPG <= 32, "miss mask is 32 bits");
+    constexpr int GPW = 32 / GW;                          // groups per warp
+    constexpr int NG = ProbeCfg<GW>::NT / 32 * GPW;    // groups per CTA
+    constexpr int IPG = FWD_CHUNK / NG;                   // ids per group
+    static_assert(IPG >= 1 && IPG <= 32, "miss mask is 32 bits");
     const int t = blockIdx.y, chunk = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane % GW, gidx = lane / GW, group = warp * GPW + gidx;
@@ -244,6 +247,93 @@ __global__ void __launch_bounds__(256) gather_kernel(const TableDesc* __restrict
 }
 
 // ------------------------------------------------------------------------------
+// K2 (fast path, float4 rows of <= 128 floats): every warp owns 32 consecutive ids of
+// the chunk.  Lane l first loads slot/id of row l (one coalesced load instead of one
+// dependent load per row), resolves the miss ordinal, and the row descriptors are then
+// broadcast by shuffle while groups of G lanes move U rows at a time (U*NGW rows, i.e.
+// up to 4 KB, in flight per warp).
+// ------------------------------------------------------------------------------
+template <int G, bool POOL_P1>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const TableDesc* __restrict__ tabs, int tb,
+                                                          const int64_t* __restrict__ ids, int64_t ld_ids, int n_idx,
+                                                          int32_t* __restrict__ slots, int64_t ld_slots,
+                                                          const int32_t* __restrict__ miss_cnt, int chunks,
+                                                          float* __restrict__ out, int64_t ld_out,
+                                                          int32_t* __restrict__ n_miss, uint32_t* __restrict__ flags,
+                                                          int dim, int ways, int64_t aux_rows) {
+    constexpr int NGW = 32 / G;               // rows moved per warp instruction
+    constexpr int ITERS = 32 / NGW;           // == G
+    constexpr int U = ITERS < 8 ? ITERS : 8;  // row batches in flight
+    const int t = blockIdx.y, chunk = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int s_prefix;
+    if (warp == 0) {
+        int acc = 0;
+        for (int c = lane; c < chunk; c += 32) acc += miss_cnt[t * chunks + c];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            s_prefix = acc;
+            if (chunk == chunks - 1) n_miss[t] = acc + miss_cnt[t * chunks + chunk];
+        }
+    }
+    const TableDesc& T = tabs[tb + t];
+    float* __restrict__ weight = T.weight;
+    const float* __restrict__ master = T.master;
+    int32_t* tsl = slots + (int64_t)t * ld_slots;
+    float* tout = POOL_P1 ? out + (int64_t)t * ld_out : nullptr;
+    const int64_t aux_base = T.num_sets * ways;
+    const int cpr = dim >> 2;
+    const int gl = lane % G, g = lane / G;
+    // lane-parallel descriptor of row (j0 + lane)
+    const int j0 = chunk * FWD_CHUNK + warp * 32;
+    const int jl = j0 + lane;
+    const bool in_range = jl < n_idx;
+    const int32_t sl = in_range ? tsl[jl] : 0;
+    const int64_t id = (in_range && sl < 0) ? __ldg(ids + (int64_t)t * ld_ids + jl) : 0;
+    __syncthreads();
+    const int prefix = s_prefix;
+    const float* src_l = nullptr;     // null: nothing to move for this row
+    int64_t aux_l = -1;
+    if (in_range) {
+        if (sl < 0) {
+            const int64_t ord = (int64_t)prefix + (-(int64_t)sl - 1);
+            if (ord >= aux_rows) {
+                atomicOr(flags, 1u);               // IndexError in the reference
+            } else {
+                aux_l = aux_base + ord;
+                src_l = master + id * dim;
+                tsl[jl] = (int32_t)aux_l;
+            }
+        } else if (POOL_P1) {
+            src_l = weight + (int64_t)sl * dim;
+        }
+    }
+    const unsigned long long src_bits = (unsigned long long)src_l;
+#pragma unroll 1
+    for (int it0 = 0; it0 < ITERS; it0 += U) {
+        float4 v[U];
+        unsigned long long sp[U];
+        long long ax[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rr = (it0 + u) * NGW + g;                 // row (within the warp's 32) of this group
+            sp[u] = __shfl_sync(0xffffffffu, src_bits, rr);
+            ax[u] = __shfl_sync(0xffffffffu, (long long)aux_l, rr);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (sp[u] && gl < cpr) v[u] = reinterpret_cast<const float4*>(sp[u])[gl];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!sp[u] || gl >= cpr) continue;
+            const int rr = (it0 + u) * NGW + g;
+            if (POOL_P1) reinterpret_cast<float4*>(tout + (int64_t)(j0 + rr) * dim)[gl] = v[u];
+            if (ax[u] >= 0) reinterpret_cast<float4*>(weight + ax[u] * dim)[gl] = v[u];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------
 // K3: EmbeddingBag(mode="sum") over final slots for general offsets
 // (model_no_ddp.py:191,200-202).  One group of G lanes per bag.
 // ------------------------------------------------------------------------------
@@ -285,9 +375,9 @@ constexpr int PLAN_NT = 1024;
 constexpr int PLAN_MAX_ROUNDS = CDLRM_SORT_MAX / 1024;  // 16 keys per thread at most
 
 struct PlanView {
-    int32_t* sorted_slots;  // [tc][n_idx]
-    int32_t* sorted_pos;    // [tc][n_idx] absolute position j
-    uint32_t* chunks;       // [tc][n_idx] start | len<<16 | first<<30 | excl<<31 (start relative to the sub-batch)
+    int32_t* sorted_pos;    // [tc][n_idx] absolute position j, grouped by slot (stable)
+    int4* chunks;           // [tc][n_idx] {slot, start (index into sorted_pos, relative to the table),
+                            //              len | first<<30 | excl<<31, position of the first element}
     int32_t* n_chunks;      // [tc][nsub]
 };
 
@@ -298,9 +388,8 @@ __host__ inline PlanView plan_view(void* plan, int tc, int n_idx) {
     char* p = (char*)plan;
     size_t a = (size_t)tc * n_idx * sizeof(int32_t);
     a = (a + 255) & ~(size_t)255;
-    v.sorted_slots = (int32_t*)p; p += a;
     v.sorted_pos = (int32_t*)p; p += a;
-    v.chunks = (uint32_t*)p; p += a;
+    v.chunks = (int4*)p; p += 4 * a;
     v.n_chunks = (int32_t*)p;
     return v;
 }
@@ -480,21 +569,90 @@ __global__ void __launch_bounds__(PLAN_NT, 1) bwd_plan_kernel(const TableDesc* _
             int len = 1;
             while (len < CH && i + len < n && keyA[i + len] == k) ++len;
             bool last = (i + len == n) || keyA[i + len] != k;
-            uint32_t desc = (uint32_t)i | ((uint32_t)len << 16) | (head ? (1u << 30) : 0u) |
-                            ((head && last) ? (1u << 31) : 0u);
-            pv.chunks[obase + cidx++] = desc;
+            uint32_t desc = (uint32_t)len | (head ? (1u << 30) : 0u) | ((head && last) ? (1u << 31) : 0u);
+            pv.chunks[obase + cidx++] = make_int4((int)k, j0 + i, (int)desc, j0 + (int)valA[i]);
         }
-        pv.sorted_slots[obase + i] = (int32_t)keyA[i];
         pv.sorted_pos[obase + i] = j0 + (int)valA[i];
     }
     if (tid == 0) pv.n_chunks[t * nsub + sub] = total;
 }
 
 // ------------------------------------------------------------------------------
-// Backward apply: one group of G lanes per chunk.  acc = sum of the chunk's
+// Backward apply.  A chunk = up to CH gradient rows that hit the same slot; its record
+// {slot, start, len|flags, first position} is one 16-byte load.  acc = sum of the chunk's
 // upstream gradient rows (ascending position: deterministic), then
-// weight[slot] += -lr * acc -- plain RMW when the chunk owns the slot.
+// weight[slot] += -lr * acc -- a plain read-modify-write when the chunk owns the slot,
+// a vector red otherwise (only slots with more than CH contributions).
+// Fast path (float4 rows, dim <= 128): a warp takes 32 consecutive chunk records with one
+// coalesced load and groups of G lanes work on U chunks at a time, so that U gradient
+// rows and U weight rows are in flight per group.
 // ------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256) bwd_sgd_rows_kernel(const TableDesc* __restrict__ tabs, int tb,
+                                                           PlanView pv, int n_idx, int j0, int sub, int nsub,
+                                                           const int32_t* __restrict__ bag_ids, int64_t ld_bag,
+                                                           const float* __restrict__ d_out, int64_t ld_dout,
+                                                           int64_t row_stride, float lr, int dim) {
+    constexpr int NGW = 32 / G;
+    constexpr int ITERS = 32 / NGW;
+    constexpr int U = ITERS < 4 ? ITERS : 4;
+    const int t = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nch = pv.n_chunks[t * nsub + sub];
+    const int c0 = (blockIdx.x * 8 + warp) * 32;
+    if (c0 >= nch) return;
+    const int64_t obase = (int64_t)t * n_idx + j0;
+    const int64_t tbase = (int64_t)t * n_idx;
+    const int gl = lane % G, g = lane / G;
+    const int cpr = dim >> 2;
+    const TableDesc& T = tabs[tb + t];
+    float* __restrict__ weight = T.weight;
+    const int32_t* bag = bag_ids ? bag_ids + (int64_t)t * ld_bag : nullptr;
+    const float* gbase = d_out + (int64_t)t * ld_dout;
+    int4 rec = make_int4(0, 0, 0, 0);
+    if (c0 + lane < nch) rec = pv.chunks[obase + c0 + lane];
+    if (bag && (rec.z & 0xff)) rec.w = bag[rec.w];
+    const bool act = gl < cpr;
+#pragma unroll 1
+    for (int it0 = 0; it0 < ITERS; it0 += U) {
+        int slot[U], start[U], meta[U], p0[U];
+        float4 gv[U], wv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int cc = (it0 + u) * NGW + g;
+            slot[u] = __shfl_sync(0xffffffffu, rec.x, cc);
+            start[u] = __shfl_sync(0xffffffffu, rec.y, cc);
+            meta[u] = __shfl_sync(0xffffffffu, rec.z, cc);
+            p0[u] = __shfl_sync(0xffffffffu, rec.w, cc);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if ((meta[u] & 0xff) && act) {
+                gv[u] = reinterpret_cast<const float4*>(gbase + (int64_t)p0[u] * row_stride)[gl];
+                if (meta[u] < 0) wv[u] = reinterpret_cast<const float4*>(weight + (int64_t)slot[u] * dim)[gl];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int len = meta[u] & 0xff;
+            if (!len) continue;
+            if (act) {
+                float4 acc = gv[u];
+                for (int i = 1; i < len; ++i) {     // rare: duplicates of one slot inside the batch
+                    int p = pv.sorted_pos[tbase + start[u] + i];
+                    if (bag) p = bag[p];
+                    acc = vadd(acc, reinterpret_cast<const float4*>(gbase + (int64_t)p * row_stride)[gl]);
+                }
+                float4* wp = reinterpret_cast<float4*>(weight + (int64_t)slot[u] * dim) + gl;
+                if (meta[u] < 0) *wp = vfma(-lr, acc, wv[u]);   // bit 31: the chunk owns the slot
+                else red_add(wp, vscale(-lr, acc));
+            }
+            if (((meta[u] >> 30) & 1) && gl == 0 && T.dirty) atomicOr(T.dirty + (slot[u] >> 5), 1u << (slot[u] & 31));
+        }
+    }
+}
+
+// generic fallback (any dim / alignment): one group of G lanes per chunk
 template <int VEC>
 __global__ void __launch_bounds__(256) bwd_sgd_kernel(const TableDesc* __restrict__ tabs, int tb,
                                                       PlanView pv, int n_idx, int j0, int sub, int nsub,
@@ -507,11 +665,11 @@ __global__ void __launch_bounds__(256) bwd_sgd_kernel(const TableDesc* __restric
     const int c = blockIdx.x * NG + group;
     if (c >= pv.n_chunks[t * nsub + sub]) return;
     const int64_t obase = (int64_t)t * n_idx + j0;
-    const uint32_t desc = pv.chunks[obase + c];
-    const int start = desc & 0xffff, len = (desc >> 16) & 0xff;
-    const bool first = (desc >> 30) & 1u, excl = (desc >> 31) & 1u;
-    const int32_t slot = pv.sorted_slots[obase + start];
-    const int32_t* pos = pv.sorted_pos + obase + start;
+    const int4 rec = pv.chunks[obase + c];
+    const int len = rec.z & 0xff;
+    const bool first = (rec.z >> 30) & 1, excl = rec.z < 0;
+    const int32_t slot = rec.x;
+    const int32_t* pos = pv.sorted_pos + (int64_t)t * n_idx + rec.y;
     const int32_t* bag = bag_ids ? bag_ids + (int64_t)t * ld_bag : nullptr;
     const float* g = d_out + (int64_t)t * ld_dout;
     const TableDesc& T = tabs[tb + t];
@@ -520,17 +678,7 @@ __global__ void __launch_bounds__(256) bwd_sgd_kernel(const TableDesc* __restric
     for (int cc = gl; cc < cpr; cc += G) {
         V acc;
         vzero(acc);
-        int i = 0;
-        for (; i + 4 <= len; i += 4) {
-            int p0 = pos[i], p1 = pos[i + 1], p2 = pos[i + 2], p3 = pos[i + 3];
-            if (bag) { p0 = bag[p0]; p1 = bag[p1]; p2 = bag[p2]; p3 = bag[p3]; }
-            V a0 = reinterpret_cast<const V*>(g + (int64_t)p0 * row_stride)[cc];
-            V a1 = reinterpret_cast<const V*>(g + (int64_t)p1 * row_stride)[cc];
-            V a2 = reinterpret_cast<const V*>(g + (int64_t)p2 * row_stride)[cc];
-            V a3 = reinterpret_cast<const V*>(g + (int64_t)p3 * row_stride)[cc];
-            acc = vadd(vadd(vadd(vadd(acc, a0), a1), a2), a3);
-        }
-        for (; i < len; ++i) {
+        for (int i = 0; i < len; ++i) {
             int p0 = pos[i];
             if (bag) p0 = bag[p0];
             acc = vadd(acc, reinterpret_cast<const V*>(g + (int64_t)p0 * row_stride)[cc]);
@@ -592,7 +740,7 @@ extern "C" int cdlrm_embed_fwd(cdlrm_ctx* c, int tb, int tc, const int64_t* ids,
     const int chunks = (n_idx + FWD_CHUNK - 1) / FWD_CHUNK;
     dim3 grid(chunks, tc);
     const int gw = pow2_ceil(c->ways) > 32 ? 32 : pow2_ceil(c->ways);
-#define LAUNCH_PROBE(GW) probe_kernel<GW><<<grid, 256, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_miss_cnt, chunks, c->ways)
+#define LAUNCH_PROBE(GW) LAUNCH(K_PROBE, s, probe_kernel<GW><<<grid, ProbeCfg<GW>::NT, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_miss_cnt, chunks, c->ways))
     switch (gw) {
         case 1: LAUNCH_PROBE(1); break;
         case 2: LAUNCH_PROBE(2); break;
@@ -614,21 +762,35 @@ extern "C" int cdlrm_embed_fwd(cdlrm_ctx* c, int tb, int tc, const int64_t* ids,
     if (vec == 2 && !al8) vec = 1;
     const int cpr = c->dim / vec;
     const int G = pow2_ceil(cpr) > 32 ? 32 : pow2_ceil(cpr);
-#define LAUNCH_GATHER(VEC, P1) gather_kernel<VEC, P1><<<grid, 256, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_miss_cnt, chunks, out, ld_out, n_miss, c->d_flags, c->dim, c->ways, c->aux, G)
-    if (p1) {
+#define LAUNCH_GATHER(VEC, P1) LAUNCH(K_GATHER, s, (gather_kernel<VEC, P1><<<grid, 256, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_miss_cnt, chunks, out, ld_out, n_miss, c->d_flags, c->dim, c->ways, c->aux, G)))
+#define LAUNCH_GROWS(GG, P1) LAUNCH(K_GATHER, s, (gather_rows_kernel<GG, P1><<<grid, 256, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_miss_cnt, chunks, out, ld_out, n_miss, c->d_flags, c->dim, c->ways, c->aux)))
+#define GROWS_SWITCH(P1)                                  \
+    switch (G) {                                          \
+        case 1: LAUNCH_GROWS(1, P1); break;               \
+        case 2: LAUNCH_GROWS(2, P1); break;               \
+        case 4: LAUNCH_GROWS(4, P1); break;               \
+        case 8: LAUNCH_GROWS(8, P1); break;               \
+        case 16: LAUNCH_GROWS(16, P1); break;             \
+        default: LAUNCH_GROWS(32, P1); break;             \
+    }
+    if (vec == 4 && cpr <= 32) {
+        if (p1) { GROWS_SWITCH(true) } else { GROWS_SWITCH(false) }
+    } else if (p1) {
         if (vec == 4) LAUNCH_GATHER(4, true); else if (vec == 2) LAUNCH_GATHER(2, true); else LAUNCH_GATHER(1, true);
     } else {
         if (vec == 4) LAUNCH_GATHER(4, false); else if (vec == 2) LAUNCH_GATHER(2, false); else LAUNCH_GATHER(1, false);
     }
+#undef GROWS_SWITCH
+#undef LAUNCH_GROWS
 #undef LAUNCH_GATHER
     CU_CHECK(cudaGetLastError());
     if (!p1) {
         if (n_bags > 0) {
             const int NG = 256 / G;
             dim3 pg((n_bags + NG - 1) / NG, tc);
-            if (vec == 4) pool_kernel<4><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G);
-            else if (vec == 2) pool_kernel<2><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G);
-            else pool_kernel<1><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G);
+            if (vec == 4) LAUNCH(K_POOL, s, pool_kernel<4><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G));
+            else if (vec == 2) LAUNCH(K_POOL, s, pool_kernel<2><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G));
+            else LAUNCH(K_POOL, s, pool_kernel<1><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G));
             CU_CHECK(cudaGetLastError());
         }
     }
@@ -640,7 +802,7 @@ extern "C" int64_t cdlrm_embed_bwd_plan_bytes(int tc, int32_t n_idx) {
     size_t a = (size_t)tc * (size_t)(n_idx > 0 ? n_idx : 1) * sizeof(int32_t);
     a = (a + 255) & ~(size_t)255;
     size_t nsub = (size_t)plan_nsub(n_idx > 0 ? n_idx : 1);
-    return (int64_t)(3 * a + (((size_t)tc * nsub * sizeof(int32_t)) + 255 & ~(size_t)255));
+    return (int64_t)(5 * a + ((((size_t)tc * nsub * sizeof(int32_t)) + 255) & ~(size_t)255));
 }
 
 extern "C" int cdlrm_embed_bwd_plan(cdlrm_ctx* c, int tb, int tc, const int32_t* slots, int64_t ld_slots,
@@ -666,7 +828,7 @@ extern "C" int cdlrm_embed_bwd_plan(cdlrm_ctx* c, int tb, int tc, const int32_t*
         const int n = n_idx - j0 < CDLRM_SORT_MAX ? n_idx - j0 : CDLRM_SORT_MAX;
         const int npad = (n + 7) & ~7;
         const int smem = npad * 12 + 8192 * 2 + 64 * 4;
-        bwd_plan_kernel<<<tc, PLAN_NT, smem, s>>>(c->d_tabs, tb, slots, ld_slots, n_idx, j0, n, sub, nsub, pv);
+        LAUNCH(K_BWD_PLAN, s, bwd_plan_kernel<<<tc, PLAN_NT, smem, s>>>(c->d_tabs, tb, slots, ld_slots, n_idx, j0, n, sub, nsub, pv));
     }
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
@@ -693,10 +855,24 @@ extern "C" int cdlrm_embed_bwd_sgd(cdlrm_ctx* c, int tb, int tc, const void* pla
     for (int sub = 0; sub < nsub; ++sub) {
         const int j0 = sub * CDLRM_SORT_MAX;
         const int n = n_idx - j0 < CDLRM_SORT_MAX ? n_idx - j0 : CDLRM_SORT_MAX;
-        dim3 grid((n + NG - 1) / NG, tc);
-        if (vec == 4) bwd_sgd_kernel<4><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G);
-        else if (vec == 2) bwd_sgd_kernel<2><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G);
-        else bwd_sgd_kernel<1><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G);
+        if (vec == 4 && cpr <= 32) {
+            dim3 grid((n + 255) / 256, tc);     // 8 warps x 32 chunk records per CTA
+#define LAUNCH_SGD(GG) LAUNCH(K_BWD_SGD, s, (bwd_sgd_rows_kernel<GG><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim)))
+            switch (G) {
+                case 1: LAUNCH_SGD(1); break;
+                case 2: LAUNCH_SGD(2); break;
+                case 4: LAUNCH_SGD(4); break;
+                case 8: LAUNCH_SGD(8); break;
+                case 16: LAUNCH_SGD(16); break;
+                default: LAUNCH_SGD(32); break;
+            }
+#undef LAUNCH_SGD
+        } else {
+            dim3 grid((n + NG - 1) / NG, tc);
+            if (vec == 4) LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<4><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
+            else if (vec == 2) LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<2><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
+            else LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<1><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
+        }
     }
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;

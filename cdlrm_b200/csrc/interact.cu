@@ -15,6 +15,9 @@
 // Backward: lanes are independent along dim (no reduction), so TPS = dim/VEC threads
 // own one sample with VEC = 2 to keep 2*F*VEC accumulators + operands in registers;
 // the dZ coefficients are loaded coalesced (one per lane) and broadcast by shuffle.
+#include <type_traits>
+#include <utility>
+
 #include "common.cuh"
 
 namespace {
@@ -34,19 +37,35 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
     return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
 }
 
+// compile-time loops: every index into the register arrays below must be a constant,
+// otherwise the arrays fall into local memory (that cost 12x in the first version)
+template <int... Is, class Fn>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, Fn&& f) {
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class Fn>
+__device__ __forceinline__ void static_for(Fn&& f) {
+    static_for_impl(std::make_integer_sequence<int, N>{}, static_cast<Fn&&>(f));
+}
+
+template <int OFF, int LPS>
+__device__ __forceinline__ void butterfly_level(float (&v)[LPS], int sub) {
+    if constexpr (OFF >= 1) {
+        const bool hi = (sub & OFF) != 0;
+        static_for<OFF>([&](auto Q) {
+            constexpr int q = decltype(Q)::value;
+            const float send = hi ? v[q] : v[q + OFF];
+            const float keep = hi ? v[q + OFF] : v[q];
+            v[q] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        });
+        butterfly_level<OFF / 2, LPS>(v, sub);
+    }
+}
+
+// after the call lane `sub` holds sum over the LPS lanes of v[sub]
 template <int LPS>
 __device__ __forceinline__ float butterfly(float (&v)[LPS], int sub) {
-    // after the loop lane `sub` holds sum over lanes of v[sub]
-#pragma unroll
-    for (int off = LPS / 2; off >= 1; off >>= 1) {
-        const bool hi = (sub & off) != 0;
-#pragma unroll
-        for (int q = 0; q < off; ++q) {
-            float send = hi ? v[q] : v[q + off];
-            float keep = hi ? v[q + off] : v[q];
-            v[q] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
+    butterfly_level<LPS / 2, LPS>(v, sub);
     return v[0];
 }
 
@@ -62,67 +81,81 @@ __global__ void __launch_bounds__(128) interact_fwd_kernel(FeatPtrs fp, int64_t 
     const int b = gwarp * SPW + lane / LPS;
     const bool live = b < B;
     float4 t[F];
-#pragma unroll
-    for (int i = 0; i < F; ++i)
+    static_for<F>([&](auto I) {
+        constexpr int i = decltype(I)::value;
         t[i] = live ? reinterpret_cast<const float4*>(fp.p[i] + (int64_t)b * row_stride)[sub]
                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    });
     float* orow = out + (int64_t)b * ld_out;
     if (live) {  // dense features pass through (model_no_ddp.py:293)
         orow[sub * 4 + 0] = t[0].x; orow[sub * 4 + 1] = t[0].y;
         orow[sub * 4 + 2] = t[0].z; orow[sub * 4 + 3] = t[0].w;
     }
     float v[LPS];
-    int p = 0;
-#pragma unroll
-    for (int i = ITSELF ? 0 : 1; i < F; ++i) {
-#pragma unroll
-        for (int j = 0; j < i + (ITSELF ? 1 : 0); ++j) {
+    static_for<F>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        constexpr int nj = ITSELF ? i + 1 : i;
+        constexpr int p0 = ITSELF ? i * (i + 1) / 2 : i * (i - 1) / 2;   // row-major triangle offset
+        static_for<nj>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            constexpr int p = p0 + j;
             v[p % LPS] = dot4(t[i], t[j]);
-            ++p;
-            if (p % LPS == 0 || p == NP) {
-                const int blk = (p - 1) / LPS;
-                const int cnt = p - blk * LPS;
-#pragma unroll
-                for (int q = 0; q < LPS; ++q)
-                    if (q >= cnt) v[q] = 0.f;
-                float r = butterfly<LPS>(v, sub);
+            if constexpr ((p + 1) % LPS == 0 || p + 1 == NP) {
+                constexpr int blk = p / LPS;
+                constexpr int cnt = p + 1 - blk * LPS;
+                static_for<LPS>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    if constexpr (q >= cnt) v[q] = 0.f;
+                });
+                const float r = butterfly<LPS>(v, sub);
                 if (live && sub < cnt) orow[DIM + blk * LPS + sub] = r;
             }
-        }
-    }
+        });
+    });
 }
 
 template <int F, int TPS, bool ITSELF>
 __global__ void __launch_bounds__(128) interact_bwd_kernel(FeatPtrs fp, int64_t row_stride, int B,
                                                            const float* __restrict__ d_out, int64_t ld_dout,
                                                            float* __restrict__ d_feat, int64_t ld_dfeat) {
-    // TPS threads per sample, each owning a float2 column slice: dim = 2*TPS.
+    // TPS threads per sample, each owning a float2 column slice: dim = 2*TPS.  The NP pair
+    // coefficients of a sample are staged once in shared memory (coalesced) and read back as
+    // broadcast float4 loads -- one LDS.128 per four pairs instead of one shuffle per pair.
     constexpr int DIM = TPS * 2;
-    constexpr int CB = TPS < 32 ? TPS : 32;      // lanes that share one sample inside a warp
+    constexpr int SPB = 128 / TPS;                  // samples per block
     constexpr int NP = Pairs<F, ITSELF>::N;
-    const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = gthread / TPS;
-    const int col = gthread % TPS;
-    const int lane = threadIdx.x & 31;
-    const int cl = lane % CB;
+    constexpr int NPP = (NP + 3) & ~3;
+    __shared__ __align__(16) float s_c[SPB][NPP];
+    const int ls = threadIdx.x / TPS;               // sample within the block
+    const int col = threadIdx.x % TPS;
+    const int b = blockIdx.x * SPB + ls;
     const bool live = b < B;
+    for (int e = threadIdx.x; e < SPB * NPP; e += 128) {
+        const int sm = e / NPP, p = e - sm * NPP;
+        const int bb = blockIdx.x * SPB + sm;
+        s_c[sm][p] = (bb < B && p < NP) ? d_out[(int64_t)bb * ld_dout + DIM + p] : 0.f;
+    }
     float2 t[F], g[F];
-#pragma unroll
-    for (int i = 0; i < F; ++i) {
+    static_for<F>([&](auto I) {
+        constexpr int i = decltype(I)::value;
         t[i] = live ? reinterpret_cast<const float2*>(fp.p[i] + (int64_t)b * row_stride)[col] : make_float2(0.f, 0.f);
         g[i] = make_float2(0.f, 0.f);
-    }
+    });
     const float* drow = d_out + (int64_t)b * ld_dout;
-    if (live) g[0] = make_float2(drow[col * 2], drow[col * 2 + 1]);  // d/dx of the pass-through (rows of d_out may be odd-sized)
-    float cv = 0.f;
-    int p = 0;
-#pragma unroll
-    for (int i = ITSELF ? 0 : 1; i < F; ++i) {
-#pragma unroll
-        for (int j = 0; j < i + (ITSELF ? 1 : 0); ++j) {
-            if (p % CB == 0) cv = (live && p + cl < NP) ? drow[DIM + p + cl] : 0.f;
-            const float c = __shfl_sync(0xffffffffu, cv, p % CB, CB);
-            if (i == j) {  // d(T_i.T_i) = 2 T_i
+    if (live) g[0] = make_float2(drow[col * 2], drow[col * 2 + 1]);  // d/dx of the pass-through (rows may be odd-sized)
+    __syncthreads();
+    const float4* c4p = reinterpret_cast<const float4*>(&s_c[ls][0]);
+    float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
+    static_for<F>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        constexpr int nj = ITSELF ? i + 1 : i;
+        constexpr int p0 = ITSELF ? i * (i + 1) / 2 : i * (i - 1) / 2;
+        static_for<nj>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            constexpr int p = p0 + j;
+            if constexpr (p % 4 == 0) cq = c4p[p / 4];
+            const float c = (p % 4 == 0) ? cq.x : (p % 4 == 1) ? cq.y : (p % 4 == 2) ? cq.z : cq.w;
+            if constexpr (i == j) {  // d(T_i.T_i) = 2 T_i
                 g[i].x = fmaf(2.f * c, t[i].x, g[i].x);
                 g[i].y = fmaf(2.f * c, t[i].y, g[i].y);
             } else {
@@ -131,13 +164,13 @@ __global__ void __launch_bounds__(128) interact_bwd_kernel(FeatPtrs fp, int64_t 
                 g[j].x = fmaf(c, t[i].x, g[j].x);
                 g[j].y = fmaf(c, t[i].y, g[j].y);
             }
-            ++p;
-        }
-    }
+        });
+    });
     if (live) {
-#pragma unroll
-        for (int i = 0; i < F; ++i)
+        static_for<F>([&](auto I) {
+            constexpr int i = decltype(I)::value;
             reinterpret_cast<float2*>(d_feat + (int64_t)i * ld_dfeat + (int64_t)b * DIM)[col] = g[i];
+        });
     }
 }
 
@@ -191,7 +224,7 @@ void launch_fwd(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_ou
     constexpr int SPW = 32 / LPS;
     const int warps = (B + SPW - 1) / SPW;
     const int blocks = (warps + 3) / 4;
-    interact_fwd_kernel<F, LPS, ITSELF><<<blocks, 128, 0, s>>>(fp, rs, B, out, ld_out);
+    LAUNCH(K_INT_FWD, s, (interact_fwd_kernel<F, LPS, ITSELF><<<blocks, 128, 0, s>>>(fp, rs, B, out, ld_out)));
 }
 
 template <int F, int TPS, bool ITSELF>
@@ -199,7 +232,7 @@ void launch_bwd(const FeatPtrs& fp, int64_t rs, int B, const float* d_out, int64
                 int64_t ld_dfeat, cudaStream_t s) {
     const int64_t threads = (int64_t)B * TPS;
     const int blocks = (int)((threads + 127) / 128);
-    interact_bwd_kernel<F, TPS, ITSELF><<<blocks, 128, 0, s>>>(fp, rs, B, d_out, ld_dout, d_feat, ld_dfeat);
+    LAUNCH(K_INT_BWD, s, (interact_bwd_kernel<F, TPS, ITSELF><<<blocks, 128, 0, s>>>(fp, rs, B, d_out, ld_dout, d_feat, ld_dfeat)));
 }
 
 bool aligned_for(const FeatPtrs& fp, int n, int64_t rs, int bytes) {
@@ -239,7 +272,7 @@ extern "C" int cdlrm_interact_fwd(int device, const float* const* h_feat, int n_
     bool done = false;
     FWD_CASE(27, 128) FWD_CASE(27, 64) FWD_CASE(27, 32) FWD_CASE(27, 16)
     FWD_CASE(9, 128) FWD_CASE(9, 64) FWD_CASE(9, 32) FWD_CASE(9, 16)
-    if (!done) interact_fwd_generic<<<batch, 128, 0, s>>>(fp, n_feat, rs, batch, dim, itself, out, ld_out);
+    if (!done) LAUNCH(K_INT_FWD, s, interact_fwd_generic<<<batch, 128, 0, s>>>(fp, n_feat, rs, batch, dim, itself, out, ld_out));
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
 }
@@ -264,7 +297,7 @@ extern "C" int cdlrm_interact_bwd(int device, const float* const* h_feat, int n_
     BWD_CASE(27, 128) BWD_CASE(27, 64) BWD_CASE(27, 32) BWD_CASE(27, 16)
     BWD_CASE(9, 128) BWD_CASE(9, 64) BWD_CASE(9, 32) BWD_CASE(9, 16)
     if (!done)
-        interact_bwd_generic<<<batch, 128, 0, s>>>(fp, n_feat, rs, batch, dim, itself, d_out, ld_dout, d_feat, ld_dfeat);
+        LAUNCH(K_INT_BWD, s, interact_bwd_generic<<<batch, 128, 0, s>>>(fp, n_feat, rs, batch, dim, itself, d_out, ld_dout, d_feat, ld_dfeat));
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
 }

@@ -132,6 +132,11 @@ inline int vec_for(int dim, const void* a, const void* b) {
     return 1;
 }
 
+constexpr int mode_kid(int mode) {
+    return mode == 0 ? K_MOVE_EVICT : mode == 1 ? K_MOVE_GATHER : mode == 2 ? K_MOVE_FILL
+         : mode == 3 ? K_AGG_PACK : mode == 4 ? K_AGG_UNPACK : K_MOVE_SCATTER;
+}
+
 template <int MODE>
 int launch_rows(cdlrm_ctx* c, int k, const int64_t* ids, const int32_t* slots, const uint8_t* primary, int64_t n,
                 float* rows, const int64_t* src_index, int write_master, int average, float divisor,
@@ -144,9 +149,9 @@ int launch_rows(cdlrm_ctx* c, int k, const int64_t* ids, const int32_t* slots, c
     const int NG = 256 / G;
     int64_t blocks = (n + NG * 4 - 1) / (NG * 4);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    if (vec == 4) rows_kernel<4, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G);
-    else if (vec == 2) rows_kernel<2, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G);
-    else rows_kernel<1, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G);
+    if (vec == 4) LAUNCH(mode_kid(MODE), s, (rows_kernel<4, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G)));
+    else if (vec == 2) LAUNCH(mode_kid(MODE), s, (rows_kernel<2, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G)));
+    else LAUNCH(mode_kid(MODE), s, (rows_kernel<1, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G)));
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
 }
@@ -230,7 +235,7 @@ extern "C" int cdlrm_agg_mark(cdlrm_ctx* c, const int32_t* idxs, int64_t ld, int
         ARG_CHECK(c->tabs[k].dirty);
         int64_t blocks = (n + 255) / 256;
         if (blocks > 1184) blocks = 1184;
-        mark_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(c->tabs[k], idxs + k * ld, n);
+        LAUNCH(K_AGG_MARK, (cudaStream_t)stream, mark_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(c->tabs[k], idxs + k * ld, n));
     }
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
@@ -252,7 +257,7 @@ extern "C" int cdlrm_agg_or_bitmaps(cdlrm_ctx* c, const uint32_t* gathered, int 
         return CDLRM_ERR_STATE;
     }
     CU_CHECK(cudaSetDevice(c->device));
-    or_bitmaps_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(c->tabs[0].dirty, gathered, world, words_total);
+    LAUNCH(K_AGG_OR, (cudaStream_t)stream, or_bitmaps_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(c->tabs[0].dirty, gathered, world, words_total));
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
 }
@@ -281,9 +286,9 @@ extern "C" int cdlrm_agg_collect(cdlrm_ctx* c, int32_t* slot_list, int64_t* d_co
         const TableDesc& t = c->tabs[k];
         const int64_t nwords = (t.cache_rows + 31) / 32;
         const int nblk = (int)((nwords + TILE - 1) / TILE);
-        bitmap_count_kernel<<<nblk, 256, 0, s>>>(t.dirty, nwords, bs);
-        scan_tiles_kernel<<<1, 1024, 0, s>>>(bs, nblk, reinterpret_cast<unsigned long long*>(d_counts + k));
-        bitmap_emit_kernel<int32_t, false><<<nblk, 256, 0, s>>>(t.dirty, nwords, bs, slot_list + cap_off);
+        LAUNCH(K_AGG_COLLECT, s, bitmap_count_kernel<<<nblk, 256, 0, s>>>(t.dirty, nwords, bs));
+        LAUNCH(K_AGG_COLLECT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(bs, nblk, reinterpret_cast<unsigned long long*>(d_counts + k)));
+        LAUNCH(K_AGG_COLLECT, s, (bitmap_emit_kernel<int32_t, false><<<nblk, 256, 0, s>>>(t.dirty, nwords, bs, slot_list + cap_off)));
         cap_off += t.cache_rows;
     }
     CU_CHECK(cudaGetLastError());

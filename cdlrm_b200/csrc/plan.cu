@@ -408,24 +408,24 @@ static int plan_impl(cdlrm_ctx* c, const int64_t* win_ids, int64_t ld, int64_t n
             ubound = h_uniq_len[k];
             if (ubound)
                 CU_CHECK(cudaMemcpyAsync(p.uniq, win_ids + k * ld, sizeof(int64_t) * ubound, cudaMemcpyDeviceToDevice, s));
-            set_u64_kernel<<<1, 1, 0, s>>>(ck + CNT_U, (unsigned long long)ubound);
+            LAUNCH(K_MISC, s, set_u64_kernel<<<1, 1, 0, s>>>(ck + CNT_U, (unsigned long long)ubound));
         } else {
             ubound = p.umax < n ? p.umax : n;
             if (n > 0) {
                 const int64_t nwords = (t.n_rows + 31) / 32;
                 int g1 = (int)((n + 1023) / 1024 < 148 * 16 ? (n + 1023) / 1024 : 148 * 16);
-                bitmap_set_kernel<<<g1 > 0 ? g1 : 1, 256, 0, s>>>(win_ids + k * ld, n, p.bitmap, t.n_rows, c->d_flags);
+                LAUNCH(K_PLAN_BITMAP_SET, s, bitmap_set_kernel<<<g1 > 0 ? g1 : 1, 256, 0, s>>>(win_ids + k * ld, n, p.bitmap, t.n_rows, c->d_flags));
                 const int nblk = (int)((nwords + TILE - 1) / TILE);
-                bitmap_count_kernel<<<nblk, 256, 0, s>>>(p.bitmap, nwords, c->p_blocksum);
-                scan_tiles_kernel<<<1, 1024, 0, s>>>(c->p_blocksum, nblk, ck + CNT_U);
-                bitmap_emit_kernel<int64_t, true><<<nblk, 256, 0, s>>>(p.bitmap, nwords, c->p_blocksum, p.uniq);
+                LAUNCH(K_PLAN_COMPACT, s, bitmap_count_kernel<<<nblk, 256, 0, s>>>(p.bitmap, nwords, c->p_blocksum));
+                LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(c->p_blocksum, nblk, ck + CNT_U));
+                LAUNCH(K_PLAN_COMPACT, s, (bitmap_emit_kernel<int64_t, true><<<nblk, 256, 0, s>>>(p.bitmap, nwords, c->p_blocksum, p.uniq)));
             }
         }
         if (unique_only) continue;
         CU_CHECK(cudaMemsetAsync(pins[k], 0, sizeof(unsigned long long) * t.num_sets, s));
         if (ubound > 0) {
             const int g5 = (int)((ubound + 255) / 256);
-#define LAUNCH_PP(GW) plan_probe_kernel<GW><<<g5, 256, 0, s>>>(p.uniq, ck + CNT_U, t.plan_tags, t.num_sets, c->ways, pins[k], c->p_state, ck + CNT_HIT)
+#define LAUNCH_PP(GW) LAUNCH(K_PLAN_PROBE, s, plan_probe_kernel<GW><<<g5, 256, 0, s>>>(p.uniq, ck + CNT_U, t.plan_tags, t.num_sets, c->ways, pins[k], c->p_state, ck + CNT_HIT))
             switch (gw) {
                 case 1: LAUNCH_PP(1); break;
                 case 2: LAUNCH_PP(2); break;
@@ -436,9 +436,9 @@ static int plan_impl(cdlrm_ctx* c, const int64_t* win_ids, int64_t ld, int64_t n
             }
 #undef LAUNCH_PP
             const int nblk = (int)((ubound + TILE - 1) / TILE);
-            surv_kernel<false><<<nblk, 256, 0, s>>>(p.uniq, ck + CNT_U, c->p_state, pins[k], t.num_sets, full, c->p_blocksum, p.surv, ck + CNT_DROP);
-            scan_tiles_kernel<<<1, 1024, 0, s>>>(c->p_blocksum, nblk, ck + CNT_ROWS);
-            surv_kernel<true><<<nblk, 256, 0, s>>>(p.uniq, ck + CNT_U, c->p_state, pins[k], t.num_sets, full, c->p_blocksum, p.surv, ck + CNT_DROP);
+            LAUNCH(K_PLAN_SURV, s, surv_kernel<false><<<nblk, 256, 0, s>>>(p.uniq, ck + CNT_U, c->p_state, pins[k], t.num_sets, full, c->p_blocksum, p.surv, ck + CNT_DROP));
+            LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(c->p_blocksum, nblk, ck + CNT_ROWS));
+            LAUNCH(K_PLAN_SURV, s, surv_kernel<true><<<nblk, 256, 0, s>>>(p.uniq, ck + CNT_U, c->p_state, pins[k], t.num_sets, full, c->p_blocksum, p.surv, ck + CNT_DROP));
         }
         CU_CHECK(cudaGetLastError());
     }
@@ -476,7 +476,7 @@ extern "C" int cdlrm_plan_phase_b(cdlrm_ctx* c, const float* q, const int64_t* h
             const int NG = 256 / gw;
             const int g1 = (int)((R + NG - 1) / NG);
             const float* qk = q + off * c->ways;
-#define LAUNCH_SEL(GW) select_kernel<GW><<<g1, 256, 0, s>>>(p.uniq, p.surv, R, qk, pins[k], t.plan_tags, t.num_sets, c->ways, full, c->p_slot, c->p_old, c->p_claim)
+#define LAUNCH_SEL(GW) LAUNCH(K_PLAN_SELECT, s, select_kernel<GW><<<g1, 256, 0, s>>>(p.uniq, p.surv, R, qk, pins[k], t.plan_tags, t.num_sets, c->ways, full, c->p_slot, c->p_old, c->p_claim))
             switch (gw) {
                 case 1: LAUNCH_SEL(1); break;
                 case 2: LAUNCH_SEL(2); break;
@@ -487,10 +487,10 @@ extern "C" int cdlrm_plan_phase_b(cdlrm_ctx* c, const float* q, const int64_t* h
             }
 #undef LAUNCH_SEL
             const int nblk = (int)((R + TILE - 1) / TILE);
-            lists_kernel<false><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, bsE, bsF, t.plan_tags, t.num_sets, c->ways, nullptr, nullptr, nullptr, nullptr, nullptr);
-            scan_tiles_kernel<<<1, 1024, 0, s>>>(bsE, nblk, ck + CNT_E);
-            scan_tiles_kernel<<<1, 1024, 0, s>>>(bsF, nblk, ck + CNT_F);
-            lists_kernel<true><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, bsE, bsF, t.plan_tags, t.num_sets, c->ways, evict_ids + off, evict_slots + off, evict_primary + off, fill_ids + off, fill_slots + off);
+            LAUNCH(K_PLAN_LISTS, s, lists_kernel<false><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, bsE, bsF, t.plan_tags, t.num_sets, c->ways, nullptr, nullptr, nullptr, nullptr, nullptr));
+            LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(bsE, nblk, ck + CNT_E));
+            LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(bsF, nblk, ck + CNT_F));
+            LAUNCH(K_PLAN_LISTS, s, lists_kernel<true><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, bsE, bsF, t.plan_tags, t.num_sets, c->ways, evict_ids + off, evict_slots + off, evict_primary + off, fill_ids + off, fill_slots + off));
             CU_CHECK(cudaGetLastError());
         }
         off += R;

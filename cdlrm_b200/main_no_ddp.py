@@ -317,7 +317,7 @@ class Trainer:
         background; windows must be submitted in training order."""
         import threading
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.dev))
+        ev.record(torch.cuda.current_stream(self.dev))   # ids produced on the current stream are ready
         prev = self._plan_thread
 
         def work():
@@ -345,6 +345,7 @@ class Trainer:
             self.steps_since_agg = 0
         self.planner.install(rec, write_master=(self.rank == 0),
                              average_on_writeback=self.args.average_on_writeback)
+        self._installed = rec            # keep the lists alive until the next boundary
         if self.world > 1:
             # rank 0's write-back must be visible to every rank's next master reads
             torch.cuda.current_stream(self.dev).synchronize()
@@ -353,7 +354,7 @@ class Trainer:
         return rec
 
     # -- one training step -------------------------------------------------------------------
-    def step(self, X, lS_o, lS_i, T):
+    def _step_eager(self, X, lS_o, lS_i, T):
         lookups, _idxs = self.cache_group(lS_o, lS_i, self.emb_tables, self.dev.index)
         Z = self.dlrm(X, lookups)
         E = loss_fn_wrap(Z, T, self.loss_fn, self.args, self.loss_ws)
@@ -363,8 +364,35 @@ class Trainer:
         self.optimizer_embeds.step()          # applies the fused sparse update (pre-step hook)
         wait_wrap(reqs)
         self.optimizer_mlps.step()
-        self.steps_since_agg += 1
         return E, Z
+
+    def capture_graph(self, X, lS_o, lS_i, T):
+        """Capture one whole training step (forward, backward, both optimizers, the MLP-grad
+        all-reduce) into a CUDA graph.  The captured step is NOT executed by the capture; the
+        caller replays it through ``step``.  Call while no window plan is running."""
+        dev = self.dev
+        self._g_in = (torch.empty_like(X, device=dev), torch.empty(tuple(lS_i.shape), dtype=torch.int64, device=dev),
+                      torch.empty_like(T, device=dev))
+        self._g_lso = lS_o
+        self.cache_group._ensure_ctx(self.emb_tables)
+        check(lib.cdlrm_ctx_reserve(self.cache_group._ctx, int(lS_i.shape[1])))
+        torch.cuda.synchronize(dev)
+        self._graph = torch.cuda.CUDAGraph()
+        n0 = lib.cdlrm_prof_launches(0)
+        with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
+            self._g_out = self._step_eager(self._g_in[0], lS_o, self._g_in[1], self._g_in[2])
+        self.graph_launches = int(lib.cdlrm_prof_launches(0) - n0)   # library kernels per replay
+        return self._graph
+
+    def step(self, X, lS_o, lS_i, T):
+        self.steps_since_agg += 1
+        if getattr(self, "_graph", None) is not None and tuple(lS_i.shape) == tuple(self._g_in[1].shape):
+            self._g_in[0].copy_(X, non_blocking=True)
+            self._g_in[1].copy_(lS_i, non_blocking=True)
+            self._g_in[2].copy_(T, non_blocking=True)
+            self._graph.replay()
+            return self._g_out
+        return self._step_eager(X, lS_o, lS_i, T)
 
     def maybe_aggregate(self, j):
         if self.world > 1 and j > 0 and j % self.args.table_agg_freq == 0:     # :418-420

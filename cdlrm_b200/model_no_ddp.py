@@ -53,6 +53,7 @@ class Embedding_Table_Group(nn.Module):
                 raise NotImplementedError("QR / mixed-dimension embeddings are outside the cache hot path")
             self.qr_flag = qr_flag
             self.md_flag = md_flag
+            self._mapped_file = isinstance(init, str) and init.startswith("shm:")
             self.emb_l = self.create_emb(m_spa, np.asarray(ln_emb), init)
 
     def create_emb(self, m, ln, init="reference"):
@@ -62,7 +63,25 @@ class Embedding_Table_Group(nn.Module):
             if init == "reference":
                 W = np.random.uniform(low=-np.sqrt(1 / n), high=np.sqrt(1 / n), size=(n, m)).astype(np.float32)
                 wt = torch.from_numpy(W)
-            else:  # "fast": same distribution, chunked float32 generation for 40M-row tables
+            elif init == "device" or (isinstance(init, str) and init.startswith("shm:")):
+                # same distribution, generated on the GPU and copied into page-locked host
+                # memory (or into a /dev/shm file shared by all ranks: "shm:<prefix>")
+                bound = float(np.sqrt(1 / n))
+                if init == "device":
+                    wt = torch.empty(n, m, dtype=torch.float32, pin_memory=True)
+                    fill = True
+                else:
+                    prefix, role = init[4:].rsplit(":", 1)          # role: "create" | "attach"
+                    wt = torch.from_file(f"{prefix}_{i}.bin", shared=True, size=n * m,
+                                         dtype=torch.float32).view(n, m)
+                    fill = role == "create"
+                if fill:
+                    g = torch.Generator(device="cuda").manual_seed(1000 + i)
+                    step = 1 << 22
+                    for lo in range(0, n, step):
+                        hi = min(n, lo + step)
+                        wt[lo:hi].copy_(torch.empty(hi - lo, m, device="cuda").uniform_(-bound, bound, generator=g))
+            else:  # "fast": same distribution, chunked float32 generation on the host
                 wt = torch.empty(n, m, dtype=torch.float32)
                 bound = float(np.sqrt(1 / n))
                 g = torch.Generator().manual_seed(1000 + i)
@@ -93,7 +112,7 @@ class Embedding_Table_Group(nn.Module):
             if w.is_cuda:                       # master kept in HBM (optional mode)
                 ptrs.append(w.data_ptr())
                 continue
-            if not w.is_pinned() and not w.is_shared():
+            if not w.is_pinned() and not w.is_shared() and not getattr(self, "_mapped_file", False):
                 # ordinary heap memory shares pages with its neighbours; registering it would
                 # leave those neighbours "partially pinned" and break their later copies.
                 # Re-home the table in page-locked memory of its own (one copy, at bind time).
@@ -148,6 +167,9 @@ class _LookupFn(torch.autograd.Function):
         ctx.slots = slots
         ctx.bag_ids = bag_ids
         ctx.n_idx = n_idx
+        # the backward's de-duplication plan only needs the slots: build it now on a side
+        # stream so that it overlaps the MLP forward instead of sitting on the critical path
+        ctx.plan = group._early_plan(tb, slots, n_idx) if group.early_plan else None
         ctx.mark_non_differentiable(slots)
         return (slots,) + tuple(out.unbind(0))
 
@@ -172,7 +194,7 @@ class _LookupFn(torch.autograd.Function):
             zero = torch.zeros_like(g0)
             keep = torch.stack([g if g is not None else zero for g in grads]).contiguous()
             base, rs, ld = keep, d, keep.stride(0)
-        group._queue_update(ctx.tb, ctx.slots, ctx.bag_ids, ctx.n_idx, base, ld, rs, keep)
+        group._queue_update(ctx.tb, ctx.slots, ctx.bag_ids, ctx.n_idx, base, ld, rs, keep, ctx.plan)
         return (None,) * 7
 
 
@@ -200,6 +222,8 @@ class Embedding_Table_Cache_Group(nn.Module):
         self.record_victims = False        # True: fill victim_cache_entries (costs a device sync)
         self.assume_one_id_per_bag = None  # None: check lS_o on the host when it is a CPU tensor
         self.fused_lr = None               # set to apply the SGD update inside backward
+        self.early_plan = True             # build the backward plan during forward, on a side stream
+        self._plan_stream = None
         self.last_n_miss = None
         self._ctx = None
         self._bound_key = None
@@ -391,8 +415,29 @@ class Embedding_Table_Cache_Group(nn.Module):
         return f.value
 
     # -- backward + SGD (main_no_ddp.py:376,409,413) ----------------------------------------------
-    def _queue_update(self, tb, slots, bag_ids, n_idx, dbase, ld, rs, keep):
-        item = (tb, slots, bag_ids, n_idx, dbase, ld, rs, keep)
+    def _early_plan(self, tb, slots, n_idx):
+        if n_idx == 0:
+            return None
+        dev = self.device
+        if self._plan_stream is None:
+            self._plan_stream = torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        ps = self._plan_stream
+        T = slots.shape[0]
+        nbytes = lib.cdlrm_embed_bwd_plan_bytes(T, n_idx)
+        ps.wait_stream(cur)
+        with torch.cuda.stream(ps):
+            buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            base = (buf.data_ptr() + 255) // 256 * 256
+            check(lib.cdlrm_embed_bwd_plan(self._ctx, tb, T, _vp(slots.data_ptr()), slots.stride(0), n_idx,
+                                           _vp(base), _vp(ps.cuda_stream)))
+            done = torch.cuda.Event()
+            done.record(ps)
+        slots.record_stream(ps)
+        return (buf, base, done)
+
+    def _queue_update(self, tb, slots, bag_ids, n_idx, dbase, ld, rs, keep, plan=None):
+        item = (tb, slots, bag_ids, n_idx, dbase, ld, rs, keep, plan)
         if self.fused_lr is not None:
             self._apply_update(item, float(self.fused_lr))
         else:
@@ -400,18 +445,25 @@ class Embedding_Table_Cache_Group(nn.Module):
             _GROUPS.add(self)
 
     def _apply_update(self, item, lr):
-        tb, slots, bag_ids, n_idx, dbase, ld, rs, _keep = item
+        tb, slots, bag_ids, n_idx, dbase, ld, rs, _keep, plan = item
         if n_idx == 0:
             return
         dev = self.device
         T = slots.shape[0]
-        nbytes = lib.cdlrm_embed_bwd_plan_bytes(T, n_idx)
-        if self._plan_buf is None or self._plan_buf.numel() < nbytes:
-            self._plan_buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        s = _stream_ptr(dev)
-        check(lib.cdlrm_embed_bwd_plan(self._ctx, tb, T, _vp(slots.data_ptr()), slots.stride(0), n_idx,
-                                       _vp(self._plan_buf.data_ptr()), s))
-        check(lib.cdlrm_embed_bwd_sgd(self._ctx, tb, T, _vp(self._plan_buf.data_ptr()), n_idx,
+        cur = torch.cuda.current_stream(dev)
+        s = _vp(cur.cuda_stream)
+        if plan is not None:
+            buf, base, done = plan
+            cur.wait_event(done)
+            buf.record_stream(cur)
+        else:
+            nbytes = lib.cdlrm_embed_bwd_plan_bytes(T, n_idx)
+            if self._plan_buf is None or self._plan_buf.numel() < nbytes + 256:
+                self._plan_buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            base = (self._plan_buf.data_ptr() + 255) // 256 * 256
+            check(lib.cdlrm_embed_bwd_plan(self._ctx, tb, T, _vp(slots.data_ptr()), slots.stride(0), n_idx,
+                                           _vp(base), s))
+        check(lib.cdlrm_embed_bwd_sgd(self._ctx, tb, T, _vp(base), n_idx,
                                       _vp(bag_ids.data_ptr()) if bag_ids is not None else None,
                                       bag_ids.stride(0) if bag_ids is not None else 0,
                                       _vp(dbase.data_ptr()), ld, rs, lr, s))

@@ -205,6 +205,15 @@ int cdlrm_agg_unpack(cdlrm_ctx* ctx, const int32_t* slot_list, const int64_t* h_
 int cdlrm_host_register(int device, void* h_ptr, int64_t bytes, void** dev_ptr);
 int cdlrm_host_unregister(void* h_ptr);
 
+/* ---- measurement: every kernel launch of the library is counted; with profiling enabled
+ *      each launch is additionally bracketed by CUDA events on its own stream ------------- */
+int cdlrm_prof_enable(int on);
+int64_t cdlrm_prof_launches(int reset);          /* launches since the last reset */
+int cdlrm_prof_num_kernels(void);
+const char* cdlrm_prof_kernel_name(int id);
+/* synchronises the device; h_ms[id] = summed duration, h_calls[id] = launches; clears */
+int cdlrm_prof_report(double* h_ms, int64_t* h_calls, int n);
+
 /* ---- victim-way RNG (host): the torch CPU mt19937 stream consumed by
  *      torch.distributions.Categorical(...).sample(), main_no_ddp.py:183-185 -------
  * out[i] = float32(-log1p(-u_i)), u_i = (r64 & (2^53-1)) * 2^-53,

@@ -389,3 +389,39 @@ def install_window(cache: OracleCache, master, window_ids, gen: TorchCpuGenerato
     ev, plans = cache_embeddings(rows, uniq, maps, cache, gen.exponential_f32)
     eviction_writeback(master, ev, average_on_writeback)
     return ev, plans, uniq
+
+
+# --------------------------------------------------------------------------
+# vectorised variants used ONLY by the timed cpu_baseline / --impl reference legs of
+# bench.py (same results as the functions above; tests/test_oracle_golden.py checks that)
+# --------------------------------------------------------------------------
+
+
+def backward_sgd_table_fast(w, slots, dV, lr):
+    """P=1 sparse SGD: duplicates merged with a stable sort + segmented sum, then one
+    update per distinct slot (what torch's coalesce + add does)."""
+    s = slots.astype(np.int64)
+    order = np.argsort(s, kind="stable")
+    ss = s[order]
+    starts = np.flatnonzero(np.r_[True, ss[1:] != ss[:-1]])
+    sums = np.add.reduceat(dV[order], starts, axis=0)
+    w[ss[starts]] += (-np.float32(lr)) * sums
+
+
+def interact_fwd_fast(x, ly, itself=False):
+    """float32 batched sgemm like torch.bmm (model_no_ddp.py:276-293)."""
+    B, d = x.shape
+    T = np.concatenate([x] + list(ly), axis=1).reshape(B, -1, d)
+    Z = np.matmul(T, T.transpose(0, 2, 1))
+    li, lj = tril_pairs(T.shape[1], itself)
+    return np.concatenate([x, Z[:, li, lj]], axis=1), T
+
+
+def interact_bwd_fast(T, dR, itself=False):
+    B, nf, d = T.shape
+    li, lj = tril_pairs(nf, itself)
+    dZ = np.zeros((B, nf, nf), dtype=np.float32)
+    dZ[:, li, lj] = dR[:, d:]
+    dT = np.matmul(dZ + dZ.transpose(0, 2, 1), T)
+    dT[:, 0, :] += dR[:, :d]
+    return dT

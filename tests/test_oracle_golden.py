@@ -73,3 +73,33 @@ def test_aggregate_matches_reference(op):
     for r in range(2):
         for k in range(3):
             np.testing.assert_allclose(weights[r][k], g[f"{op}_r{r}_after_{k}"], rtol=1e-6, atol=1e-7)
+
+
+def test_fast_variants_equal_reference_variants():
+    """The vectorised functions timed by bench.py's cpu_baseline give the same results."""
+    rng = np.random.default_rng(2)
+    w1 = rng.standard_normal((300, 8)).astype(np.float32)
+    w2 = w1.copy()
+    slots = rng.integers(0, 300, size=256).astype(np.int32)
+    dV = rng.standard_normal((256, 8)).astype(np.float32)
+    O.backward_sgd_table(w1, slots, np.arange(256), dV, 0.3)
+    O.backward_sgd_table_fast(w2, slots, dV, 0.3)
+    np.testing.assert_allclose(w1, w2, rtol=1e-5, atol=1e-6)
+    x = rng.standard_normal((7, 16)).astype(np.float32)
+    ly = [rng.standard_normal((7, 16)).astype(np.float32) for _ in range(5)]
+    R1 = O.interact_fwd(x, ly)
+    R2, T = O.interact_fwd_fast(x, ly)
+    np.testing.assert_allclose(R1, R2, rtol=1e-5, atol=1e-5)
+    dR = rng.standard_normal(R1.shape).astype(np.float32)
+    dx, dly = O.interact_bwd(x, ly, dR)
+    dT = O.interact_bwd_fast(T, dR)
+    np.testing.assert_allclose(dT[:, 0], dx, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dT[:, 1:].transpose(1, 0, 2), np.stack(dly), rtol=1e-5, atol=1e-5)
+    cache = O.OracleCache(8, [1000, 40], 64, 32, 4)
+    master = [rng.standard_normal((n, 8)).astype(np.float32) for n in (1000, 40)]
+    ids = np.stack([rng.integers(0, n, size=32) for n in (1000, 40)])
+    O.install_window(cache, master, ids, O.TorchCpuGenerator(1))
+    for k in range(2):
+        a, sa, ma = O.forward_table(cache, k, np.arange(32), ids[k], master[k])
+        b, sb, mb = O.forward_table_fast(cache, k, ids[k], master[k])
+        assert np.array_equal(sa, sb) and ma == mb and np.array_equal(a, b)

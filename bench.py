@@ -419,12 +419,15 @@ def gpu_run(a, wl, ln_emb):
     if rank == 0:
         NK = lib.cdlrm_prof_num_kernels()
         lib.cdlrm_prof_enable(1)
-        nprof = 20
-        for _ in range(nprof):
+        nprof = 0
+        graph, tr._graph = getattr(tr, "_graph", None), None     # eager launches so that events can bracket them
+        for _ in range(20):
             if j % L == 0:
                 break
             one_step(j)
             j += 1
+            nprof += 1
+        tr._graph = graph
         msv = (ctypes.c_double * NK)()
         calls = (ctypes.c_int64 * NK)()
         _lib.check(lib.cdlrm_prof_report(msv, calls, NK))
@@ -433,10 +436,15 @@ def gpu_run(a, wl, ln_emb):
         w, b = divmod(j - 1, L)
         lo = b * lb
         ids = window(w)[0][:, lo:lo + lb]
-        uniq_slots = 0
+        n_single = rows_multi = slots_multi = chunks_multi = 0
         with torch.no_grad():
             _, sl = tr.cache_group(lS_o, ids, master, dev.index)
-            uniq_slots = sum(int(torch.unique(s).numel()) for s in sl)
+            for s_ in sl:
+                _, cnt = torch.unique(s_, return_counts=True)
+                n_single += int((cnt == 1).sum())
+                rows_multi += int(cnt[cnt > 1].sum())
+                slots_multi += int((cnt > 1).sum())
+                chunks_multi += int(((cnt[cnt > 1] + 7) // 8).sum())
         n = T * lb
         nfe = T + 1
         npair = nfe * (nfe - 1) // 2
@@ -444,7 +452,8 @@ def gpu_run(a, wl, ln_emb):
             "probe": n * (8 + 8 * wl["ways"] + 4),
             "gather": n * (4 + 4 * d + 4 * d) + n_miss * (8 + 4 * d),
             "bwd_plan": n * (4 + 12),
-            "bwd_sgd": n * (12 + 4 * d) + uniq_slots * 8 * d,
+            "bwd_sgd": n_single * (16 + 4 * d + 8 * d),
+            "bwd_sgd_multi": chunks_multi * 16 + rows_multi * (4 + 4 * d) + slots_multi * 8 * d,
             "interact_fwd": lb * (nfe * 4 * d + (d + npair) * 4),
             "interact_bwd": lb * (2 * nfe * 4 * d + (d + npair) * 4),
         }

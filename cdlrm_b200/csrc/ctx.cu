@@ -214,7 +214,7 @@ static std::mutex g_prof_mu;
 struct ProfRec { int id; cudaEvent_t b, e; };
 static std::vector<ProfRec> g_prof;
 static const char* const g_knames[K_COUNT] = {
-    "probe", "gather", "pool", "bwd_plan", "bwd_sgd", "interact_fwd", "interact_bwd",
+    "probe", "gather", "pool", "bwd_plan", "bwd_sgd", "bwd_sgd_multi", "interact_fwd", "interact_bwd",
     "plan_bitmap_set", "plan_compact", "plan_probe", "plan_surv", "plan_select", "plan_lists",
     "move_evict", "move_gather", "move_fill", "move_scatter", "agg_mark", "agg_or", "agg_collect",
     "agg_pack", "agg_unpack", "misc"};

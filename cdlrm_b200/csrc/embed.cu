@@ -8,7 +8,7 @@
 namespace {
 
 constexpr int FWD_CHUNK = 256;  // ids per CTA in the probe; rows per CTA in the gather
-constexpr int CH = 32;          // max contributions merged by one group in the backward
+constexpr int CH = 8;           // max contributions merged by one chunk in the backward
 
 template <int VEC> struct VecT;
 template <> struct VecT<4> { using type = float4; };
@@ -378,7 +378,7 @@ struct PlanView {
     int32_t* sorted_pos;    // [tc][n_idx] absolute position j, grouped by slot (stable)
     int4* chunks;           // [tc][n_idx] {slot, start (index into sorted_pos, relative to the table),
                             //              len | first<<30 | excl<<31, position of the first element}
-    int32_t* n_chunks;      // [tc][nsub]
+    int32_t* n_chunks;      // [tc][nsub][2] {singles (listed from the front), multis (from the back)}
 };
 
 __host__ __device__ inline int plan_nsub(int n_idx) { return (n_idx + CDLRM_SORT_MAX - 1) / CDLRM_SORT_MAX; }
@@ -552,29 +552,42 @@ __global__ void __launch_bounds__(PLAN_NT, 1) bwd_plan_kernel(const TableDesc* _
     for (int i = i0; i < i1; ++i)
         if (i == 0 || keyA[i] != keyA[i - 1]) last_head = i;
     int carry = block_excl_maxscan_1024(last_head, s_scr);
-    int cur = carry, nch = 0;
+    // singles (one gradient row, sole owner of its slot: the common case) are listed from the
+    // front of the chunk array, multi-row / shared-slot chunks from the back, so that each kind
+    // gets its own specialised apply kernel
+    int cur = carry, n_single = 0, n_multi = 0;
     for (int i = i0; i < i1; ++i) {
-        if (i == 0 || keyA[i] != keyA[i - 1]) cur = i;
-        if (((i - cur) % CH) == 0) ++nch;
+        const bool head = (i == 0 || keyA[i] != keyA[i - 1]);
+        if (head) cur = i;
+        if (((i - cur) % CH) == 0) {
+            const bool single = head && (i + 1 == n || keyA[i + 1] != keyA[i]);
+            if (single) ++n_single; else ++n_multi;
+        }
     }
-    int total;
-    int cidx = block_excl_scan_1024(nch, s_scr, total);
+    int tot_single, tot_multi;
+    int sidx = block_excl_scan_1024(n_single, s_scr, tot_single);
+    int midx = block_excl_scan_1024(n_multi, s_scr, tot_multi);
     const int64_t obase = (int64_t)t * n_idx + j0;
     cur = carry;
     for (int i = i0; i < i1; ++i) {
-        bool head = (i == 0 || keyA[i] != keyA[i - 1]);
+        const bool head = (i == 0 || keyA[i] != keyA[i - 1]);
         if (head) cur = i;
         if (((i - cur) % CH) == 0) {
-            uint32_t k = keyA[i];
+            const uint32_t k = keyA[i];
             int len = 1;
             while (len < CH && i + len < n && keyA[i + len] == k) ++len;
-            bool last = (i + len == n) || keyA[i + len] != k;
-            uint32_t desc = (uint32_t)len | (head ? (1u << 30) : 0u) | ((head && last) ? (1u << 31) : 0u);
-            pv.chunks[obase + cidx++] = make_int4((int)k, j0 + i, (int)desc, j0 + (int)valA[i]);
+            const bool last = (i + len == n) || keyA[i + len] != k;
+            const uint32_t desc = (uint32_t)len | (head ? (1u << 30) : 0u) | ((head && last) ? (1u << 31) : 0u);
+            const int4 rec = make_int4((int)k, j0 + i, (int)desc, j0 + (int)valA[i]);
+            if (head && last && len == 1) pv.chunks[obase + sidx++] = rec;
+            else pv.chunks[obase + n - 1 - midx++] = rec;
         }
         pv.sorted_pos[obase + i] = j0 + (int)valA[i];
     }
-    if (tid == 0) pv.n_chunks[t * nsub + sub] = total;
+    if (tid == 0) {
+        pv.n_chunks[(t * nsub + sub) * 2 + 0] = tot_single;
+        pv.n_chunks[(t * nsub + sub) * 2 + 1] = tot_multi;
+    }
 }
 
 // ------------------------------------------------------------------------------
@@ -588,74 +601,107 @@ __global__ void __launch_bounds__(PLAN_NT, 1) bwd_plan_kernel(const TableDesc* _
 // rows and U weight rows are in flight per group.
 // ------------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(256) bwd_sgd_rows_kernel(const TableDesc* __restrict__ tabs, int tb,
-                                                           PlanView pv, int n_idx, int j0, int sub, int nsub,
-                                                           const int32_t* __restrict__ bag_ids, int64_t ld_bag,
-                                                           const float* __restrict__ d_out, int64_t ld_dout,
-                                                           int64_t row_stride, float lr, int dim) {
+__global__ void __launch_bounds__(256, 4) bwd_sgd_single_kernel(const TableDesc* __restrict__ tabs, int tb,
+                                                                PlanView pv, int n_idx, int j0, int sub, int nsub,
+                                                                const int32_t* __restrict__ bag_ids, int64_t ld_bag,
+                                                                const float* __restrict__ d_out, int64_t ld_dout,
+                                                                int64_t row_stride, float lr, int dim) {
+    // singles: weight[slot] = fma(-lr, d_out[pos], weight[slot]) -- a pure streaming RMW
+    // a warp takes RPW records: few enough that even a short singles list spreads over all SMs
     constexpr int NGW = 32 / G;
-    constexpr int ITERS = 32 / NGW;
+    constexpr int RPW = NGW > 8 ? NGW : 8;
+    constexpr int ITERS = RPW / NGW;
     constexpr int U = ITERS < 4 ? ITERS : 4;
     const int t = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nch = pv.n_chunks[t * nsub + sub];
-    const int c0 = (blockIdx.x * 8 + warp) * 32;
+    const int nch = pv.n_chunks[(t * nsub + sub) * 2];
+    const int c0 = (blockIdx.x * 8 + warp) * RPW;
     if (c0 >= nch) return;
     const int64_t obase = (int64_t)t * n_idx + j0;
-    const int64_t tbase = (int64_t)t * n_idx;
     const int gl = lane % G, g = lane / G;
     const int cpr = dim >> 2;
     const TableDesc& T = tabs[tb + t];
     float* __restrict__ weight = T.weight;
-    const int32_t* bag = bag_ids ? bag_ids + (int64_t)t * ld_bag : nullptr;
     const float* gbase = d_out + (int64_t)t * ld_dout;
-    int4 rec = make_int4(0, 0, 0, 0);
-    if (c0 + lane < nch) rec = pv.chunks[obase + c0 + lane];
-    if (bag && (rec.z & 0xff)) rec.w = bag[rec.w];
+    int slot_l = -1, pos_l = 0;
+    if (lane < RPW && c0 + lane < nch) {
+        const int4 rec = pv.chunks[obase + c0 + lane];
+        slot_l = rec.x;
+        pos_l = bag_ids ? bag_ids[(int64_t)t * ld_bag + rec.w] : rec.w;
+        if (T.dirty) atomicOr(T.dirty + (slot_l >> 5), 1u << (slot_l & 31));
+    }
     const bool act = gl < cpr;
 #pragma unroll 1
     for (int it0 = 0; it0 < ITERS; it0 += U) {
-        int slot[U], start[U], meta[U], p0[U];
+        int slot[U], pos[U];
         float4 gv[U], wv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int cc = (it0 + u) * NGW + g;
-            slot[u] = __shfl_sync(0xffffffffu, rec.x, cc);
-            start[u] = __shfl_sync(0xffffffffu, rec.y, cc);
-            meta[u] = __shfl_sync(0xffffffffu, rec.z, cc);
-            p0[u] = __shfl_sync(0xffffffffu, rec.w, cc);
+            slot[u] = __shfl_sync(0xffffffffu, slot_l, cc);
+            pos[u] = __shfl_sync(0xffffffffu, pos_l, cc);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if ((meta[u] & 0xff) && act) {
-                gv[u] = reinterpret_cast<const float4*>(gbase + (int64_t)p0[u] * row_stride)[gl];
-                if (meta[u] < 0) wv[u] = reinterpret_cast<const float4*>(weight + (int64_t)slot[u] * dim)[gl];
+            if (slot[u] >= 0 && act) {
+                gv[u] = reinterpret_cast<const float4*>(gbase + (int64_t)pos[u] * row_stride)[gl];
+                wv[u] = reinterpret_cast<const float4*>(weight + (int64_t)slot[u] * dim)[gl];
             }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int len = meta[u] & 0xff;
-            if (!len) continue;
-            if (act) {
-                float4 acc = gv[u];
-                for (int i = 1; i < len; ++i) {     // rare: duplicates of one slot inside the batch
-                    int p = pv.sorted_pos[tbase + start[u] + i];
-                    if (bag) p = bag[p];
-                    acc = vadd(acc, reinterpret_cast<const float4*>(gbase + (int64_t)p * row_stride)[gl]);
-                }
-                float4* wp = reinterpret_cast<float4*>(weight + (int64_t)slot[u] * dim) + gl;
-                if (meta[u] < 0) *wp = vfma(-lr, acc, wv[u]);   // bit 31: the chunk owns the slot
-                else red_add(wp, vscale(-lr, acc));
-            }
-            if (((meta[u] >> 30) & 1) && gl == 0 && T.dirty) atomicOr(T.dirty + (slot[u] >> 5), 1u << (slot[u] & 31));
-        }
+        for (int u = 0; u < U; ++u)
+            if (slot[u] >= 0 && act)
+                reinterpret_cast<float4*>(weight + (int64_t)slot[u] * dim)[gl] = vfma(-lr, gv[u], wv[u]);
     }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) bwd_sgd_multi_kernel(const TableDesc* __restrict__ tabs, int tb,
+                                                            PlanView pv, int n_idx, int j0, int n, int sub, int nsub,
+                                                            const int32_t* __restrict__ bag_ids, int64_t ld_bag,
+                                                            const float* __restrict__ d_out, int64_t ld_dout,
+                                                            int64_t row_stride, float lr, int dim) {
+    // multis: up to CH gradient rows of one slot are loaded together, summed in ascending
+    // position and applied with a plain RMW when the chunk is the slot's only chunk, else a red
+    constexpr int NG = 256 / G;
+    const int t = blockIdx.y;
+    const int gl = threadIdx.x % G, group = threadIdx.x / G;
+    const int m = blockIdx.x * NG + group;
+    if (m >= pv.n_chunks[(t * nsub + sub) * 2 + 1]) return;
+    const int64_t obase = (int64_t)t * n_idx + j0;
+    const int64_t tbase = (int64_t)t * n_idx;
+    const int4 rec = pv.chunks[obase + n - 1 - m];
+    const int len = rec.z & 0xff;
+    const int32_t* bag = bag_ids ? bag_ids + (int64_t)t * ld_bag : nullptr;
+    const float* gbase = d_out + (int64_t)t * ld_dout;
+    const TableDesc& T = tabs[tb + t];
+    if (((rec.z >> 30) & 1) && gl == 0 && T.dirty) atomicOr(T.dirty + (rec.x >> 5), 1u << (rec.x & 31));
+    if (gl >= (dim >> 2)) return;
+    int pp[CH];
+    float4 ga[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        pp[i] = i < len ? pv.sorted_pos[tbase + rec.y + i] : 0;
+        if (bag && i < len) pp[i] = bag[pp[i]];
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+        if (i < len) ga[i] = reinterpret_cast<const float4*>(gbase + (int64_t)pp[i] * row_stride)[gl];
+    float4* wp = reinterpret_cast<float4*>(T.weight + (int64_t)rec.x * dim) + gl;
+    float4 wv;
+    if (rec.z < 0) wv = *wp;
+    float4 acc = ga[0];
+#pragma unroll
+    for (int i = 1; i < CH; ++i)
+        if (i < len) acc = vadd(acc, ga[i]);
+    if (rec.z < 0) *wp = vfma(-lr, acc, wv);
+    else red_add(wp, vscale(-lr, acc));
 }
 
 // generic fallback (any dim / alignment): one group of G lanes per chunk
 template <int VEC>
 __global__ void __launch_bounds__(256) bwd_sgd_kernel(const TableDesc* __restrict__ tabs, int tb,
-                                                      PlanView pv, int n_idx, int j0, int sub, int nsub,
+                                                      PlanView pv, int n_idx, int j0, int n, int sub, int nsub,
                                                       const int32_t* __restrict__ bag_ids, int64_t ld_bag,
                                                       const float* __restrict__ d_out, int64_t ld_dout,
                                                       int64_t row_stride, float lr, int dim, int G) {
@@ -663,9 +709,10 @@ __global__ void __launch_bounds__(256) bwd_sgd_kernel(const TableDesc* __restric
     const int t = blockIdx.y;
     const int gl = threadIdx.x % G, group = threadIdx.x / G, NG = 256 / G;
     const int c = blockIdx.x * NG + group;
-    if (c >= pv.n_chunks[t * nsub + sub]) return;
+    const int ns = pv.n_chunks[(t * nsub + sub) * 2], nm = pv.n_chunks[(t * nsub + sub) * 2 + 1];
+    if (c >= ns + nm) return;
     const int64_t obase = (int64_t)t * n_idx + j0;
-    const int4 rec = pv.chunks[obase + c];
+    const int4 rec = c < ns ? pv.chunks[obase + c] : pv.chunks[obase + n - 1 - (c - ns)];
     const int len = rec.z & 0xff;
     const bool first = (rec.z >> 30) & 1, excl = rec.z < 0;
     const int32_t slot = rec.x;
@@ -802,7 +849,7 @@ extern "C" int64_t cdlrm_embed_bwd_plan_bytes(int tc, int32_t n_idx) {
     size_t a = (size_t)tc * (size_t)(n_idx > 0 ? n_idx : 1) * sizeof(int32_t);
     a = (a + 255) & ~(size_t)255;
     size_t nsub = (size_t)plan_nsub(n_idx > 0 ? n_idx : 1);
-    return (int64_t)(5 * a + ((((size_t)tc * nsub * sizeof(int32_t)) + 255) & ~(size_t)255));
+    return (int64_t)(5 * a + ((((size_t)tc * nsub * 2 * sizeof(int32_t)) + 255) & ~(size_t)255));
 }
 
 extern "C" int cdlrm_embed_bwd_plan(cdlrm_ctx* c, int tb, int tc, const int32_t* slots, int64_t ld_slots,
@@ -856,8 +903,12 @@ extern "C" int cdlrm_embed_bwd_sgd(cdlrm_ctx* c, int tb, int tc, const void* pla
         const int j0 = sub * CDLRM_SORT_MAX;
         const int n = n_idx - j0 < CDLRM_SORT_MAX ? n_idx - j0 : CDLRM_SORT_MAX;
         if (vec == 4 && cpr <= 32) {
-            dim3 grid((n + 255) / 256, tc);     // 8 warps x 32 chunk records per CTA
-#define LAUNCH_SGD(GG) LAUNCH(K_BWD_SGD, s, (bwd_sgd_rows_kernel<GG><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim)))
+            const int rpw = (32 / G) > 8 ? (32 / G) : 8;
+            dim3 grid((n + 8 * rpw - 1) / (8 * rpw), tc);       // singles: 8 warps x RPW records per CTA
+            dim3 gridm((n / 2 + NG - 1) / NG + 1, tc);          // multis: at most n/2 chunks, one group each
+#define LAUNCH_SGD(GG)                                                                                         \
+    LAUNCH(K_BWD_SGD, s, (bwd_sgd_single_kernel<GG><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim))); \
+    LAUNCH(K_BWD_SGD_MULTI, s, (bwd_sgd_multi_kernel<GG><<<gridm, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim)))
             switch (G) {
                 case 1: LAUNCH_SGD(1); break;
                 case 2: LAUNCH_SGD(2); break;
@@ -869,9 +920,9 @@ extern "C" int cdlrm_embed_bwd_sgd(cdlrm_ctx* c, int tb, int tc, const void* pla
 #undef LAUNCH_SGD
         } else {
             dim3 grid((n + NG - 1) / NG, tc);
-            if (vec == 4) LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<4><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
-            else if (vec == 2) LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<2><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
-            else LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<1><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
+            if (vec == 4) LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<4><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
+            else if (vec == 2) LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<2><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
+            else LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<1><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
         }
     }
     CU_CHECK(cudaGetLastError());

@@ -95,7 +95,7 @@ int cdlrm_embed_fwd(cdlrm_ctx* ctx, int table_begin, int table_count,
 /* ---- backward + SGD: autograd of EmbeddingBag(sparse=True) followed by
  *      optimizer_embeds.step(), main_no_ddp.py:376,409,413 -------------------------
  * weight[slot] -= lr * sum_{j: slot_j == slot} d_out[bag(j)], duplicates merged by a
- * per-table sort (no atomics unless one slot has more than 32 contributions).
+ * per-table sort (no atomics unless one slot has more than 8 contributions in the batch).
  * d_out row of bag b of table k: d_out + (k-table_begin)*ld_dout + b*dout_row_stride.
  * Marks touched slots in the dirty bitmaps when bound.  */
 int64_t cdlrm_embed_bwd_plan_bytes(int table_count, int32_t n_idx);

@@ -136,6 +136,8 @@ class WindowPlanner:
         ascending-unique int64 tensors (the reference-API path)."""
         s = self.stream
         rec = PlanRecord()
+        import time as _t
+        t_a = _t.perf_counter()
         with torch.cuda.stream(s):
             if uniq_lists is not None:
                 lens = [int(u.numel()) for u in uniq_lists]
@@ -163,7 +165,9 @@ class WindowPlanner:
             for k in range(1, self.T):
                 rec.off[k] = rec.off[k - 1] + rec.rows[k - 1]
             # q for table 0..T-1 in one draw: the stream is split-invariant
+            t_b = _t.perf_counter()
             q_host = self.rng.exponential(total * self.ways)
+            t_c = _t.perf_counter()
             q = q_host.to(self.dev, non_blocking=True) if total else torch.empty(0, device=self.dev)
             n = max(total, 1)
             rec.evict_ids = torch.empty(n, dtype=torch.int64, device=self.dev)
@@ -180,6 +184,8 @@ class WindowPlanner:
             rec.E = c2[:, 0].tolist()
             rec.F = c2[:, 1].tolist()
             del q_host
+            self.last_timing = {"phase_a_s": round(t_b - t_a, 4), "rng_s": round(t_c - t_b, 4),
+                                "phase_b_s": round(_t.perf_counter() - t_c, 4)}
         rec.event = None
         return rec
 

@@ -62,7 +62,7 @@ struct cdlrm_ctx {
     TableDesc* d_tabs = nullptr;
     bool tabs_dirty = true;
     // forward/backward scratch
-    int32_t* d_miss_cnt = nullptr;  // [T][max_chunks]
+    uint32_t* d_missmap = nullptr;  // [T][ceil(max_idx/32)] forward miss bitmap
     int64_t scratch_max_idx = 0;
     uint32_t* d_flags = nullptr;    // sticky error flags
     // planner

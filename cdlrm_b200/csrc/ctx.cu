@@ -90,7 +90,7 @@ extern "C" int cdlrm_ctx_destroy(cdlrm_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_tabs);
     cudaFree(c->d_flags);
-    cudaFree(c->d_miss_cnt);
+    cudaFree(c->d_missmap);
     cudaFree(c->p_counts);
     cudaFree(c->d_ptabs);
     delete c;
@@ -160,14 +160,14 @@ int cdlrm_sync_tabs(cdlrm_ctx* c, cudaStream_t s) {
 extern "C" int cdlrm_ctx_reserve(cdlrm_ctx* c, int64_t max_idx) {
     ARG_CHECK(c && max_idx >= 0);
     CU_CHECK(cudaSetDevice(c->device));
-    if (max_idx <= c->scratch_max_idx && c->d_miss_cnt) return CDLRM_OK;
-    if (c->d_miss_cnt) {
+    if (max_idx <= c->scratch_max_idx && c->d_missmap) return CDLRM_OK;
+    if (c->d_missmap) {
         CU_CHECK(cudaDeviceSynchronize());
-        CU_CHECK(cudaFree(c->d_miss_cnt));
-        c->d_miss_cnt = nullptr;
+        CU_CHECK(cudaFree(c->d_missmap));
+        c->d_missmap = nullptr;
     }
-    int64_t chunks = (max_idx + 255) / 256 + 1;
-    CU_CHECK(cudaMalloc(&c->d_miss_cnt, sizeof(int32_t) * c->T * chunks));
+    int64_t words = (max_idx + 31) / 32 + 1;
+    CU_CHECK(cudaMalloc(&c->d_missmap, sizeof(uint32_t) * c->T * words));
     c->scratch_max_idx = max_idx;
     return CDLRM_OK;
 }
@@ -214,7 +214,7 @@ static std::mutex g_prof_mu;
 struct ProfRec { int id; cudaEvent_t b, e; };
 static std::vector<ProfRec> g_prof;
 static const char* const g_knames[K_COUNT] = {
-    "probe", "gather", "pool", "bwd_plan", "bwd_sgd", "bwd_sgd_multi", "interact_fwd", "interact_bwd",
+    "embed_fwd", "embed_miss", "pool", "bwd_plan", "bwd_sgd", "bwd_sgd_multi", "interact_fwd", "interact_bwd",
     "plan_bitmap_set", "plan_compact", "plan_probe", "plan_surv", "plan_select", "plan_lists",
     "move_evict", "move_gather", "move_fill", "move_scatter", "agg_mark", "agg_or", "agg_collect",
     "agg_pack", "agg_unpack", "misc"};

@@ -7,7 +7,6 @@
 
 namespace {
 
-constexpr int FWD_CHUNK = 256;  // ids per CTA in the probe; rows per CTA in the gather
 constexpr int CH = 8;           // max contributions merged by one chunk in the backward
 
 template <int VEC> struct VecT;
@@ -44,291 +43,183 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 // ------------------------------------------------------------------------------
-// K1: probe.  A group of GW lanes (GW = pow2 >= ways, <= 32) probes one id: lane w
-// loads tag w of the set (one coalesced 8*ways-byte line), the hit way comes from a
-// warp ballot.  Hits get their final slot; misses get -(1 + ordinal inside this
-// chunk) and the chunk's miss count is published for K2's cross-chunk prefix.
-// model_no_ddp.py:166-174.
+// K1: fused probe + slot + row copy (model_no_ddp.py:166-174,200-202).
+// A warp owns 32 consecutive ids of one table (= one word of the miss bitmap).
+//   phase 1  lane l loads id l (one coalesced 256-byte load), set = id mod num_sets;
+//   phase 2  lane l reads the whole tag line of its set (8*ways bytes: one 128-byte
+//            line at 16 ways, as 16-byte loads that are all in flight together) and
+//            compares in registers -> way, slot = num_sets*way + set;
+//   phase 3  COPY (one id per bag, Criteo): the 32 cache rows of the warp are moved to
+//            out[] by groups of G lanes, U rows (U*512 B at dim 128) in flight per
+//            group; row descriptors travel by shuffle.
+// Misses only set their bit in the miss bitmap (one plain store per warp, the bitmap
+// is rewritten completely by every launch): the batch-order ordinal they need
+// (model_no_ddp.py:177) is resolved by K2.
 // ------------------------------------------------------------------------------
-template <int GW>
-struct ProbeCfg { static constexpr int NT = GW >= 4 ? 1024 : 256; };   // 4 ids per group -> one batch in flight
+constexpr int FWD_NT = 128;
 
-template <int GW>
-__global__ void __launch_bounds__(ProbeCfg<GW>::NT) probe_kernel(const TableDesc* __restrict__ tabs, int tb,
-                                                    const int64_t* __restrict__ ids, int64_t ld_ids, int n_idx,
-                                                    int32_t* __restrict__ slots, int64_t ld_slots,
-                                                    int32_t* __restrict__ miss_cnt, int chunks, int ways) {
-    constexpr int GPW = 32 / GW;                          // groups per warp
-    constexpr int NG = ProbeCfg<GW>::NT / 32 * GPW;    // groups per CTA
-    constexpr int IPG = FWD_CHUNK / NG;                   // ids per group
-    static_assert(IPG >= 1 && IPG <= 32, "miss mask is 32 bits");
-    const int t = blockIdx.y, chunk = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gl = lane % GW, gidx = lane / GW, group = warp * GPW + gidx;
-    const uint32_t gmask = GW == 32 ? 0xffffffffu : ((1u << GW) - 1u);
-    const TableDesc& T = tabs[tb + t];
-    const int64_t S = T.num_sets;
-    const int64_t* __restrict__ tags = T.tags;
-    const int64_t* tid = ids + (int64_t)t * ld_ids;
-    int32_t* tsl = slots + (int64_t)t * ld_slots;
-    const int base = chunk * FWD_CHUNK + group * IPG;
-    uint32_t missmask = 0;
-
-    constexpr int U = 4;  // ids in flight per group
-#pragma unroll 1
-    for (int i0 = 0; i0 < IPG; i0 += U) {
-        int64_t id[U], s[U], tag[U];
-        bool valid[U];
+template <int WAYS>
+__device__ __forceinline__ int probe_line(const int64_t* __restrict__ tags, int64_t s, int64_t id, int ways) {
+    int way = -1;
+    if constexpr (WAYS >= 2) {
+        const longlong2* line = reinterpret_cast<const longlong2*>(tags + s * WAYS);
+        longlong2 v[WAYS / 2];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            int j = base + i0 + u;
-            valid[u] = (i0 + u) < IPG && j < n_idx;
-            id[u] = valid[u] ? __ldg(tid + j) : 0;
-            s[u] = set_index(id[u], S);
+        for (int i = 0; i < WAYS / 2; ++i) v[i] = __ldg(line + i);
+#pragma unroll
+        for (int i = WAYS / 2 - 1; i >= 0; --i) {   // descending: the lowest matching way wins
+            if (v[i].y == id) way = 2 * i + 1;
+            if (v[i].x == id) way = 2 * i;
         }
-        int way[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) way[u] = -1;
-        for (int w0 = 0; w0 < ways; w0 += GW) {
-            const int w = w0 + gl;
-#pragma unroll
-            for (int u = 0; u < U; ++u) tag[u] = (valid[u] && w < ways) ? tags[s[u] * ways + w] : 0;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                bool m = valid[u] && w < ways && tag[u] == id[u];
-                uint32_t gb = (__ballot_sync(0xffffffffu, m) >> (gidx * GW)) & gmask;
-                if (gb && way[u] < 0) way[u] = w0 + __ffs(gb) - 1;
-            }
-        }
-        if (gl == 0) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!valid[u]) continue;
-                if (way[u] >= 0) tsl[base + i0 + u] = (int32_t)(S * way[u] + s[u]);
-                else missmask |= 1u << (i0 + u);
-            }
-        }
+    } else {
+        const int64_t* line = tags + s * ways;
+        for (int w = ways - 1; w >= 0; --w)
+            if (__ldg(line + w) == id) way = w;
     }
-    __shared__ int s_cnt[NG];
-    if (gl == 0) s_cnt[group] = __popc(missmask);
-    __syncthreads();
-    if (gl == 0 && missmask) {
-        int b = 0;
-        for (int g = 0; g < group; ++g) b += s_cnt[g];
-        while (missmask) {
-            int i = __ffs(missmask) - 1;
-            missmask &= missmask - 1;
-            tsl[base + i] = -(1 + b++);
-        }
-    }
-    if (threadIdx.x == 0) {
-        int tot = 0;
-        for (int g = 0; g < NG; ++g) tot += s_cnt[g];
-        miss_cnt[t * chunks + chunk] = tot;
-    }
+    return way;
 }
 
-// ------------------------------------------------------------------------------
-// K2: resolve misses + gather (+ copy-out when every bag holds exactly one id).
-// A group of G lanes moves one row with 16-byte accesses (G*VEC*4 bytes per pass,
-// 512 B for dim 128); U rows are in flight per group.  Misses take aux slot
-// num_sets*ways + ordinal (batch order, model_no_ddp.py:177), read the master row
-// (zero-copy from pinned host memory) and park it in the aux row (:179).
-// POOL_P1: also write out[j] = row (EmbeddingBag sum with one id per bag, :202).
-// ------------------------------------------------------------------------------
-template <int VEC, bool POOL_P1>
-__global__ void __launch_bounds__(256) gather_kernel(const TableDesc* __restrict__ tabs, int tb,
-                                                     const int64_t* __restrict__ ids, int64_t ld_ids, int n_idx,
-                                                     int32_t* __restrict__ slots, int64_t ld_slots,
-                                                     const int32_t* __restrict__ miss_cnt, int chunks,
-                                                     float* __restrict__ out, int64_t ld_out,
-                                                     int32_t* __restrict__ n_miss, uint32_t* __restrict__ flags,
-                                                     int dim, int ways, int64_t aux_rows, int G) {
-    using V = typename VecT<VEC>::type;
-    const int t = blockIdx.y, chunk = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ int s_prefix;
-    if (warp == 0) {
-        int acc = 0;
-        for (int c = lane; c < chunk; c += 32) acc += miss_cnt[t * chunks + c];
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            s_prefix = acc;
-            if (chunk == chunks - 1) n_miss[t] = acc + miss_cnt[t * chunks + chunk];
-        }
-    }
-    __syncthreads();
-    const int prefix = s_prefix;
+template <int WAYS, int G, bool COPY>
+__global__ void __launch_bounds__(FWD_NT) fwd_fused_kernel(const TableDesc* __restrict__ tabs, int tb,
+                                                            const int64_t* __restrict__ ids, int64_t ld_ids, int n_idx,
+                                                            int32_t* __restrict__ slots, int64_t ld_slots,
+                                                            uint32_t* __restrict__ missmap, int words,
+                                                            float* __restrict__ out, int64_t ld_out, int dim, int ways) {
+    const int t = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (FWD_NT / 32) + (threadIdx.x >> 5);
+    if (w >= words) return;
     const TableDesc& T = tabs[tb + t];
     const int64_t S = T.num_sets;
-    float* __restrict__ weight = T.weight;
-    const float* __restrict__ master = T.master;
-    const int64_t* tid = ids + (int64_t)t * ld_ids;
-    int32_t* tsl = slots + (int64_t)t * ld_slots;
-    float* tout = POOL_P1 ? out + (int64_t)t * ld_out : nullptr;
-    const int cpr = dim / VEC;             // vector chunks per row
-    const int gl = threadIdx.x % G, group = threadIdx.x / G, NG = 256 / G;
-    const int64_t aux_base = S * ways;
-
-    constexpr int U = 4;
-    if (cpr <= G) {
-        for (int r0 = group; r0 < FWD_CHUNK; r0 += NG * U) {
-            const float* src[U];
-            int64_t dst_aux[U];
-            int j[U];
-            bool valid[U];
+    const int j0 = w * 32, j = j0 + lane;
+    const bool valid = j < n_idx;
+    const int64_t id = valid ? __ldg(ids + (int64_t)t * ld_ids + j) : 0;
+    const int64_t s = set_index(id, S);
+    const int way = probe_line<WAYS>(T.tags, s, id, ways);
+    const bool miss = valid && way < 0;
+    const int32_t slot = (valid && way >= 0) ? (int32_t)(S * way + s) : -1;
+    if (valid) slots[(int64_t)t * ld_slots + j] = slot;
+    const uint32_t mm = __ballot_sync(0xffffffffu, miss);
+    if (lane == 0) missmap[(int64_t)t * words + w] = mm;
+    if constexpr (COPY) {
+        constexpr int NGW = 32 / G;               // rows moved per warp instruction
+        constexpr int ITERS = G;                  // 32 rows / NGW
+        constexpr int U = ITERS < 8 ? ITERS : 8;  // row batches in flight
+        const float* __restrict__ weight = T.weight;
+        float* tout = out + (int64_t)t * ld_out + (int64_t)j0 * dim;
+        const int cpr = dim >> 2;
+        const int gl = lane % G, g = lane / G;
+#pragma unroll 1
+        for (int it0 = 0; it0 < ITERS; it0 += U) {
+            float4 v[U];
+            int32_t sl[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                int r = r0 + u * NG;
-                j[u] = chunk * FWD_CHUNK + r;
-                valid[u] = r < FWD_CHUNK && j[u] < n_idx;
-                dst_aux[u] = -1;
-                src[u] = nullptr;
-                if (valid[u]) {
-                    int32_t sl = tsl[j[u]];
-                    if (sl < 0) {
-                        int64_t ord = (int64_t)prefix + (-(int64_t)sl - 1);
-                        if (ord >= aux_rows) {        // IndexError in the reference
-                            if (gl == 0) atomicOr(flags, 1u);
-                            valid[u] = false;
-                        } else {
-                            dst_aux[u] = aux_base + ord;
-                            src[u] = master + __ldg(tid + j[u]) * dim;
-                        }
-                    } else if (POOL_P1) {
-                        src[u] = weight + (int64_t)sl * dim;
-                    } else {
-                        valid[u] = false;            // hits need no work without copy-out
-                    }
-                }
-            }
-            V v[U];
+            for (int u = 0; u < U; ++u) sl[u] = __shfl_sync(0xffffffffu, slot, (it0 + u) * NGW + g);
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (valid[u] && gl < cpr) v[u] = reinterpret_cast<const V*>(src[u])[gl];
+                if (sl[u] >= 0 && gl < cpr) v[u] = reinterpret_cast<const float4*>(weight + (int64_t)sl[u] * dim)[gl];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!valid[u]) continue;
-                if (gl < cpr) {
-                    if (POOL_P1) reinterpret_cast<V*>(tout + (int64_t)j[u] * dim)[gl] = v[u];
-                    if (dst_aux[u] >= 0) reinterpret_cast<V*>(weight + dst_aux[u] * dim)[gl] = v[u];
-                }
-                if (dst_aux[u] >= 0 && gl == 0) tsl[j[u]] = (int32_t)dst_aux[u];
-            }
-        }
-    } else {  // wide rows: several passes per row
-        for (int r = group; r < FWD_CHUNK; r += NG) {
-            int j = chunk * FWD_CHUNK + r;
-            if (j >= n_idx) break;
-            int32_t sl = tsl[j];
-            const float* src;
-            int64_t dst_aux = -1;
-            if (sl < 0) {
-                int64_t ord = (int64_t)prefix + (-(int64_t)sl - 1);
-                if (ord >= aux_rows) {
-                    if (gl == 0) atomicOr(flags, 1u);
-                    continue;
-                }
-                dst_aux = aux_base + ord;
-                src = master + __ldg(tid + j) * dim;
-            } else if (POOL_P1) {
-                src = weight + (int64_t)sl * dim;
-            } else {
-                continue;
-            }
-            for (int c = gl; c < cpr; c += G) {
-                V v = reinterpret_cast<const V*>(src)[c];
-                if (POOL_P1) reinterpret_cast<V*>(tout + (int64_t)j * dim)[c] = v;
-                if (dst_aux >= 0) reinterpret_cast<V*>(weight + dst_aux * dim)[c] = v;
-            }
-            if (dst_aux >= 0 && gl == 0) tsl[j] = (int32_t)dst_aux;
+            for (int u = 0; u < U; ++u)
+                if (sl[u] >= 0 && gl < cpr)
+                    reinterpret_cast<float4*>(tout + (int64_t)((it0 + u) * NGW + g) * dim)[gl] = v[u];
         }
     }
 }
 
 // ------------------------------------------------------------------------------
-// K2 (fast path, float4 rows of <= 128 floats): every warp owns 32 consecutive ids of
-// the chunk.  Lane l first loads slot/id of row l (one coalesced load instead of one
-// dependent load per row), resolves the miss ordinal, and the row descriptors are then
-// broadcast by shuffle while groups of G lanes move U rows at a time (U*NGW rows, i.e.
-// up to 4 KB, in flight per warp).
+// K2: resolve the misses (model_no_ddp.py:176-179).  Miss i (batch order = rank of its
+// bit in the table's miss bitmap) takes aux slot num_sets*ways + i, reads the master row
+// (zero-copy from pinned host memory), parks it in the aux row and, when every bag
+// holds one id, also writes out[j].  CTA c of table t owns a contiguous range of bitmap
+// words; the ordinal base of the range is the popcount of everything before it.  With
+// no misses (the common case) every CTA leaves after reading the bitmap.
 // ------------------------------------------------------------------------------
-template <int G, bool POOL_P1>
-__global__ void __launch_bounds__(256) gather_rows_kernel(const TableDesc* __restrict__ tabs, int tb,
-                                                          const int64_t* __restrict__ ids, int64_t ld_ids, int n_idx,
-                                                          int32_t* __restrict__ slots, int64_t ld_slots,
-                                                          const int32_t* __restrict__ miss_cnt, int chunks,
-                                                          float* __restrict__ out, int64_t ld_out,
-                                                          int32_t* __restrict__ n_miss, uint32_t* __restrict__ flags,
-                                                          int dim, int ways, int64_t aux_rows) {
-    constexpr int NGW = 32 / G;               // rows moved per warp instruction
-    constexpr int ITERS = 32 / NGW;           // == G
-    constexpr int U = ITERS < 8 ? ITERS : 8;  // row batches in flight
-    const int t = blockIdx.y, chunk = blockIdx.x;
+constexpr int MISS_NT = 256;
+
+template <int VEC, bool COPY>
+__global__ void __launch_bounds__(MISS_NT) fwd_miss_kernel(const TableDesc* __restrict__ tabs, int tb,
+                                                            const int64_t* __restrict__ ids, int64_t ld_ids, int n_idx,
+                                                            int32_t* __restrict__ slots, int64_t ld_slots,
+                                                            const uint32_t* __restrict__ missmap, int words, int wpc,
+                                                            float* __restrict__ out, int64_t ld_out,
+                                                            int32_t* __restrict__ n_miss, uint32_t* __restrict__ flags,
+                                                            int dim, int ways, int64_t aux_rows) {
+    using V = typename VecT<VEC>::type;
+    constexpr int NW = MISS_NT / 32;
+    __shared__ int s_red[2][NW];
+    const int t = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ int s_prefix;
-    if (warp == 0) {
-        int acc = 0;
-        for (int c = lane; c < chunk; c += 32) acc += miss_cnt[t * chunks + c];
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            s_prefix = acc;
-            if (chunk == chunks - 1) n_miss[t] = acc + miss_cnt[t * chunks + chunk];
-        }
+    const uint32_t* mm = missmap + (int64_t)t * words;
+    const int w_lo = blockIdx.x * wpc, w_hi = min(words, w_lo + wpc);
+    // popcount of the words before the range (ordinal base) and inside it
+    int before = 0, inside = 0;
+    for (int w = threadIdx.x; w < w_hi; w += MISS_NT) {
+        const int c = __popc(mm[w]);
+        if (w < w_lo) before += c; else inside += c;
     }
+    before = warp_sum(before);
+    inside = warp_sum(inside);
+    if (lane == 0) { s_red[0][warp] = before; s_red[1][warp] = inside; }
+    __syncthreads();
+    before = inside = 0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) { before += s_red[0][i]; inside += s_red[1][i]; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) n_miss[t] = before + inside;
+    if (inside == 0) return;
     const TableDesc& T = tabs[tb + t];
     float* __restrict__ weight = T.weight;
     const float* __restrict__ master = T.master;
-    int32_t* tsl = slots + (int64_t)t * ld_slots;
-    float* tout = POOL_P1 ? out + (int64_t)t * ld_out : nullptr;
     const int64_t aux_base = T.num_sets * ways;
-    const int cpr = dim >> 2;
-    const int gl = lane % G, g = lane / G;
-    // lane-parallel descriptor of row (j0 + lane)
-    const int j0 = chunk * FWD_CHUNK + warp * 32;
-    const int jl = j0 + lane;
-    const bool in_range = jl < n_idx;
-    const int32_t sl = in_range ? tsl[jl] : 0;
-    const int64_t id = (in_range && sl < 0) ? __ldg(ids + (int64_t)t * ld_ids + jl) : 0;
-    __syncthreads();
-    const int prefix = s_prefix;
-    const float* src_l = nullptr;     // null: nothing to move for this row
-    int64_t aux_l = -1;
-    if (in_range) {
-        if (sl < 0) {
-            const int64_t ord = (int64_t)prefix + (-(int64_t)sl - 1);
+    const int cpr = dim / VEC;
+    // warp `warp` owns words w_lo + warp, w_lo + warp + NW, ... ; its running ordinal starts at the
+    // popcount of the range's words that precede each of them, recomputed per word (ranges are short)
+    for (int w = w_lo + warp; w < w_hi; w += NW) {
+        const uint32_t bits = mm[w];
+        if (!bits) continue;
+        int ord0 = 0;
+        for (int x = w_lo + lane; x < w; x += 32) ord0 += __popc(mm[x]);
+        ord0 = warp_sum(ord0) + before;
+        const bool mine = (bits >> lane) & 1u;
+        const int j = w * 32 + lane;
+        const int64_t ord = ord0 + __popc(bits & ((1u << lane) - 1u));
+        const float* src_l = nullptr;
+        int64_t aux_l = -1;
+        if (mine) {
             if (ord >= aux_rows) {
-                atomicOr(flags, 1u);               // IndexError in the reference
+                atomicOr(flags, 1u);                 // IndexError in the reference
             } else {
                 aux_l = aux_base + ord;
-                src_l = master + id * dim;
-                tsl[jl] = (int32_t)aux_l;
+                src_l = master + __ldg(ids + (int64_t)t * ld_ids + j) * dim;
+                slots[(int64_t)t * ld_slots + j] = (int32_t)aux_l;
             }
-        } else if (POOL_P1) {
-            src_l = weight + (int64_t)sl * dim;
         }
-    }
-    const unsigned long long src_bits = (unsigned long long)src_l;
-#pragma unroll 1
-    for (int it0 = 0; it0 < ITERS; it0 += U) {
-        float4 v[U];
-        unsigned long long sp[U];
-        long long ax[U];
+        const unsigned long long src_bits = (unsigned long long)src_l;
+        uint32_t rem = bits;
+        constexpr int U = 4;
+        while (rem) {
+            int b[U];
+            unsigned long long sp[U];
+            long long ax[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int rr = (it0 + u) * NGW + g;                 // row (within the warp's 32) of this group
-            sp[u] = __shfl_sync(0xffffffffu, src_bits, rr);
-            ax[u] = __shfl_sync(0xffffffffu, (long long)aux_l, rr);
-        }
+            for (int u = 0; u < U; ++u) {
+                b[u] = rem ? __ffs(rem) - 1 : -1;
+                if (rem) rem &= rem - 1;
+                sp[u] = __shfl_sync(0xffffffffu, src_bits, b[u] < 0 ? 0 : b[u]);
+                ax[u] = __shfl_sync(0xffffffffu, (long long)aux_l, b[u] < 0 ? 0 : b[u]);
+                if (b[u] < 0) sp[u] = 0;
+            }
+            for (int c = lane; c < cpr; c += 32) {
+                V v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (sp[u] && gl < cpr) v[u] = reinterpret_cast<const float4*>(sp[u])[gl];
+                for (int u = 0; u < U; ++u)
+                    if (sp[u]) v[u] = reinterpret_cast<const V*>(sp[u])[c];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (!sp[u] || gl >= cpr) continue;
-            const int rr = (it0 + u) * NGW + g;
-            if (POOL_P1) reinterpret_cast<float4*>(tout + (int64_t)(j0 + rr) * dim)[gl] = v[u];
-            if (ax[u] >= 0) reinterpret_cast<float4*>(weight + ax[u] * dim)[gl] = v[u];
+                for (int u = 0; u < U; ++u) {
+                    if (!sp[u]) continue;
+                    reinterpret_cast<V*>(weight + ax[u] * dim)[c] = v[u];
+                    if (COPY) reinterpret_cast<V*>(out + (int64_t)t * ld_out + (int64_t)(w * 32 + b[u]) * dim)[c] = v[u];
+                }
+            }
         }
     }
 }
@@ -349,9 +240,9 @@ __global__ void __launch_bounds__(256) pool_kernel(const TableDesc* __restrict__
     const int b = blockIdx.x * NG + group;
     if (b >= n_bags) return;
     const float* __restrict__ weight = tabs[tb + t].weight;
-    const int64_t* off = offsets + (int64_t)t * ld_off;
+    const int64_t* off = offsets ? offsets + (int64_t)t * ld_off : nullptr;   // null: bag b = id b
     const int32_t* tsl = slots + (int64_t)t * ld_slots;
-    int64_t lo = off[b], hi = (b + 1 < n_bags) ? off[b + 1] : n_idx;
+    int64_t lo = off ? off[b] : b, hi = off ? ((b + 1 < n_bags) ? off[b + 1] : n_idx) : b + 1;
     const int cpr = dim / VEC;
     if (bag_ids && gl == 0)
         for (int64_t j = lo; j < hi; ++j) bag_ids[(int64_t)t * ld_bag + j] = b;
@@ -753,7 +644,7 @@ inline int pick_vec(int dim, const void* a, const void* b, int64_t s1, int64_t s
 }  // namespace
 
 static int ensure_scratch(cdlrm_ctx* c, int64_t n_idx) {
-    if (n_idx <= c->scratch_max_idx && c->d_miss_cnt) return CDLRM_OK;
+    if (n_idx <= c->scratch_max_idx && c->d_missmap) return CDLRM_OK;
     return cdlrm_ctx_reserve(c, n_idx > 8192 ? n_idx : 8192);
 }
 
@@ -784,62 +675,64 @@ extern "C" int cdlrm_embed_fwd(cdlrm_ctx* c, int tb, int tc, const int64_t* ids,
     }
     rc = ensure_scratch(c, n_idx);
     if (rc) return rc;
-    const int chunks = (n_idx + FWD_CHUNK - 1) / FWD_CHUNK;
-    dim3 grid(chunks, tc);
-    const int gw = pow2_ceil(c->ways) > 32 ? 32 : pow2_ceil(c->ways);
-#define LAUNCH_PROBE(GW) LAUNCH(K_PROBE, s, probe_kernel<GW><<<grid, ProbeCfg<GW>::NT, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_miss_cnt, chunks, c->ways))
-    switch (gw) {
-        case 1: LAUNCH_PROBE(1); break;
-        case 2: LAUNCH_PROBE(2); break;
-        case 4: LAUNCH_PROBE(4); break;
-        case 8: LAUNCH_PROBE(8); break;
-        case 16: LAUNCH_PROBE(16); break;
-        default: LAUNCH_PROBE(32); break;
-    }
-#undef LAUNCH_PROBE
-    CU_CHECK(cudaGetLastError());
     const bool p1 = offsets == nullptr;
-    bool al16 = true, al8 = true;
+    bool al16 = true, al8 = true, tags16 = true;
     for (int k = tb; k < tb + tc; ++k) {
         al16 = al16 && ((uintptr_t)c->tabs[k].master % 16 == 0);
         al8 = al8 && ((uintptr_t)c->tabs[k].master % 8 == 0);
+        tags16 = tags16 && ((uintptr_t)c->tabs[k].tags % 16 == 0);
     }
     int vec = pick_vec(c->dim, out, nullptr, ld_out, c->dim);
     if (vec == 4 && !al16) vec = 2;
     if (vec == 2 && !al8) vec = 1;
     const int cpr = c->dim / vec;
     const int G = pow2_ceil(cpr) > 32 ? 32 : pow2_ceil(cpr);
-#define LAUNCH_GATHER(VEC, P1) LAUNCH(K_GATHER, s, (gather_kernel<VEC, P1><<<grid, 256, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_miss_cnt, chunks, out, ld_out, n_miss, c->d_flags, c->dim, c->ways, c->aux, G)))
-#define LAUNCH_GROWS(GG, P1) LAUNCH(K_GATHER, s, (gather_rows_kernel<GG, P1><<<grid, 256, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_miss_cnt, chunks, out, ld_out, n_miss, c->d_flags, c->dim, c->ways, c->aux)))
-#define GROWS_SWITCH(P1)                                  \
-    switch (G) {                                          \
-        case 1: LAUNCH_GROWS(1, P1); break;               \
-        case 2: LAUNCH_GROWS(2, P1); break;               \
-        case 4: LAUNCH_GROWS(4, P1); break;               \
-        case 8: LAUNCH_GROWS(8, P1); break;               \
-        case 16: LAUNCH_GROWS(16, P1); break;             \
-        default: LAUNCH_GROWS(32, P1); break;             \
+    // K1 copies the hit rows itself when every bag holds one id and rows are <= 32 float4 wide;
+    // otherwise it only probes and K3 (pool) produces the output rows from the final slots.
+    const bool copy = p1 && vec == 4 && cpr <= 32;
+    const int words = (n_idx + 31) / 32;
+    dim3 grid((words + FWD_NT / 32 - 1) / (FWD_NT / 32), tc);
+    const int wsel = !tags16 ? 0 : (c->ways == 16 ? 16 : c->ways == 8 ? 8 : c->ways == 4 ? 4 : c->ways == 2 ? 2 : 0);
+#define LAUNCH_FUSED(WW, GG, CP) LAUNCH(K_PROBE, s, (fwd_fused_kernel<WW, GG, CP><<<grid, FWD_NT, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_missmap, words, out, ld_out, c->dim, c->ways)))
+#define FUSED_G(WW)                                             \
+    if (!copy) { LAUNCH_FUSED(WW, 32, false); }                 \
+    else switch (G) {                                           \
+        case 1: LAUNCH_FUSED(WW, 1, true); break;               \
+        case 2: LAUNCH_FUSED(WW, 2, true); break;               \
+        case 4: LAUNCH_FUSED(WW, 4, true); break;               \
+        case 8: LAUNCH_FUSED(WW, 8, true); break;               \
+        case 16: LAUNCH_FUSED(WW, 16, true); break;             \
+        default: LAUNCH_FUSED(WW, 32, true); break;             \
     }
-    if (vec == 4 && cpr <= 32) {
-        if (p1) { GROWS_SWITCH(true) } else { GROWS_SWITCH(false) }
-    } else if (p1) {
-        if (vec == 4) LAUNCH_GATHER(4, true); else if (vec == 2) LAUNCH_GATHER(2, true); else LAUNCH_GATHER(1, true);
-    } else {
-        if (vec == 4) LAUNCH_GATHER(4, false); else if (vec == 2) LAUNCH_GATHER(2, false); else LAUNCH_GATHER(1, false);
+    switch (wsel) {
+        case 16: FUSED_G(16) break;
+        case 8: FUSED_G(8) break;
+        case 4: FUSED_G(4) break;
+        case 2: FUSED_G(2) break;
+        default: FUSED_G(0) break;
     }
-#undef GROWS_SWITCH
-#undef LAUNCH_GROWS
-#undef LAUNCH_GATHER
+#undef FUSED_G
+#undef LAUNCH_FUSED
     CU_CHECK(cudaGetLastError());
-    if (!p1) {
-        if (n_bags > 0) {
-            const int NG = 256 / G;
-            dim3 pg((n_bags + NG - 1) / NG, tc);
-            if (vec == 4) LAUNCH(K_POOL, s, pool_kernel<4><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G));
-            else if (vec == 2) LAUNCH(K_POOL, s, pool_kernel<2><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G));
-            else LAUNCH(K_POOL, s, pool_kernel<1><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G));
-            CU_CHECK(cudaGetLastError());
-        }
+    // K2: a CTA owns at most 64 bitmap words; at most 64 CTAs per table
+    int mctas = (words + 63) / 64;
+    if (mctas > 64) mctas = 64;
+    const int wpc = (words + mctas - 1) / mctas;
+    dim3 mgrid(mctas, tc);
+#define LAUNCH_MISS(VEC, CP) LAUNCH(K_GATHER, s, (fwd_miss_kernel<VEC, CP><<<mgrid, MISS_NT, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_missmap, words, wpc, out, ld_out, n_miss, c->d_flags, c->dim, c->ways, c->aux)))
+    if (copy) LAUNCH_MISS(4, true);
+    else if (vec == 4) LAUNCH_MISS(4, false);
+    else if (vec == 2) LAUNCH_MISS(2, false);
+    else LAUNCH_MISS(1, false);
+#undef LAUNCH_MISS
+    CU_CHECK(cudaGetLastError());
+    if (!copy && n_bags > 0) {
+        const int NG = 256 / G;
+        dim3 pg((n_bags + NG - 1) / NG, tc);
+        if (vec == 4) LAUNCH(K_POOL, s, pool_kernel<4><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G));
+        else if (vec == 2) LAUNCH(K_POOL, s, pool_kernel<2><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G));
+        else LAUNCH(K_POOL, s, pool_kernel<1><<<pg, 256, 0, s>>>(c->d_tabs, tb, slots, ld_slots, offsets, ld_off, n_idx, n_bags, out, ld_out, bag_ids, ld_bag, c->dim, G));
+        CU_CHECK(cudaGetLastError());
     }
     return CDLRM_OK;
 }

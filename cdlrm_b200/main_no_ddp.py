@@ -304,6 +304,9 @@ class Trainer:
         self.cache_group._ensure_ctx(emb_tables)
         self.cache_group.assume_one_id_per_bag = True              # Criteo batches (:390)
         self.side = torch.cuda.Stream(self.dev)
+        # the lookup runs on its own stream beside the bottom MLP (joined before the interaction)
+        self.cache_group.forward_stream = torch.cuda.Stream(self.dev)
+        self.dlrm.pre_interact = self.cache_group.join_forward
         self.planner = WindowPlanner(self.cache_group, emb_tables, args.lookahead * args.mini_batch_size,
                                      rng=VictimRng(args.numpy_rand_seed), stream=self.side, lookahead_tags=True)
         self._plan_q = queue.Queue()

@@ -223,6 +223,8 @@ class Embedding_Table_Cache_Group(nn.Module):
         self.assume_one_id_per_bag = None  # None: check lS_o on the host when it is a CPU tensor
         self.fused_lr = None               # set to apply the SGD update inside backward
         self.early_plan = True             # build the backward plan during forward, on a side stream
+        self.forward_stream = None         # set: lookup kernels run on this stream; consumers call join_forward()
+        self._fwd_done = None
         self._plan_stream = None
         self.last_n_miss = None
         self._ctx = None
@@ -323,13 +325,27 @@ class Embedding_Table_Cache_Group(nn.Module):
         bag_ids = None
         if offsets is not None:
             bag_ids = torch.empty(T, max(n_idx, 1), dtype=torch.int32, device=dev)
+        fs = self.forward_stream
+        if fs is not None:
+            # fork: the lookup (HBM gather + zero-copy PCIe miss fetch) overlaps whatever the caller
+            # enqueues next on the current stream (the bottom MLP); join_forward() is the join
+            fs.wait_stream(torch.cuda.current_stream(dev))
+            sptr = _vp(fs.cuda_stream)
+            ids.record_stream(fs)              # inputs may be temporaries of the caller's stream
+            if offsets is not None:
+                offsets.record_stream(fs)
+        else:
+            sptr = _stream_ptr(dev)
         check(lib.cdlrm_embed_fwd(
             self._ctx, tb, T, _vp(ids.data_ptr()), ids.stride(0),
             _vp(offsets.data_ptr()) if offsets is not None else None,
             offsets.stride(0) if offsets is not None else 0,
             n_idx, n_bags, _vp(out.data_ptr()), out.stride(0), _vp(slots.data_ptr()), slots.stride(0),
             _vp(n_miss.data_ptr()), _vp(bag_ids.data_ptr()) if bag_ids is not None else None,
-            bag_ids.stride(0) if bag_ids is not None else 0, _stream_ptr(dev)))
+            bag_ids.stride(0) if bag_ids is not None else 0, sptr))
+        if fs is not None:
+            self._fwd_done = torch.cuda.Event()
+            self._fwd_done.record(fs)
         if tb == 0 and T == len(self.emb_l):
             self.last_n_miss = n_miss
         else:
@@ -337,6 +353,12 @@ class Embedding_Table_Cache_Group(nn.Module):
                 self.last_n_miss = torch.zeros(len(self.emb_l), dtype=torch.int32, device=dev)
             self.last_n_miss[tb:tb + T] = n_miss
         return out, slots, bag_ids
+
+    def join_forward(self):
+        """Make the current stream wait for the lookup kernels launched on ``forward_stream``."""
+        if self._fwd_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._fwd_done)
+            self._fwd_done = None
 
     def _one_id_per_bag(self, lS_o, n_idx, n_bags):
         if n_idx != n_bags:
@@ -374,6 +396,7 @@ class Embedding_Table_Cache_Group(nn.Module):
         if len(self.emb_l) != len(outs):
             sys.exit("ERROR: corrupted intermediate result in parallel_forward call")
         if self.record_victims:
+            self.join_forward()
             nm = self.last_n_miss.tolist()
             for k in range(len(self.emb_l)):
                 base = self.cache_sizes[k] * self.num_ways
@@ -419,13 +442,16 @@ class Embedding_Table_Cache_Group(nn.Module):
         if n_idx == 0:
             return None
         dev = self.device
-        if self._plan_stream is None:
-            self._plan_stream = torch.cuda.Stream(dev)
         cur = torch.cuda.current_stream(dev)
-        ps = self._plan_stream
+        if self.forward_stream is not None:
+            ps = self.forward_stream           # stream order after the lookup that produced the slots
+        else:
+            if self._plan_stream is None:
+                self._plan_stream = torch.cuda.Stream(dev)
+            ps = self._plan_stream
+            ps.wait_stream(cur)
         T = slots.shape[0]
         nbytes = lib.cdlrm_embed_bwd_plan_bytes(T, n_idx)
-        ps.wait_stream(cur)
         with torch.cuda.stream(ps):
             buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
             base = (buf.data_ptr() + 255) // 256 * 256
@@ -565,6 +591,7 @@ class DLRM_Net(nn.Module):
             self.cpu = torch.device("cpu")
             self.bot_l = self.create_mlp(ln_bot, sigmoid_bot)
             self.top_l = self.create_mlp(ln_top, sigmoid_top)
+        self.pre_interact = None   # optional callable run between the bottom MLP and the interaction
 
     def create_mlp(self, ln, sigmoid_layer):
         """:244-270 -- numpy-RNG initialisation in the reference's draw order."""
@@ -592,6 +619,8 @@ class DLRM_Net(nn.Module):
 
     def forward(self, dense_x, ly):
         x = self.bot_l(dense_x)
+        if self.pre_interact is not None:
+            self.pre_interact()    # e.g. cache_group.join_forward: lookups ran beside the bottom MLP
         z = self.interact_features(x, ly)
         p = self.top_l(z)
         if 0.0 < self.loss_threshold < 1.0:

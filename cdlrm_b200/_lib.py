@@ -67,6 +67,13 @@ SIGNATURES = {
     "cdlrm_rng_destroy": (C.c_int, [vp]),
     "cdlrm_rng_exponential": (C.c_int, [vp, vp, C.c_int64, C.c_int]),
     "cdlrm_rng_draws": (C.c_uint64, [vp]),
+    "cdlrm_rngdev_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_uint64]),
+    "cdlrm_rngdev_destroy": (C.c_int, [vp]),
+    "cdlrm_rngdev_raw": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "cdlrm_rngdev_exponential": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "cdlrm_rngdev_draws": (C.c_uint64, [vp]),
+    "cdlrm_exp_from_raw": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "cdlrm_plan_phase_b_dev": (C.c_int, [vp, vp, vp, C.c_int64, c_i64p, vp, vp, vp, vp, vp, vp, vp]),
 }
 
 

@@ -60,6 +60,39 @@ class VictimRng:
             pass
 
 
+class VictimRngDevice:
+    """The same stream as ``VictimRng`` generated on the GPU (cdlrm_rngdev_*): one CTA refreshes
+    the mt19937 state in three parallel phases, the select kernel applies the exponential
+    transform.  No host work and no PCIe traffic for the draws; every rank of a data-parallel
+    job evolves an identical copy."""
+
+    on_device = True
+
+    def __init__(self, seed, device):
+        self.device = torch.device(device)
+        self._h = _vp()
+        check(lib.cdlrm_rngdev_create(ctypes.byref(self._h), self.device.index, int(seed)))
+
+    def exponential(self, n, stream=None):
+        """float32 [n] device tensor of draws (tests / tools; the planner consumes raw words)."""
+        s = stream or torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(s):
+            out = torch.empty(max(int(n), 1), dtype=torch.float32, device=self.device)
+            raw = torch.empty(2 * max(int(n), 1), dtype=torch.int32, device=self.device)
+            check(lib.cdlrm_rngdev_exponential(self._h, _vp(out.data_ptr()), int(n), _vp(raw.data_ptr()), _sp(s)))
+        return out[:n]
+
+    @property
+    def draws(self):
+        return int(lib.cdlrm_rngdev_draws(self._h))
+
+    def __del__(self):
+        try:
+            lib.cdlrm_rngdev_destroy(self._h)
+        except Exception:
+            pass
+
+
 class TorchGlobalRng:
     """Draws from torch's global CPU generator -- literally what the reference's
     ``Categorical(...).sample()`` does, so interleaving with any other consumer of the
@@ -166,19 +199,28 @@ class WindowPlanner:
                 rec.off[k] = rec.off[k - 1] + rec.rows[k - 1]
             # q for table 0..T-1 in one draw: the stream is split-invariant
             t_b = _t.perf_counter()
-            q_host = self.rng.exponential(total * self.ways)
+            dev_rng = getattr(self.rng, "on_device", False)
+            q_host = None if dev_rng else self.rng.exponential(total * self.ways)
             t_c = _t.perf_counter()
-            q = q_host.to(self.dev, non_blocking=True) if total else torch.empty(0, device=self.dev)
+            if not dev_rng:
+                q = q_host.to(self.dev, non_blocking=True) if total else torch.empty(0, device=self.dev)
             n = max(total, 1)
             rec.evict_ids = torch.empty(n, dtype=torch.int64, device=self.dev)
             rec.evict_slots = torch.empty(n, dtype=torch.int32, device=self.dev)
             rec.evict_primary = torch.empty(n, dtype=torch.uint8, device=self.dev)
             rec.fill_ids = torch.empty(n, dtype=torch.int64, device=self.dev)
             rec.fill_slots = torch.empty(n, dtype=torch.int32, device=self.dev)
-            check(lib.cdlrm_plan_phase_b(self.ctx, _vp(q.data_ptr()) if total else None, _lib.i64_array(rec.rows),
-                                         _vp(rec.evict_ids.data_ptr()), _vp(rec.evict_slots.data_ptr()),
-                                         _vp(rec.evict_primary.data_ptr()), _vp(rec.fill_ids.data_ptr()),
-                                         _vp(rec.fill_slots.data_ptr()), _vp(self._h_counts2.data_ptr()), _sp(s)))
+            outs = (_vp(rec.evict_ids.data_ptr()), _vp(rec.evict_slots.data_ptr()),
+                    _vp(rec.evict_primary.data_ptr()), _vp(rec.fill_ids.data_ptr()),
+                    _vp(rec.fill_slots.data_ptr()), _vp(self._h_counts2.data_ptr()), _sp(s))
+            if dev_rng:
+                cap = max(max(rec.rows) * self.ways, 1)          # draws of the largest table
+                raw = torch.empty(2 * cap, dtype=torch.int32, device=self.dev)
+                check(lib.cdlrm_plan_phase_b_dev(self.ctx, self.rng._h, _vp(raw.data_ptr()), cap,
+                                                 _lib.i64_array(rec.rows), *outs))
+            else:
+                check(lib.cdlrm_plan_phase_b(self.ctx, _vp(q.data_ptr()) if total else None,
+                                             _lib.i64_array(rec.rows), *outs))
             s.synchronize()
             c2 = self._h_counts2.view(self.T, 2).clone()
             rec.E = c2[:, 0].tolist()

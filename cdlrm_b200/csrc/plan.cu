@@ -17,6 +17,7 @@
 // and form the fill list.
 #include "common.cuh"
 #include "compact.cuh"
+#include "expdraw.cuh"
 
 namespace {
 
@@ -122,10 +123,12 @@ __global__ void __launch_bounds__(256) surv_kernel(const int64_t* __restrict__ u
 }
 
 // ---- B1: way = argmax(probs / q) among un-pinned ways; claim the slot -----------------------------
-template <int GW>
+// RAW: q holds the raw mt19937 word pairs (uint2 per draw) of the device-resident stream and the
+// exponential transform is applied here; otherwise q holds host-drawn float32 exponentials.
+template <int GW, bool RAW>
 __global__ void __launch_bounds__(256) select_kernel(const int64_t* __restrict__ uniq,
                                                      const int32_t* __restrict__ surv, int64_t R,
-                                                     const float* __restrict__ q,
+                                                     const void* __restrict__ q,
                                                      const unsigned long long* __restrict__ pin,
                                                      const int64_t* __restrict__ tags, int64_t S, int ways,
                                                      unsigned long long full, int32_t* __restrict__ slot_out,
@@ -147,7 +150,11 @@ __global__ void __launch_bounds__(256) select_kernel(const int64_t* __restrict__
     float best = -1.0f;
     int bw = 0x7fffffff;
     for (int w = gl; w < ways; w += GW) {
-        const float qv = valid ? q[r * ways + w] : 1.0f;
+        float qv = 1.0f;
+        if (valid) {
+            if (RAW) qv = exp_draw_from_raw(reinterpret_cast<const uint2*>(q)[r * ways + w]);
+            else qv = reinterpret_cast<const float*>(q)[r * ways + w];
+        }
         const float v = __fdiv_rn(((avail >> w) & 1ull) ? p : 0.0f, qv);
         if (v > best) {  // strict: first index wins ties (torch.argmax)
             best = v;
@@ -448,7 +455,11 @@ static int plan_impl(cdlrm_ctx* c, const int64_t* win_ids, int64_t ld, int64_t n
     return CDLRM_OK;
 }
 
-extern "C" int cdlrm_plan_phase_b(cdlrm_ctx* c, const float* q, const int64_t* h_rows, int64_t* evict_ids,
+struct cdlrm_rngdev;
+extern "C" int cdlrm_rngdev_raw(cdlrm_rngdev* r, uint32_t* d_out, int64_t n_draws, cdlrm_stream stream);
+
+static int phase_b_impl(cdlrm_ctx* c, const float* q, cdlrm_rngdev* rng, uint32_t* raw, int64_t raw_draws,
+                        const int64_t* h_rows, int64_t* evict_ids,
                                   int32_t* evict_slots, uint8_t* evict_primary, int64_t* fill_ids,
                                   int32_t* fill_slots, int64_t* h_counts2, cdlrm_stream stream) {
     ARG_CHECK(c && h_rows && h_counts2);
@@ -472,11 +483,16 @@ extern "C" int cdlrm_plan_phase_b(cdlrm_ctx* c, const float* q, const int64_t* h
         ARG_CHECK(R >= 0 && R <= p.umax);
         unsigned long long* ck = cnt + k * 8;
         if (R > 0) {
-            ARG_CHECK(q && evict_ids && evict_slots && evict_primary && fill_ids && fill_slots);
+            ARG_CHECK((q || rng) && evict_ids && evict_slots && evict_primary && fill_ids && fill_slots);
             const int NG = 256 / gw;
             const int g1 = (int)((R + NG - 1) / NG);
-            const float* qk = q + off * c->ways;
-#define LAUNCH_SEL(GW) LAUNCH(K_PLAN_SELECT, s, select_kernel<GW><<<g1, 256, 0, s>>>(p.uniq, p.surv, R, qk, pins[k], t.plan_tags, t.num_sets, c->ways, full, c->p_slot, c->p_old, c->p_claim))
+            const void* qk = q ? (const void*)(q + off * c->ways) : (const void*)raw;
+            if (!q) {   // device stream: the draws of table k, in table order (split-invariant stream)
+                ARG_CHECK(raw && R * c->ways <= raw_draws);
+                int rc = cdlrm_rngdev_raw(rng, raw, R * c->ways, stream);
+                if (rc) return rc;
+            }
+#define LAUNCH_SEL(GW) do { if (q) LAUNCH(K_PLAN_SELECT, s, (select_kernel<GW, false><<<g1, 256, 0, s>>>(p.uniq, p.surv, R, qk, pins[k], t.plan_tags, t.num_sets, c->ways, full, c->p_slot, c->p_old, c->p_claim))); else LAUNCH(K_PLAN_SELECT, s, (select_kernel<GW, true><<<g1, 256, 0, s>>>(p.uniq, p.surv, R, qk, pins[k], t.plan_tags, t.num_sets, c->ways, full, c->p_slot, c->p_old, c->p_claim))); } while (0)
             switch (gw) {
                 case 1: LAUNCH_SEL(1); break;
                 case 2: LAUNCH_SEL(2); break;
@@ -498,4 +514,24 @@ extern "C" int cdlrm_plan_phase_b(cdlrm_ctx* c, const float* q, const int64_t* h
     for (int k = 0; k < c->T; ++k)
         CU_CHECK(cudaMemcpyAsync(h_counts2 + k * 2, c->p_counts + k * 8 + CNT_E, sizeof(int64_t) * 2, cudaMemcpyDeviceToHost, s));
     return CDLRM_OK;
+}
+
+extern "C" int cdlrm_plan_phase_b(cdlrm_ctx* c, const float* q, const int64_t* h_rows, int64_t* evict_ids,
+                                  int32_t* evict_slots, uint8_t* evict_primary, int64_t* fill_ids,
+                                  int32_t* fill_slots, int64_t* h_counts2, cdlrm_stream stream) {
+    int64_t total = 0;
+    if (c && h_rows)
+        for (int k = 0; k < c->T; ++k) total += h_rows[k];
+    ARG_CHECK(q || total == 0);
+    return phase_b_impl(c, q, nullptr, nullptr, 0, h_rows, evict_ids, evict_slots, evict_primary, fill_ids, fill_slots,
+                        h_counts2, stream);
+}
+
+extern "C" int cdlrm_plan_phase_b_dev(cdlrm_ctx* c, cdlrm_rngdev* rng, uint32_t* raw_scratch, int64_t raw_draws,
+                                      const int64_t* h_rows, int64_t* evict_ids, int32_t* evict_slots,
+                                      uint8_t* evict_primary, int64_t* fill_ids, int32_t* fill_slots,
+                                      int64_t* h_counts2, cdlrm_stream stream) {
+    ARG_CHECK(rng);
+    return phase_b_impl(c, nullptr, rng, raw_scratch, raw_draws, h_rows, evict_ids, evict_slots, evict_primary,
+                        fill_ids, fill_slots, h_counts2, stream);
 }

@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import check, lib
-from .cache_manager import Prefetcher, TorchGlobalRng, VictimRng, WindowPlanner
+from .cache_manager import Prefetcher, TorchGlobalRng, VictimRng, VictimRngDevice, WindowPlanner
 from .model_no_ddp import DLRM_Net, Embedding_Table_Cache_Group, Embedding_Table_Group
 
 _vp = ctypes.c_void_p
@@ -308,7 +308,8 @@ class Trainer:
         self.cache_group.forward_stream = torch.cuda.Stream(self.dev)
         self.dlrm.pre_interact = self.cache_group.join_forward
         self.planner = WindowPlanner(self.cache_group, emb_tables, args.lookahead * args.mini_batch_size,
-                                     rng=VictimRng(args.numpy_rand_seed), stream=self.side, lookahead_tags=True)
+                                     rng=VictimRngDevice(args.numpy_rand_seed, self.dev), stream=self.side,
+                                     lookahead_tags=True)
         self._plan_q = queue.Queue()
         self._plan_thread = None
         self.steps_since_agg = 0

@@ -38,6 +38,7 @@ extern "C" {
 
 typedef struct cdlrm_ctx cdlrm_ctx;
 typedef struct cdlrm_rng cdlrm_rng;
+typedef struct cdlrm_rngdev cdlrm_rngdev;
 typedef void* cdlrm_stream;        /* cudaStream_t */
 
 /* ---- status -------------------------------------------------------------------- */
@@ -153,6 +154,15 @@ int cdlrm_plan_phase_b(cdlrm_ctx* ctx, const float* q, const int64_t* h_rows,
                        int64_t* evict_ids, int32_t* evict_slots, uint8_t* evict_primary,
                        int64_t* fill_ids, int32_t* fill_slots,
                        int64_t* h_counts2, cdlrm_stream stream);
+/* phase B with the device-resident victim stream (cdlrm_rngdev_*): the draws of table k are
+ * generated on the GPU into raw_scratch (uint32 pairs, capacity raw_draws >= max_k rows_k * num_ways
+ * draws) right before table k's selection and transformed inside the select kernel; the stream
+ * advances by exactly sum_k rows_k * num_ways draws, as the reference's generator does. */
+int cdlrm_plan_phase_b_dev(cdlrm_ctx* ctx, cdlrm_rngdev* rng, uint32_t* raw_scratch, int64_t raw_draws,
+                           const int64_t* h_rows,
+                           int64_t* evict_ids, int32_t* evict_slots, uint8_t* evict_primary,
+                           int64_t* fill_ids, int32_t* fill_slots,
+                           int64_t* h_counts2, cdlrm_stream stream);
 /* unique ids of table k found by the last phase A (device pointer into the
  * workspace, ascending, h_counts[k*4] entries) */
 const int64_t* cdlrm_plan_unique_ptr(const cdlrm_ctx* ctx, int table);
@@ -223,6 +233,19 @@ int cdlrm_rng_create(cdlrm_rng** out, uint64_t seed);
 int cdlrm_rng_destroy(cdlrm_rng* rng);
 int cdlrm_rng_exponential(cdlrm_rng* rng, float* h_out, int64_t n, int threads);
 uint64_t cdlrm_rng_draws(const cdlrm_rng* rng);
+
+/* ---- victim-way RNG (device): the same mt19937 stream generated on the GPU by one CTA
+ *      (three-phase parallel state refresh), state resident in HBM.  raw: 2 uint32 words
+ *      {hi, lo} per draw; exponential: float32(-log1p(-u)) with glibc's log1p restated
+ *      bit-exactly in IEEE double intrinsics (csrc/expdraw.cuh).  d_raw_scratch: 2*n uint32. */
+int cdlrm_rngdev_create(cdlrm_rngdev** out, int device, uint64_t seed);
+int cdlrm_rngdev_destroy(cdlrm_rngdev* rng);
+int cdlrm_rngdev_raw(cdlrm_rngdev* rng, uint32_t* d_out, int64_t n_draws, cdlrm_stream stream);
+int cdlrm_rngdev_exponential(cdlrm_rngdev* rng, float* d_out, int64_t n, uint32_t* d_raw_scratch,
+                             cdlrm_stream stream);
+uint64_t cdlrm_rngdev_draws(const cdlrm_rngdev* rng);
+/* d_out[i] = exponential draw of the raw word pair {d_raw[2i], d_raw[2i+1]} (the transform alone) */
+int cdlrm_exp_from_raw(const uint32_t* d_raw, float* d_out, int64_t n, cdlrm_stream stream);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,8 @@ def _run_cuda_trace(cfg, mode):
     """mode 'api': the reference-shaped calls (process_batch_slice -> CacheEmbeddings ->
     eviction data applied to the master -> forward/backward/SGD.step).
     mode 'fast': WindowPlanner on raw window ids with the C++ victim RNG and zero-copy
-    evict/fill against the pinned master."""
+    evict/fill against the pinned master.  mode 'fast_devrng': the same with the victim stream
+    generated on the GPU (cdlrm_rngdev_*)."""
     C, R, M = _mods()
     seed = cfg["seed"]
     np.random.seed(seed)
@@ -46,9 +47,10 @@ def _run_cuda_trace(cfg, mode):
     lS_o = torch.arange(B).reshape(1, -1).repeat(T, 1)
     torch.manual_seed(seed)
     planner = None
-    if mode == "fast":
+    if mode in ("fast", "fast_devrng"):
         cg._ensure_ctx(master)
-        planner = C.WindowPlanner(cg, master, L * B, rng=C.VictimRng(seed), lookahead_tags=True)
+        rng = C.VictimRng(seed) if mode == "fast" else C.VictimRngDevice(seed, DEV)
+        planner = C.WindowPlanner(cg, master, L * B, rng=rng, lookahead_tags=True)
     step = 0
     for w in range(cfg["n_windows"]):
         win = torch.from_numpy(ids[:, w * L * B:(w + 1) * L * B])
@@ -93,7 +95,7 @@ def _run_cuda_trace(cfg, mode):
 
 @pytest.mark.parametrize("name", ["trace_tiny.npz", "trace_pressure.npz", "trace_pressure_avgwb.npz",
                                   "trace_cfg0_small.npz"])
-@pytest.mark.parametrize("mode", ["api", "fast"])
+@pytest.mark.parametrize("mode", ["api", "fast", "fast_devrng"])
 def test_trace_matches_reference_golden(name, mode):
     g = util.load_golden(name)
     cfg = util.golden_cfg(g)
@@ -215,3 +217,52 @@ def test_aggregate_single_rank_matches_reference_golden():
             off += cg._cache_rows[k]
             assert np.array_equal(cg.emb_l[k].weight.data.cpu().numpy(), g[f"{op}_r0_before_{k}"])
         assert int(cg.dirty_bitmap().abs().sum()) == 0
+
+
+def test_device_victim_stream_equals_host_stream():
+    """cdlrm_rngdev_* (mt19937 on the GPU + IEEE restatement of glibc's log1p) against
+    cdlrm_rng_exponential (std::mt19937 + libm on the host), bit for bit, over calls of awkward
+    sizes (state refresh boundaries at multiples of 312 draws) and 20 M draws; and against the
+    torch stream recorded in tests/golden/rng.npz."""
+    C, _R, _M = _mods()
+    g = util.load_golden("rng.npz")
+    for seed in (123, 7):    # the torch stream itself, as recorded from the reference's sampler
+        r = C.VictimRngDevice(seed, DEV)
+        assert np.array_equal(r.exponential(257 * 16).cpu().numpy().reshape(257, 16), g[f"q_{seed}"])
+        assert np.array_equal(r.exponential(20).cpu().numpy().reshape(5, 4), g[f"q2_{seed}"])
+    seed = 123
+    host, dev = C.VictimRng(seed), C.VictimRngDevice(seed, DEV)
+    for n in [1, 5, 311, 312, 313, 1, 624, 100_003, 20_000_000, 7]:
+        h = host.exponential(n, pin=False)
+        d_ = dev.exponential(n).cpu()
+        assert torch.equal(h.view(torch.int32), d_.view(torch.int32)), f"draw block of {n} differs"
+    assert host.draws == dev.draws
+    # hard arguments for log1p: u -> 0 (|x| < 2^-29, < 2^-54, 0) and u -> 1
+    raw = []
+    for m in [0, 1, 2, (1 << 24) - 1, 1 << 24, (1 << 29) + 12345, (1 << 53) - 1, (1 << 53) - 2, (1 << 52) + 1,
+              (1 << 52), 0x000a827999fcef, 0x12bec333018866, 0x15f619980c4337]:
+        raw.append(m)
+    rng = np.random.default_rng(5)
+    raw += [int(x) for x in rng.integers(0, 1 << 53, size=4096)]
+    raw += [int(x) >> int(s) for x, s in zip(rng.integers(0, 1 << 53, size=4096), rng.integers(0, 53, size=4096))]
+    raw = np.asarray(raw, dtype=np.uint64)
+    u = raw.astype(np.float64) * 2.0 ** -53
+    want = (-np.log1p(-u)).astype(np.float32)
+    got = _device_exp_from_raw(raw)
+    assert np.array_equal(want.view(np.int32), got.view(np.int32))
+
+
+def _device_exp_from_raw(raw_u64):
+    """Runs csrc/expdraw.cuh on given 53-bit integers through the select kernel's twin
+    (cdlrm_rngdev_exponential's transform) by planting them as a fake raw stream."""
+    import ctypes
+    from cdlrm_b200._lib import lib, check
+    n = len(raw_u64)
+    words = np.empty(2 * n, dtype=np.uint32)
+    words[0::2] = (raw_u64 >> np.uint64(32)).astype(np.uint32)
+    words[1::2] = (raw_u64 & np.uint64(0xffffffff)).astype(np.uint32)
+    d_raw = torch.from_numpy(words.view(np.int32)).to(DEV)
+    out = torch.empty(n, dtype=torch.float32, device=DEV)
+    check(lib.cdlrm_exp_from_raw(ctypes.c_void_p(d_raw.data_ptr()), ctypes.c_void_p(out.data_ptr()), n,
+                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out.cpu().numpy()

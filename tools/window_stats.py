@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--dist", default="zipf")
     ap.add_argument("--zipf-a", type=float, default=1.05)
     ap.add_argument("--per-table", action="store_true")
+    ap.add_argument("--host-rng", action="store_true")
     a = ap.parse_args()
     wl = dict(bench.WORKLOADS[a.workload])
     if a.lookahead:
@@ -40,7 +41,7 @@ def main():
     T, L, B, d = len(ln), wl["lookahead"], wl["batch"], wl["dim"]
     cg = M.Embedding_Table_Cache_Group(d, np.asarray(ln), wl["cache"], B, wl["ways"], device=dev)
     cg._ensure_ctx(None)
-    pl = C.WindowPlanner(cg, None, L * B, rng=C.VictimRng(123), lookahead_tags=True)
+    pl = C.WindowPlanner(cg, None, L * B, rng=C.VictimRngDevice(123, dev) if not a.host_rng else C.VictimRng(123), lookahead_tags=True)
     st = SyntheticStream(ln, B, dev, dist=a.dist, zipf_a=a.zipf_a, seed=123)
     for w in range(a.windows):
         ids = st.window_ids(w, L)

@@ -39,6 +39,12 @@ WORKLOADS = {
 }
 
 
+def log(msg):
+    if os.environ.get("CDLRM_BENCH_LOG", "1") != "0":
+        sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')} rank {os.environ.get('RANK', '0')}] {msg}\n")
+        sys.stderr.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -267,6 +273,7 @@ def gpu_run(a, wl, ln_emb):
 
     # -- master tables in page-locked host memory (one copy per box, shared by the ranks) --------
     t0 = time.time()
+    log(f"start: world {world}, {T} tables, master {sum(ln_emb) * d * 4 / 1e9:.1f} GB")
     if world == 1:
         master = Embedding_Table_Group(d, np.asarray(ln_emb), init="device")
     else:
@@ -276,7 +283,9 @@ def gpu_run(a, wl, ln_emb):
         dist.barrier()
         if rank != 0:
             master = Embedding_Table_Group(d, np.asarray(ln_emb), init=f"shm:{prefix}:attach")
+    log(f"master tables ready ({time.time() - t0:.1f} s)")
     tr = Trainer(args, d, np.asarray(ln_emb), ln_bot, ln_top, master, rank=rank, world=world, device=dev)
+    log(f"trainer ready ({time.time() - t0:.1f} s)")
     if world > 1:
         dist.barrier()
         if rank == 0:
@@ -341,6 +350,7 @@ def gpu_run(a, wl, ln_emb):
     # first window: plan + install (untimed set-up), look-ahead plan of window 1 starts
     prepare(0)
     tr.install_window()
+    log("window 0 installed")
     j = 0
     for _ in range(3):                 # eager steps: lazy initialisation (cuBLAS handles, scratch)
         one_step(j)
@@ -348,6 +358,7 @@ def gpu_run(a, wl, ln_emb):
     if not a.no_graph:                 # capture one whole step; no plan thread is running right now
         ids0, X0, Y0 = window(0)
         tr.capture_graph(X0[:lb], lS_o, ids0[:, :lb], Y0[:lb])
+    log("graph captured" if not a.no_graph else "eager mode")
     prepare(1)
     for _ in range(max(W - 3, 0)):
         one_step(j)
@@ -355,6 +366,7 @@ def gpu_run(a, wl, ln_emb):
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
+    log("warm-up done, timing")
     sampler = ClockSampler(local_rank) if rank == 0 else None
     lib.cdlrm_prof_launches(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -377,6 +389,7 @@ def gpu_run(a, wl, ln_emb):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if sampler else None
+    log(f"timed region done: {ms / K:.3f} ms/step")
     value = K * lb * world / (ms / 1000.0)
 
     # -- end to end through the public API with host buffers ---------------------------------------
@@ -416,7 +429,7 @@ def gpu_run(a, wl, ln_emb):
 
     # -- per-kernel durations (CUDA events around every launch of the library) ------------------
     roof = kernels = None
-    if rank == 0:
+    if True:    # every rank takes these steps (they contain collectives); rank 0 reports
         NK = lib.cdlrm_prof_num_kernels()
         lib.cdlrm_prof_enable(1)
         nprof = 0

@@ -112,7 +112,14 @@ class PlanRecord:
     """Decisions for one window (all device tensors are concatenated over tables; the
     lists of table k start at ``off[k]``)."""
     __slots__ = ("uniq", "hits", "dropped", "rows", "E", "F", "off", "evict_ids", "evict_slots",
-                 "evict_primary", "fill_ids", "fill_slots", "event")
+                 "evict_primary", "fill_ids", "fill_slots", "event",
+                 # look-ahead staging (WindowPlanner.stage / install_staged)
+                 "L", "loser_off", "loser_ids", "loser_stage", "fill_stage", "fill_soff", "evict_stage",
+                 "staged", "wb_done")
+
+    def loser_list(self, k):
+        o, n = self.loser_off[k], self.L[k]
+        return self.loser_ids[o:o + n]
 
     def evict_list(self, k):
         o, e = self.off[k], self.E[k]
@@ -143,6 +150,10 @@ class WindowPlanner:
         check(lib.cdlrm_plan_bind_workspace(self.ctx, _vp(base), nbytes, self.window_len))
         self._h_counts = torch.zeros(self.T * 4, dtype=torch.int64).pin_memory()
         self._h_counts2 = torch.zeros(self.T * 2, dtype=torch.int64).pin_memory()
+        self._h_counts3 = torch.zeros(self.T, dtype=torch.int64).pin_memory()
+        self.collect_losers = False      # also list the window's un-cached ids (for the HBM loser store)
+        self._bufs = {}                  # persistent grow-only staging buffers (no cudaMalloc per window)
+        self._stage_no = 0
         self.plan_tags = None
         if lookahead_tags:
             self.enable_lookahead_tags()
@@ -226,9 +237,123 @@ class WindowPlanner:
             rec.E = c2[:, 0].tolist()
             rec.F = c2[:, 1].tolist()
             del q_host
+            rec.L = rec.loser_ids = rec.loser_off = None
+            if self.collect_losers:
+                cap = [rec.dropped[k] + rec.rows[k] for k in range(self.T)]
+                rec.loser_off = [0] * self.T
+                for k in range(1, self.T):
+                    rec.loser_off[k] = rec.loser_off[k - 1] + cap[k - 1]
+                rec.loser_ids = torch.empty(max(sum(cap), 1), dtype=torch.int64, device=self.dev)
+                check(lib.cdlrm_plan_losers(self.ctx, _lib.i64_array(rec.uniq), _lib.i64_array(rec.loser_off),
+                                            _vp(rec.loser_ids.data_ptr()), _vp(self._h_counts3.data_ptr()), _sp(s)))
+                s.synchronize()
+                rec.L = self._h_counts3.clone().tolist()
             self.last_timing = {"phase_a_s": round(t_b - t_a, 4), "rng_s": round(t_c - t_b, 4),
                                 "phase_b_s": round(_t.perf_counter() - t_c, 4)}
         rec.event = None
+        rec.staged = rec.wb_done = rec.fill_stage = rec.loser_stage = rec.evict_stage = None
+        return rec
+
+    def _buf(self, name, rows):
+        """Persistent [rows, dim] fp32 staging buffer, grown (x1.25) only when a window needs more:
+        allocation inside the steady state would synchronise the device."""
+        b = self._bufs.get(name)
+        if b is None or b.shape[0] < rows:
+            b = None
+            self._bufs[name] = None
+            b = torch.empty(int(rows * 1.25) + 16, self.dim, dtype=torch.float32, device=self.dev)
+            self._bufs[name] = b
+        return b
+
+    # -- look-ahead staging -------------------------------------------------------------------
+    def stage(self, rec):
+        """Prefetch, on the planner's stream, everything window w+1 needs from the host master
+        while window w still trains: the rows of the fill list and (with ``collect_losers``) the
+        rows of the ids that stay un-cached, gathered zero-copy over PCIe into HBM staging
+        buffers.  Exact under the sequential schedule: none of these ids
+        is cached during window w, so their master rows cannot change before the boundary, and
+        the write-back of the previous boundary precedes these reads in stream order."""
+        s = self.stream
+        d = self.dim
+        with torch.cuda.stream(s):
+            rec.fill_soff = [0] * self.T
+            for k in range(1, self.T):
+                rec.fill_soff[k] = rec.fill_soff[k - 1] + rec.F[k - 1]
+            rec.fill_stage = self._buf("fill", max(sum(rec.F), 1))
+            for k in range(self.T):
+                if rec.F[k]:
+                    ids, _slots = rec.fill_list(k)
+                    check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(ids.data_ptr()), rec.F[k],
+                                                       _vp(rec.fill_stage[rec.fill_soff[k]:].data_ptr()), _sp(s)))
+            if rec.L is not None:
+                # two loser stores alternate: the previous window's is read by the forward until the boundary
+                self._stage_no += 1
+                rec.loser_stage = self._buf("loser%d" % (self._stage_no & 1), max(rec.loser_off[-1] + rec.L[-1], 1))
+                for k in range(self.T):
+                    if rec.L[k]:
+                        o = rec.loser_off[k]
+                        check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(rec.loser_ids[o:].data_ptr()), rec.L[k],
+                                                           _vp(rec.loser_stage[o:].data_ptr()), _sp(s)))
+            rec.staged = torch.cuda.Event()
+            rec.staged.record(s)
+        return rec
+
+    def install_staged(self, rec, write_master=True, average_on_writeback=False, stream=None):
+        """Window boundary with staged data: on ``stream`` (default: current) the evicted rows are
+        copied HBM->HBM into a write-back buffer, the fills come HBM->HBM from the staging buffer
+        and the loser store is switched; the write-back to the host master then runs on the
+        planner's stream beside the next window's training steps."""
+        s = stream or torch.cuda.current_stream(self.dev)
+        d = self.dim
+        if rec.staged is None:
+            self.stage(rec)
+        s.wait_event(rec.staged)
+        for t in (rec.evict_ids, rec.evict_slots, rec.evict_primary, rec.fill_ids, rec.fill_slots, rec.fill_stage,
+                  rec.loser_ids, rec.loser_stage):
+            if t is not None and s != self.stream:
+                t.record_stream(s)
+        with torch.cuda.stream(s):
+            eoff = [0] * self.T
+            for k in range(1, self.T):
+                eoff[k] = eoff[k - 1] + rec.E[k - 1]
+            # (the write-back that last read this buffer precedes rec.staged on the planner stream)
+            rec.evict_stage = self._buf("evict", max(sum(rec.E), 1))
+            for k in range(self.T):
+                if rec.E[k]:
+                    ids, slots, prim = rec.evict_list(k)
+                    check(lib.cdlrm_move_evict(self.ctx, k, _vp(ids.data_ptr()), _vp(slots.data_ptr()),
+                                               _vp(prim.data_ptr()), rec.E[k],
+                                               _vp(rec.evict_stage[eoff[k]:].data_ptr()), 0, 0, _sp(s)))
+            for k in range(self.T):
+                if rec.F[k]:
+                    ids, slots = rec.fill_list(k)
+                    check(lib.cdlrm_move_fill(self.ctx, k, _vp(ids.data_ptr()), _vp(slots.data_ptr()), rec.F[k],
+                                              _vp(rec.fill_stage[rec.fill_soff[k]:].data_ptr()), None, _sp(s)))
+            if rec.L is not None:
+                check(lib.cdlrm_ctx_bind_losers(
+                    self.ctx,
+                    _lib.ptr_array([rec.loser_ids[rec.loser_off[k]:].data_ptr() if rec.L[k] else 0
+                                    for k in range(self.T)]),
+                    _lib.ptr_array([rec.loser_stage[rec.loser_off[k]:].data_ptr() if rec.L[k] else 0
+                                    for k in range(self.T)]),
+                    _lib.i64_array(rec.L), _sp(s)))
+            else:
+                check(lib.cdlrm_ctx_bind_losers(self.ctx, None, None, None, _sp(s)))
+            moved = torch.cuda.Event()
+            moved.record(s)
+        ws = self.stream
+        ws.wait_event(moved)       # later planner-stream work (next prefetch) may reuse the staging buffers
+        if write_master and sum(rec.E):
+            rec.evict_stage.record_stream(ws)
+            with torch.cuda.stream(ws):
+                for k in range(self.T):
+                    if rec.E[k]:
+                        ids, _slots, prim = rec.evict_list(k)
+                        check(lib.cdlrm_move_scatter_master2(self.ctx, k, _vp(ids.data_ptr()), _vp(prim.data_ptr()),
+                                                             rec.E[k], _vp(rec.evict_stage[eoff[k]:].data_ptr()),
+                                                             int(average_on_writeback), _sp(ws)))
+        rec.wb_done = torch.cuda.Event()
+        rec.wb_done.record(self.stream)
         return rec
 
     # -- install ---------------------------------------------------------------------------

@@ -50,7 +50,17 @@ struct PlanTable {
     uint32_t* bitmap;   // n_rows bits
     int64_t* uniq;      // [umax]
     int32_t* surv;      // [umax] survivor r -> index into uniq
+    uint8_t* state;     // [umax] per-unique state: hit way, 255 = miss (not cached), 254 = miss that won a slot
     int64_t umax;
+};
+
+// Loser store of one table: the window's ids that are NOT cached after the install (lost a
+// contested slot, or dropped because their set was fully pinned), ascending, with a copy of
+// their master rows staged in HBM; the forward serves these misses from HBM instead of PCIe.
+struct LoserDesc {
+    const int64_t* ids;
+    const float* rows;
+    int64_t n;
 };
 
 struct cdlrm_ctx {
@@ -65,11 +75,13 @@ struct cdlrm_ctx {
     uint32_t* d_missmap = nullptr;  // [T][ceil(max_idx/32)] forward miss bitmap
     int64_t scratch_max_idx = 0;
     uint32_t* d_flags = nullptr;    // sticky error flags
+    LoserDesc* d_losers = nullptr;  // [T] (device), updated in stream order by cdlrm_ctx_bind_losers
+    LoserDesc* h_losers = nullptr;  // [2][T] pinned staging for the async update
+    int losers_flip = 0;
     // planner
     std::vector<PlanTable> ptabs;
     PlanTable* d_ptabs = nullptr;
     int64_t plan_window_len = 0;
-    uint8_t* p_state = nullptr;     // [umax_max] per-unique state (way or miss)
     std::vector<unsigned long long*> pins;  // per table [num_sets] pin masks of the window being planned
     int32_t* p_blocksum2 = nullptr; // second tile-sum array
     int32_t* p_blocksum = nullptr;  // [nblk_max + 1]

@@ -91,6 +91,8 @@ extern "C" int cdlrm_ctx_destroy(cdlrm_ctx* c) {
     cudaFree(c->d_tabs);
     cudaFree(c->d_flags);
     cudaFree(c->d_missmap);
+    cudaFree(c->d_losers);
+    if (c->h_losers) cudaFreeHost(c->h_losers);
     cudaFree(c->p_counts);
     cudaFree(c->d_ptabs);
     delete c;

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(MISS_NT) fwd_miss_kernel(const TableDesc* __re
                                                             const int64_t* __restrict__ ids, int64_t ld_ids, int n_idx,
                                                             int32_t* __restrict__ slots, int64_t ld_slots,
                                                             const uint32_t* __restrict__ missmap, int words, int wpc,
+                                                            const LoserDesc* __restrict__ losers,
                                                             float* __restrict__ out, int64_t ld_out,
                                                             int32_t* __restrict__ n_miss, uint32_t* __restrict__ flags,
                                                             int dim, int ways, int64_t aux_rows) {
@@ -171,6 +172,14 @@ __global__ void __launch_bounds__(MISS_NT) fwd_miss_kernel(const TableDesc* __re
     const float* __restrict__ master = T.master;
     const int64_t aux_base = T.num_sets * ways;
     const int cpr = dim / VEC;
+    // loser store of the installed window: ascending ids + their master rows staged in HBM
+    const int64_t* __restrict__ l_ids = nullptr;
+    const float* __restrict__ l_rows = nullptr;
+    int64_t l_n = 0;
+    if (losers) {
+        const LoserDesc L = losers[tb + t];
+        l_ids = L.ids; l_rows = L.rows; l_n = L.n;
+    }
     // warp `warp` owns words w_lo + warp, w_lo + warp + NW, ... ; its running ordinal starts at the
     // popcount of the range's words that precede each of them, recomputed per word (ranges are short)
     for (int w = w_lo + warp; w < w_hi; w += NW) {
@@ -189,7 +198,14 @@ __global__ void __launch_bounds__(MISS_NT) fwd_miss_kernel(const TableDesc* __re
                 atomicOr(flags, 1u);                 // IndexError in the reference
             } else {
                 aux_l = aux_base + ord;
-                src_l = master + __ldg(ids + (int64_t)t * ld_ids + j) * dim;
+                const int64_t id = __ldg(ids + (int64_t)t * ld_ids + j);
+                int64_t lo = 0, hi = l_n;              // first index with l_ids[idx] >= id
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (__ldg(l_ids + mid) < id) lo = mid + 1; else hi = mid;
+                }
+                if (lo < l_n && __ldg(l_ids + lo) == id) src_l = l_rows + lo * dim;   // HBM
+                else src_l = master + id * dim;                                        // zero-copy PCIe
                 slots[(int64_t)t * ld_slots + j] = (int32_t)aux_l;
             }
         }
@@ -714,12 +730,13 @@ extern "C" int cdlrm_embed_fwd(cdlrm_ctx* c, int tb, int tc, const int64_t* ids,
 #undef FUSED_G
 #undef LAUNCH_FUSED
     CU_CHECK(cudaGetLastError());
-    // K2: a CTA owns at most 64 bitmap words; at most 64 CTAs per table
-    int mctas = (words + 63) / 64;
-    if (mctas > 64) mctas = 64;
+    // K2: one warp per bitmap word (8 words per CTA) up to 256 CTAs per table, so that the dependent
+    // chain of a miss (bitmap -> id -> loser search -> row) is paid once, by all warps at the same time
+    int mctas = (words + MISS_NT / 32 - 1) / (MISS_NT / 32);
+    if (mctas > 256) mctas = 256;
     const int wpc = (words + mctas - 1) / mctas;
     dim3 mgrid(mctas, tc);
-#define LAUNCH_MISS(VEC, CP) LAUNCH(K_GATHER, s, (fwd_miss_kernel<VEC, CP><<<mgrid, MISS_NT, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_missmap, words, wpc, out, ld_out, n_miss, c->d_flags, c->dim, c->ways, c->aux)))
+#define LAUNCH_MISS(VEC, CP) LAUNCH(K_GATHER, s, (fwd_miss_kernel<VEC, CP><<<mgrid, MISS_NT, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_missmap, words, wpc, c->d_losers, out, ld_out, n_miss, c->d_flags, c->dim, c->ways, c->aux)))
     if (copy) LAUNCH_MISS(4, true);
     else if (vec == 4) LAUNCH_MISS(4, false);
     else if (vec == 2) LAUNCH_MISS(2, false);

@@ -76,8 +76,10 @@ __global__ void __launch_bounds__(256) rows_kernel(TableDesc T, const int64_t* _
                     dst[u] = T.weight + (int64_t)slots[i] * dim;
                 } else {
                     src[u] = rows + i * dim;
-                    dst2[u] = master + ids[i] * dim;
-                    avg[u] = average != 0;
+                    if (!primary || primary[i]) {   // duplicates carry identical rows: written once
+                        dst2[u] = master + ids[i] * dim;
+                        avg[u] = average != 0;
+                    }
                 }
             }
 #pragma unroll
@@ -158,6 +160,9 @@ int launch_rows(cdlrm_ctx* c, int k, const int64_t* ids, const int32_t* slots, c
 
 }  // namespace
 
+extern "C" int cdlrm_move_scatter_master2(cdlrm_ctx* c, int k, const int64_t* ids, const uint8_t* primary, int64_t n,
+                                          const float* rows, int average, cdlrm_stream stream);
+
 extern "C" int cdlrm_move_evict(cdlrm_ctx* c, int k, const int64_t* evict_ids, const int32_t* evict_slots,
                                 const uint8_t* evict_primary, int64_t n, float* rows_out, int write_master,
                                 int average, cdlrm_stream stream) {
@@ -193,12 +198,40 @@ extern "C" int cdlrm_move_fill(cdlrm_ctx* c, int k, const int64_t* fill_ids, con
 
 extern "C" int cdlrm_move_scatter_master(cdlrm_ctx* c, int k, const int64_t* ids, int64_t n, const float* rows,
                                          int average, cdlrm_stream stream) {
+    return cdlrm_move_scatter_master2(c, k, ids, nullptr, n, rows, average, stream);
+}
+
+extern "C" int cdlrm_move_scatter_master2(cdlrm_ctx* c, int k, const int64_t* ids, const uint8_t* primary, int64_t n,
+                                          const float* rows, int average, cdlrm_stream stream) {
     ARG_CHECK(c && k >= 0 && k < c->T && n >= 0);
     if (n == 0) return CDLRM_OK;
     ARG_CHECK(ids && rows && c->tabs[k].master);
     CU_CHECK(cudaSetDevice(c->device));
-    return launch_rows<5>(c, k, ids, nullptr, nullptr, n, const_cast<float*>(rows), nullptr, 1, average, 1.0f, true,
+    return launch_rows<5>(c, k, ids, nullptr, primary, n, const_cast<float*>(rows), nullptr, 1, average, 1.0f, true,
                           (cudaStream_t)stream);
+}
+
+// Loser store (see LoserDesc): the descriptors reach the device in stream order, so the forward
+// launched after this call on `stream` sees the new store and the ones before it the old one.
+extern "C" int cdlrm_ctx_bind_losers(cdlrm_ctx* c, const int64_t* const* h_ids, const float* const* h_rows,
+                                     const int64_t* h_n, cdlrm_stream stream) {
+    ARG_CHECK(c);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(c->device));
+    if (!c->d_losers) {
+        CU_CHECK(cudaMalloc(&c->d_losers, sizeof(LoserDesc) * c->T));
+        CU_CHECK(cudaMemset(c->d_losers, 0, sizeof(LoserDesc) * c->T));
+        CU_CHECK(cudaHostAlloc(&c->h_losers, sizeof(LoserDesc) * c->T * 4, cudaHostAllocDefault));
+    }
+    LoserDesc* h = c->h_losers + (size_t)(c->losers_flip++ & 3) * c->T;   // 4 updates may be in flight
+    for (int k = 0; k < c->T; ++k) {
+        h[k].ids = h_ids ? h_ids[k] : nullptr;
+        h[k].rows = h_rows ? h_rows[k] : nullptr;
+        h[k].n = (h_ids && h_rows && h_n) ? h_n[k] : 0;
+        ARG_CHECK(h[k].n >= 0 && (h[k].n == 0 || (h[k].ids && h[k].rows)));
+    }
+    CU_CHECK(cudaMemcpyAsync(c->d_losers, h, sizeof(LoserDesc) * c->T, cudaMemcpyHostToDevice, s));
+    return CDLRM_OK;
 }
 
 extern "C" int cdlrm_host_register(int device, void* h_ptr, int64_t bytes, void** dev_ptr) {

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(256) lists_kernel(int64_t R, const int64_t* __
                                                     const int32_t* __restrict__ surv,
                                                     const int32_t* __restrict__ slot, const int64_t* __restrict__ old,
                                                     int32_t* __restrict__ claim, uint8_t* __restrict__ flag,
+                                                    uint8_t* __restrict__ state,
                                                     int32_t* __restrict__ bsE, int32_t* __restrict__ bsF,
                                                     int64_t* __restrict__ tags, int64_t S, int ways,
                                                     int64_t* __restrict__ evict_ids, int32_t* __restrict__ evict_slots,
@@ -233,7 +234,9 @@ __global__ void __launch_bounds__(256) lists_kernel(int64_t R, const int64_t* __
             ++oe;
         }
         if (f[qq] & 2) {
-            const int64_t id = uniq[surv[r]];
+            const int32_t u = surv[r];
+            const int64_t id = uniq[u];
+            state[u] = 254;   // cached after this install: not a loser
             fill_ids[of] = id;
             fill_slots[of] = sl;
             ++of;
@@ -241,6 +244,32 @@ __global__ void __launch_bounds__(256) lists_kernel(int64_t R, const int64_t* __
             tags[s * ways + way] = id;  // main_no_ddp.py:204
         }
         claim[sl] = -1;  // leave the claim array clean for the next table / window
+    }
+}
+
+// ---- losers: unique ids of the window that stay un-cached (state 255), ascending ------------------
+template <bool EMIT>
+__global__ void __launch_bounds__(256) losers_kernel(const int64_t* __restrict__ uniq, int64_t U,
+                                                     const uint8_t* __restrict__ state,
+                                                     int32_t* __restrict__ blocksum, int64_t* __restrict__ out) {
+    __shared__ int s_w[33];
+    const int64_t u0 = (int64_t)blockIdx.x * TILE + threadIdx.x * 4;
+    bool lose[4];
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        lose[q] = (u0 + q < U) && state[u0 + q] == 255;
+        c += lose[q];
+    }
+    int total;
+    const int ex = block_excl_scan<256>(c, s_w, total);
+    if (!EMIT) {
+        if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
+    } else {
+        int64_t off = (int64_t)blocksum[blockIdx.x] + ex;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (lose[q]) out[off++] = uniq[u0 + q];
     }
 }
 
@@ -282,6 +311,7 @@ size_t carve_workspace(const cdlrm_ctx* c, int64_t N, char* base, std::vector<Pl
         p.bitmap = cv.take<uint32_t>(words);
         p.uniq = cv.take<int64_t>(umax);
         p.surv = cv.take<int32_t>(umax);
+        p.state = cv.take<uint8_t>(umax);
         p.umax = umax;
         unsigned long long* pin = cv.take<unsigned long long>(t.num_sets);
         if (pt) pt->push_back(p);
@@ -293,7 +323,6 @@ size_t carve_workspace(const cdlrm_ctx* c, int64_t N, char* base, std::vector<Pl
     }
     const int64_t items_max = umax_max > words_max ? umax_max : words_max;
     const int64_t nblk = (items_max + TILE - 1) / TILE + 1;
-    uint8_t* state = cv.take<uint8_t>(umax_max);
     int32_t* bs1 = cv.take<int32_t>(nblk);
     int32_t* bs2 = cv.take<int32_t>(nblk);
     int32_t* claim = cv.take<int32_t>(rows_max);
@@ -301,7 +330,6 @@ size_t carve_workspace(const cdlrm_ctx* c, int64_t N, char* base, std::vector<Pl
     int64_t* old = cv.take<int64_t>(umax_max);
     uint8_t* flag = cv.take<uint8_t>(umax_max);
     if (out) {
-        out->p_state = state;
         out->p_blocksum = bs1;
         out->p_claim = claim;
         out->p_slot = slot;
@@ -432,7 +460,7 @@ static int plan_impl(cdlrm_ctx* c, const int64_t* win_ids, int64_t ld, int64_t n
         CU_CHECK(cudaMemsetAsync(pins[k], 0, sizeof(unsigned long long) * t.num_sets, s));
         if (ubound > 0) {
             const int g5 = (int)((ubound + 255) / 256);
-#define LAUNCH_PP(GW) LAUNCH(K_PLAN_PROBE, s, plan_probe_kernel<GW><<<g5, 256, 0, s>>>(p.uniq, ck + CNT_U, t.plan_tags, t.num_sets, c->ways, pins[k], c->p_state, ck + CNT_HIT))
+#define LAUNCH_PP(GW) LAUNCH(K_PLAN_PROBE, s, plan_probe_kernel<GW><<<g5, 256, 0, s>>>(p.uniq, ck + CNT_U, t.plan_tags, t.num_sets, c->ways, pins[k], p.state, ck + CNT_HIT))
             switch (gw) {
                 case 1: LAUNCH_PP(1); break;
                 case 2: LAUNCH_PP(2); break;
@@ -443,9 +471,9 @@ static int plan_impl(cdlrm_ctx* c, const int64_t* win_ids, int64_t ld, int64_t n
             }
 #undef LAUNCH_PP
             const int nblk = (int)((ubound + TILE - 1) / TILE);
-            LAUNCH(K_PLAN_SURV, s, surv_kernel<false><<<nblk, 256, 0, s>>>(p.uniq, ck + CNT_U, c->p_state, pins[k], t.num_sets, full, c->p_blocksum, p.surv, ck + CNT_DROP));
+            LAUNCH(K_PLAN_SURV, s, surv_kernel<false><<<nblk, 256, 0, s>>>(p.uniq, ck + CNT_U, p.state, pins[k], t.num_sets, full, c->p_blocksum, p.surv, ck + CNT_DROP));
             LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(c->p_blocksum, nblk, ck + CNT_ROWS));
-            LAUNCH(K_PLAN_SURV, s, surv_kernel<true><<<nblk, 256, 0, s>>>(p.uniq, ck + CNT_U, c->p_state, pins[k], t.num_sets, full, c->p_blocksum, p.surv, ck + CNT_DROP));
+            LAUNCH(K_PLAN_SURV, s, surv_kernel<true><<<nblk, 256, 0, s>>>(p.uniq, ck + CNT_U, p.state, pins[k], t.num_sets, full, c->p_blocksum, p.surv, ck + CNT_DROP));
         }
         CU_CHECK(cudaGetLastError());
     }
@@ -503,10 +531,10 @@ static int phase_b_impl(cdlrm_ctx* c, const float* q, cdlrm_rngdev* rng, uint32_
             }
 #undef LAUNCH_SEL
             const int nblk = (int)((R + TILE - 1) / TILE);
-            LAUNCH(K_PLAN_LISTS, s, lists_kernel<false><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, bsE, bsF, t.plan_tags, t.num_sets, c->ways, nullptr, nullptr, nullptr, nullptr, nullptr));
+            LAUNCH(K_PLAN_LISTS, s, lists_kernel<false><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, p.state, bsE, bsF, t.plan_tags, t.num_sets, c->ways, nullptr, nullptr, nullptr, nullptr, nullptr));
             LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(bsE, nblk, ck + CNT_E));
             LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(bsF, nblk, ck + CNT_F));
-            LAUNCH(K_PLAN_LISTS, s, lists_kernel<true><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, bsE, bsF, t.plan_tags, t.num_sets, c->ways, evict_ids + off, evict_slots + off, evict_primary + off, fill_ids + off, fill_slots + off));
+            LAUNCH(K_PLAN_LISTS, s, lists_kernel<true><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, p.state, bsE, bsF, t.plan_tags, t.num_sets, c->ways, evict_ids + off, evict_slots + off, evict_primary + off, fill_ids + off, fill_slots + off));
             CU_CHECK(cudaGetLastError());
         }
         off += R;
@@ -534,4 +562,38 @@ extern "C" int cdlrm_plan_phase_b_dev(cdlrm_ctx* c, cdlrm_rngdev* rng, uint32_t*
     ARG_CHECK(rng);
     return phase_b_impl(c, nullptr, rng, raw_scratch, raw_draws, h_rows, evict_ids, evict_slots, evict_primary,
                         fill_ids, fill_slots, h_counts2, stream);
+}
+
+// Ascending list of the window's un-cached ids per table (call after phase B on the same
+// stream).  h_uniq[k] = unique count of phase A; the list of table k is written at
+// loser_ids + h_off[k] (capacity dropped_k + rows_k); h_counts3[k] = its length.
+extern "C" int cdlrm_plan_losers(cdlrm_ctx* c, const int64_t* h_uniq, const int64_t* h_off, int64_t* loser_ids,
+                                 int64_t* h_counts3, cdlrm_stream stream) {
+    ARG_CHECK(c && h_uniq && h_off && h_counts3);
+    if (c->ptabs.empty()) {
+        cdlrm_set_error("planner workspace not bound");
+        return CDLRM_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(c->device));
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(c->p_counts);
+    for (int k = 0; k < c->T; ++k) {
+        const PlanTable& p = c->ptabs[k];
+        const int64_t U = h_uniq[k];
+        ARG_CHECK(U >= 0 && U <= p.umax);
+        unsigned long long* ck = cnt + k * 8 + 6;
+        if (U == 0) {
+            CU_CHECK(cudaMemsetAsync(ck, 0, sizeof(unsigned long long), s));
+            continue;
+        }
+        ARG_CHECK(loser_ids);
+        const int nblk = (int)((U + TILE - 1) / TILE);
+        LAUNCH(K_PLAN_LISTS, s, losers_kernel<false><<<nblk, 256, 0, s>>>(p.uniq, U, p.state, c->p_blocksum, nullptr));
+        LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(c->p_blocksum, nblk, ck));
+        LAUNCH(K_PLAN_LISTS, s, losers_kernel<true><<<nblk, 256, 0, s>>>(p.uniq, U, p.state, c->p_blocksum, loser_ids + h_off[k]));
+    }
+    CU_CHECK(cudaGetLastError());
+    for (int k = 0; k < c->T; ++k)
+        CU_CHECK(cudaMemcpyAsync(h_counts3 + k, c->p_counts + k * 8 + 6, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    return CDLRM_OK;
 }

@@ -310,6 +310,9 @@ class Trainer:
         self.planner = WindowPlanner(self.cache_group, emb_tables, args.lookahead * args.mini_batch_size,
                                      rng=VictimRngDevice(args.numpy_rand_seed, self.dev), stream=self.side,
                                      lookahead_tags=True)
+        self.planner.collect_losers = True     # un-cached ids of a window are served from an HBM loser store
+        self._host_group = dist.new_group(backend="gloo") if world > 1 else None   # plan-thread barrier
+        self._installed = None
         self._plan_q = queue.Queue()
         self._plan_thread = None
         self.steps_since_agg = 0
@@ -330,7 +333,15 @@ class Trainer:
             torch.cuda.set_device(self.dev)
             self.side.wait_event(ev)
             try:
-                self._plan_q.put(self.planner.plan(win_ids=win_ids))
+                rec = self.planner.plan(win_ids=win_ids)
+                if self.world > 1:
+                    # the prefetch below reads master rows: rank 0's write-back of the previous
+                    # boundary (asynchronous, on its planner stream) must have landed first
+                    prev_rec = self._installed
+                    if self.rank == 0 and prev_rec is not None and prev_rec.wb_done is not None:
+                        prev_rec.wb_done.synchronize()
+                    dist.barrier(group=self._host_group)
+                self._plan_q.put(self.planner.stage(rec))
             except Exception as e:  # surfaced by install_window
                 self._plan_q.put(e)
 
@@ -347,13 +358,11 @@ class Trainer:
         if self.world > 1:
             broadcast_and_aggregate(self.cache_group, None, self.rank, self.args.table_agg_op)
             self.steps_since_agg = 0
-        self.planner.install(rec, write_master=(self.rank == 0),
-                             average_on_writeback=self.args.average_on_writeback)
-        self._installed = rec            # keep the lists alive until the next boundary
-        if self.world > 1:
-            # rank 0's write-back must be visible to every rank's next master reads
-            torch.cuda.current_stream(self.dev).synchronize()
-            dist.barrier()
+        # evict / fill are HBM->HBM against the staging buffers the plan thread filled during the
+        # previous window; the host write-back runs on the planner stream beside the next steps
+        self.planner.install_staged(rec, write_master=(self.rank == 0),
+                                    average_on_writeback=self.args.average_on_writeback)
+        self._installed = rec            # keeps the loser store of this window alive
         self.caching_overhead.append(time.perf_counter() - t0)
         return rec
 

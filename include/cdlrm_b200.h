@@ -163,6 +163,18 @@ int cdlrm_plan_phase_b_dev(cdlrm_ctx* ctx, cdlrm_rngdev* rng, uint32_t* raw_scra
                            int64_t* evict_ids, int32_t* evict_slots, uint8_t* evict_primary,
                            int64_t* fill_ids, int32_t* fill_slots,
                            int64_t* h_counts2, cdlrm_stream stream);
+/* Loser list: ascending ids of the window that are NOT cached after the install (lost a contested
+ * slot, main_no_ddp.py:204 last-wins, or dropped because their set was fully pinned, :173-180).
+ * Call after phase B on the same stream.  h_uniq[k] = unique count of phase A; the list of table k
+ * is written at loser_ids + h_off[k] (capacity dropped_k + rows_k); h_counts3[k] = its length. */
+int cdlrm_plan_losers(cdlrm_ctx* ctx, const int64_t* h_uniq, const int64_t* h_off, int64_t* loser_ids,
+                      int64_t* h_counts3, cdlrm_stream stream);
+/* Loser store: per table the ascending loser ids and a copy of their master rows staged in HBM
+ * (h_* are host arrays of device pointers / counts; NULL clears).  The forward's miss path
+ * (model_no_ddp.py:176-179) then reads those rows from HBM instead of the host master; ids that
+ * are not in the store still go to the master.  Takes effect in stream order. */
+int cdlrm_ctx_bind_losers(cdlrm_ctx* ctx, const int64_t* const* h_ids, const float* const* h_rows,
+                          const int64_t* h_n, cdlrm_stream stream);
 /* unique ids of table k found by the last phase A (device pointer into the
  * workspace, ascending, h_counts[k*4] entries) */
 const int64_t* cdlrm_plan_unique_ptr(const cdlrm_ctx* ctx, int table);
@@ -182,6 +194,10 @@ int cdlrm_move_evict(cdlrm_ctx* ctx, int table, const int64_t* evict_ids, const 
  * averaging */
 int cdlrm_move_scatter_master(cdlrm_ctx* ctx, int table, const int64_t* ids, int64_t n, const float* rows,
                               int average_on_writeback, cdlrm_stream stream);
+/* the same with a per-entry primary mask (may be NULL): entries with primary[i] == 0 are skipped
+ * (an evict list keeps duplicates of a slot; they carry identical rows) */
+int cdlrm_move_scatter_master2(cdlrm_ctx* ctx, int table, const int64_t* ids, const uint8_t* primary, int64_t n,
+                               const float* rows, int average_on_writeback, cdlrm_stream stream);
 /* rows_out[i] = master[k][ids[i]]: Embedding_Table_Group.fetch_unique_idx_slices,
  * model_no_ddp.py:80-87 (zero-copy gather over PCIe when the master is host-pinned) */
 int cdlrm_move_gather_master(cdlrm_ctx* ctx, int table, const int64_t* ids, int64_t n,

@@ -47,10 +47,11 @@ def _run_cuda_trace(cfg, mode):
     lS_o = torch.arange(B).reshape(1, -1).repeat(T, 1)
     torch.manual_seed(seed)
     planner = None
-    if mode in ("fast", "fast_devrng"):
+    if mode in ("fast", "fast_devrng", "staged"):
         cg._ensure_ctx(master)
         rng = C.VictimRng(seed) if mode == "fast" else C.VictimRngDevice(seed, DEV)
         planner = C.WindowPlanner(cg, master, L * B, rng=rng, lookahead_tags=True)
+        planner.collect_losers = mode == "staged"
     step = 0
     for w in range(cfg["n_windows"]):
         win = torch.from_numpy(ids[:, w * L * B:(w + 1) * L * B])
@@ -63,6 +64,23 @@ def _run_cuda_trace(cfg, mode):
             ev_ids = [e[0].numpy() for e in ev]
             ev_rows = [e[1].numpy() for e in ev]
             rng_digest = util.digest(torch.get_rng_state().numpy())
+        elif mode == "staged":
+            # look-ahead staging: fills and loser rows prefetched into HBM, evictions written back
+            # asynchronously, forward misses served from the HBM loser store
+            pr = planner.plan(win_ids=win.to(DEV))
+            planner.stage(pr)
+            planner.install_staged(pr, write_master=True, average_on_writeback=cfg.get("avg_wb", False))
+            torch.cuda.synchronize()
+            eo = np.concatenate([[0], np.cumsum(pr.E)])
+            ev = [(pr.evict_list(k)[0], pr.evict_stage[eo[k]:eo[k] + pr.E[k]]) for k in range(T)]
+            for k in range(T):   # losers = window ids that are not cached now, ascending
+                u = np.unique(win[k].numpy())
+                tags = cg.occupancy_tables[k].cpu().numpy()
+                cached = (tags[u % tags.shape[0]] == u[:, None]).any(1)
+                assert np.array_equal(pr.loser_list(k).cpu().numpy(), u[~cached])
+            uniq_len = pr.uniq
+            ev_ids = [e[0].cpu().numpy() for e in ev]
+            ev_rows = [e[1].cpu().numpy() for e in ev]
         else:
             pr = planner.plan(win_ids=win.to(DEV))
             ev = planner.install(pr, write_master=True, average_on_writeback=cfg.get("avg_wb", False),
@@ -71,6 +89,7 @@ def _run_cuda_trace(cfg, mode):
             uniq_len = pr.uniq
             ev_ids = [e[0].cpu().numpy() for e in ev]
             ev_rows = [e[1].cpu().numpy() for e in ev]
+        if mode != "api":
             rng_digest = None
             for k in range(T):   # the planner's tags and the live tags agree after install
                 assert torch.equal(planner.plan_tags[k], cg.occupancy_tables[k])
@@ -95,7 +114,7 @@ def _run_cuda_trace(cfg, mode):
 
 @pytest.mark.parametrize("name", ["trace_tiny.npz", "trace_pressure.npz", "trace_pressure_avgwb.npz",
                                   "trace_cfg0_small.npz"])
-@pytest.mark.parametrize("mode", ["api", "fast", "fast_devrng"])
+@pytest.mark.parametrize("mode", ["api", "fast", "fast_devrng", "staged"])
 def test_trace_matches_reference_golden(name, mode):
     g = util.load_golden(name)
     cfg = util.golden_cfg(g)

@@ -371,6 +371,9 @@ def gpu_run(a, wl, ln_emb):
     lib.cdlrm_prof_launches(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_boundaries = 0
+    cuprof = os.environ.get("CDLRM_BENCH_CUPROF", "0") == "1"   # ncu --profile-from-start off: timed region only
+    if cuprof:
+        torch.cuda.profiler.start()
     ev0.record()
     for _ in range(K):
         if j % L == 0:
@@ -379,6 +382,8 @@ def gpu_run(a, wl, ln_emb):
         j += 1
     ev1.record()
     torch.cuda.synchronize(dev)
+    if cuprof:
+        torch.cuda.profiler.stop()
     launches = int(lib.cdlrm_prof_launches(0))
     if getattr(tr, "_graph", None) is not None:
         launches += K * tr.graph_launches      # graph replays re-issue the captured launches
@@ -463,7 +468,7 @@ def gpu_run(a, wl, ln_emb):
                 n_single += int((cnt == 1).sum())
                 rows_multi += int(cnt[cnt > 1].sum())
                 slots_multi += int((cnt > 1).sum())
-                chunks_multi += int(((cnt[cnt > 1] + 7) // 8).sum())
+                chunks_multi += int(((cnt[cnt > 1] + 31) // 32).sum())
         n = T * lb
         nfe = T + 1
         npair = nfe * (nfe - 1) // 2
@@ -473,8 +478,10 @@ def gpu_run(a, wl, ln_emb):
             # bitmap read; per miss: id + slot + master row (PCIe) + aux row + out row
             "embed_miss": n // 8 + n_miss * (8 + 4 + 12 * d),
             "bwd_plan": n * (4 + 12),
-            "bwd_sgd": n_single * (16 + 4 * d + 8 * d),
-            "bwd_sgd_multi": chunks_multi * 16 + rows_multi * (4 + 4 * d) + slots_multi * 8 * d,
+            # singles: record + gradient row + weight RMW; multi-row chunks: record, position + gradient row
+            # per contribution, weight RMW per distinct slot
+            "bwd_sgd": n_single * (16 + 4 * d + 8 * d) + chunks_multi * 16 + rows_multi * (4 + 4 * d)
+                       + slots_multi * 8 * d,
             "interact_fwd": lb * (nfe * 4 * d + (d + npair) * 4),
             "interact_bwd": lb * (2 * nfe * 4 * d + (d + npair) * 4),
         }

@@ -65,6 +65,7 @@ struct LoserDesc {
 
 struct cdlrm_ctx {
     int device = 0;
+    int num_sms = 148;
     int T = 0, dim = 0, ways = 0;
     int64_t aux = 0;
     int64_t max_cache_size = 0;  // after find_next_prime

@@ -53,6 +53,7 @@ extern "C" int cdlrm_ctx_create(cdlrm_ctx** out, int device, int T, int dim, int
     CU_CHECK(cudaSetDevice(device));
     cdlrm_ctx* c = new cdlrm_ctx();
     c->device = device;
+    if (cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->num_sms <= 0) c->num_sms = 148;
     c->T = T;
     c->dim = dim;
     c->ways = ways;

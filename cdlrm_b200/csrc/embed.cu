@@ -7,7 +7,7 @@
 
 namespace {
 
-constexpr int CH = 8;           // max contributions merged by one chunk in the backward
+constexpr int CH = 32;          // max contributions merged by one chunk in the backward
 
 template <int VEC> struct VecT;
 template <> struct VecT<4> { using type = float4; };
@@ -502,107 +502,128 @@ __global__ void __launch_bounds__(PLAN_NT, 1) bwd_plan_kernel(const TableDesc* _
 // {slot, start, len|flags, first position} is one 16-byte load.  acc = sum of the chunk's
 // upstream gradient rows (ascending position: deterministic), then
 // weight[slot] += -lr * acc -- a plain read-modify-write when the chunk owns the slot,
-// a vector red otherwise (only slots with more than CH contributions).
-// Fast path (float4 rows, dim <= 128): a warp takes 32 consecutive chunk records with one
-// coalesced load and groups of G lanes work on U chunks at a time, so that U gradient
-// rows and U weight rows are in flight per group.
+// a vector red otherwise (only slots with more than CH contributions: the hot rows of
+// a skewed stream and the tiny tables, where one red per CH rows keeps the same-address
+// traffic at the L2 low).
+// Fast path (float4 rows, dim <= 128): ONE persistent launch over all tables.  The work
+// is flattened into warp units -- first the multi-row chunks of every table (the long
+// ones, so that they do not form the tail), then the singles, RPW records per unit -- and
+// the warps of the grid stride over the units; no CTA is launched for work that does not
+// exist.  Groups of G lanes own a row (G = dim/4 rounded up to a power of two), CHB rows
+// are in flight per group.
 // ------------------------------------------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(256, 4) bwd_sgd_single_kernel(const TableDesc* __restrict__ tabs, int tb,
-                                                                PlanView pv, int n_idx, int j0, int sub, int nsub,
-                                                                const int32_t* __restrict__ bag_ids, int64_t ld_bag,
-                                                                const float* __restrict__ d_out, int64_t ld_dout,
-                                                                int64_t row_stride, float lr, int dim) {
-    // singles: weight[slot] = fma(-lr, d_out[pos], weight[slot]) -- a pure streaming RMW
-    // a warp takes RPW records: few enough that even a short singles list spreads over all SMs
-    constexpr int NGW = 32 / G;
-    constexpr int RPW = NGW > 8 ? NGW : 8;
-    constexpr int ITERS = RPW / NGW;
-    constexpr int U = ITERS < 4 ? ITERS : 4;
-    const int t = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nch = pv.n_chunks[(t * nsub + sub) * 2];
-    const int c0 = (blockIdx.x * 8 + warp) * RPW;
-    if (c0 >= nch) return;
-    const int64_t obase = (int64_t)t * n_idx + j0;
-    const int gl = lane % G, g = lane / G;
-    const int cpr = dim >> 2;
-    const TableDesc& T = tabs[tb + t];
-    float* __restrict__ weight = T.weight;
-    const float* gbase = d_out + (int64_t)t * ld_dout;
-    int slot_l = -1, pos_l = 0;
-    if (lane < RPW && c0 + lane < nch) {
-        const int4 rec = pv.chunks[obase + c0 + lane];
-        slot_l = rec.x;
-        pos_l = bag_ids ? bag_ids[(int64_t)t * ld_bag + rec.w] : rec.w;
-        if (T.dirty) atomicOr(T.dirty + (slot_l >> 5), 1u << (slot_l & 31));
-    }
-    const bool act = gl < cpr;
-#pragma unroll 1
-    for (int it0 = 0; it0 < ITERS; it0 += U) {
-        int slot[U], pos[U];
-        float4 gv[U], wv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int cc = (it0 + u) * NGW + g;
-            slot[u] = __shfl_sync(0xffffffffu, slot_l, cc);
-            pos[u] = __shfl_sync(0xffffffffu, pos_l, cc);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (slot[u] >= 0 && act) {
-                gv[u] = reinterpret_cast<const float4*>(gbase + (int64_t)pos[u] * row_stride)[gl];
-                wv[u] = reinterpret_cast<const float4*>(weight + (int64_t)slot[u] * dim)[gl];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (slot[u] >= 0 && act)
-                reinterpret_cast<float4*>(weight + (int64_t)slot[u] * dim)[gl] = vfma(-lr, gv[u], wv[u]);
-    }
-}
+constexpr int CHB = 8;          // gradient rows in flight per lane group
+constexpr int APPLY_NT = 256;
 
 template <int G>
-__global__ void __launch_bounds__(256) bwd_sgd_multi_kernel(const TableDesc* __restrict__ tabs, int tb,
-                                                            PlanView pv, int n_idx, int j0, int n, int sub, int nsub,
-                                                            const int32_t* __restrict__ bag_ids, int64_t ld_bag,
-                                                            const float* __restrict__ d_out, int64_t ld_dout,
-                                                            int64_t row_stride, float lr, int dim) {
-    // multis: up to CH gradient rows of one slot are loaded together, summed in ascending
-    // position and applied with a plain RMW when the chunk is the slot's only chunk, else a red
-    constexpr int NG = 256 / G;
-    const int t = blockIdx.y;
-    const int gl = threadIdx.x % G, group = threadIdx.x / G;
-    const int m = blockIdx.x * NG + group;
-    if (m >= pv.n_chunks[(t * nsub + sub) * 2 + 1]) return;
-    const int64_t obase = (int64_t)t * n_idx + j0;
-    const int64_t tbase = (int64_t)t * n_idx;
-    const int4 rec = pv.chunks[obase + n - 1 - m];
-    const int len = rec.z & 0xff;
-    const int32_t* bag = bag_ids ? bag_ids + (int64_t)t * ld_bag : nullptr;
-    const float* gbase = d_out + (int64_t)t * ld_dout;
-    const TableDesc& T = tabs[tb + t];
-    if (((rec.z >> 30) & 1) && gl == 0 && T.dirty) atomicOr(T.dirty + (rec.x >> 5), 1u << (rec.x & 31));
-    if (gl >= (dim >> 2)) return;
-    int pp[CH];
-    float4 ga[CH];
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-        pp[i] = i < len ? pv.sorted_pos[tbase + rec.y + i] : 0;
-        if (bag && i < len) pp[i] = bag[pp[i]];
+__global__ void __launch_bounds__(APPLY_NT, 2) bwd_sgd_apply_kernel(const TableDesc* __restrict__ tabs, int tb, int tc,
+                                                                     PlanView pv, int n_idx, int j0, int n, int sub, int nsub,
+                                                                     const int32_t* __restrict__ bag_ids, int64_t ld_bag,
+                                                                     const float* __restrict__ d_out, int64_t ld_dout,
+                                                                     int64_t row_stride, float lr, int dim) {
+    constexpr int NGW = 32 / G;               // rows moved per warp instruction
+    constexpr int RPW = NGW > 8 ? NGW : 8;    // single records per warp unit
+    constexpr int ITERS = RPW / NGW;
+    constexpr int U = ITERS < 4 ? ITERS : 4;
+    extern __shared__ int s_pref[];           // [2*tc + 1] exclusive prefix of the unit counts
+    for (int i = threadIdx.x; i < 2 * tc; i += APPLY_NT) {
+        const int t = i < tc ? i : i - tc;
+        const int cnt = pv.n_chunks[(t * nsub + sub) * 2 + (i < tc ? 1 : 0)];
+        s_pref[i + 1] = i < tc ? (cnt + NGW - 1) / NGW : (cnt + RPW - 1) / RPW;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        s_pref[0] = 0;
+        for (int i = 1; i <= 2 * tc; ++i) { run += s_pref[i]; s_pref[i] = run; }
+    }
+    __syncthreads();
+    const int total = s_pref[2 * tc];
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G, g = lane / G;
+    const int cpr = dim >> 2;
+    const bool act = gl < cpr;
+    const int nwarps = gridDim.x * (APPLY_NT / 32);
+    for (int u = blockIdx.x * (APPLY_NT / 32) + (threadIdx.x >> 5); u < total; u += nwarps) {
+        int lo = 0, hi = 2 * tc;              // segment: s_pref[seg] <= u < s_pref[seg + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_pref[mid] <= u) lo = mid; else hi = mid;
+        }
+        const int seg = lo, local = u - s_pref[seg];
+        const int t = seg < tc ? seg : seg - tc;
+        const TableDesc& T = tabs[tb + t];
+        float* __restrict__ weight = T.weight;
+        const float* gbase = d_out + (int64_t)t * ld_dout;
+        const int32_t* bag = bag_ids ? bag_ids + (int64_t)t * ld_bag : nullptr;
+        const int64_t obase = (int64_t)t * n_idx + j0;
+        if (seg < tc) {
+            // ---- multi-row chunk: one per lane group ------------------------------------------
+            const int nm = pv.n_chunks[(t * nsub + sub) * 2 + 1];
+            const int m = local * NGW + g;
+            if (m >= nm || !act) continue;
+            const int4 rec = pv.chunks[obase + n - 1 - m];
+            const int len = rec.z & 0xff;
+            const bool excl = rec.z < 0;
+            if (((rec.z >> 30) & 1) && gl == 0 && T.dirty) atomicOr(T.dirty + (rec.x >> 5), 1u << (rec.x & 31));
+            float4* wp = reinterpret_cast<float4*>(weight + (int64_t)rec.x * dim) + gl;
+            float4 wv;
+            if (excl) wv = *wp;
+            const int32_t* sp = pv.sorted_pos + (int64_t)t * n_idx + rec.y;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int i0 = 0; i0 < len; i0 += CHB) {
+                int pp[CHB];
+                float4 ga[CHB];
 #pragma unroll
-    for (int i = 0; i < CH; ++i)
-        if (i < len) ga[i] = reinterpret_cast<const float4*>(gbase + (int64_t)pp[i] * row_stride)[gl];
-    float4* wp = reinterpret_cast<float4*>(T.weight + (int64_t)rec.x * dim) + gl;
-    float4 wv;
-    if (rec.z < 0) wv = *wp;
-    float4 acc = ga[0];
+                for (int i = 0; i < CHB; ++i) {
+                    pp[i] = i0 + i < len ? sp[i0 + i] : 0;
+                    if (bag && i0 + i < len) pp[i] = bag[pp[i]];
+                }
 #pragma unroll
-    for (int i = 1; i < CH; ++i)
-        if (i < len) acc = vadd(acc, ga[i]);
-    if (rec.z < 0) *wp = vfma(-lr, acc, wv);
-    else red_add(wp, vscale(-lr, acc));
+                for (int i = 0; i < CHB; ++i)
+                    if (i0 + i < len) ga[i] = reinterpret_cast<const float4*>(gbase + (int64_t)pp[i] * row_stride)[gl];
+#pragma unroll
+                for (int i = 0; i < CHB; ++i)
+                    if (i0 + i < len) acc = vadd(acc, ga[i]);
+            }
+            if (excl) *wp = vfma(-lr, acc, wv);
+            else red_add(wp, vscale(-lr, acc));
+        } else {
+            // ---- singles: weight[slot] = fma(-lr, d_out[pos], weight[slot]), RPW records per warp ----
+            const int ns = pv.n_chunks[(t * nsub + sub) * 2];
+            const int c0 = local * RPW;
+            int slot_l = -1, pos_l = 0;
+            if (lane < RPW && c0 + lane < ns) {
+                const int4 rec = pv.chunks[obase + c0 + lane];
+                slot_l = rec.x;
+                pos_l = bag ? bag[rec.w] : rec.w;
+                if (T.dirty) atomicOr(T.dirty + (slot_l >> 5), 1u << (slot_l & 31));
+            }
+#pragma unroll 1
+            for (int it0 = 0; it0 < ITERS; it0 += U) {
+                int slot[U], pos[U];
+                float4 gv[U], wv[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    const int cc = (it0 + q) * NGW + g;
+                    slot[q] = __shfl_sync(0xffffffffu, slot_l, cc);
+                    pos[q] = __shfl_sync(0xffffffffu, pos_l, cc);
+                }
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    if (slot[q] >= 0 && act) {
+                        gv[q] = reinterpret_cast<const float4*>(gbase + (int64_t)pos[q] * row_stride)[gl];
+                        wv[q] = reinterpret_cast<const float4*>(weight + (int64_t)slot[q] * dim)[gl];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < U; ++q)
+                    if (slot[q] >= 0 && act)
+                        reinterpret_cast<float4*>(weight + (int64_t)slot[q] * dim)[gl] = vfma(-lr, gv[q], wv[q]);
+            }
+        }
+    }
 }
 
 // generic fallback (any dim / alignment): one group of G lanes per chunk
@@ -813,12 +834,13 @@ extern "C" int cdlrm_embed_bwd_sgd(cdlrm_ctx* c, int tb, int tc, const void* pla
         const int j0 = sub * CDLRM_SORT_MAX;
         const int n = n_idx - j0 < CDLRM_SORT_MAX ? n_idx - j0 : CDLRM_SORT_MAX;
         if (vec == 4 && cpr <= 32) {
-            const int rpw = (32 / G) > 8 ? (32 / G) : 8;
-            dim3 grid((n + 8 * rpw - 1) / (8 * rpw), tc);       // singles: 8 warps x RPW records per CTA
-            dim3 gridm((n / 2 + NG - 1) / NG + 1, tc);          // multis: at most n/2 chunks, one group each
+            // persistent grid: 2 CTAs per SM at most, never more warps than units can exist
+            const int64_t max_units = (int64_t)tc * ((n + 7) / 8 + 1);
+            int ctas = c->num_sms * 2;
+            if ((int64_t)ctas * (APPLY_NT / 32) > max_units) ctas = (int)((max_units + APPLY_NT / 32 - 1) / (APPLY_NT / 32));
+            const int smem = (2 * tc + 1) * (int)sizeof(int);
 #define LAUNCH_SGD(GG)                                                                                         \
-    LAUNCH(K_BWD_SGD, s, (bwd_sgd_single_kernel<GG><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim))); \
-    LAUNCH(K_BWD_SGD_MULTI, s, (bwd_sgd_multi_kernel<GG><<<gridm, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim)))
+    LAUNCH(K_BWD_SGD, s, (bwd_sgd_apply_kernel<GG><<<ctas, APPLY_NT, smem, s>>>(c->d_tabs, tb, tc, pv, n_idx, j0, n, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim)))
             switch (G) {
                 case 1: LAUNCH_SGD(1); break;
                 case 2: LAUNCH_SGD(2); break;

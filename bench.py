@@ -459,16 +459,12 @@ def gpu_run(a, wl, ln_emb):
         w, b = divmod(j - 1, L)
         lo = b * lb
         ids = window(w)[0][:, lo:lo + lb]
-        n_single = rows_multi = slots_multi = chunks_multi = 0
+        n_distinct = 0
         with torch.no_grad():
             _, sl = tr.cache_group(lS_o, ids, master, dev.index)
             tr.cache_group.join_forward()
             for s_ in sl:
-                _, cnt = torch.unique(s_, return_counts=True)
-                n_single += int((cnt == 1).sum())
-                rows_multi += int(cnt[cnt > 1].sum())
-                slots_multi += int((cnt > 1).sum())
-                chunks_multi += int(((cnt[cnt > 1] + 31) // 32).sum())
+                n_distinct += int(torch.unique(s_).numel())
         n = T * lb
         nfe = T + 1
         npair = nfe * (nfe - 1) // 2
@@ -477,11 +473,9 @@ def gpu_run(a, wl, ln_emb):
             "embed_fwd": n * (8 + 8 * wl["ways"] + 4) + n // 8 + (n - n_miss) * 8 * d,
             # bitmap read; per miss: id + slot + master row (PCIe) + aux row + out row
             "embed_miss": n // 8 + n_miss * (8 + 4 + 12 * d),
-            "bwd_plan": n * (4 + 12),
-            # singles: record + gradient row + weight RMW; multi-row chunks: record, position + gradient row
-            # per contribution, weight RMW per distinct slot
-            "bwd_sgd": n_single * (16 + 4 * d + 8 * d) + chunks_multi * 16 + rows_multi * (4 + 4 * d)
-                       + slots_multi * 8 * d,
+            "bwd_plan": n * (4 + 8),
+            # per id: sorted (slot, position) pair + its gradient row; per distinct slot: weight row read + write
+            "bwd_sgd": n * (8 + 4 * d) + n_distinct * 8 * d,
             "interact_fwd": lb * (nfe * 4 * d + (d + npair) * 4),
             "interact_bwd": lb * (2 * nfe * 4 * d + (d + npair) * 4),
         }

@@ -7,7 +7,6 @@
 
 namespace {
 
-constexpr int CH = 32;          // max contributions merged by one chunk in the backward
 
 template <int VEC> struct VecT;
 template <> struct VecT<4> { using type = float4; };
@@ -282,10 +281,8 @@ constexpr int PLAN_NT = 1024;
 constexpr int PLAN_MAX_ROUNDS = CDLRM_SORT_MAX / 1024;  // 16 keys per thread at most
 
 struct PlanView {
-    int32_t* sorted_pos;    // [tc][n_idx] absolute position j, grouped by slot (stable)
-    int4* chunks;           // [tc][n_idx] {slot, start (index into sorted_pos, relative to the table),
-                            //              len | first<<30 | excl<<31, position of the first element}
-    int32_t* n_chunks;      // [tc][nsub][2] {singles (listed from the front), multis (from the back)}
+    int32_t* sorted_pos;    // [tc][n_idx] absolute position j, grouped by slot (stable: ascending j within a slot)
+    uint32_t* sorted_key;   // [tc][n_idx] the slot of each sorted entry
 };
 
 __host__ __device__ inline int plan_nsub(int n_idx) { return (n_idx + CDLRM_SORT_MAX - 1) / CDLRM_SORT_MAX; }
@@ -296,8 +293,7 @@ __host__ inline PlanView plan_view(void* plan, int tc, int n_idx) {
     size_t a = (size_t)tc * n_idx * sizeof(int32_t);
     a = (a + 255) & ~(size_t)255;
     v.sorted_pos = (int32_t*)p; p += a;
-    v.chunks = (int4*)p; p += 4 * a;
-    v.n_chunks = (int32_t*)p;
+    v.sorted_key = (uint32_t*)p;
     return v;
 }
 
@@ -362,8 +358,7 @@ __device__ __forceinline__ int block_excl_maxscan_1024(int v, int* s_warp) {
 
 __global__ void __launch_bounds__(PLAN_NT, 1) bwd_plan_kernel(const TableDesc* __restrict__ tabs, int tb,
                                                               const int32_t* __restrict__ slots, int64_t ld_slots,
-                                                              int n_idx, int j0, int n, int sub, int nsub,
-                                                              PlanView pv) {
+                                                              int n_idx, int j0, int n, PlanView pv) {
     extern __shared__ __align__(16) unsigned char smem[];
     // layout: keyA[n] keyB[n] (u32) | valA[n] valB[n] (u16) | cnt[8192] (u16) | scratch[40] (int)
     const int npad = (n + 7) & ~7;
@@ -452,217 +447,141 @@ __global__ void __launch_bounds__(PLAN_NT, 1) bwd_plan_kernel(const TableDesc* _
         uint16_t* tv = valA; valA = valB; valB = tv;
     }
 
-    // ---- cut into chunks ---------------------------------------------------------
-    const int items = (n + PLAN_NT - 1) / PLAN_NT;
-    const int i0 = tid * items, i1 = min(n, i0 + items);
-    int last_head = -1;
-    for (int i = i0; i < i1; ++i)
-        if (i == 0 || keyA[i] != keyA[i - 1]) last_head = i;
-    int carry = block_excl_maxscan_1024(last_head, s_scr);
-    // singles (one gradient row, sole owner of its slot: the common case) are listed from the
-    // front of the chunk array, multi-row / shared-slot chunks from the back, so that each kind
-    // gets its own specialised apply kernel
-    int cur = carry, n_single = 0, n_multi = 0;
-    for (int i = i0; i < i1; ++i) {
-        const bool head = (i == 0 || keyA[i] != keyA[i - 1]);
-        if (head) cur = i;
-        if (((i - cur) % CH) == 0) {
-            const bool single = head && (i + 1 == n || keyA[i + 1] != keyA[i]);
-            if (single) ++n_single; else ++n_multi;
-        }
-    }
-    int tot_single, tot_multi;
-    int sidx = block_excl_scan_1024(n_single, s_scr, tot_single);
-    int midx = block_excl_scan_1024(n_multi, s_scr, tot_multi);
+    // ---- the sorted run: slot keys and the positions that carry them ----------------
     const int64_t obase = (int64_t)t * n_idx + j0;
-    cur = carry;
-    for (int i = i0; i < i1; ++i) {
-        const bool head = (i == 0 || keyA[i] != keyA[i - 1]);
-        if (head) cur = i;
-        if (((i - cur) % CH) == 0) {
-            const uint32_t k = keyA[i];
-            int len = 1;
-            while (len < CH && i + len < n && keyA[i + len] == k) ++len;
-            const bool last = (i + len == n) || keyA[i + len] != k;
-            const uint32_t desc = (uint32_t)len | (head ? (1u << 30) : 0u) | ((head && last) ? (1u << 31) : 0u);
-            const int4 rec = make_int4((int)k, j0 + i, (int)desc, j0 + (int)valA[i]);
-            if (head && last && len == 1) pv.chunks[obase + sidx++] = rec;
-            else pv.chunks[obase + n - 1 - midx++] = rec;
-        }
+    for (int i = tid; i < n; i += PLAN_NT) {
+        pv.sorted_key[obase + i] = keyA[i];
         pv.sorted_pos[obase + i] = j0 + (int)valA[i];
-    }
-    if (tid == 0) {
-        pv.n_chunks[(t * nsub + sub) * 2 + 0] = tot_single;
-        pv.n_chunks[(t * nsub + sub) * 2 + 1] = tot_multi;
     }
 }
 
 // ------------------------------------------------------------------------------
-// Backward apply.  A chunk = up to CH gradient rows that hit the same slot; its record
-// {slot, start, len|flags, first position} is one 16-byte load.  acc = sum of the chunk's
-// upstream gradient rows (ascending position: deterministic), then
-// weight[slot] += -lr * acc -- a plain read-modify-write when the chunk owns the slot,
-// a vector red otherwise (only slots with more than CH contributions: the hot rows of
-// a skewed stream and the tiny tables, where one red per CH rows keeps the same-address
-// traffic at the L2 low).
-// Fast path (float4 rows, dim <= 128): ONE persistent launch over all tables.  The work
-// is flattened into warp units -- first the multi-row chunks of every table (the long
-// ones, so that they do not form the tail), then the singles, RPW records per unit -- and
-// the warps of the grid stride over the units; no CTA is launched for work that does not
-// exist.  Groups of G lanes own a row (G = dim/4 rounded up to a power of two), CHB rows
-// are in flight per group.
+// Backward apply over the sorted run (slot keys ascending, positions ascending within a
+// slot).  A warp owns 32 consecutive sorted entries of one table: one coalesced load
+// brings their (slot, position) pairs, everything after that is independent row traffic.
+// Groups of G lanes own a row (G = dim/4 rounded up to a power of two; 32 at dim 128), so
+// a warp works on NGW = 32/G sub-ranges of EPG = G entries side by side.  A group walks
+// its entries in order, CHB at a time: the gradient rows of the batch -- and the weight
+// rows of the runs that end inside it -- are all in flight together; then
+//     acc += g[pos]   ...   at the end of a run:  weight[slot] = fma(-lr, acc, weight[slot])
+// as a plain read-modify-write when the whole run lies inside the group's entries
+// (deterministic: ascending position), or a vector red when the run continues in a
+// neighbouring sub-range (the hot rows of a skewed stream, the tiny tables: one red per
+// 32 rows at dim 128).  No per-table counts, no chunk records, no empty CTAs: the grid is
+// ceil(n/32) warps per table.
 // ------------------------------------------------------------------------------
-constexpr int CHB = 8;          // gradient rows in flight per lane group
+constexpr int CHB = 8;          // entries in flight per lane group
 constexpr int APPLY_NT = 256;
 
 template <int G>
-__global__ void __launch_bounds__(APPLY_NT, 2) bwd_sgd_apply_kernel(const TableDesc* __restrict__ tabs, int tb, int tc,
-                                                                     PlanView pv, int n_idx, int j0, int n, int sub, int nsub,
+__global__ void __launch_bounds__(APPLY_NT, 2) bwd_sgd_apply_kernel(const TableDesc* __restrict__ tabs, int tb,
+                                                                     PlanView pv, int n_idx, int j0, int n,
                                                                      const int32_t* __restrict__ bag_ids, int64_t ld_bag,
                                                                      const float* __restrict__ d_out, int64_t ld_dout,
                                                                      int64_t row_stride, float lr, int dim) {
-    constexpr int NGW = 32 / G;               // rows moved per warp instruction
-    constexpr int RPW = NGW > 8 ? NGW : 8;    // single records per warp unit
-    constexpr int ITERS = RPW / NGW;
-    constexpr int U = ITERS < 4 ? ITERS : 4;
-    extern __shared__ int s_pref[];           // [2*tc + 1] exclusive prefix of the unit counts
-    for (int i = threadIdx.x; i < 2 * tc; i += APPLY_NT) {
-        const int t = i < tc ? i : i - tc;
-        const int cnt = pv.n_chunks[(t * nsub + sub) * 2 + (i < tc ? 1 : 0)];
-        s_pref[i + 1] = i < tc ? (cnt + NGW - 1) / NGW : (cnt + RPW - 1) / RPW;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        s_pref[0] = 0;
-        for (int i = 1; i <= 2 * tc; ++i) { run += s_pref[i]; s_pref[i] = run; }
-    }
-    __syncthreads();
-    const int total = s_pref[2 * tc];
+    constexpr int NGW = 32 / G;               // lane groups per warp
+    constexpr int EPG = G;                    // sorted entries per group (32 / NGW)
+    constexpr int NB = EPG < CHB ? EPG : CHB; // entries per batch
+    const int t = blockIdx.y;
     const int lane = threadIdx.x & 31;
+    const int e0 = (blockIdx.x * (APPLY_NT / 32) + (threadIdx.x >> 5)) * 32;   // first entry of the warp
+    if (e0 >= n) return;
+    const TableDesc& T = tabs[tb + t];
+    float* __restrict__ weight = T.weight;
+    const float* gbase = d_out + (int64_t)t * ld_dout;
+    const int64_t obase = (int64_t)t * n_idx + j0;
+    const uint32_t* keys = pv.sorted_key + obase;
+    const bool valid_l = e0 + lane < n;
+    const uint32_t key_l = valid_l ? keys[e0 + lane] : 0xffffffffu;
+    int pos_l = valid_l ? pv.sorted_pos[obase + e0 + lane] : 0;
+    if (bag_ids && valid_l) pos_l = bag_ids[(int64_t)t * ld_bag + pos_l];
+    // neighbours across the warp's range
+    const uint32_t key_before = e0 > 0 ? keys[e0 - 1] : 0xffffffffu;
+    const uint32_t key_after = e0 + 32 < n ? keys[e0 + 32] : 0xffffffffu;
+    uint32_t kp = __shfl_up_sync(0xffffffffu, key_l, 1);
+    uint32_t kn = __shfl_down_sync(0xffffffffu, key_l, 1);
+    if (lane == 0) kp = key_before;
+    if (lane == 31) kn = key_after;
+    // run structure relative to the GROUP's sub-range [g*EPG, (g+1)*EPG)
+    const int within = lane % EPG;
+    const bool head_true = valid_l && key_l != kp;                    // first entry of its slot
+    const bool tail_true = valid_l && key_l != kn;                    // last entry of its slot
+    const bool seg_head = valid_l && (head_true || within == 0);      // the group starts accumulating here
+    const bool seg_tail = valid_l && (tail_true || within == EPG - 1 || e0 + lane + 1 >= n);
+    if (head_true && T.dirty) atomicOr(T.dirty + (key_l >> 5), 1u << (key_l & 31));
+    // a segment is the slot's only contribution iff it starts at a true head and ends at a true tail
+    const uint32_t head_mask = __ballot_sync(0xffffffffu, seg_head);
+    const uint32_t headtrue_mask = __ballot_sync(0xffffffffu, head_true);
+    int excl_l = 0;
+    if (seg_tail) {
+        const uint32_t upto = head_mask & (0xffffffffu >> (31 - lane));   // segment heads at or before this lane
+        const int h = 31 - __clz(upto);                                   // this segment's head lane
+        excl_l = (tail_true && ((headtrue_mask >> h) & 1u)) ? 1 : 0;
+    }
+    const int flags_l = (seg_tail ? 1 : 0) | (excl_l << 1);
+
     const int gl = lane % G, g = lane / G;
     const int cpr = dim >> 2;
     const bool act = gl < cpr;
-    const int nwarps = gridDim.x * (APPLY_NT / 32);
-    for (int u = blockIdx.x * (APPLY_NT / 32) + (threadIdx.x >> 5); u < total; u += nwarps) {
-        int lo = 0, hi = 2 * tc;              // segment: s_pref[seg] <= u < s_pref[seg + 1]
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_pref[mid] <= u) lo = mid; else hi = mid;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int b0 = 0; b0 < EPG; b0 += NB) {
+        uint32_t key[NB];
+        int pos[NB], fl[NB];
+        float4 gv[NB], wv[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int src = g * EPG + b0 + q;
+            key[q] = __shfl_sync(0xffffffffu, key_l, src);
+            pos[q] = __shfl_sync(0xffffffffu, pos_l, src);
+            fl[q] = __shfl_sync(0xffffffffu, flags_l, src);
+            if (e0 + src >= n) fl[q] = -1;                            // past the end of the run
         }
-        const int seg = lo, local = u - s_pref[seg];
-        const int t = seg < tc ? seg : seg - tc;
-        const TableDesc& T = tabs[tb + t];
-        float* __restrict__ weight = T.weight;
-        const float* gbase = d_out + (int64_t)t * ld_dout;
-        const int32_t* bag = bag_ids ? bag_ids + (int64_t)t * ld_bag : nullptr;
-        const int64_t obase = (int64_t)t * n_idx + j0;
-        if (seg < tc) {
-            // ---- multi-row chunk: one per lane group ------------------------------------------
-            const int nm = pv.n_chunks[(t * nsub + sub) * 2 + 1];
-            const int m = local * NGW + g;
-            if (m >= nm || !act) continue;
-            const int4 rec = pv.chunks[obase + n - 1 - m];
-            const int len = rec.z & 0xff;
-            const bool excl = rec.z < 0;
-            if (((rec.z >> 30) & 1) && gl == 0 && T.dirty) atomicOr(T.dirty + (rec.x >> 5), 1u << (rec.x & 31));
-            float4* wp = reinterpret_cast<float4*>(weight + (int64_t)rec.x * dim) + gl;
-            float4 wv;
-            if (excl) wv = *wp;
-            const int32_t* sp = pv.sorted_pos + (int64_t)t * n_idx + rec.y;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-            for (int i0 = 0; i0 < len; i0 += CHB) {
-                int pp[CHB];
-                float4 ga[CHB];
 #pragma unroll
-                for (int i = 0; i < CHB; ++i) {
-                    pp[i] = i0 + i < len ? sp[i0 + i] : 0;
-                    if (bag && i0 + i < len) pp[i] = bag[pp[i]];
-                }
-#pragma unroll
-                for (int i = 0; i < CHB; ++i)
-                    if (i0 + i < len) ga[i] = reinterpret_cast<const float4*>(gbase + (int64_t)pp[i] * row_stride)[gl];
-#pragma unroll
-                for (int i = 0; i < CHB; ++i)
-                    if (i0 + i < len) acc = vadd(acc, ga[i]);
+        for (int q = 0; q < NB; ++q) {
+            if (fl[q] >= 0 && act) {
+                gv[q] = reinterpret_cast<const float4*>(gbase + (int64_t)pos[q] * row_stride)[gl];
+                if (fl[q] == 3) wv[q] = reinterpret_cast<const float4*>(weight + (int64_t)key[q] * dim)[gl];
             }
-            if (excl) *wp = vfma(-lr, acc, wv);
-            else red_add(wp, vscale(-lr, acc));
-        } else {
-            // ---- singles: weight[slot] = fma(-lr, d_out[pos], weight[slot]), RPW records per warp ----
-            const int ns = pv.n_chunks[(t * nsub + sub) * 2];
-            const int c0 = local * RPW;
-            int slot_l = -1, pos_l = 0;
-            if (lane < RPW && c0 + lane < ns) {
-                const int4 rec = pv.chunks[obase + c0 + lane];
-                slot_l = rec.x;
-                pos_l = bag ? bag[rec.w] : rec.w;
-                if (T.dirty) atomicOr(T.dirty + (slot_l >> 5), 1u << (slot_l & 31));
-            }
-#pragma unroll 1
-            for (int it0 = 0; it0 < ITERS; it0 += U) {
-                int slot[U], pos[U];
-                float4 gv[U], wv[U];
+        }
 #pragma unroll
-                for (int q = 0; q < U; ++q) {
-                    const int cc = (it0 + q) * NGW + g;
-                    slot[q] = __shfl_sync(0xffffffffu, slot_l, cc);
-                    pos[q] = __shfl_sync(0xffffffffu, pos_l, cc);
+        for (int q = 0; q < NB; ++q) {
+            if (fl[q] >= 0 && act) {
+                acc = vadd(acc, gv[q]);
+                if (fl[q] & 1) {
+                    float4* wp = reinterpret_cast<float4*>(weight + (int64_t)key[q] * dim) + gl;
+                    if (fl[q] == 3) *wp = vfma(-lr, acc, wv[q]);
+                    else red_add(wp, vscale(-lr, acc));
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-#pragma unroll
-                for (int q = 0; q < U; ++q) {
-                    if (slot[q] >= 0 && act) {
-                        gv[q] = reinterpret_cast<const float4*>(gbase + (int64_t)pos[q] * row_stride)[gl];
-                        wv[q] = reinterpret_cast<const float4*>(weight + (int64_t)slot[q] * dim)[gl];
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < U; ++q)
-                    if (slot[q] >= 0 && act)
-                        reinterpret_cast<float4*>(weight + (int64_t)slot[q] * dim)[gl] = vfma(-lr, gv[q], wv[q]);
             }
         }
     }
 }
 
-// generic fallback (any dim / alignment): one group of G lanes per chunk
+// generic fallback (any dim / alignment): one lane group per sorted entry, always atomic
 template <int VEC>
 __global__ void __launch_bounds__(256) bwd_sgd_kernel(const TableDesc* __restrict__ tabs, int tb,
-                                                      PlanView pv, int n_idx, int j0, int n, int sub, int nsub,
+                                                      PlanView pv, int n_idx, int j0, int n,
                                                       const int32_t* __restrict__ bag_ids, int64_t ld_bag,
                                                       const float* __restrict__ d_out, int64_t ld_dout,
                                                       int64_t row_stride, float lr, int dim, int G) {
     using V = typename VecT<VEC>::type;
     const int t = blockIdx.y;
     const int gl = threadIdx.x % G, group = threadIdx.x / G, NG = 256 / G;
-    const int c = blockIdx.x * NG + group;
-    const int ns = pv.n_chunks[(t * nsub + sub) * 2], nm = pv.n_chunks[(t * nsub + sub) * 2 + 1];
-    if (c >= ns + nm) return;
+    const int e = blockIdx.x * NG + group;
+    if (e >= n) return;
     const int64_t obase = (int64_t)t * n_idx + j0;
-    const int4 rec = c < ns ? pv.chunks[obase + c] : pv.chunks[obase + n - 1 - (c - ns)];
-    const int len = rec.z & 0xff;
-    const bool first = (rec.z >> 30) & 1, excl = rec.z < 0;
-    const int32_t slot = rec.x;
-    const int32_t* pos = pv.sorted_pos + (int64_t)t * n_idx + rec.y;
-    const int32_t* bag = bag_ids ? bag_ids + (int64_t)t * ld_bag : nullptr;
-    const float* g = d_out + (int64_t)t * ld_dout;
+    const uint32_t slot = pv.sorted_key[obase + e];
+    int p0 = pv.sorted_pos[obase + e];
+    if (bag_ids) p0 = bag_ids[(int64_t)t * ld_bag + p0];
     const TableDesc& T = tabs[tb + t];
+    const float* g = d_out + (int64_t)t * ld_dout + (int64_t)p0 * row_stride;
     float* wrow = T.weight + (int64_t)slot * dim;
     const int cpr = dim / VEC;
-    for (int cc = gl; cc < cpr; cc += G) {
-        V acc;
-        vzero(acc);
-        for (int i = 0; i < len; ++i) {
-            int p0 = pos[i];
-            if (bag) p0 = bag[p0];
-            acc = vadd(acc, reinterpret_cast<const V*>(g + (int64_t)p0 * row_stride)[cc]);
-        }
-        V* wp = reinterpret_cast<V*>(wrow) + cc;
-        if (excl) *wp = vfma(-lr, acc, *wp);
-        else red_add(wp, vscale(-lr, acc));
-    }
-    if (first && gl == 0 && T.dirty) atomicOr(T.dirty + (slot >> 5), 1u << (slot & 31));
+    for (int cc = gl; cc < cpr; cc += G)
+        red_add(reinterpret_cast<V*>(wrow) + cc, vscale(-lr, reinterpret_cast<const V*>(g)[cc]));
+    if (gl == 0 && T.dirty) atomicOr(T.dirty + (slot >> 5), 1u << (slot & 31));
 }
 
 inline int pow2_ceil(int v) {
@@ -779,8 +698,7 @@ extern "C" int64_t cdlrm_embed_bwd_plan_bytes(int tc, int32_t n_idx) {
     if (tc <= 0 || n_idx < 0) return -1;
     size_t a = (size_t)tc * (size_t)(n_idx > 0 ? n_idx : 1) * sizeof(int32_t);
     a = (a + 255) & ~(size_t)255;
-    size_t nsub = (size_t)plan_nsub(n_idx > 0 ? n_idx : 1);
-    return (int64_t)(5 * a + ((((size_t)tc * nsub * 2 * sizeof(int32_t)) + 255) & ~(size_t)255));
+    return (int64_t)(2 * a);
 }
 
 extern "C" int cdlrm_embed_bwd_plan(cdlrm_ctx* c, int tb, int tc, const int32_t* slots, int64_t ld_slots,
@@ -806,7 +724,7 @@ extern "C" int cdlrm_embed_bwd_plan(cdlrm_ctx* c, int tb, int tc, const int32_t*
         const int n = n_idx - j0 < CDLRM_SORT_MAX ? n_idx - j0 : CDLRM_SORT_MAX;
         const int npad = (n + 7) & ~7;
         const int smem = npad * 12 + 8192 * 2 + 64 * 4;
-        LAUNCH(K_BWD_PLAN, s, bwd_plan_kernel<<<tc, PLAN_NT, smem, s>>>(c->d_tabs, tb, slots, ld_slots, n_idx, j0, n, sub, nsub, pv));
+        LAUNCH(K_BWD_PLAN, s, bwd_plan_kernel<<<tc, PLAN_NT, smem, s>>>(c->d_tabs, tb, slots, ld_slots, n_idx, j0, n, pv));
     }
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
@@ -828,19 +746,15 @@ extern "C" int cdlrm_embed_bwd_sgd(cdlrm_ctx* c, int tb, int tc, const void* pla
     const int cpr = c->dim / vec;
     const int G = pow2_ceil(cpr) > 32 ? 32 : pow2_ceil(cpr);
     const int NG = 256 / G;
-    // sub-batches are applied one after the other: the update is additive in the
-    // gradients, so the split only changes fp32 rounding order.
+    // sub-batches (sorted separately) are applied one after the other in stream order: two
+    // sub-batches may hold the same slot, and each treats its own runs as exclusive
     for (int sub = 0; sub < nsub; ++sub) {
         const int j0 = sub * CDLRM_SORT_MAX;
         const int n = n_idx - j0 < CDLRM_SORT_MAX ? n_idx - j0 : CDLRM_SORT_MAX;
         if (vec == 4 && cpr <= 32) {
-            // persistent grid: 2 CTAs per SM at most, never more warps than units can exist
-            const int64_t max_units = (int64_t)tc * ((n + 7) / 8 + 1);
-            int ctas = c->num_sms * 2;
-            if ((int64_t)ctas * (APPLY_NT / 32) > max_units) ctas = (int)((max_units + APPLY_NT / 32 - 1) / (APPLY_NT / 32));
-            const int smem = (2 * tc + 1) * (int)sizeof(int);
+            dim3 grid((n + APPLY_NT - 1) / APPLY_NT, tc);     // a warp per 32 sorted entries
 #define LAUNCH_SGD(GG)                                                                                         \
-    LAUNCH(K_BWD_SGD, s, (bwd_sgd_apply_kernel<GG><<<ctas, APPLY_NT, smem, s>>>(c->d_tabs, tb, tc, pv, n_idx, j0, n, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim)))
+    LAUNCH(K_BWD_SGD, s, (bwd_sgd_apply_kernel<GG><<<grid, APPLY_NT, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim)))
             switch (G) {
                 case 1: LAUNCH_SGD(1); break;
                 case 2: LAUNCH_SGD(2); break;
@@ -852,9 +766,9 @@ extern "C" int cdlrm_embed_bwd_sgd(cdlrm_ctx* c, int tb, int tc, const void* pla
 #undef LAUNCH_SGD
         } else {
             dim3 grid((n + NG - 1) / NG, tc);
-            if (vec == 4) LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<4><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
-            else if (vec == 2) LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<2><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
-            else LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<1><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, sub, nsub, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
+            if (vec == 4) LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<4><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
+            else if (vec == 2) LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<2><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
+            else LAUNCH(K_BWD_SGD, s, bwd_sgd_kernel<1><<<grid, 256, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim, G));
         }
     }
     CU_CHECK(cudaGetLastError());

@@ -1,0 +1,636 @@
+// mlp.cu -- the bottom / top MLPs of DLRM_Net (create_mlp / forward, model_no_ddp.py:244-270,
+// 306-316 of the reference: Linear + ReLU, Sigmoid on the last top layer) on the 5th-gen
+// tensor cores, at FP32 accuracy.
+//
+// The reference trains in FP32 and the parity bar on the loss is 1e-5 relative, so a plain
+// TF32 product (10-bit mantissa) is not an option.  Every FP32 operand x is split into
+//     hi = x with the low 13 mantissa bits cleared   (exactly a TF32 number)
+//     lo = (x - hi) with the low 13 bits cleared      (the next 11 bits)
+// and a product is evaluated as  hi*hi + hi*lo + lo*hi  (3xTF32) with FP32 accumulation in
+// TMEM: relative error ~2^-21 per product, the same order as an FP32 FMA chain.
+//
+// One GEMM kernel serves forward, data-gradient and weight-gradient:
+//     D[M,N] = A[M,K] * B[N,K]^T        A, B row-major with K contiguous ("K-major"),
+// A_hi/A_lo/B_hi/B_lo are four tensors in HBM, moved by TMA (128-byte swizzle) into a
+// 3-stage shared-memory ring; one elected thread issues tcgen05.mma.kind::tf32
+// (128x128x8, 12 per 32-wide k-block: 4 k-steps x 3 products) into a 128-column TMEM
+// accumulator; four epilogue warps read it back with tcgen05.ld and apply the fused
+// epilogue (bias, ReLU / sigmoid, ReLU-backward mask, hi/lo split of the result in
+// row-major AND transposed form -- the operand layouts the next GEMM needs -- or a
+// split-K atomic accumulation for the weight gradient).
+//   forward    Y  = act(X W^T + b)        A = X [B,K],      B = W   [N,K]
+//   dgrad      dX = (dZ W) * relu'(X)     A = dZ [B,N],     B = W^T [K,N]
+//   wgrad      dW = dZ^T X , db = dZ^T 1  A = dZ^T [N,B],   B = [X^T ; 1] [K+1,B]   (split-K)
+// The transposed copies are written by the epilogues that produce the tensors (the TMEM
+// lane = row mapping makes the transposed store the coalesced one).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;        // tile; BK fp32 = 128 bytes = one swizzle row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB per operand tile
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi, A_lo, B_hi, B_lo
+constexpr int GEMM_THREADS = 192;                 // warp 0: TMA, warp 1: MMA + TMEM, warps 2-5: epilogue
+constexpr int TMEM_COLS = 128;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
+
+struct Epi {
+    int M, N, K;                 // GEMM extents: rows of A, rows of B, reduction length
+    int kb_per_split;            // k-blocks per blockIdx.z
+    const float* bias;           // [N] added per column (or null)
+    int act;                     // ACT_*
+    const float* mask;           // relu-backward: result passes where mask[row, col] > 0 (or null)
+    int64_t ld_mask;
+    float* C;                    // fp32 result, row-major (or null)
+    int64_t ldc;
+    float* C_hi;                 // hi/lo split of the result, row-major (or null)
+    float* C_lo;
+    int64_t ld_split;
+    float* CT_hi;                // hi/lo split of the result, transposed [N][ld_t] (or null)
+    float* CT_lo;
+    int64_t ld_t;
+    int atomic;                  // 1: C += result with red.global.add (split-K)
+    int vec_col;                 // >= 0: this column of the result goes to vec[row] instead of C
+    float* vec;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol error becomes a trap (launch failure), never a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 28)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO),
+// LBO unused (1), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u); }
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                   const Epi ep) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+    uint8_t* smem = smem_raw + pad;                              // 1024-byte aligned tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                                   // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;                         // [STAGES]
+    uint64_t* accum_bar = bars + 2 * STAGES;                     // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int num_kb_total = (ep.K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * ep.kb_per_split;
+    const int kb1 = min(num_kb_total, kb0 + ep.kb_per_split);
+    const int num_kb = kb1 - kb0;                                // >= 1 by construction of the grid
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                const int k = (kb0 + i) * BK;
+                tma_load_2d(base + 0 * TILE_BYTES, &map_a_hi, k, m0, &full_bar[s]);
+                tma_load_2d(base + 1 * TILE_BYTES, &map_a_lo, k, m0, &full_bar[s]);
+                tma_load_2d(base + 2 * TILE_BYTES, &map_b_hi, k, n0, &full_bar[s]);
+                tma_load_2d(base + 3 * TILE_BYTES, &map_b_lo, k, n0, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread =====
+        if (lane == 0) {
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t a_hi = make_smem_desc(base + 0 * TILE_BYTES);
+                const uint64_t a_lo = make_smem_desc(base + 1 * TILE_BYTES);
+                const uint64_t b_hi = make_smem_desc(base + 2 * TILE_BYTES);
+                const uint64_t b_lo = make_smem_desc(base + 3 * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per k-step, in 16-byte units
+                    // the small cross terms first, the hi*hi term last
+                    tc_mma_tf32(tmem_base, a_lo + adv, b_hi + adv, IDESC_TF32, (i | k) != 0);
+                    tc_mma_tf32(tmem_base, a_hi + adv, b_lo + adv, IDESC_TF32, 1u);
+                    tc_mma_tf32(tmem_base, a_hi + adv, b_hi + adv, IDESC_TF32, 1u);
+                }
+                tc_commit(&empty_bar[s]);          // the stage is free once these MMAs have read it
+            }
+            tc_commit(accum_bar);                  // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), +32) =====
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const bool row_ok = row < ep.M;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            const int col0 = n0 + c * 32;
+            if (col0 >= ep.N) break;                               // warp-uniform
+            float v[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            if (ep.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < ep.N) v[j] += __ldg(ep.bias + col0 + j);
+            }
+            if (ep.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (ep.act == ACT_SIGMOID) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+            }
+            if (ep.mask && row_ok) {
+                const float* mrow = ep.mask + (int64_t)row * ep.ld_mask + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < ep.N && !(__ldg(mrow + j) > 0.f)) v[j] = 0.f;
+            }
+            if (ep.atomic) {
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = col0 + j;
+                        if (col >= ep.N) continue;
+                        if (col == ep.vec_col) atomicAdd(ep.vec + row, v[j]);
+                        else atomicAdd(ep.C + (int64_t)row * ep.ldc + col, v[j]);
+                    }
+                }
+                continue;
+            }
+            if (ep.C && row_ok) {
+                float* crow = ep.C + (int64_t)row * ep.ldc + col0;
+                if (col0 + 32 <= ep.N && (ep.ldc & 3) == 0 && ((uintptr_t)ep.C & 15) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < ep.N) crow[j] = v[j];
+                }
+            }
+            if (ep.C_hi || ep.CT_hi) {
+                float hi[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { hi[j] = tf32_hi(v[j]); lo[j] = tf32_lo(v[j], hi[j]); }
+                if (ep.C_hi && row_ok) {
+                    float* hrow = ep.C_hi + (int64_t)row * ep.ld_split + col0;
+                    float* lrow = ep.C_lo + (int64_t)row * ep.ld_split + col0;
+                    if (col0 + 32 <= ep.N) {     // ld_split is a multiple of 4 and the bases are 16-byte aligned
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            *reinterpret_cast<float4*>(hrow + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+                            *reinterpret_cast<float4*>(lrow + j) = make_float4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < ep.N) { hrow[j] = hi[j]; lrow[j] = lo[j]; }
+                    }
+                }
+                if (ep.CT_hi && row_ok) {        // transposed: lanes = consecutive rows -> coalesced
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (col0 + j < ep.N) {
+                            ep.CT_hi[(int64_t)(col0 + j) * ep.ld_t + row] = hi[j];
+                            ep.CT_lo[(int64_t)(col0 + j) * ep.ld_t + row] = lo[j];
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// split: dst = f(src) as hi/lo TF32 pairs, row-major [rows, ld_o] and/or transposed
+// [cols, ld_t]; f is the identity or the activation derivative applied to an upstream
+// gradient (relu': src * (y > 0), sigmoid': src * y * (1 - y)).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ src, int64_t lds, int rows, int cols,
+                                                    const float* __restrict__ y, int64_t ldy, int dmode,
+                                                    float* __restrict__ hi, float* __restrict__ lo, int64_t ld_o,
+                                                    float* __restrict__ thi, float* __restrict__ tlo, int64_t ld_t) {
+    __shared__ float s_hi[32][33], s_lo[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        float h = 0.f, l = 0.f;
+        if (r < rows && c < cols) {
+            float v = src[(int64_t)r * lds + c];
+            if (dmode == ACT_RELU) v = y[(int64_t)r * ldy + c] > 0.f ? v : 0.f;
+            else if (dmode == ACT_SIGMOID) { const float p = y[(int64_t)r * ldy + c]; v = v * p * (1.f - p); }
+            h = tf32_hi(v);
+            l = tf32_lo(v, h);
+            if (hi) { hi[(int64_t)r * ld_o + c] = h; lo[(int64_t)r * ld_o + c] = l; }
+        }
+        s_hi[ty + 8 * i][tx] = h;
+        s_lo[ty + 8 * i][tx] = l;
+    }
+    if (!thi) return;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        if (r < rows && c < cols) {
+            thi[(int64_t)c * ld_t + r] = s_hi[tx][ty + 8 * i];
+            tlo[(int64_t)c * ld_t + r] = s_lo[tx][ty + 8 * i];
+        }
+    }
+}
+
+__global__ void fill_kernel(float* p, int64_t n, float v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [rows, inner] fp32, row stride ld elements (multiple of 4), box = 32 x 128, 128-byte swizzle;
+// out-of-range box elements read as zero
+int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t rows, int64_t ld) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        cdlrm_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return CDLRM_ERR_CUDA;
+    }
+    if (((uintptr_t)base & 15) || (ld & 3) || inner <= 0 || rows <= 0) {
+        cdlrm_set_error("tensor map operand must be 16-byte aligned with a row stride multiple of 4 (base %p ld %lld)", (const void*)base, (long long)ld);
+        return CDLRM_ERR_ARG;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cdlrm_set_error("cuTensorMapEncodeTiled failed (%d): inner %lld rows %lld ld %lld", (int)r, (long long)inner, (long long)rows, (long long)ld);
+        return CDLRM_ERR_CUDA;
+    }
+    return CDLRM_OK;
+}
+
+int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
+                Epi ep, int splits, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        attr_done = true;
+    }
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = make_map(&ma_hi, a_hi, ep.K, ep.M, lda))) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, ep.K, ep.M, lda))) return rc;
+    if ((rc = make_map(&mb_hi, b_hi, ep.K, ep.N, ldb))) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, ep.K, ep.N, ldb))) return rc;
+    const int num_kb = (ep.K + BK - 1) / BK;
+    if (splits < 1) splits = 1;
+    if (splits > num_kb) splits = num_kb;
+    ep.kb_per_split = (num_kb + splits - 1) / splits;
+    splits = (num_kb + ep.kb_per_split - 1) / ep.kb_per_split;      // no empty split
+    dim3 grid((ep.N + BN - 1) / BN, (ep.M + BM - 1) / BM, splits);
+    LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep)));
+    CU_CHECK(cudaGetLastError());
+    return CDLRM_OK;
+}
+
+int launch_split(const float* src, int64_t lds, int rows, int cols, const float* y, int64_t ldy, int dmode, float* hi,
+                 float* lo, int64_t ld_o, float* thi, float* tlo, int64_t ld_t, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return CDLRM_OK;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    LAUNCH(K_MLP_SPLIT, s, (split_kernel<<<grid, 256, 0, s>>>(src, lds, rows, cols, y, ldy, dmode, hi, lo, ld_o, thi, tlo, ld_t)));
+    CU_CHECK(cudaGetLastError());
+    return CDLRM_OK;
+}
+
+inline int64_t pad4(int64_t v) { return (v + 3) & ~(int64_t)3; }
+inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+}  // namespace
+
+// One MLP (bottom or top): dims[0..L], batch capacity, the layer that ends in a sigmoid.
+// Workspace carve-up (all fp32, every region 256-byte aligned):
+//   per layer l:  w_hi/w_lo [N_l, pad4(K_l)]   wt_hi/wt_lo [K_l, pad4(N_l)]
+//   per level i = 0..L (activation entering layer i; level L is the output):
+//        x_hi/x_lo [cap, pad4(D_i)]   xt_hi/xt_lo [D_i + 1, pad4(cap)]  (last row = ones: bias gradient)
+//        g_hi/g_lo [cap, pad4(D_i)]   gt_hi/gt_lo [D_i, pad4(cap)]      (gradient w.r.t. the pre-activation)
+//   y_out [cap, pad4(D_L)]  fp32 output of the last layer (activation derivative input)
+struct cdlrm_mlp {
+    int device = 0;
+    int L = 0;
+    int cap = 0;
+    int sigmoid_layer = -1;
+    std::vector<int> D;
+    std::vector<float*> w_hi, w_lo, wt_hi, wt_lo;
+    std::vector<float*> x_hi, x_lo, xt_hi, xt_lo, g_hi, g_lo, gt_hi, gt_lo;
+    float* y_out = nullptr;
+    int last_batch = 0;
+    bool ones_set = false;
+    int num_sms = 148;
+};
+
+static int64_t mlp_carve(cdlrm_mlp* m, char* base) {
+    int64_t off = 0;
+    auto take = [&](int64_t elems) {
+        float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+        off += align256(elems * 4);
+        return p;
+    };
+    const int L = m->L;
+    const int64_t cap = m->cap, capp = pad4(m->cap);
+    m->w_hi.assign(L, nullptr); m->w_lo.assign(L, nullptr); m->wt_hi.assign(L, nullptr); m->wt_lo.assign(L, nullptr);
+    for (int l = 0; l < L; ++l) {
+        const int64_t K = m->D[l], N = m->D[l + 1];
+        m->w_hi[l] = take(N * pad4(K)); m->w_lo[l] = take(N * pad4(K));
+        m->wt_hi[l] = take(K * pad4(N)); m->wt_lo[l] = take(K * pad4(N));
+    }
+    m->x_hi.assign(L + 1, nullptr); m->x_lo.assign(L + 1, nullptr); m->xt_hi.assign(L + 1, nullptr); m->xt_lo.assign(L + 1, nullptr);
+    m->g_hi.assign(L + 1, nullptr); m->g_lo.assign(L + 1, nullptr); m->gt_hi.assign(L + 1, nullptr); m->gt_lo.assign(L + 1, nullptr);
+    for (int i = 0; i <= L; ++i) {
+        const int64_t Di = m->D[i];
+        if (i < L) {
+            m->x_hi[i] = take(cap * pad4(Di)); m->x_lo[i] = take(cap * pad4(Di));
+            m->xt_hi[i] = take((Di + 1) * capp); m->xt_lo[i] = take((Di + 1) * capp);
+        }
+        if (i > 0) {
+            m->g_hi[i] = take(cap * pad4(Di)); m->g_lo[i] = take(cap * pad4(Di));
+            m->gt_hi[i] = take(Di * capp); m->gt_lo[i] = take(Di * capp);
+        }
+    }
+    m->y_out = take(cap * pad4(m->D[L]));
+    return off;
+}
+
+extern "C" int64_t cdlrm_mlp_workspace_bytes(int n_layers, const int32_t* h_dims, int32_t batch_cap) {
+    if (n_layers < 1 || !h_dims || batch_cap < 1) return -1;
+    cdlrm_mlp m;
+    m.L = n_layers;
+    m.cap = batch_cap;
+    m.D.assign(h_dims, h_dims + n_layers + 1);
+    for (int v : m.D)
+        if (v < 1) return -1;
+    return mlp_carve(&m, nullptr);
+}
+
+extern "C" int cdlrm_mlp_create(cdlrm_mlp** out, int device, int n_layers, const int32_t* h_dims, int32_t batch_cap,
+                                int sigmoid_layer, void* workspace, int64_t workspace_bytes) {
+    ARG_CHECK(out && h_dims && workspace);
+    ARG_CHECK(n_layers >= 1 && batch_cap >= 1);
+    ARG_CHECK(((uintptr_t)workspace & 255) == 0);
+    CU_CHECK(cudaSetDevice(device));
+    cdlrm_mlp* m = new cdlrm_mlp();
+    m->device = device;
+    m->L = n_layers;
+    m->cap = batch_cap;
+    m->sigmoid_layer = sigmoid_layer;
+    m->D.assign(h_dims, h_dims + n_layers + 1);
+    for (int v : m->D) {
+        if (v < 1) {
+            delete m;
+            cdlrm_set_error("layer width must be positive");
+            return CDLRM_ERR_ARG;
+        }
+    }
+    const int64_t need = mlp_carve(m, (char*)workspace);
+    if (need > workspace_bytes) {
+        delete m;
+        cdlrm_set_error("MLP workspace too small: %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+        return CDLRM_ERR_ARG;
+    }
+    if (cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || m->num_sms <= 0) m->num_sms = 148;
+    *out = m;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_mlp_destroy(cdlrm_mlp* m) {
+    delete m;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_mlp_forward(cdlrm_mlp* m, const float* x, int64_t ldx, int32_t batch, const float* const* h_W,
+                                 const float* const* h_b, float* y, int64_t ldy, cdlrm_stream stream) {
+    ARG_CHECK(m && x && h_W && h_b && y);
+    ARG_CHECK(batch >= 0 && batch <= m->cap && ldx >= m->D[0] && ldy >= m->D[m->L]);
+    if (batch == 0) return CDLRM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(m->device));
+    const int L = m->L;
+    const int64_t capp = pad4(m->cap);
+    int rc;
+    if (!m->ones_set) {     // the ones rows of the transposed activations (bias gradient); lo part = 0
+        for (int i = 0; i < L; ++i) {
+            LAUNCH(K_MLP_SPLIT, s, (fill_kernel<<<64, 256, 0, s>>>(m->xt_hi[i] + (int64_t)m->D[i] * capp, capp, 1.f)));
+            LAUNCH(K_MLP_SPLIT, s, (fill_kernel<<<64, 256, 0, s>>>(m->xt_lo[i] + (int64_t)m->D[i] * capp, capp, 0.f)));
+        }
+        CU_CHECK(cudaGetLastError());
+        m->ones_set = true;
+    }
+    // weights: W [N,K] -> hi/lo K-major and transposed (the dgrad operand)
+    for (int l = 0; l < L; ++l) {
+        ARG_CHECK(h_W[l] && h_b[l]);
+        const int K = m->D[l], N = m->D[l + 1];
+        if ((rc = launch_split(h_W[l], K, N, K, nullptr, 0, ACT_NONE, m->w_hi[l], m->w_lo[l], pad4(K), m->wt_hi[l], m->wt_lo[l], pad4(N), s))) return rc;
+    }
+    // input
+    if ((rc = launch_split(x, ldx, batch, m->D[0], nullptr, 0, ACT_NONE, m->x_hi[0], m->x_lo[0], pad4(m->D[0]), m->xt_hi[0], m->xt_lo[0], capp, s))) return rc;
+    for (int l = 0; l < L; ++l) {
+        const int K = m->D[l], N = m->D[l + 1];
+        Epi ep = {};
+        ep.M = batch; ep.N = N; ep.K = K;
+        ep.bias = h_b[l];
+        ep.act = (l == m->sigmoid_layer) ? ACT_SIGMOID : ACT_RELU;
+        ep.vec_col = -1;
+        if (l + 1 < L) {
+            ep.C_hi = m->x_hi[l + 1]; ep.C_lo = m->x_lo[l + 1]; ep.ld_split = pad4(N);
+            ep.CT_hi = m->xt_hi[l + 1]; ep.CT_lo = m->xt_lo[l + 1]; ep.ld_t = capp;
+        } else {
+            ep.C = m->y_out; ep.ldc = pad4(N);
+        }
+        if ((rc = launch_gemm(m->x_hi[l], m->x_lo[l], pad4(K), m->w_hi[l], m->w_lo[l], pad4(K), ep, 1, s))) return rc;
+    }
+    CU_CHECK(cudaMemcpy2DAsync(y, ldy * 4, m->y_out, pad4(m->D[L]) * 4, (size_t)m->D[L] * 4, batch, cudaMemcpyDeviceToDevice, s));
+    m->last_batch = batch;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, float* dx, int64_t lddx, float* const* h_dW,
+                                  float* const* h_db, cdlrm_stream stream) {
+    ARG_CHECK(m && dy && h_dW && h_db);
+    const int batch = m->last_batch;
+    if (batch <= 0) {
+        cdlrm_set_error("cdlrm_mlp_backward without a preceding forward");
+        return CDLRM_ERR_STATE;
+    }
+    ARG_CHECK(lddy >= m->D[m->L] && (dx == nullptr || lddx >= m->D[0]));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(m->device));
+    const int L = m->L;
+    const int64_t capp = pad4(m->cap);
+    int rc;
+    // gradient w.r.t. the last pre-activation: dy * act'(y), as hi/lo, row-major and transposed
+    const int last_act = (L - 1 == m->sigmoid_layer) ? ACT_SIGMOID : ACT_RELU;
+    if ((rc = launch_split(dy, lddy, batch, m->D[L], m->y_out, pad4(m->D[L]), last_act, m->g_hi[L], m->g_lo[L], pad4(m->D[L]),
+                           m->gt_hi[L], m->gt_lo[L], capp, s))) return rc;
+    for (int l = L - 1; l >= 0; --l) {
+        const int K = m->D[l], N = m->D[l + 1];
+        ARG_CHECK(h_dW[l] && h_db[l]);
+        // wgrad: [dW | db] = dZ^T [X^T ; 1]   (split-K over the batch, atomics into zeroed buffers)
+        CU_CHECK(cudaMemsetAsync(h_dW[l], 0, (size_t)N * K * 4, s));
+        CU_CHECK(cudaMemsetAsync(h_db[l], 0, (size_t)N * 4, s));
+        {
+            Epi ep = {};
+            ep.M = N; ep.N = K + 1; ep.K = batch;
+            ep.C = h_dW[l]; ep.ldc = K;
+            ep.atomic = 1;
+            ep.vec_col = K; ep.vec = h_db[l];
+            const int tiles = ((N + BM - 1) / BM) * ((K + 1 + BN - 1) / BN);
+            int splits = (m->num_sms + tiles - 1) / tiles;
+            if ((rc = launch_gemm(m->gt_hi[l + 1], m->gt_lo[l + 1], capp, m->xt_hi[l], m->xt_lo[l], capp, ep, splits, s))) return rc;
+        }
+        // dgrad: dX = dZ W, then the ReLU mask of the layer below -> its dZ (split, both layouts)
+        if (l > 0) {
+            Epi ep = {};
+            ep.M = batch; ep.N = K; ep.K = N;
+            ep.vec_col = -1;
+            ep.mask = m->x_hi[l]; ep.ld_mask = pad4(K);     // x_l = relu(...) > 0  <=>  its hi part > 0
+            ep.C_hi = m->g_hi[l]; ep.C_lo = m->g_lo[l]; ep.ld_split = pad4(K);
+            ep.CT_hi = m->gt_hi[l]; ep.CT_lo = m->gt_lo[l]; ep.ld_t = capp;
+            if ((rc = launch_gemm(m->g_hi[l + 1], m->g_lo[l + 1], pad4(N), m->wt_hi[l], m->wt_lo[l], pad4(N), ep, 1, s))) return rc;
+        } else if (dx) {
+            Epi ep = {};
+            ep.M = batch; ep.N = K; ep.K = N;
+            ep.vec_col = -1;
+            ep.C = dx; ep.ldc = lddx;
+            if ((rc = launch_gemm(m->g_hi[l + 1], m->g_lo[l + 1], pad4(N), m->wt_hi[l], m->wt_lo[l], pad4(N), ep, 1, s))) return rc;
+        }
+    }
+    return CDLRM_OK;
+}

@@ -9,6 +9,7 @@ group or the dot interaction without a CUDA device raises.
 Reference citations are ``file:line`` in the reference tree.
 """
 import ctypes
+import os
 import sys
 import weakref
 
@@ -573,6 +574,100 @@ class _InteractFn(torch.autograd.Function):
         return (None,) + tuple(dfeat.unbind(0))
 
 
+# ------------------------------------------------------------------------------------
+# dense MLPs on the tensor cores (cdlrm_mlp_*: 3xTF32 split GEMMs, FP32 accuracy)
+# ------------------------------------------------------------------------------------
+
+
+class _MlpState:
+    """One cdlrm_mlp object (C ABI) + its workspace for an nn.Sequential built by
+    DLRM_Net.create_mlp (model_no_ddp.py:244-270): the layer list, the batch capacity and the
+    activations the last forward left behind for the backward."""
+
+    def __init__(self, seq, sigmoid_layer):
+        self.linears = [m for m in seq if isinstance(m, nn.Linear)]
+        self.dims = [self.linears[0].in_features] + [m.out_features for m in self.linears]
+        self.sigmoid_layer = int(sigmoid_layer)
+        self.handle = None
+        self.cap = 0
+        self.ws = None
+        self.fwd_id = 0
+
+    def ensure(self, batch, dev):
+        if self.handle is not None and batch <= self.cap and self.ws.device == dev:
+            return
+        self.close()
+        L = len(self.linears)
+        dims = (ctypes.c_int32 * (L + 1))(*self.dims)
+        need = lib.cdlrm_mlp_workspace_bytes(L, dims, batch)
+        if need <= 0:
+            raise _lib.CdlrmError("cdlrm_mlp_workspace_bytes failed")
+        self.ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        base = (self.ws.data_ptr() + 255) & ~255
+        h = ctypes.c_void_p()
+        check(lib.cdlrm_mlp_create(ctypes.byref(h), dev.index, L, dims, batch, self.sigmoid_layer, _vp(base), need))
+        self.handle, self.cap = h, batch
+
+    def close(self):
+        if self.handle is not None:
+            lib.cdlrm_mlp_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _MlpFn(torch.autograd.Function):
+    """y = seq(x) for a create_mlp Sequential; params = W_0, b_0, W_1, b_1, ..."""
+
+    @staticmethod
+    def forward(ctx, state, x, *params):
+        dev = x.device
+        if x.dtype != torch.float32 or x.stride(1) != 1:
+            x = x.contiguous().float()
+        B = x.shape[0]
+        state.ensure(B, dev)
+        Ws = [p if p.is_contiguous() else p.contiguous() for p in params[0::2]]
+        bs = [p if p.is_contiguous() else p.contiguous() for p in params[1::2]]
+        y = torch.empty(B, state.dims[-1], dtype=torch.float32, device=dev)
+        check(lib.cdlrm_mlp_forward(state.handle, _vp(x.data_ptr()), x.stride(0), B,
+                                    _lib.ptr_array([w.data_ptr() for w in Ws]),
+                                    _lib.ptr_array([b.data_ptr() for b in bs]),
+                                    _vp(y.data_ptr()), y.stride(0), _stream_ptr(dev)))
+        state.fwd_id += 1
+        ctx.state, ctx.fwd_id, ctx.batch = state, state.fwd_id, B
+        ctx.need_dx = ctx.needs_input_grad[1]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        st = ctx.state
+        if ctx.fwd_id != st.fwd_id:
+            raise _lib.CdlrmError("MLP backward after another forward of the same MLP: its saved activations are gone")
+        dev = dy.device
+        if dy.stride(1) != 1 or dy.dtype != torch.float32:
+            dy = dy.contiguous().float()
+        B = ctx.batch
+        dWs = [torch.empty(st.dims[i + 1], st.dims[i], dtype=torch.float32, device=dev) for i in range(len(st.linears))]
+        dbs = [torch.empty(st.dims[i + 1], dtype=torch.float32, device=dev) for i in range(len(st.linears))]
+        dx = None
+        dx_ptr, lddx = None, 0
+        if ctx.need_dx:
+            ld = (st.dims[0] + 3) & ~3
+            dx = torch.empty(B, ld, dtype=torch.float32, device=dev)[:, :st.dims[0]]
+            dx_ptr, lddx = dx.data_ptr(), ld
+        check(lib.cdlrm_mlp_backward(st.handle, _vp(dy.data_ptr()), dy.stride(0), _vp(dx_ptr), lddx,
+                                     _lib.ptr_array([t.data_ptr() for t in dWs]),
+                                     _lib.ptr_array([t.data_ptr() for t in dbs]), _stream_ptr(dev)))
+        grads = []
+        for w, b in zip(dWs, dbs):
+            grads += [w, b]
+        return (None, dx) + tuple(grads)
+
+
 class DLRM_Net(nn.Module):
     """model_no_ddp.py:215-316.  MLPs and loss stay stock PyTorch (cuBLAS); the pairwise-dot
     interaction (:272-293) runs in cdlrm_interact_fwd/_bwd."""
@@ -591,7 +686,12 @@ class DLRM_Net(nn.Module):
             self.cpu = torch.device("cpu")
             self.bot_l = self.create_mlp(ln_bot, sigmoid_bot)
             self.top_l = self.create_mlp(ln_top, sigmoid_top)
+            self._sigmoid = {"bot": int(sigmoid_bot), "top": int(sigmoid_top)}
         self.pre_interact = None   # optional callable run between the bottom MLP and the interaction
+        # "tcgen05": cdlrm_mlp_* (3xTF32 tensor-core GEMMs with fused epilogues, FP32 accuracy);
+        # "torch": the stock nn.Sequential (cuBLAS SIMT sgemm)
+        self.mlp_impl = os.environ.get("CDLRM_MLP", "torch")
+        self._mlp_state = {}
 
     def create_mlp(self, ln, sigmoid_layer):
         """:244-270 -- numpy-RNG initialisation in the reference's draw order."""
@@ -617,12 +717,26 @@ class DLRM_Net(nn.Module):
         else:
             sys.exit("ERROR: --arch-interaction-op=" + self.arch_interaction_op + " is not supported")
 
+    def apply_mlp(self, which, x):
+        """bot_l / top_l (:306-309).  On CUDA with mlp_impl == "tcgen05" the whole Sequential runs
+        in cdlrm_mlp_forward/_backward; the nn.Linear parameters stay the trainable state."""
+        seq = self.bot_l if which == "bot" else self.top_l
+        if self.mlp_impl != "tcgen05" or not x.is_cuda:
+            return seq(x)
+        st = self._mlp_state.get(which)
+        if st is None:
+            st = self._mlp_state[which] = _MlpState(seq, getattr(self, "_sigmoid", {}).get(which, -1))
+        params = []
+        for m in st.linears:
+            params += [m.weight, m.bias]
+        return _MlpFn.apply(st, x, *params)
+
     def forward(self, dense_x, ly):
-        x = self.bot_l(dense_x)
+        x = self.apply_mlp("bot", dense_x)
         if self.pre_interact is not None:
             self.pre_interact()    # e.g. cache_group.join_forward: lookups ran beside the bottom MLP
         z = self.interact_features(x, ly)
-        p = self.top_l(z)
+        p = self.apply_mlp("top", z)
         if 0.0 < self.loss_threshold < 1.0:
             return torch.clamp(p, min=self.loss_threshold, max=(1.0 - self.loss_threshold))
         return p

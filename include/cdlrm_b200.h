@@ -96,7 +96,8 @@ int cdlrm_embed_fwd(cdlrm_ctx* ctx, int table_begin, int table_count,
 /* ---- backward + SGD: autograd of EmbeddingBag(sparse=True) followed by
  *      optimizer_embeds.step(), main_no_ddp.py:376,409,413 -------------------------
  * weight[slot] -= lr * sum_{j: slot_j == slot} d_out[bag(j)], duplicates merged by a
- * per-table sort (no atomics unless one slot has more than 8 contributions in the batch).
+ * per-table sort (plain read-modify-write per slot; atomics only where the run of one slot
+ * crosses a 32-entry range of the sorted order: hot rows, tiny tables).
  * d_out row of bag b of table k: d_out + (k-table_begin)*ld_dout + b*dout_row_stride.
  * Marks touched slots in the dirty bitmaps when bound.  */
 int64_t cdlrm_embed_bwd_plan_bytes(int table_count, int32_t n_idx);
@@ -122,6 +123,27 @@ int cdlrm_interact_fwd(int device, const float* const* h_feat, int n_feat, int64
 int cdlrm_interact_bwd(int device, const float* const* h_feat, int n_feat, int64_t feat_row_stride,
                        int32_t batch, int dim, int itself, const float* d_out, int64_t ld_dout,
                        float* d_feat, int64_t ld_dfeat, cdlrm_stream stream);
+
+/* ---- dense MLPs: DLRM_Net.create_mlp / bot_l / top_l, model_no_ddp.py:244-270,306-316
+ *      (the layers either side of the interaction) --------
+ * Layer l: y = act(x W_l^T + b_l), W_l float32 [dims[l+1], dims[l]] (nn.Linear layout),
+ * act = ReLU, or Sigmoid for l == sigmoid_layer (:262-265).  FP32 results (3xTF32 split
+ * products with FP32 accumulation on the tensor cores; see csrc/mlp.cu).
+ * The object keeps the activations of the last forward in the caller's workspace
+ * (256-byte aligned, cdlrm_mlp_workspace_bytes) for the backward:
+ *   dW_l = dZ_l^T x_l, db_l = column sums of dZ_l, dx = dZ_0 W_0 (optional, may be NULL),
+ * with dZ the gradient w.r.t. the pre-activation.  h_W/h_b/h_dW/h_db are HOST arrays of
+ * n_layers DEVICE pointers; dW_l [dims[l+1], dims[l]] and db_l [dims[l+1]] are dense. */
+typedef struct cdlrm_mlp cdlrm_mlp;
+int64_t cdlrm_mlp_workspace_bytes(int n_layers, const int32_t* h_dims, int32_t batch_cap);
+int cdlrm_mlp_create(cdlrm_mlp** out, int device, int n_layers, const int32_t* h_dims,
+                     int32_t batch_cap, int sigmoid_layer, void* workspace, int64_t workspace_bytes);
+int cdlrm_mlp_destroy(cdlrm_mlp* mlp);
+int cdlrm_mlp_forward(cdlrm_mlp* mlp, const float* x, int64_t ldx, int32_t batch,
+                      const float* const* h_W, const float* const* h_b,
+                      float* y, int64_t ldy, cdlrm_stream stream);
+int cdlrm_mlp_backward(cdlrm_mlp* mlp, const float* dy, int64_t lddy, float* dx, int64_t lddx,
+                       float* const* h_dW, float* const* h_db, cdlrm_stream stream);
 
 /* ---- window planner: Prefetcher.process_batch_slice (cache_manager.py:27-46, the
  *      torch.unique at :32) + the decision part of CacheEmbeddings

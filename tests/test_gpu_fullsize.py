@@ -71,8 +71,12 @@ def test_terabyte_shape_steps_match_oracle(losers):
             n_miss_seen += int(cg.last_n_miss.sum())
             for k in range(T):
                 assert np.array_equal(slots[k].cpu().numpy(), oslots[k]), f"slots of table {k} differ"
-                # one id per bag: the pooled row is a copy of the cache row -> bit-exact
-                assert np.array_equal(ly[k].detach().cpu().numpy(), oly[k]), f"pooled rows of table {k} differ"
+                # one id per bag: the pooled row is a copy of the cache row -> bit-exact until the first
+                # update; afterwards the rows carry the rounding of a different (deterministic) sum order
+                if w == 0 and b == 0:
+                    assert np.array_equal(ly[k].detach().cpu().numpy(), oly[k]), f"pooled rows of table {k} differ"
+                else:
+                    util.assert_close_fp32(ly[k].detach().cpu().numpy(), oly[k], err_msg=f"pooled rows of table {k}")
                 O.backward_sgd_table(oc.weight[k], oslots[k], off, G[k], lr)
     assert n_miss_seen > 0, "the stream was meant to overflow the cache of the largest table"
     cg.check_device_flags()
@@ -100,6 +104,9 @@ def test_update_is_linear_and_applies_every_gradient_row_once():
     planner.install(rec, write_master=False)
     for e in cg.emb_l:
         e.weight.data.zero_()
+    for e in master.emb_l:      # ids that lost a contested way are served from the master through the aux rows
+        e.weight.data.zero_()
+    torch.cuda.synchronize()
     lS_o = torch.arange(B).reshape(1, -1).repeat(T, 1)
     opt = torch.optim.SGD(cg.parameters(), lr=1.0)
     ly, slots = cg(lS_o, torch.from_numpy(ids), master, 0)

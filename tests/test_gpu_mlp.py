@@ -1,0 +1,102 @@
+"""GPU parity of the tensor-core MLP path (cdlrm_mlp_*: 3xTF32 split GEMMs, csrc/mlp.cu) against
+the stock nn.Sequential the reference builds in DLRM_Net.create_mlp (model_no_ddp.py:244-270).
+
+Floating point, so the bar is the north_star tolerance (1e-5 relative to the tensor's scale,
+util.assert_close_fp32) against an FP64 evaluation of the same layers, and -- to show that the
+split products really deliver FP32 accuracy -- the error must stay within a small factor of
+the error torch's own FP32 (SIMT sgemm) path makes against the same FP64 reference."""
+import numpy as np
+import pytest
+import torch
+
+import util
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _net(ln_bot, ln_top, impl):
+    from cdlrm_b200 import model_no_ddp as M
+    np.random.seed(17)
+    net = M.DLRM_Net(np.asarray(ln_bot), np.asarray(ln_top), arch_interaction_op="dot", arch_interaction_itself=False,
+                     sigmoid_bot=-1, sigmoid_top=len(ln_top) - 2).to(DEV)
+    net.mlp_impl = impl
+    return net
+
+
+def _ref64(seq, x, dy):
+    seq64 = torch.nn.Sequential(*[type(m)(m.in_features, m.out_features) if isinstance(m, torch.nn.Linear) else type(m)()
+                                  for m in seq]).double().to(DEV)
+    seq64.load_state_dict({k: v.double() for k, v in seq.state_dict().items()})
+    x64 = x.double().requires_grad_()
+    y = seq64(x64)
+    y.backward(dy.double())
+    return y.detach(), x64.grad, [p.grad for p in seq64.parameters()]
+
+
+def _err(a, ref):
+    ref = ref.double()
+    return float((a.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("which,dims,B", [
+    ("bot", [13, 512, 256, 128], 8192),
+    ("top", [479, 512, 512, 256, 1], 8192),
+    ("top", [479, 512, 512, 256, 1], 1000),       # ragged batch: partial M tile
+    ("bot", [13, 64, 16], 77),                     # configs[0]-sized layers, N below one tile
+    ("top", [367, 512, 256, 1], 2048),             # configs[1] (Kaggle shape) top MLP
+])
+def test_mlp_matches_fp64_reference(which, dims, B):
+    ln_bot = dims if which == "bot" else [13, 32, 16]
+    ln_top = dims if which == "top" else [40, 8, 1]
+    net = _net(ln_bot, ln_top, "tcgen05")
+    seq = net.bot_l if which == "bot" else net.top_l
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn(B, dims[0], device=DEV, generator=g)
+    if which == "top":
+        x = x * 3.0
+    dy = torch.randn(B, dims[-1], device=DEV, generator=g)
+    y64, dx64, gp64 = _ref64(seq, x, dy)
+
+    def run(impl):
+        net.mlp_impl = impl
+        for p in seq.parameters():
+            p.grad = None
+        xi = x.clone().requires_grad_()
+        y = net.apply_mlp(which, xi)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        return y.detach(), xi.grad, [p.grad.clone() for p in seq.parameters()]
+
+    y_t, dx_t, gp_t = run("torch")
+    y_c, dx_c, gp_c = run("tcgen05")
+    pairs = [("y", y_c, y_t, y64), ("dx", dx_c, dx_t, dx64)] + \
+            [(f"grad{i}", a, b, c) for i, (a, b, c) in enumerate(zip(gp_c, gp_t, gp64))]
+    for name, mine, theirs, ref in pairs:
+        e_mine, e_torch = _err(mine, ref), _err(theirs, ref)
+        assert e_mine <= 1e-5, f"{which} {name}: {e_mine:.3e} off the FP64 reference (torch FP32: {e_torch:.3e})"
+        assert e_mine <= 8 * e_torch + 2e-7, f"{which} {name}: {e_mine:.3e} vs torch FP32 {e_torch:.3e}: not FP32-grade"
+        util.assert_close_fp32(mine.cpu().numpy(), ref.float().cpu().numpy(), err_msg=f"{which} {name}")
+
+
+def test_dlrm_step_same_loss_and_grads_both_mlp_paths():
+    """One full DLRM_Net forward/backward (bottom MLP -> interaction -> top MLP -> BCE) with the
+    tensor-core MLPs against the stock Sequential path: loss and every parameter gradient."""
+    ln_bot, ln_top = [13, 512, 256, 128], [479, 512, 512, 256, 1]
+    B, d, T = 2048, 128, 26
+    net = _net(ln_bot, ln_top, "torch")
+    g = torch.Generator(device=DEV).manual_seed(1)
+    X = torch.randn(B, 13, device=DEV, generator=g)
+    ly = [torch.randn(B, d, device=DEV, generator=g) * 0.05 for _ in range(T)]
+    Y = (torch.rand(B, 1, device=DEV, generator=g) < 0.25).float()
+    out = {}
+    for impl in ("torch", "tcgen05"):
+        net.mlp_impl = impl
+        net.zero_grad(set_to_none=True)
+        lyi = [t.clone().requires_grad_() for t in ly]
+        loss = torch.nn.functional.binary_cross_entropy(net(X, lyi), Y)
+        loss.backward()
+        out[impl] = (loss.item(), [p.grad.clone() for p in net.parameters()], [t.grad.clone() for t in lyi])
+    assert abs(out["tcgen05"][0] - out["torch"][0]) <= 1e-5 * abs(out["torch"][0])
+    for a, b in zip(out["tcgen05"][1] + out["tcgen05"][2], out["torch"][1] + out["torch"][2]):
+        util.assert_close_fp32(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-5)

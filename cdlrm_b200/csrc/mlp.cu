@@ -34,7 +34,11 @@ constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB per operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi, A_lo, B_hi, B_lo
 constexpr int GEMM_THREADS = 192;                 // warp 0: TMA, warp 1: MMA + TMEM, warps 2-5: epilogue
-constexpr int TMEM_COLS = 128;
+// NACC TMEM accumulators of 128 columns.  The tensor core's FP32 accumulation is not
+// round-to-nearest, so the error of one accumulator grows with the number of MMAs chained
+// into it.  NACC > 1: the two small cross terms go to the last accumulator, the hi*hi
+// terms of successive k-steps rotate over the others; the epilogue adds them up in
+// registers (round-to-nearest).
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
@@ -135,9 +139,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 128
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-__device__ __forceinline__ float tf32_lo(float x, float hi) { return __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u); }
+// round-to-nearest TF32 (ties away from zero in magnitude): the residual x - hi is then signed and
+// at most half a TF32 ulp, and the same rounding of the residual leaves an error <= 2^-24 |x|
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_tr(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ int g_split_trunc = 0;       // test hook: 1 = truncating split (the first version)
+__device__ __forceinline__ float tf32_hi(float x) { return g_split_trunc ? tf32_tr(x) : tf32_rn(x); }
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return g_split_trunc ? tf32_tr(x - hi) : tf32_rn(x - hi); }
 
+template <int NACC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -168,6 +178,7 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
     }
+    constexpr int TMEM_COLS = 128 * NACC;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -196,6 +207,7 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     } else if (warp == 1) {
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
+            uint32_t used = 0;                     // accumulators that already hold a value
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
@@ -209,10 +221,13 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
                     const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per k-step, in 16-byte units
-                    // the small cross terms first, the hi*hi term last
-                    tc_mma_tf32(tmem_base, a_lo + adv, b_hi + adv, IDESC_TF32, (i | k) != 0);
-                    tc_mma_tf32(tmem_base, a_hi + adv, b_lo + adv, IDESC_TF32, 1u);
-                    tc_mma_tf32(tmem_base, a_hi + adv, b_hi + adv, IDESC_TF32, 1u);
+                    constexpr int SMALL = NACC - 1;                              // accumulator of the cross terms
+                    const int big = NACC > 1 ? (i * (BK / 8) + k) % (NACC - 1) : 0;   // accumulator of this k-step's hi*hi
+                    tc_mma_tf32(tmem_base + SMALL * 128, a_lo + adv, b_hi + adv, IDESC_TF32, (used >> SMALL) & 1u);
+                    used |= 1u << SMALL;
+                    tc_mma_tf32(tmem_base + SMALL * 128, a_hi + adv, b_lo + adv, IDESC_TF32, 1u);
+                    tc_mma_tf32(tmem_base + big * 128, a_hi + adv, b_hi + adv, IDESC_TF32, (used >> big) & 1u);
+                    used |= 1u << big;
                 }
                 tc_commit(&empty_bar[s]);          // the stage is free once these MMAs have read it
             }
@@ -231,6 +246,19 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             if (col0 >= ep.N) break;                               // warp-uniform
             float v[32];
             tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            if constexpr (NACC > 1) {
+                // accumulators that never received an MMA (short reductions) hold garbage: skip them
+                const int n_big = min(NACC - 1, num_kb * (BK / 8));
+#pragma unroll
+                for (int a = 1; a < NACC; ++a) {
+                    if (a < n_big || a == NACC - 1) {
+                        float w[32];
+                        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 128 + c * 32), w);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += w[j];
+                    }
+                }
+            }
             if (ep.bias) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -398,11 +426,15 @@ int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t rows, int
     return CDLRM_OK;
 }
 
+int g_nacc = 4;      // TMEM accumulators per tile (1, 2 or 4); cdlrm_mlp_set_option(1, .)
+
 int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
                 Epi ep, int splits, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
-        CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         attr_done = true;
     }
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -417,7 +449,9 @@ int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* 
     ep.kb_per_split = (num_kb + splits - 1) / splits;
     splits = (num_kb + ep.kb_per_split - 1) / ep.kb_per_split;      // no empty split
     dim3 grid((ep.N + BN - 1) / BN, (ep.M + BM - 1) / BM, splits);
-    LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep)));
+    if (g_nacc == 1) LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep)));
+    else if (g_nacc == 2) LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep)));
+    else LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<4><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep)));
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
 }
@@ -530,6 +564,20 @@ extern "C" int cdlrm_mlp_create(cdlrm_mlp** out, int device, int n_layers, const
     return CDLRM_OK;
 }
 
+// key 0: split rounding (0 = round to nearest, 1 = truncate); key 1: TMEM accumulators per tile (1, 2, 4)
+extern "C" int cdlrm_mlp_set_option(int key, int value) {
+    if (key == 0) {
+        const int v = value ? 1 : 0;
+        CU_CHECK(cudaMemcpyToSymbol(g_split_trunc, &v, sizeof(int)));
+    } else if (key == 1) {
+        ARG_CHECK(value == 1 || value == 2 || value == 4);
+        g_nacc = value;
+    } else {
+        ARG_CHECK(false && "unknown option");
+    }
+    return CDLRM_OK;
+}
+
 extern "C" int cdlrm_mlp_destroy(cdlrm_mlp* m) {
     delete m;
     return CDLRM_OK;
@@ -566,7 +614,7 @@ extern "C" int cdlrm_mlp_forward(cdlrm_mlp* m, const float* x, int64_t ldx, int3
         Epi ep = {};
         ep.M = batch; ep.N = N; ep.K = K;
         ep.bias = h_b[l];
-        ep.act = (l == m->sigmoid_layer) ? ACT_SIGMOID : ACT_RELU;
+        ep.act = (l == m->sigmoid_layer) ? ACT_SIGMOID : ((m->sigmoid_layer == -2 && l == L - 1) ? ACT_NONE : ACT_RELU);
         ep.vec_col = -1;
         if (l + 1 < L) {
             ep.C_hi = m->x_hi[l + 1]; ep.C_lo = m->x_lo[l + 1]; ep.ld_split = pad4(N);
@@ -596,7 +644,7 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
     const int64_t capp = pad4(m->cap);
     int rc;
     // gradient w.r.t. the last pre-activation: dy * act'(y), as hi/lo, row-major and transposed
-    const int last_act = (L - 1 == m->sigmoid_layer) ? ACT_SIGMOID : ACT_RELU;
+    const int last_act = (L - 1 == m->sigmoid_layer) ? ACT_SIGMOID : (m->sigmoid_layer == -2 ? ACT_NONE : ACT_RELU);
     if ((rc = launch_split(dy, lddy, batch, m->D[L], m->y_out, pad4(m->D[L]), last_act, m->g_hi[L], m->g_lo[L], pad4(m->D[L]),
                            m->gt_hi[L], m->gt_lo[L], capp, s))) return rc;
     for (int l = L - 1; l >= 0; --l) {

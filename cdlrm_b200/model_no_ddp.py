@@ -690,7 +690,7 @@ class DLRM_Net(nn.Module):
         self.pre_interact = None   # optional callable run between the bottom MLP and the interaction
         # "tcgen05": cdlrm_mlp_* (3xTF32 tensor-core GEMMs with fused epilogues, FP32 accuracy);
         # "torch": the stock nn.Sequential (cuBLAS SIMT sgemm)
-        self.mlp_impl = os.environ.get("CDLRM_MLP", "torch")
+        self.mlp_impl = os.environ.get("CDLRM_MLP", "tcgen05")
         self._mlp_state = {}
 
     def create_mlp(self, ln, sigmoid_layer):

@@ -139,6 +139,10 @@ int64_t cdlrm_mlp_workspace_bytes(int n_layers, const int32_t* h_dims, int32_t b
 int cdlrm_mlp_create(cdlrm_mlp** out, int device, int n_layers, const int32_t* h_dims,
                      int32_t batch_cap, int sigmoid_layer, void* workspace, int64_t workspace_bytes);
 int cdlrm_mlp_destroy(cdlrm_mlp* mlp);
+/* sigmoid_layer == -2: the last layer has no activation (plain affine layer; test hook).
+ * Numerics knobs (process-wide; defaults are the accurate settings): key 0 = operand split
+ * rounding (0 nearest, 1 truncate), key 1 = TMEM accumulators per output tile (1, 2 or 4). */
+int cdlrm_mlp_set_option(int key, int value);
 int cdlrm_mlp_forward(cdlrm_mlp* mlp, const float* x, int64_t ldx, int32_t batch,
                       const float* const* h_W, const float* const* h_b,
                       float* y, int64_t ldy, cdlrm_stream stream);

@@ -130,5 +130,7 @@ def test_update_is_linear_and_applies_every_gradient_row_once():
         opt.step()
     for k in range(T):
         # per-slot sums of up to thousands of N(0,1) rows: the round trip is exact to rounding of the sum
-        err = (cg.emb_l[k].weight.data - W0[k]).abs().max().item()
+        # (cache rows only: the aux rows are rewritten from the master by every forward)
+        nc = cg.cache_sizes[k] * ways
+        err = (cg.emb_l[k].weight.data[:nc] - W0[k][:nc]).abs().max().item()
         assert err < 2e-2 * 1e-5 * B + 1e-4, f"table {k}: +G/-G round trip off by {err}"

@@ -162,8 +162,10 @@ def test_interaction_matches_oracle_at_size(shape):
     util.assert_close_fp32(torch.stack([t.grad for t in lyt]).cpu().numpy(), np.stack(dly))
 
 
-def test_dlrm_tiny_loss_matches_reference_golden():
-    """End to end: cache + interaction kernels + stock MLPs, BCE loss, both optimizers."""
+@pytest.mark.parametrize("mlp_impl", ["tcgen05", "torch"])
+def test_dlrm_tiny_loss_matches_reference_golden(mlp_impl):
+    """End to end: cache + interaction kernels + MLPs (tensor-core path and stock PyTorch), BCE
+    loss, both optimizers, against the loss curve and final parameters of the reference."""
     C, R, M = _mods()
     g = util.load_golden("dlrm_tiny.npz")
     cfg = util.golden_cfg(g)
@@ -183,6 +185,7 @@ def test_dlrm_tiny_loss_matches_reference_golden():
     for i, p in enumerate(dlrm.parameters()):
         assert np.array_equal(p.detach().numpy(), g[f"mlp_init_{i}"])   # same numpy-RNG init order
     dlrm = dlrm.to(DEV)
+    dlrm.mlp_impl = mlp_impl
     loss_fn = torch.nn.BCELoss(reduction="mean")
     opt_m = torch.optim.SGD(dlrm.parameters(), lr=0.1)
     opt_e = torch.optim.SGD(cg.parameters(), lr=cfg["lr_embeds"])

@@ -50,17 +50,16 @@ struct Epi {
     int act;                     // ACT_*
     const float* mask;           // relu-backward: result passes where mask[row, col] > 0 (or null)
     int64_t ld_mask;
-    float* C;                    // fp32 result, row-major (or null)
-    int64_t ldc;
-    float* C_hi;                 // hi/lo split of the result, row-major (or null)
-    float* C_lo;
-    int64_t ld_split;
-    float* CT_hi;                // hi/lo split of the result, transposed [N][ld_t] (or null)
-    float* CT_lo;
-    int64_t ld_t;
-    int atomic;                  // 1: C += result with red.global.add (split-K)
-    int vec_col;                 // >= 0: this column of the result goes to vec[row] instead of C
-    float* vec;
+    int out_c;                   // 1: fp32 result row-major through map_c (2: reduce-add into it, split-K)
+    int out_split;               // 1: hi/lo split row-major through map_c_hi / map_c_lo
+    int out_t;                   // 1: hi/lo split transposed through map_t_hi / map_t_lo
+};
+
+// tensor maps of one launch: 4 operand maps (box 32 x 128, 128-byte swizzle) and up to 5 result
+// maps (box 32 x 32: row-major ones with the 128-byte swizzle, transposed ones dense)
+struct Maps {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap c, c_hi, c_lo, t_hi, t_lo;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,6 +93,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -149,9 +156,7 @@ __device__ __forceinline__ float tf32_lo(float x, float hi) { return g_split_tru
 
 template <int NACC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                   const Epi ep) {
+gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -173,10 +178,10 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_lo) : "memory");
     }
     constexpr int TMEM_COLS = 128 * NACC;
     if (warp == 1) {
@@ -198,10 +203,10 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
                 mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                 const int k = (kb0 + i) * BK;
-                tma_load_2d(base + 0 * TILE_BYTES, &map_a_hi, k, m0, &full_bar[s]);
-                tma_load_2d(base + 1 * TILE_BYTES, &map_a_lo, k, m0, &full_bar[s]);
-                tma_load_2d(base + 2 * TILE_BYTES, &map_b_hi, k, n0, &full_bar[s]);
-                tma_load_2d(base + 3 * TILE_BYTES, &map_b_lo, k, n0, &full_bar[s]);
+                tma_load_2d(base + 0 * TILE_BYTES, &maps.a_hi, k, m0, &full_bar[s]);
+                tma_load_2d(base + 1 * TILE_BYTES, &maps.a_lo, k, m0, &full_bar[s]);
+                tma_load_2d(base + 2 * TILE_BYTES, &maps.b_hi, k, n0, &full_bar[s]);
+                tma_load_2d(base + 3 * TILE_BYTES, &maps.b_lo, k, n0, &full_bar[s]);
             }
         }
     } else if (warp == 1) {
@@ -235,11 +240,18 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
     } else {
         // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), +32) =====
+        // Results leave through shared memory and TMA stores: per 32-column chunk a warp stages up
+        // to four 32x32 fp32 tiles (4 KB each; row-major tiles in the 128-byte swizzle, transposed
+        // tiles dense) in the ring's memory -- every MMA has retired, the ring is free -- double
+        // buffered, so that the stores of chunk c overlap the TMEM reads of chunk c+1.  The TMA
+        // clips rows >= M and columns >= N.
         const int q = warp & 3;
         const int row = m0 + q * 32 + lane;
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         const bool row_ok = row < ep.M;
+        uint8_t* wbase = smem + q * (2 * 4 * 4096);               // 32 KB per warp: 2 buffers x 4 tiles
+        const int sw = lane & 7;                                  // swizzle phase of this thread's row
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             const int col0 = n0 + c * 32;
@@ -247,16 +259,12 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             float v[32];
             tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
             if constexpr (NACC > 1) {
-                // accumulators that never received an MMA (short reductions) hold garbage: skip them
-                const int n_big = min(NACC - 1, num_kb * (BK / 8));
 #pragma unroll
                 for (int a = 1; a < NACC; ++a) {
-                    if (a < n_big || a == NACC - 1) {
-                        float w[32];
-                        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 128 + c * 32), w);
+                    float w[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 128 + c * 32), w);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += w[j];
-                    }
+                    for (int j = 0; j < 32; ++j) v[j] += w[j];
                 }
             }
             if (ep.bias) {
@@ -273,63 +281,71 @@ gemm3x_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             }
             if (ep.mask && row_ok) {
                 const float* mrow = ep.mask + (int64_t)row * ep.ld_mask + col0;
+                if (col0 + 32 <= ep.ld_mask) {                    // rows are 16-byte aligned (ld multiple of 4)
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < ep.N && !(__ldg(mrow + j) > 0.f)) v[j] = 0.f;
-            }
-            if (ep.atomic) {
-                if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = col0 + j;
-                        if (col >= ep.N) continue;
-                        if (col == ep.vec_col) atomicAdd(ep.vec + row, v[j]);
-                        else atomicAdd(ep.C + (int64_t)row * ep.ldc + col, v[j]);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 mk = __ldg(reinterpret_cast<const float4*>(mrow + j));
+                        if (!(mk.x > 0.f)) v[j] = 0.f;
+                        if (!(mk.y > 0.f)) v[j + 1] = 0.f;
+                        if (!(mk.z > 0.f)) v[j + 2] = 0.f;
+                        if (!(mk.w > 0.f)) v[j + 3] = 0.f;
                     }
-                }
-                continue;
-            }
-            if (ep.C && row_ok) {
-                float* crow = ep.C + (int64_t)row * ep.ldc + col0;
-                if (col0 + 32 <= ep.N && (ep.ldc & 3) == 0 && ((uintptr_t)ep.C & 15) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (col0 + j < ep.N) crow[j] = v[j];
+                        if (col0 + j < ep.N && !(__ldg(mrow + j) > 0.f)) v[j] = 0.f;
                 }
             }
-            if (ep.C_hi || ep.CT_hi) {
+            uint8_t* buf = wbase + (c & 1) * (4 * 4096);
+            if (c >= 2) {                                          // the stores that last read this buffer
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+            }
+            // tile 0: v (row-major); tiles 0/1: hi, lo (row-major); tiles 2/3: hi, lo (transposed)
+            float4* t0 = reinterpret_cast<float4*>(buf + lane * 128);
+            if (ep.out_c) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t0[j ^ sw] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (ep.out_split || ep.out_t) {
                 float hi[32], lo[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { hi[j] = tf32_hi(v[j]); lo[j] = tf32_lo(v[j], hi[j]); }
-                if (ep.C_hi && row_ok) {
-                    float* hrow = ep.C_hi + (int64_t)row * ep.ld_split + col0;
-                    float* lrow = ep.C_lo + (int64_t)row * ep.ld_split + col0;
-                    if (col0 + 32 <= ep.N) {     // ld_split is a multiple of 4 and the bases are 16-byte aligned
+                if (ep.out_split) {
+                    float4* t1 = reinterpret_cast<float4*>(buf + 4096 + lane * 128);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            *reinterpret_cast<float4*>(hrow + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
-                            *reinterpret_cast<float4*>(lrow + j) = make_float4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < ep.N) { hrow[j] = hi[j]; lrow[j] = lo[j]; }
+                    for (int j = 0; j < 8; ++j) {
+                        t0[j ^ sw] = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        t1[j ^ sw] = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
                 }
-                if (ep.CT_hi && row_ok) {        // transposed: lanes = consecutive rows -> coalesced
+                if (ep.out_t) {
+                    float* t2 = reinterpret_cast<float*>(buf + 2 * 4096);
+                    float* t3 = reinterpret_cast<float*>(buf + 3 * 4096);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (col0 + j < ep.N) {
-                            ep.CT_hi[(int64_t)(col0 + j) * ep.ld_t + row] = hi[j];
-                            ep.CT_lo[(int64_t)(col0 + j) * ep.ld_t + row] = lo[j];
-                        }
-                    }
+                    for (int j = 0; j < 32; ++j) { t2[j * 32 + lane] = hi[j]; t3[j * 32 + lane] = lo[j]; }
                 }
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t sb = smem_u32(buf);
+                const int r0 = m0 + q * 32;
+                if (ep.out_c == 1) tma_store_2d(&maps.c, sb, col0, r0);
+                else if (ep.out_c == 2) tma_reduce_add_2d(&maps.c, sb, col0, r0);
+                if (ep.out_split) {
+                    tma_store_2d(&maps.c_hi, sb, col0, r0);
+                    tma_store_2d(&maps.c_lo, sb + 4096, col0, r0);
+                }
+                if (ep.out_t) {
+                    tma_store_2d(&maps.t_hi, sb + 2 * 4096, r0, col0);
+                    tma_store_2d(&maps.t_lo, sb + 3 * 4096, r0, col0);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
         tc_fence_before();
     }
     __syncthreads();
@@ -401,9 +417,9 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// [rows, inner] fp32, row stride ld elements (multiple of 4), box = 32 x 128, 128-byte swizzle;
-// out-of-range box elements read as zero
-int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t rows, int64_t ld) {
+// [rows, inner] fp32, row stride ld elements (multiple of 4); box = 32 x box_rows; out-of-range
+// box elements read as zero and are not written
+int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t rows, int64_t ld, int box_rows, bool swizzle) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         cdlrm_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -415,10 +431,11 @@ int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t rows, int
     }
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         cdlrm_set_error("cuTensorMapEncodeTiled failed (%d): inner %lld rows %lld ld %lld", (int)r, (long long)inner, (long long)rows, (long long)ld);
         return CDLRM_ERR_CUDA;
@@ -426,10 +443,23 @@ int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t rows, int
     return CDLRM_OK;
 }
 
+// where the result of a GEMM goes
+struct Out {
+    float* c = nullptr;          // fp32 [M, N] row-major
+    int64_t ldc = 0;
+    bool reduce = false;         // add into c (split-K) instead of storing
+    float* c_hi = nullptr;       // hi/lo split [M, N] row-major
+    float* c_lo = nullptr;
+    int64_t ld_split = 0;
+    float* t_hi = nullptr;       // hi/lo split transposed [N, M]
+    float* t_lo = nullptr;
+    int64_t ld_t = 0;
+};
+
 int g_nacc = 4;      // TMEM accumulators per tile (1, 2 or 4); cdlrm_mlp_set_option(1, .)
 
 int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
-                Epi ep, int splits, cudaStream_t s) {
+                Epi ep, const Out& o, int splits, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
         CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
@@ -437,23 +467,56 @@ int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* 
         CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         attr_done = true;
     }
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    Maps mp;
+    memset(&mp, 0, sizeof(mp));
     int rc;
-    if ((rc = make_map(&ma_hi, a_hi, ep.K, ep.M, lda))) return rc;
-    if ((rc = make_map(&ma_lo, a_lo, ep.K, ep.M, lda))) return rc;
-    if ((rc = make_map(&mb_hi, b_hi, ep.K, ep.N, ldb))) return rc;
-    if ((rc = make_map(&mb_lo, b_lo, ep.K, ep.N, ldb))) return rc;
+    if ((rc = make_map(&mp.a_hi, a_hi, ep.K, ep.M, lda, BM, true))) return rc;
+    if ((rc = make_map(&mp.a_lo, a_lo, ep.K, ep.M, lda, BM, true))) return rc;
+    if ((rc = make_map(&mp.b_hi, b_hi, ep.K, ep.N, ldb, BN, true))) return rc;
+    if ((rc = make_map(&mp.b_lo, b_lo, ep.K, ep.N, ldb, BN, true))) return rc;
+    ep.out_c = o.c ? (o.reduce ? 2 : 1) : 0;
+    ep.out_split = o.c_hi ? 1 : 0;
+    ep.out_t = o.t_hi ? 1 : 0;
+    if (ep.out_c && ep.out_split) {
+        cdlrm_set_error("a GEMM writes either the fp32 result or its hi/lo split row-major, not both");
+        return CDLRM_ERR_ARG;
+    }
+    if (o.c && (rc = make_map(&mp.c, o.c, ep.N, ep.M, o.ldc, 32, true))) return rc;
+    if (o.c_hi) {
+        if ((rc = make_map(&mp.c_hi, o.c_hi, ep.N, ep.M, o.ld_split, 32, true))) return rc;
+        if ((rc = make_map(&mp.c_lo, o.c_lo, ep.N, ep.M, o.ld_split, 32, true))) return rc;
+    }
+    if (o.t_hi) {
+        if ((rc = make_map(&mp.t_hi, o.t_hi, ep.M, ep.N, o.ld_t, 32, false))) return rc;
+        if ((rc = make_map(&mp.t_lo, o.t_lo, ep.M, ep.N, o.ld_t, 32, false))) return rc;
+    }
     const int num_kb = (ep.K + BK - 1) / BK;
     if (splits < 1) splits = 1;
     if (splits > num_kb) splits = num_kb;
     ep.kb_per_split = (num_kb + splits - 1) / splits;
     splits = (num_kb + ep.kb_per_split - 1) / ep.kb_per_split;      // no empty split
+    if (splits > 1 && ep.out_c != 2) {
+        cdlrm_set_error("split-K needs the reduce-add output");
+        return CDLRM_ERR_ARG;
+    }
     dim3 grid((ep.N + BN - 1) / BN, (ep.M + BM - 1) / BM, splits);
-    if (g_nacc == 1) LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep)));
-    else if (g_nacc == 2) LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep)));
-    else LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<4><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep)));
+    if (g_nacc == 1) LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(mp, ep)));
+    else if (g_nacc == 2) LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(mp, ep)));
+    else LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<4><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(mp, ep)));
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
+}
+
+// dW [N, K] and db [N] out of the padded split-K accumulator [N, ldp] (column K = bias gradient)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ acc, int64_t ldp, int N, int K, float* __restrict__ dW,
+                                    float* __restrict__ db) {
+    const int64_t total = (int64_t)N * (K + 1);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / (K + 1)), k = (int)(i - (int64_t)n * (K + 1));
+        const float v = acc[(int64_t)n * ldp + k];
+        if (k < K) dW[(int64_t)n * K + k] = v;
+        else db[n] = v;
+    }
 }
 
 int launch_split(const float* src, int64_t lds, int rows, int cols, const float* y, int64_t ldy, int dmode, float* hi,
@@ -485,6 +548,7 @@ struct cdlrm_mlp {
     std::vector<int> D;
     std::vector<float*> w_hi, w_lo, wt_hi, wt_lo;
     std::vector<float*> x_hi, x_lo, xt_hi, xt_lo, g_hi, g_lo, gt_hi, gt_lo;
+    std::vector<float*> dwp;     // per layer: split-K accumulator [N_l, pad4(K_l + 1)]
     float* y_out = nullptr;
     int last_batch = 0;
     bool ones_set = false;
@@ -520,6 +584,8 @@ static int64_t mlp_carve(cdlrm_mlp* m, char* base) {
         }
     }
     m->y_out = take(cap * pad4(m->D[L]));
+    m->dwp.assign(L, nullptr);
+    for (int l = 0; l < L; ++l) m->dwp[l] = take((int64_t)m->D[l + 1] * pad4(m->D[l] + 1));
     return off;
 }
 
@@ -612,17 +678,17 @@ extern "C" int cdlrm_mlp_forward(cdlrm_mlp* m, const float* x, int64_t ldx, int3
     for (int l = 0; l < L; ++l) {
         const int K = m->D[l], N = m->D[l + 1];
         Epi ep = {};
+        Out o;
         ep.M = batch; ep.N = N; ep.K = K;
         ep.bias = h_b[l];
         ep.act = (l == m->sigmoid_layer) ? ACT_SIGMOID : ((m->sigmoid_layer == -2 && l == L - 1) ? ACT_NONE : ACT_RELU);
-        ep.vec_col = -1;
         if (l + 1 < L) {
-            ep.C_hi = m->x_hi[l + 1]; ep.C_lo = m->x_lo[l + 1]; ep.ld_split = pad4(N);
-            ep.CT_hi = m->xt_hi[l + 1]; ep.CT_lo = m->xt_lo[l + 1]; ep.ld_t = capp;
+            o.c_hi = m->x_hi[l + 1]; o.c_lo = m->x_lo[l + 1]; o.ld_split = pad4(N);
+            o.t_hi = m->xt_hi[l + 1]; o.t_lo = m->xt_lo[l + 1]; o.ld_t = capp;
         } else {
-            ep.C = m->y_out; ep.ldc = pad4(N);
+            o.c = m->y_out; o.ldc = pad4(N);
         }
-        if ((rc = launch_gemm(m->x_hi[l], m->x_lo[l], pad4(K), m->w_hi[l], m->w_lo[l], pad4(K), ep, 1, s))) return rc;
+        if ((rc = launch_gemm(m->x_hi[l], m->x_lo[l], pad4(K), m->w_hi[l], m->w_lo[l], pad4(K), ep, o, 1, s))) return rc;
     }
     CU_CHECK(cudaMemcpy2DAsync(y, ldy * 4, m->y_out, pad4(m->D[L]) * 4, (size_t)m->D[L] * 4, batch, cudaMemcpyDeviceToDevice, s));
     m->last_batch = batch;
@@ -650,34 +716,39 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
     for (int l = L - 1; l >= 0; --l) {
         const int K = m->D[l], N = m->D[l + 1];
         ARG_CHECK(h_dW[l] && h_db[l]);
-        // wgrad: [dW | db] = dZ^T [X^T ; 1]   (split-K over the batch, atomics into zeroed buffers)
-        CU_CHECK(cudaMemsetAsync(h_dW[l], 0, (size_t)N * K * 4, s));
-        CU_CHECK(cudaMemsetAsync(h_db[l], 0, (size_t)N * 4, s));
+        // wgrad: [dW | db] = dZ^T [X^T ; 1]: split-K over the batch, TMA reduce-add into a zeroed
+        // padded accumulator, then unpacked into the dense dW / db the optimizer sees
         {
+            const int64_t ldp = pad4(K + 1);
+            CU_CHECK(cudaMemsetAsync(m->dwp[l], 0, (size_t)N * ldp * 4, s));
             Epi ep = {};
+            Out o;
             ep.M = N; ep.N = K + 1; ep.K = batch;
-            ep.C = h_dW[l]; ep.ldc = K;
-            ep.atomic = 1;
-            ep.vec_col = K; ep.vec = h_db[l];
+            o.c = m->dwp[l]; o.ldc = ldp; o.reduce = true;
             const int tiles = ((N + BM - 1) / BM) * ((K + 1 + BN - 1) / BN);
             int splits = (m->num_sms + tiles - 1) / tiles;
-            if ((rc = launch_gemm(m->gt_hi[l + 1], m->gt_lo[l + 1], capp, m->xt_hi[l], m->xt_lo[l], capp, ep, splits, s))) return rc;
+            if ((rc = launch_gemm(m->gt_hi[l + 1], m->gt_lo[l + 1], capp, m->xt_hi[l], m->xt_lo[l], capp, ep, o, splits, s))) return rc;
+            const int64_t total = (int64_t)N * (K + 1);
+            int blocks = (int)((total + 255) / 256);
+            if (blocks > 1184) blocks = 1184;
+            LAUNCH(K_MLP_SPLIT, s, (unpack_wgrad_kernel<<<blocks, 256, 0, s>>>(m->dwp[l], ldp, N, K, h_dW[l], h_db[l])));
+            CU_CHECK(cudaGetLastError());
         }
         // dgrad: dX = dZ W, then the ReLU mask of the layer below -> its dZ (split, both layouts)
         if (l > 0) {
             Epi ep = {};
+            Out o;
             ep.M = batch; ep.N = K; ep.K = N;
-            ep.vec_col = -1;
             ep.mask = m->x_hi[l]; ep.ld_mask = pad4(K);     // x_l = relu(...) > 0  <=>  its hi part > 0
-            ep.C_hi = m->g_hi[l]; ep.C_lo = m->g_lo[l]; ep.ld_split = pad4(K);
-            ep.CT_hi = m->gt_hi[l]; ep.CT_lo = m->gt_lo[l]; ep.ld_t = capp;
-            if ((rc = launch_gemm(m->g_hi[l + 1], m->g_lo[l + 1], pad4(N), m->wt_hi[l], m->wt_lo[l], pad4(N), ep, 1, s))) return rc;
+            o.c_hi = m->g_hi[l]; o.c_lo = m->g_lo[l]; o.ld_split = pad4(K);
+            o.t_hi = m->gt_hi[l]; o.t_lo = m->gt_lo[l]; o.ld_t = capp;
+            if ((rc = launch_gemm(m->g_hi[l + 1], m->g_lo[l + 1], pad4(N), m->wt_hi[l], m->wt_lo[l], pad4(N), ep, o, 1, s))) return rc;
         } else if (dx) {
             Epi ep = {};
+            Out o;
             ep.M = batch; ep.N = K; ep.K = N;
-            ep.vec_col = -1;
-            ep.C = dx; ep.ldc = lddx;
-            if ((rc = launch_gemm(m->g_hi[l + 1], m->g_lo[l + 1], pad4(N), m->wt_hi[l], m->wt_lo[l], pad4(N), ep, 1, s))) return rc;
+            o.c = dx; o.ldc = lddx;
+            if ((rc = launch_gemm(m->g_hi[l + 1], m->g_lo[l + 1], pad4(N), m->wt_hi[l], m->wt_lo[l], pad4(N), ep, o, 1, s))) return rc;
         }
     }
     return CDLRM_OK;

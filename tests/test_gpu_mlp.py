@@ -122,8 +122,12 @@ def test_dlrm_step_same_loss_and_grads_both_mlp_paths():
     assert abs(out["tcgen05"][0] - out["torch"][0]) <= 1e-5 * abs(out["torch"][0])
     # gradients: a ReLU unit whose pre-activation is within rounding of zero may fire in one path and
     # not in the other (a few of 10 M units per step); that moves single rows, not the bulk
-    for a, b in zip(out["tcgen05"][1] + out["tcgen05"][2], out["torch"][1] + out["torch"][2]):
-        scale = float(b.abs().max())
-        bad = ((a - b).abs() > 2e-5 * scale).float().mean().item()
-        assert bad <= 2e-3, f"{bad:.2%} of a gradient tensor off by more than 2e-5 of its scale"
-        assert float((a - b).abs().max()) <= 0.05 * scale
+    # parameter gradients are sums over the batch: the handful of flipped units moves them by O(flips / B)
+    names = [n for n, _ in net.named_parameters()] + [f"ly{k}" for k in range(T)]
+    for nm, a, b in zip(names, out["tcgen05"][1] + out["tcgen05"][2], out["torch"][1] + out["torch"][2]):
+        rel = float((a - b).norm() / b.norm().clamp_min(1e-30))
+        assert rel <= 5e-3, f"{nm}: relative Frobenius difference {rel:.3e}"
+        if nm.startswith("ly"):      # per-sample gradients: all but the flipped rows agree to FP32 accuracy
+            scale = float(b.abs().max())
+            bad_rows = ((a - b).abs().amax(dim=1) > 2e-5 * scale).float().mean().item()
+            assert bad_rows <= 5e-3, f"{nm}: {bad_rows:.2%} of the rows off by more than 2e-5 of the scale"

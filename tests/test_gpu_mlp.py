@@ -97,7 +97,11 @@ def test_mlp_matches_fp64_reference(which, dims, B):
     for name, mine, theirs, ref in pairs:
         e_mine, e_torch = _err(mine, ref), _err(theirs, ref)
         assert e_mine <= 1e-5, f"{which} {name}: {e_mine:.3e} off the FP64 reference (torch FP32: {e_torch:.3e})"
-        assert e_mine <= 4 * e_torch + 2e-7, f"{which} {name}: {e_mine:.3e} vs torch FP32 {e_torch:.3e}: not FP32-grade"
+        # bias gradients of narrow layers are sums of B signed terms that cancel (a single scalar for the
+        # last top layer): the error is relative to sum |term|, about sqrt(B) times the result, so the
+        # floor is 1e-6 of the result's scale there, 2e-7 elsewhere
+        floor = 1e-6 if mine.numel() <= 16 else 2e-7
+        assert e_mine <= 4 * e_torch + floor, f"{which} {name}: {e_mine:.3e} vs torch FP32 {e_torch:.3e}: not FP32-grade"
         util.assert_close_fp32(mine.cpu().numpy(), ref.float().cpu().numpy(), err_msg=f"{which} {name}")
 
 

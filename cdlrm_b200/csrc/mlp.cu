@@ -12,7 +12,7 @@
 // One GEMM kernel serves forward, data-gradient and weight-gradient:
 //     D[M,N] = A[M,K] * B[N,K]^T        A, B row-major with K contiguous ("K-major"),
 // A_hi/A_lo/B_hi/B_lo are four tensors in HBM, moved by TMA (128-byte swizzle) into a
-// 3-stage shared-memory ring; one elected thread issues tcgen05.mma.kind::tf32
+// 3-stage shared-memory ring; one elected thread of a persistent CTA issues tcgen05.mma.kind::tf32
 // (128x128x8, 12 per 32-wide k-block: 4 k-steps x 3 products) into a 128-column TMEM
 // accumulator; four epilogue warps read it back with tcgen05.ld and apply the fused
 // epilogue (bias, ReLU / sigmoid, ReLU-backward mask, hi/lo split of the result in
@@ -29,23 +29,41 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;        // tile; BK fp32 = 128 bytes = one swizzle row
+// Tile 128 x 128, k-blocks of BK = 32 fp32 (one 128-byte swizzle row) in a 3-stage ring.  BK = 16
+// (64-byte swizzle, 6 stages) is supported by the code below and was measured 10 % slower.
+constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;           // 16 KB per operand tile
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi, A_lo, B_hi, B_lo
-constexpr int GEMM_THREADS = 192;                 // warp 0: TMA, warp 1: MMA + TMEM, warps 2-5: epilogue
-// NACC TMEM accumulators of 128 columns.  The tensor core's FP32 accumulation is not
-// round-to-nearest, so the error of one accumulator grows with the number of MMAs chained
-// into it.  NACC > 1: the two small cross terms go to the last accumulator, the hi*hi
-// terms of successive k-steps rotate over the others; the epilogue adds them up in
-// registers (round-to-nearest).
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi, A_lo, B_hi, B_lo (B_lo right behind B_hi: one 256-row operand)
+constexpr int EPI_WARPS = 8;                      // two per TMEM lane quarter, 64 columns each
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS; // warp 0: TMA, warp 1: MMA + TMEM, warps 2-9: epilogue
+constexpr int STG_BYTES = 4096;                   // one 32 x 32 fp32 result tile per epilogue warp
+// TMEM: two accumulator buffers of 256 columns (hi*hi | cross terms), so that the epilogue of one
+// K segment / tile overlaps the MMAs of the next.  The tensor core's FP32 accumulation is not
+// round-to-nearest, so the error of one accumulator grows with the number of MMAs chained into it:
+// the two small cross terms get their own accumulator, and K is cut into segments of `seg_kb`
+// k-blocks whose partial results the epilogue warps add up in registers (round-to-nearest).
+constexpr int TMEM_COLS = 512;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// What bounds the mainloop (tools/gemm_probe.py, tools/gemm_trace.py on B200): shared-memory
+// bandwidth.  Per k-step of 8 the three MMAs read 3 x (4 + 4) KB of operands and the TMA writes
+// 16 KB (hi and lo of A and B): 40 KB at 128 B/clk = 320 clk, against 3 x 64 clk of tensor-core
+// time; measured 0.65-0.7 us per 32-wide k-block = 330-345 clk per k-step, whatever the ring
+// depth, the k-block size or the number of TMA instructions.  (A_hi x [B_hi ; B_lo] as ONE
+// 128 x 256 x 8 MMA -- hi*hi and hi*lo side by side in TMEM -- is what the issuer does; it
+// saves an instruction, not the second read of A_hi.)
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
 
 struct Epi {
     int M, N, K;                 // GEMM extents: rows of A, rows of B, reduction length
-    int kb_per_split;            // k-blocks per blockIdx.z
+    int kb_per_split;            // k-blocks per K split
+    int splits;                  // K splits (units = tiles x splits)
+    int seg_kb;                  // k-blocks chained into one TMEM accumulator before the register add
+    long long* trace;            // measurement only (cdlrm_mlp_set_trace): CTA 0 writes %globaltimer stamps, [4][128]
+    int dbg;                     // measurement only (cdlrm_mlp_set_option(3, .)): 1 no result stores, 4 no MMAs
     const float* bias;           // [N] added per column (or null)
     int act;                     // ACT_*
     const float* mask;           // relu-backward: result passes where mask[row, col] > 0 (or null)
@@ -58,7 +76,7 @@ struct Epi {
 // tensor maps of one launch: 4 operand maps (box 32 x 128, 128-byte swizzle) and up to 5 result
 // maps (box 32 x 32: row-major ones with the 128-byte swizzle, transposed ones dense)
 struct Maps {
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap a, b;            // operands: {K, rows, 2}: the hi and lo tensors are one 3-D tensor
     CUtensorMap c, c_hi, c_lo, t_hi, t_lo;
 };
 
@@ -92,6 +110,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+// one instruction for the hi and lo tiles of an operand: 3-D map {K, rows, 2 (hi, lo)}
+__device__ __forceinline__ void tma_load_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(0), "r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -132,19 +157,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO),
-// LBO unused (1), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
+// K-major, swizzle width = one row of BK fp32 (64 or 128 bytes), 8-row groups 8 rows apart (SBO),
+// LBO unused (1), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B / 4 = SWIZZLE_64B
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3fff);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((8 * BK * 4) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;
     return d;
 }
-// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 128
-constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // round-to-nearest TF32 (ties away from zero in magnitude): the residual x - hi is then signed and
 // at most half a TF32 ulp, and the same rounding of the residual leaves an error <= 2^-24 |x|
@@ -154,36 +177,45 @@ __device__ int g_split_trunc = 0;       // test hook: 1 = truncating split (the 
 __device__ __forceinline__ float tf32_hi(float x) { return g_split_trunc ? tf32_tr(x) : tf32_rn(x); }
 __device__ __forceinline__ float tf32_lo(float x, float hi) { return g_split_trunc ? tf32_tr(x - hi) : tf32_rn(x - hi); }
 
-template <int NACC>
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(role, idx) do { if (ep.trace && blockIdx.x == 0 && (idx) < 128) ep.trace[(role) * 128 + (idx)] = gtime(); } while (0)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: CTA b works on units b, b + gridDim.x, ... ; a unit = (n tile, m tile, K split),
+// n fastest so that the CTAs running together share the A row panel in L2.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
+    constexpr int NCH = BN / 64;                                 // 32-column chunks per epilogue warp
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
     uint8_t* smem = smem_raw + pad;                              // 1024-byte aligned tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full_bar = bars;                                   // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;                         // [STAGES]
-    uint64_t* accum_bar = bars + 2 * STAGES;                     // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + EPI_WARPS * STG_BYTES);
+    uint64_t* full_bar = bars;                                   // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;                         // [STAGES]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * STAGES;                     // [2]       MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;                // [2]       epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int tiles_n = (ep.N + BN - 1) / BN, tiles_m = (ep.M + BM - 1) / BM;
     const int num_kb_total = (ep.K + BK - 1) / BK;
-    const int kb0 = blockIdx.z * ep.kb_per_split;
-    const int kb1 = min(num_kb_total, kb0 + ep.kb_per_split);
-    const int num_kb = kb1 - kb0;                                // >= 1 by construction of the grid
+    const int units = tiles_n * tiles_m * ep.splits;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a_lo) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
     }
-    constexpr int TMEM_COLS = 128 * NACC;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -192,160 +224,197 @@ gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TRACE(3, 0);
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                const int k = (kb0 + i) * BK;
-                tma_load_2d(base + 0 * TILE_BYTES, &maps.a_hi, k, m0, &full_bar[s]);
-                tma_load_2d(base + 1 * TILE_BYTES, &maps.a_lo, k, m0, &full_bar[s]);
-                tma_load_2d(base + 2 * TILE_BYTES, &maps.b_hi, k, n0, &full_bar[s]);
-                tma_load_2d(base + 3 * TILE_BYTES, &maps.b_lo, k, n0, &full_bar[s]);
+            uint32_t it = 0;                       // k-blocks issued so far (ring position)
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int n0 = (u % tiles_n) * BN, m0 = ((u / tiles_n) % tiles_m) * BM;
+                const int kb0 = (u / (tiles_n * tiles_m)) * ep.kb_per_split;
+                const int num_kb = min(num_kb_total, kb0 + ep.kb_per_split) - kb0;
+                for (int i = 0; i < num_kb; ++i, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    TRACE(0, it);
+                    const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                    const int k = (kb0 + i) * BK;
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_pair(base, &maps.a, k, m0, &full_bar[s]);
+                    tma_load_pair(base + 2 * TILE_BYTES, &maps.b, k, n0, &full_bar[s]);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
-            uint32_t used = 0;                     // accumulators that already hold a value
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-                mbar_wait(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t a_hi = make_smem_desc(base + 0 * TILE_BYTES);
-                const uint64_t a_lo = make_smem_desc(base + 1 * TILE_BYTES);
-                const uint64_t b_hi = make_smem_desc(base + 2 * TILE_BYTES);
-                const uint64_t b_lo = make_smem_desc(base + 3 * TILE_BYTES);
+            uint32_t it = 0, seg = 0;              // ring position; K segments issued so far (TMEM buffer)
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int kb0 = (u / (tiles_n * tiles_m)) * ep.kb_per_split;
+                const int num_kb = min(num_kb_total, kb0 + ep.kb_per_split) - kb0;
+                for (int i0 = 0; i0 < num_kb; i0 += ep.seg_kb, ++seg) {
+                    const uint32_t buf = seg & 1u, use = seg >> 1;
+                    mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);      // the epilogue has drained this buffer
+                    tc_fence_after();
+                    const uint32_t d_big = tmem_base + buf * 256u, d_small = d_big + 128u;
+                    const int i1 = min(num_kb, i0 + ep.seg_kb);
+                    for (int i = i0; i < i1; ++i, ++it) {
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                        mbar_wait(&full_bar[s], ph);
+                        TRACE(1, it);
+                        tc_fence_after();
+                        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                        const uint64_t a_hi = make_smem_desc(base);
+                        const uint64_t a_lo = make_smem_desc(base + TILE_BYTES);
+                        const uint64_t b_hi = make_smem_desc(base + 2 * TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per k-step, in 16-byte units
-                    constexpr int SMALL = NACC - 1;                              // accumulator of the cross terms
-                    const int big = NACC > 1 ? (i * (BK / 8) + k) % (NACC - 1) : 0;   // accumulator of this k-step's hi*hi
-                    tc_mma_tf32(tmem_base + SMALL * 128, a_lo + adv, b_hi + adv, IDESC_TF32, (used >> SMALL) & 1u);
-                    used |= 1u << SMALL;
-                    tc_mma_tf32(tmem_base + SMALL * 128, a_hi + adv, b_lo + adv, IDESC_TF32, 1u);
-                    tc_mma_tf32(tmem_base + big * 128, a_hi + adv, b_hi + adv, IDESC_TF32, (used >> big) & 1u);
-                    used |= 1u << big;
+                        for (int k = 0; k < ((ep.dbg & 4) ? 0 : BK / 8); ++k) {
+                            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per k-step, in 16-byte units
+                            const uint32_t acc = (i > i0 || k > 0) ? 1u : 0u;
+                            // [big | small] (+)= A_hi [B_hi ; B_lo]^T, then small += A_lo B_hi^T
+                            tc_mma_tf32(d_big, a_hi + adv, b_hi + adv, idesc_tf32(2 * BN), acc);
+                            tc_mma_tf32(d_small, a_lo + adv, b_hi + adv, idesc_tf32(BN), 1u);
+                        }
+                        tc_commit(&empty_bar[s]);      // the stage is free once these MMAs have read it
+                    }
+                    tc_commit(&tfull_bar[buf]);        // this segment's accumulators are complete
                 }
-                tc_commit(&empty_bar[s]);          // the stage is free once these MMAs have read it
             }
-            tc_commit(accum_bar);                  // accumulator complete
         }
     } else {
-        // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), +32) =====
-        // Results leave through shared memory and TMA stores: per 32-column chunk a warp stages up
-        // to four 32x32 fp32 tiles (4 KB each; row-major tiles in the 128-byte swizzle, transposed
-        // tiles dense) in the ring's memory -- every MMA has retired, the ring is free -- double
-        // buffered, so that the stores of chunk c overlap the TMEM reads of chunk c+1.  The TMA
-        // clips rows >= M and columns >= N.
-        const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const bool row_ok = row < ep.M;
-        uint8_t* wbase = smem + q * (2 * 4 * 4096);               // 32 KB per warp: 2 buffers x 4 tiles
+        // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), +32); two warps per quarter, 64 columns each =====
+        // Results leave through shared memory and TMA stores (32 x 32 fp32 tiles: row-major ones in the
+        // 128-byte swizzle, transposed ones dense); the TMA clips rows >= M and columns >= N.
+        const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+        uint8_t* stg = stg_base + ew * STG_BYTES;
+        const uint32_t stg_u32 = smem_u32(stg);
         const int sw = lane & 7;                                  // swizzle phase of this thread's row
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            const int col0 = n0 + c * 32;
-            if (col0 >= ep.N) break;                               // warp-uniform
-            float v[32];
-            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            if constexpr (NACC > 1) {
+        uint32_t seg = 0;
+        bool store_pending = false;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int n0 = (u % tiles_n) * BN, m0 = ((u / tiles_n) % tiles_m) * BM;
+            const int kb0 = (u / (tiles_n * tiles_m)) * ep.kb_per_split;
+            const int num_kb = min(num_kb_total, kb0 + ep.kb_per_split) - kb0;
+            float v[NCH][32];
+            for (int i0 = 0; i0 < num_kb; i0 += ep.seg_kb, ++seg) {
+                const uint32_t buf = seg & 1u, use = seg >> 1;
+                mbar_wait(&tfull_bar[buf], use & 1u);
+                if (warp == 2 && lane == 0) TRACE(2, seg);
+                tc_fence_after();
+                const uint32_t tb = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
 #pragma unroll
-                for (int a = 1; a < NACC; ++a) {
-                    float w[32];
-                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 128 + c * 32), w);
+                for (int c = 0; c < NCH; ++c) {
+                    float big[32];
+                    tc_ld32(tb + c * 32, big);
+                    {
+                        float small[32];
+                        tc_ld32(tb + 128 + c * 32, small);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += w[j];
-                }
-            }
-            if (ep.bias) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < ep.N) v[j] += __ldg(ep.bias + col0 + j);
-            }
-            if (ep.act == ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            } else if (ep.act == ACT_SIGMOID) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
-            }
-            if (ep.mask && row_ok) {
-                const float* mrow = ep.mask + (int64_t)row * ep.ld_mask + col0;
-                if (col0 + 32 <= ep.ld_mask) {                    // rows are 16-byte aligned (ld multiple of 4)
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 mk = __ldg(reinterpret_cast<const float4*>(mrow + j));
-                        if (!(mk.x > 0.f)) v[j] = 0.f;
-                        if (!(mk.y > 0.f)) v[j + 1] = 0.f;
-                        if (!(mk.z > 0.f)) v[j + 2] = 0.f;
-                        if (!(mk.w > 0.f)) v[j + 3] = 0.f;
+                        for (int j = 0; j < 32; ++j) big[j] += small[j];
                     }
-                } else {
+                    if (i0 == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[c][j] = big[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[c][j] += big[j];
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            }
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < ep.M;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int col0 = n0 + half * (BN / 2) + c * 32;
+                if (col0 >= ep.N || (ep.dbg & 1)) break;           // warp-uniform
+                float* vv = v[c];
+                if (ep.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (col0 + j < ep.N && !(__ldg(mrow + j) > 0.f)) v[j] = 0.f;
+                        if (col0 + j < ep.N) vv[j] += __ldg(ep.bias + col0 + j);
                 }
-            }
-            uint8_t* buf = wbase + (c & 1) * (4 * 4096);
-            if (c >= 2) {                                          // the stores that last read this buffer
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                __syncwarp();
-            }
-            // tile 0: v (row-major); tiles 0/1: hi, lo (row-major); tiles 2/3: hi, lo (transposed)
-            float4* t0 = reinterpret_cast<float4*>(buf + lane * 128);
-            if (ep.out_c) {
+                if (ep.act == ACT_RELU) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t0[j ^ sw] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (ep.out_split || ep.out_t) {
-                float hi[32], lo[32];
+                    for (int j = 0; j < 32; ++j) vv[j] = fmaxf(vv[j], 0.f);
+                } else if (ep.act == ACT_SIGMOID) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { hi[j] = tf32_hi(v[j]); lo[j] = tf32_lo(v[j], hi[j]); }
-                if (ep.out_split) {
-                    float4* t1 = reinterpret_cast<float4*>(buf + 4096 + lane * 128);
+                    for (int j = 0; j < 32; ++j) vv[j] = 1.f / (1.f + expf(-vv[j]));
+                }
+                if (ep.mask && row_ok) {
+                    const float* mrow = ep.mask + (int64_t)row * ep.ld_mask + col0;
+                    if (col0 + 32 <= ep.ld_mask) {                    // rows are 16-byte aligned (ld multiple of 4)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        t0[j ^ sw] = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        t1[j ^ sw] = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 mk = __ldg(reinterpret_cast<const float4*>(mrow + j));
+                            if (!(mk.x > 0.f)) vv[j] = 0.f;
+                            if (!(mk.y > 0.f)) vv[j + 1] = 0.f;
+                            if (!(mk.z > 0.f)) vv[j + 2] = 0.f;
+                            if (!(mk.w > 0.f)) vv[j + 3] = 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < ep.N && !(__ldg(mrow + j) > 0.f)) vv[j] = 0.f;
                     }
                 }
-                if (ep.out_t) {
-                    float* t2 = reinterpret_cast<float*>(buf + 2 * 4096);
-                    float* t3 = reinterpret_cast<float*>(buf + 3 * 4096);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { t2[j * 32 + lane] = hi[j]; t3[j * 32 + lane] = lo[j]; }
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                const uint32_t sb = smem_u32(buf);
                 const int r0 = m0 + q * 32;
-                if (ep.out_c == 1) tma_store_2d(&maps.c, sb, col0, r0);
-                else if (ep.out_c == 2) tma_reduce_add_2d(&maps.c, sb, col0, r0);
+                // one staging tile per warp: wait until the previous store has read it, fill, fence, store
+                auto stage_begin = [&]() {
+                    if (store_pending) {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                    }
+                };
+                auto stage_end = [&](const CUtensorMap* map, int c0, int c1, bool reduce) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (reduce) tma_reduce_add_2d(map, stg_u32, c0, c1);
+                        else tma_store_2d(map, stg_u32, c0, c1);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    store_pending = true;
+                };
+                float4* t_row = reinterpret_cast<float4*>(stg + lane * 128);
+                float* t_col = reinterpret_cast<float*>(stg);
+                if (ep.out_c) {
+                    stage_begin();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t_row[j ^ sw] = make_float4(vv[4 * j], vv[4 * j + 1], vv[4 * j + 2], vv[4 * j + 3]);
+                    stage_end(&maps.c, col0, r0, ep.out_c == 2);
+                }
+                // hi / lo are recomputed per output instead of being kept (register pressure at BN = 256)
+                auto hi_of = [&](int j) { return tf32_hi(vv[j]); };
+                auto lo_of = [&](int j) { return tf32_lo(vv[j], tf32_hi(vv[j])); };
                 if (ep.out_split) {
-                    tma_store_2d(&maps.c_hi, sb, col0, r0);
-                    tma_store_2d(&maps.c_lo, sb + 4096, col0, r0);
+                    stage_begin();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t_row[j ^ sw] = make_float4(hi_of(4 * j), hi_of(4 * j + 1), hi_of(4 * j + 2), hi_of(4 * j + 3));
+                    stage_end(&maps.c_hi, col0, r0, false);
+                    stage_begin();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t_row[j ^ sw] = make_float4(lo_of(4 * j), lo_of(4 * j + 1), lo_of(4 * j + 2), lo_of(4 * j + 3));
+                    stage_end(&maps.c_lo, col0, r0, false);
                 }
                 if (ep.out_t) {
-                    tma_store_2d(&maps.t_hi, sb + 2 * 4096, r0, col0);
-                    tma_store_2d(&maps.t_lo, sb + 3 * 4096, r0, col0);
+                    stage_begin();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t_col[j * 32 + lane] = hi_of(j);
+                    stage_end(&maps.t_hi, r0, col0, false);
+                    stage_begin();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t_col[j * 32 + lane] = lo_of(j);
+                    stage_end(&maps.t_lo, r0, col0, false);
                 }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncwarp();
+        if (warp == 2 && lane == 0) TRACE(3, 1);
         tc_fence_before();
     }
     __syncthreads();
@@ -417,9 +486,38 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// [rows, inner] fp32, row stride ld elements (multiple of 4); box = 32 x box_rows; out-of-range
+// [rows, inner] fp32, row stride ld elements (multiple of 4); box = box_inner x box_rows; out-of-range
 // box elements read as zero and are not written
-int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t rows, int64_t ld, int box_rows, bool swizzle) {
+// operand pair: hi at `hi`, lo at `lo` (same shape and row stride, lo behind hi) as one {inner, rows, 2} tensor;
+// box = BK x box_rows x 2, swizzle width = one BK row
+int make_pair_map(CUtensorMap* m, const float* hi, const float* lo, int64_t inner, int64_t rows, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        cdlrm_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return CDLRM_ERR_CUDA;
+    }
+    const int64_t gap = (const char*)lo - (const char*)hi;
+    if (((uintptr_t)hi & 15) || (ld & 3) || inner <= 0 || rows <= 0 || gap < rows * ld * 4 || (gap & 15)) {
+        cdlrm_set_error("operand pair must be 16-byte aligned, row stride multiple of 4, lo behind hi (hi %p lo %p ld %lld)", (const void*)hi,
+                        (const void*)lo, (long long)ld);
+        return CDLRM_ERR_ARG;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)gap};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)hi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cdlrm_set_error("cuTensorMapEncodeTiled (pair) failed (%d): inner %lld rows %lld ld %lld gap %lld", (int)r, (long long)inner,
+                        (long long)rows, (long long)ld, (long long)gap);
+        return CDLRM_ERR_CUDA;
+    }
+    return CDLRM_OK;
+}
+
+int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t rows, int64_t ld, int box_rows, bool swizzle, int box_inner = 32) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         cdlrm_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -431,10 +529,11 @@ int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t rows, int
     }
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : (box_inner == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         cdlrm_set_error("cuTensorMapEncodeTiled failed (%d): inner %lld rows %lld ld %lld", (int)r, (long long)inner, (long long)rows, (long long)ld);
@@ -456,24 +555,27 @@ struct Out {
     int64_t ld_t = 0;
 };
 
-int g_nacc = 4;      // TMEM accumulators per tile (1, 2 or 4); cdlrm_mlp_set_option(1, .)
+int g_seg_kb = 8;    // K segment (k-blocks of 32) per TMEM accumulation chain; cdlrm_mlp_set_option(1, .)
+int g_num_sms = 0;
+int g_dbg = 0;
+long long* g_trace = nullptr;
 
 int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb,
                 Epi ep, const Out& o, int splits, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        attr_done = true;
+    if (!g_num_sms) {
+        int dev = 0, n = 0;
+        CU_CHECK(cudaGetDevice(&dev));
+        CU_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        g_num_sms = n > 0 ? n : 148;
     }
+    const int64_t tiles_m = (ep.M + BM - 1) / BM, tiles_n = (ep.N + BN - 1) / BN;
+    if (splits == 0) splits = (int)(g_num_sms / (tiles_m * tiles_n));      // split-K sized to one round of the persistent grid
     Maps mp;
     memset(&mp, 0, sizeof(mp));
     int rc;
-    if ((rc = make_map(&mp.a_hi, a_hi, ep.K, ep.M, lda, BM, true))) return rc;
-    if ((rc = make_map(&mp.a_lo, a_lo, ep.K, ep.M, lda, BM, true))) return rc;
-    if ((rc = make_map(&mp.b_hi, b_hi, ep.K, ep.N, ldb, BN, true))) return rc;
-    if ((rc = make_map(&mp.b_lo, b_lo, ep.K, ep.N, ldb, BN, true))) return rc;
+    if ((rc = make_pair_map(&mp.a, a_hi, a_lo, ep.K, ep.M, lda, BM))) return rc;
+    if ((rc = make_pair_map(&mp.b, b_hi, b_lo, ep.K, ep.N, ldb, BN))) return rc;
     ep.out_c = o.c ? (o.reduce ? 2 : 1) : 0;
     ep.out_split = o.c_hi ? 1 : 0;
     ep.out_t = o.t_hi ? 1 : 0;
@@ -499,10 +601,13 @@ int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* 
         cdlrm_set_error("split-K needs the reduce-add output");
         return CDLRM_ERR_ARG;
     }
-    dim3 grid((ep.N + BN - 1) / BN, (ep.M + BM - 1) / BM, splits);
-    if (g_nacc == 1) LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(mp, ep)));
-    else if (g_nacc == 2) LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(mp, ep)));
-    else LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<4><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(mp, ep)));
+    ep.splits = splits;
+    ep.dbg = g_dbg;
+    ep.trace = g_trace;
+    ep.seg_kb = g_seg_kb > 0 ? g_seg_kb * (32 / BK) : num_kb;      // the option counts k-blocks of 32
+    const int64_t units = tiles_n * tiles_m * splits;
+    const int grid = (int)(units < g_num_sms ? units : g_num_sms);
+    LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(mp, ep)));
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
 }
@@ -630,17 +735,28 @@ extern "C" int cdlrm_mlp_create(cdlrm_mlp** out, int device, int n_layers, const
     return CDLRM_OK;
 }
 
-// key 0: split rounding (0 = round to nearest, 1 = truncate); key 1: TMEM accumulators per tile (1, 2, 4)
+// key 0: split rounding (0 = round to nearest, 1 = truncate); key 1: k-blocks (of 32) chained into one TMEM
+// accumulator before the partial result is added in registers (0 = the whole K; default 8)
 extern "C" int cdlrm_mlp_set_option(int key, int value) {
     if (key == 0) {
         const int v = value ? 1 : 0;
         CU_CHECK(cudaMemcpyToSymbol(g_split_trunc, &v, sizeof(int)));
     } else if (key == 1) {
-        ARG_CHECK(value == 1 || value == 2 || value == 4);
-        g_nacc = value;
+        ARG_CHECK(value >= 0 && value <= 4096);
+        g_seg_kb = value;
+    } else if (key == 3) {
+        g_dbg = value;
     } else {
         ARG_CHECK(false && "unknown option");
     }
+    return CDLRM_OK;
+}
+
+// measurement hook: device buffer of 4 x 128 int64 that CTA 0 of every following GEMM fills with
+// %globaltimer stamps (0: TMA issue per k-block, 1: operands landed per k-block, 2: accumulator
+// ready per K segment, 3: [0] prologue done, [1] last store done); null switches it off
+extern "C" int cdlrm_mlp_set_trace(void* d_buf) {
+    g_trace = reinterpret_cast<long long*>(d_buf);
     return CDLRM_OK;
 }
 
@@ -725,9 +841,7 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
             Out o;
             ep.M = N; ep.N = K + 1; ep.K = batch;
             o.c = m->dwp[l]; o.ldc = ldp; o.reduce = true;
-            const int tiles = ((N + BM - 1) / BM) * ((K + 1 + BN - 1) / BN);
-            int splits = (m->num_sms + tiles - 1) / tiles;
-            if ((rc = launch_gemm(m->gt_hi[l + 1], m->gt_lo[l + 1], capp, m->xt_hi[l], m->xt_lo[l], capp, ep, o, splits, s))) return rc;
+            if ((rc = launch_gemm(m->gt_hi[l + 1], m->gt_lo[l + 1], capp, m->xt_hi[l], m->xt_lo[l], capp, ep, o, 0 /*auto split-K*/, s))) return rc;
             const int64_t total = (int64_t)N * (K + 1);
             int blocks = (int)((total + 255) / 256);
             if (blocks > 1184) blocks = 1184;

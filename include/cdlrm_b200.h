@@ -141,8 +141,12 @@ int cdlrm_mlp_create(cdlrm_mlp** out, int device, int n_layers, const int32_t* h
 int cdlrm_mlp_destroy(cdlrm_mlp* mlp);
 /* sigmoid_layer == -2: the last layer has no activation (plain affine layer; test hook).
  * Numerics knobs (process-wide; defaults are the accurate settings): key 0 = operand split
- * rounding (0 nearest, 1 truncate), key 1 = TMEM accumulators per output tile (1, 2 or 4). */
+ * rounding (0 nearest, 1 truncate), key 1 = k-blocks of 32 chained into one TMEM accumulator
+ * before the partial sum is added in registers (0 = whole K, default 8), key 2 = tile width
+ * (0: 128 x 128, 1: 128 x 256, 2: by shape), key 3 = measurement switches (results invalid). */
 int cdlrm_mlp_set_option(int key, int value);
+/* measurement hook: CTA 0 of every following GEMM writes %globaltimer stamps into d_buf (4 x 128 int64); NULL = off */
+int cdlrm_mlp_set_trace(void* d_buf);
 int cdlrm_mlp_forward(cdlrm_mlp* mlp, const float* x, int64_t ldx, int32_t batch,
                       const float* const* h_W, const float* const* h_b,
                       float* y, int64_t ldy, cdlrm_stream stream);

@@ -1,5 +1,5 @@
 """Error of the 3xTF32 tensor-core GEMM against FP64, next to torch's FP32 matmul, for the knobs of
-cdlrm_mlp_set_option (split rounding, number of TMEM accumulators).  Run under gpurun."""
+cdlrm_mlp_set_option (split rounding, K segment per TMEM accumulation chain).  Run under gpurun."""
 import os
 import sys
 
@@ -13,9 +13,9 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 
 
-def one(K, N, Mrows, trunc, nacc):
+def one(K, N, Mrows, trunc, seg):
     check(lib.cdlrm_mlp_set_option(0, trunc))
-    check(lib.cdlrm_mlp_set_option(1, nacc))
+    check(lib.cdlrm_mlp_set_option(1, seg))
     lin = torch.nn.Linear(K, N).to(dev)
     with torch.no_grad():
         lin.weight.copy_(torch.randn(N, K, device=dev) / K ** 0.5)
@@ -32,10 +32,10 @@ def one(K, N, Mrows, trunc, nacc):
             float((yt.double() - ref).abs().max() / sc), float((yt.double() - ref).pow(2).mean().sqrt() / sc))
 
 
-print("K      trunc nacc   max_err     rms_err    | torch max   torch rms")
+print("K      trunc  seg   max_err     rms_err    | torch max   torch rms")
 for K in (32, 128, 512, 2048, 8192):
-    for trunc, nacc in ((1, 1), (0, 1), (0, 2), (0, 4)):
-        e = one(K, 256, 1024, trunc, nacc)
-        print(f"{K:6d} {trunc:5d} {nacc:4d}   {e[0]:.3e}  {e[1]:.3e}  | {e[2]:.3e}  {e[3]:.3e}")
+    for trunc, seg in ((1, 0), (0, 0), (0, 16), (0, 8), (0, 4)):
+        e = one(K, 256, 1024, trunc, seg)
+        print(f"{K:6d} {trunc:5d} {seg:4d}   {e[0]:.3e}  {e[1]:.3e}  | {e[2]:.3e}  {e[3]:.3e}")
 check(lib.cdlrm_mlp_set_option(0, 0))
-check(lib.cdlrm_mlp_set_option(1, 4))
+check(lib.cdlrm_mlp_set_option(1, 8))

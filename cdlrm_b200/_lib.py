@@ -36,6 +36,7 @@ SIGNATURES = {
     "cdlrm_embed_bwd_plan": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int64, C.c_int32, vp, vp]),
     "cdlrm_embed_bwd_sgd": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int32, vp, C.c_int64, vp, C.c_int64,
                                       C.c_int64, C.c_float, vp]),
+    "cdlrm_interact_set_option": (C.c_int, [C.c_int, C.c_int]),
     "cdlrm_interact_fwd": (C.c_int, [C.c_int, C.POINTER(vp), C.c_int, C.c_int64, C.c_int32, C.c_int, C.c_int,
                                      vp, C.c_int64, vp]),
     "cdlrm_interact_bwd": (C.c_int, [C.c_int, C.POINTER(vp), C.c_int, C.c_int64, C.c_int32, C.c_int, C.c_int,

@@ -15,6 +15,7 @@
 // Backward: lanes are independent along dim (no reduction), so TPS = dim/VEC threads
 // own one sample with VEC = 2 to keep 2*F*VEC accumulators + operands in registers;
 // the dZ coefficients are loaded coalesced (one per lane) and broadcast by shuffle.
+#include <cstdlib>
 #include <type_traits>
 #include <utility>
 
@@ -35,6 +36,13 @@ struct Pairs {
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
     return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+
+// packed FP32 (sm_100 FFMA2 / FMUL2): one issue slot for two lanes of work -- these kernels are issue-bound
+__device__ __forceinline__ float dot4_packed(const float4& a, const float4& b) {
+    float2 p = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    p = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), p);
+    return p.x + p.y;
 }
 
 // compile-time loops: every index into the register arrays below must be a constant,
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(128) interact_fwd_kernel(FeatPtrs fp, int64_t 
         static_for<nj>([&](auto J) {
             constexpr int j = decltype(J)::value;
             constexpr int p = p0 + j;
-            v[p % LPS] = dot4(t[i], t[j]);
+            v[p % LPS] = dot4_packed(t[i], t[j]);
             if constexpr ((p + 1) % LPS == 0 || p + 1 == NP) {
                 constexpr int blk = p / LPS;
                 constexpr int cnt = p + 1 - blk * LPS;
@@ -114,8 +122,67 @@ __global__ void __launch_bounds__(128) interact_fwd_kernel(FeatPtrs fp, int64_t 
     });
 }
 
+// Forward for dim = 128 (32 lanes own a sample, lane c the float4 column slice c).  Same walk over the
+// triangle as above, but a block of 32 partial dot products per lane is reduced across the lanes through
+// shared memory: every lane stores its 32 partials as one row (8 STS.128, row pitch 36 words: conflict
+// free), then lane c adds up column c (32 LDS + 31 FADD).  71 instructions per 32 pairs instead of the
+// butterfly's 31 x (2 SEL + SHFL + FADD) = 124; the rows are double-buffered so that one __syncwarp per
+// block is enough.
+template <int F, bool ITSELF>
+__global__ void __launch_bounds__(128, 4) interact_fwd_tr_kernel(FeatPtrs fp, int64_t row_stride, int B,
+                                                              float* __restrict__ out, int64_t ld_out) {
+    constexpr int DIM = 128, PITCH = 36;
+    constexpr int NP = Pairs<F, ITSELF>::N;
+    __shared__ __align__(16) float s_part[4][2][32 * PITCH];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;                                   // warp-uniform
+    float4 t[F];
+    static_for<F>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        t[i] = __ldg(reinterpret_cast<const float4*>(fp.p[i] + (int64_t)b * row_stride) + lane);
+    });
+    float* orow = out + (int64_t)b * ld_out;
+    orow[lane * 4 + 0] = t[0].x; orow[lane * 4 + 1] = t[0].y;      // dense features pass through (model_no_ddp.py:293)
+    orow[lane * 4 + 2] = t[0].z; orow[lane * 4 + 3] = t[0].w;
+    float v[32];
+    static_for<F>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        constexpr int nj = ITSELF ? i + 1 : i;
+        constexpr int p0 = ITSELF ? i * (i + 1) / 2 : i * (i - 1) / 2;   // row-major triangle offset
+        static_for<nj>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            constexpr int p = p0 + j;
+            v[p % 32] = dot4_packed(t[i], t[j]);
+            if constexpr ((p + 1) % 32 == 0 || p + 1 == NP) {
+                constexpr int blk = p / 32;
+                constexpr int cnt = p + 1 - blk * 32;
+                float* buf = s_part[wib][blk & 1];
+                float4* wr = reinterpret_cast<float4*>(buf + lane * PITCH);
+                static_for<(cnt + 3) / 4>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    wr[q] = make_float4(v[4 * q], 4 * q + 1 < cnt ? v[4 * q + 1] : 0.f, 4 * q + 2 < cnt ? v[4 * q + 2] : 0.f,
+                                        4 * q + 3 < cnt ? v[4 * q + 3] : 0.f);
+                });
+                __syncwarp();
+                if (lane < cnt) {
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; r += 4) {
+                        a0 += buf[(r + 0) * PITCH + lane];
+                        a1 += buf[(r + 1) * PITCH + lane];
+                        a2 += buf[(r + 2) * PITCH + lane];
+                        a3 += buf[(r + 3) * PITCH + lane];
+                    }
+                    orow[DIM + blk * 32 + lane] = (a0 + a1) + (a2 + a3);
+                }
+            }
+        });
+    });
+}
+
 template <int F, int TPS, bool ITSELF>
-__global__ void __launch_bounds__(128) interact_bwd_kernel(FeatPtrs fp, int64_t row_stride, int B,
+__global__ void __launch_bounds__(128, 4) interact_bwd_kernel(FeatPtrs fp, int64_t row_stride, int B,
                                                            const float* __restrict__ d_out, int64_t ld_dout,
                                                            float* __restrict__ d_feat, int64_t ld_dfeat) {
     // TPS threads per sample, each owning a float2 column slice: dim = 2*TPS.  The NP pair
@@ -156,13 +223,11 @@ __global__ void __launch_bounds__(128) interact_bwd_kernel(FeatPtrs fp, int64_t 
             if constexpr (p % 4 == 0) cq = c4p[p / 4];
             const float c = (p % 4 == 0) ? cq.x : (p % 4 == 1) ? cq.y : (p % 4 == 2) ? cq.z : cq.w;
             if constexpr (i == j) {  // d(T_i.T_i) = 2 T_i
-                g[i].x = fmaf(2.f * c, t[i].x, g[i].x);
-                g[i].y = fmaf(2.f * c, t[i].y, g[i].y);
-            } else {
-                g[i].x = fmaf(c, t[j].x, g[i].x);
-                g[i].y = fmaf(c, t[j].y, g[i].y);
-                g[j].x = fmaf(c, t[i].x, g[j].x);
-                g[j].y = fmaf(c, t[i].y, g[j].y);
+                g[i] = __ffma2_rn(make_float2(2.f * c, 2.f * c), t[i], g[i]);
+            } else {                 // packed FMAs (FFMA2): one issue slot per float2
+                const float2 cc = make_float2(c, c);
+                g[i] = __ffma2_rn(cc, t[j], g[i]);
+                g[j] = __ffma2_rn(cc, t[i], g[j]);
             }
         });
     });
@@ -171,6 +236,188 @@ __global__ void __launch_bounds__(128) interact_bwd_kernel(FeatPtrs fp, int64_t 
             constexpr int i = decltype(I)::value;
             reinterpret_cast<float2*>(d_feat + (int64_t)i * ld_dfeat + (int64_t)b * DIM)[col] = g[i];
         });
+    }
+}
+
+// ---- tensor-core path (F <= 32, dim % 32 == 0, no self-interaction) -----------------------------
+// ncu on the CUDA-core kernels above: issue-bound (3048 / 3864 warp instructions per sample, FMA pipe
+// 36 %, DRAM 35 %), because the K reduction costs one shuffle + add per pair on top of the FMAs.
+// mma.sync.m16n8k8 does that reduction inside the instruction.  FP32 accuracy is kept with the 3xTF32
+// split (hi = rna.tf32(x), lo = rna.tf32(x - hi); hi*hi + hi*lo + lo*hi, the cross terms in their own
+// accumulator); one warp owns one sample and the fragments are loaded straight from global memory
+// with 16-byte loads: the MMA's k index (forward) and n index (backward) are free permutations, so
+// lane (g, t) reads whole float4s and no shared-memory transpose is needed.
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Forward: Z = T T^T, T = [F, DIM].  Row groups of 8 rows: group r holds rows 8r + g.  Lane (g, t)
+// loads, per 16-column chunk j, the float4 at column 16j + 4t of its row in every group; (x, y) feed
+// one k-step and (z, w) the next (virtual k = t <-> x / z, k = t + 4 <-> y / w: the same permutation
+// on the A and the B side, so the dot products are unchanged).  The A fragment of m-tile i is groups
+// (2i, 2i + 1), the B fragment of n-tile n is group n: the same registers.
+template <int F, int DIM>
+__global__ void __launch_bounds__(128, 3) interact_fwd_mma_kernel(FeatPtrs fp, int64_t row_stride, int B,
+                                                                  float* __restrict__ out, int64_t ld_out) {
+    constexpr int MT = (F + 15) / 16, RG = 2 * MT;       // m-tiles, row groups
+    constexpr int NCH = DIM / 16;                        // 16-column chunks
+    // lower-triangle tiles (m-tile i, n-tile n <= 2i + 1)
+    constexpr int NTILE = MT * (MT + 1);                 // sum over i of (2i + 2)
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+        const float* rowp[RG];
+#pragma unroll
+        for (int r = 0; r < RG; ++r) rowp[r] = (8 * r + g < F) ? fp.p[8 * r + g] + (int64_t)b * row_stride + 4 * t : nullptr;
+        float big[NTILE][4], small[NTILE][4];
+#pragma unroll
+        for (int q = 0; q < NTILE; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) big[q][e] = small[q][e] = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < NCH; ++j) {
+            float4 v[RG];
+#pragma unroll
+            for (int r = 0; r < RG; ++r)
+                v[r] = rowp[r] ? __ldg(reinterpret_cast<const float4*>(rowp[r] + 16 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t hi0[RG], lo0[RG], hi1[RG], lo1[RG];
+#pragma unroll
+                for (int r = 0; r < RG; ++r) {
+                    split_tf32(h ? v[r].z : v[r].x, hi0[r], lo0[r]);
+                    split_tf32(h ? v[r].w : v[r].y, hi1[r], lo1[r]);
+                }
+                int q = 0;
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+#pragma unroll
+                    for (int n = 0; n <= 2 * i + 1; ++n, ++q) {
+                        mma_tf32(small[q], lo0[2 * i], lo0[2 * i + 1], lo1[2 * i], lo1[2 * i + 1], hi0[n], hi1[n]);
+                        mma_tf32(small[q], hi0[2 * i], hi0[2 * i + 1], hi1[2 * i], hi1[2 * i + 1], lo0[n], lo1[n]);
+                        mma_tf32(big[q], hi0[2 * i], hi0[2 * i + 1], hi1[2 * i], hi1[2 * i + 1], hi0[n], hi1[n]);
+                    }
+                }
+            }
+        }
+        float* orow = out + (int64_t)b * ld_out;
+        // dense features pass through (model_no_ddp.py:293); rows of `out` are not 16-byte aligned
+        const float* x = fp.p[0] + (int64_t)b * row_stride;
+#pragma unroll
+        for (int c = lane; c < DIM; c += 32) orow[c] = __ldg(x + c);
+        // C fragment: c0 (g, 2t), c1 (g, 2t + 1), c2 (g + 8, 2t), c3 (g + 8, 2t + 1) of the tile
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+#pragma unroll
+            for (int n = 0; n <= 2 * i + 1; ++n, ++q) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int I = 16 * i + g + 8 * (e >> 1), J = 8 * n + 2 * t + (e & 1);
+                    if (J < I && I < F) orow[DIM + I * (I - 1) / 2 + J] = big[q][e] + small[q][e];
+                }
+            }
+        }
+    }
+}
+
+// Backward: dT = S T with S the symmetric [F, F] matrix of the pair gradients (zero diagonal), plus the
+// pass-through gradient on row 0.  A = S (m-tile i, k-step ks), B = T (k-step ks = rows 8ks + t, + 4;
+// n-tile n = columns), D = dT.  The n index is permuted: virtual column c of n-tile n is the real column
+// (DIM/8) * c + n, so lane (g, t) needs DIM/8 consecutive floats of its rows and owns DIM/8
+// consecutive floats of its output rows.
+template <int F, int DIM>
+__global__ void __launch_bounds__(128, 3) interact_bwd_mma_kernel(FeatPtrs fp, int64_t row_stride, int B,
+                                                                  const float* __restrict__ d_out, int64_t ld_dout,
+                                                                  float* __restrict__ d_feat, int64_t ld_dfeat) {
+    constexpr int MT = (F + 15) / 16, KS = (F + 7) / 8;  // m-tiles, k-steps
+    constexpr int NTL = DIM / 8;                         // n-tiles = floats per lane per row
+    constexpr int NG = NTL / 4;                          // groups of four n-tiles (one float4)
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+        const float* drow = d_out + (int64_t)b * ld_dout;
+        // A fragments: a0 (I = 16i + g, J = 8ks + t), a1 (I + 8, J), a2 (I, J + 4), a3 (I + 8, J + 4)
+        uint32_t ahi[MT][KS][4], alo[MT][KS][4];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int I = 16 * i + g + 8 * (e & 1), J = 8 * ks + t + 4 * (e >> 1);
+                    float c = 0.f;
+                    if (I != J && I < F && J < F) {
+                        const int hi = max(I, J), lo = min(I, J);
+                        c = __ldg(drow + DIM + hi * (hi - 1) / 2 + lo);
+                    }
+                    split_tf32(c, ahi[i][ks][e], alo[i][ks][e]);
+                }
+        const float* rowp[2 * KS];
+#pragma unroll
+        for (int r = 0; r < 2 * KS; ++r) rowp[r] = (4 * r + t < F) ? fp.p[4 * r + t] + (int64_t)b * row_stride + NTL * g : nullptr;
+#pragma unroll 1
+        for (int c4 = 0; c4 < NG; ++c4) {
+            float4 v[2 * KS];
+#pragma unroll
+            for (int r = 0; r < 2 * KS; ++r)
+                v[r] = rowp[r] ? __ldg(reinterpret_cast<const float4*>(rowp[r]) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float acc[MT][4][4];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int n = 0; n < 4; ++n)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const float e0 = n == 0 ? v[2 * ks].x : n == 1 ? v[2 * ks].y : n == 2 ? v[2 * ks].z : v[2 * ks].w;
+                    const float e1 = n == 0 ? v[2 * ks + 1].x : n == 1 ? v[2 * ks + 1].y : n == 2 ? v[2 * ks + 1].z : v[2 * ks + 1].w;
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split_tf32(e0, bh0, bl0);
+                    split_tf32(e1, bh1, bl1);
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        mma_tf32(acc[i][n], alo[i][ks][0], alo[i][ks][1], alo[i][ks][2], alo[i][ks][3], bh0, bh1);
+                        mma_tf32(acc[i][n], ahi[i][ks][0], ahi[i][ks][1], ahi[i][ks][2], ahi[i][ks][3], bl0, bl1);
+                        mma_tf32(acc[i][n], ahi[i][ks][0], ahi[i][ks][1], ahi[i][ks][2], ahi[i][ks][3], bh0, bh1);
+                    }
+                }
+            }
+            // D fragment of n-tile n = 4 c4 + e: c0 (row g, real column NTL * 2t + n), c1 (NTL * (2t + 1) + n),
+            // c2 / c3 the same for row g + 8: four consecutive floats per (row, column half)
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+                    const int I = 16 * i + g + 8 * rh;
+                    if (I < F) {
+#pragma unroll
+                        for (int ch = 0; ch < 2; ++ch) {
+                            const int col = NTL * (2 * t + ch) + 4 * c4;
+                            float4 o = make_float4(acc[i][0][2 * rh + ch], acc[i][1][2 * rh + ch], acc[i][2][2 * rh + ch], acc[i][3][2 * rh + ch]);
+                            if (I == 0) {       // d/dx of the pass-through
+                                o.x += __ldg(drow + col); o.y += __ldg(drow + col + 1);
+                                o.z += __ldg(drow + col + 2); o.w += __ldg(drow + col + 3);
+                            }
+                            *reinterpret_cast<float4*>(d_feat + (int64_t)I * ld_dfeat + (int64_t)b * DIM + col) = o;
+                        }
+                    }
+                }
+        }
     }
 }
 
@@ -227,12 +474,44 @@ void launch_fwd(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_ou
     LAUNCH(K_INT_FWD, s, (interact_fwd_kernel<F, LPS, ITSELF><<<blocks, 128, 0, s>>>(fp, rs, B, out, ld_out)));
 }
 
+template <int F, bool ITSELF>
+void launch_fwd_tr(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_out, cudaStream_t s) {
+    const int blocks = (B + 3) / 4;                       // one warp per sample
+    LAUNCH(K_INT_FWD, s, (interact_fwd_tr_kernel<F, ITSELF><<<blocks, 128, 0, s>>>(fp, rs, B, out, ld_out)));
+}
+
 template <int F, int TPS, bool ITSELF>
 void launch_bwd(const FeatPtrs& fp, int64_t rs, int B, const float* d_out, int64_t ld_dout, float* d_feat,
                 int64_t ld_dfeat, cudaStream_t s) {
     const int64_t threads = (int64_t)B * TPS;
     const int blocks = (int)((threads + 127) / 128);
     LAUNCH(K_INT_BWD, s, (interact_bwd_kernel<F, TPS, ITSELF><<<blocks, 128, 0, s>>>(fp, rs, B, d_out, ld_dout, d_feat, ld_dfeat)));
+}
+
+int g_variant = 0;       // cdlrm_interact_set_option(0, .): 0 CUDA cores (default), 1 mma.sync 3xTF32, 2 first CUDA-core version
+bool use_simt_only() { return g_variant != 1; }
+
+int interact_grid(int B) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int need = (B + 3) / 4;                 // one warp per sample, 4 warps per block
+    const int cap = sms * 3 * 4;                  // 3 resident blocks per SM, a few samples per warp
+    return need < cap ? need : cap;
+}
+
+template <int F, int DIM>
+void launch_fwd_mma(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_out, cudaStream_t s) {
+    LAUNCH(K_INT_FWD, s, (interact_fwd_mma_kernel<F, DIM><<<interact_grid(B), 128, 0, s>>>(fp, rs, B, out, ld_out)));
+}
+
+template <int F, int DIM>
+void launch_bwd_mma(const FeatPtrs& fp, int64_t rs, int B, const float* d_out, int64_t ld_dout, float* d_feat,
+                    int64_t ld_dfeat, cudaStream_t s) {
+    LAUNCH(K_INT_BWD, s, (interact_bwd_mma_kernel<F, DIM><<<interact_grid(B), 128, 0, s>>>(fp, rs, B, d_out, ld_dout, d_feat, ld_dfeat)));
 }
 
 bool aligned_for(const FeatPtrs& fp, int n, int64_t rs, int bytes) {
@@ -243,16 +522,40 @@ bool aligned_for(const FeatPtrs& fp, int n, int64_t rs, int bytes) {
 
 }  // namespace
 
+#define FWD_MMA_CASE(F_, D_)                                                              \
+    if (!done && n_feat == F_ && dim == D_ && !itself && fast16 && !use_simt_only()) {    \
+        launch_fwd_mma<F_, D_>(fp, rs, batch, out, ld_out, s);                            \
+        done = true;                                                                      \
+    }
+#define BWD_MMA_CASE(F_, D_)                                                              \
+    if (!done && n_feat == F_ && dim == D_ && !itself && fast16 && !use_simt_only()) {    \
+        launch_bwd_mma<F_, D_>(fp, rs, batch, d_out, ld_dout, d_feat, ld_dfeat, s);        \
+        done = true;                                                                      \
+    }
+#define FWD_TR_CASE(F_)                                                                  \
+    if (!done && n_feat == F_ && dim == 128 && !itself && fast16 && g_variant == 0) {     \
+        launch_fwd_tr<F_, false>(fp, rs, batch, out, ld_out, s);                          \
+        done = true;                                                                      \
+    }
 #define FWD_CASE(F_, D_)                                                                  \
-    if (n_feat == F_ && dim == D_ && !itself && fast16) {                                 \
+    if (!done && n_feat == F_ && dim == D_ && !itself && fast16) {                        \
         launch_fwd<F_, D_ / 4, false>(fp, rs, batch, out, ld_out, s);                      \
         done = true;                                                                      \
     }
 #define BWD_CASE(F_, D_)                                                                  \
-    if (n_feat == F_ && dim == D_ && !itself && fast8) {                                  \
+    if (!done && n_feat == F_ && dim == D_ && !itself && fast8) {                         \
         launch_bwd<F_, D_ / 2, false>(fp, rs, batch, d_out, ld_dout, d_feat, ld_dfeat, s); \
         done = true;                                                                      \
     }
+
+// key 0: kernel variant (0 = CUDA cores with the shared-memory transpose reduction, the default and the fastest
+// measured; 1 = mma.sync.m16n8k8 3xTF32, kept as the evidence for "tensor cores do not pay off here":
+// 78 / 93 us against 51 / 73 us forward / backward at B = 8192, 27 x 128 on B200; 2 = the butterfly version)
+extern "C" int cdlrm_interact_set_option(int key, int value) {
+    ARG_CHECK(key == 0 && value >= 0 && value <= 2);
+    g_variant = value;
+    return CDLRM_OK;
+}
 
 extern "C" int cdlrm_interact_fwd(int device, const float* const* h_feat, int n_feat, int64_t rs, int32_t batch,
                                   int dim, int itself, float* out, int64_t ld_out, cdlrm_stream stream) {
@@ -270,6 +573,8 @@ extern "C" int cdlrm_interact_fwd(int device, const float* const* h_feat, int n_
     }
     const bool fast16 = aligned_for(fp, n_feat, rs, 16);
     bool done = false;
+    FWD_MMA_CASE(27, 128) FWD_MMA_CASE(27, 64) FWD_MMA_CASE(27, 32) FWD_MMA_CASE(9, 128) FWD_MMA_CASE(9, 64) FWD_MMA_CASE(9, 32)
+    FWD_TR_CASE(27) FWD_TR_CASE(9)
     FWD_CASE(27, 128) FWD_CASE(27, 64) FWD_CASE(27, 32) FWD_CASE(27, 16)
     FWD_CASE(9, 128) FWD_CASE(9, 64) FWD_CASE(9, 32) FWD_CASE(9, 16)
     if (!done) LAUNCH(K_INT_FWD, s, interact_fwd_generic<<<batch, 128, 0, s>>>(fp, n_feat, rs, batch, dim, itself, out, ld_out));
@@ -293,7 +598,9 @@ extern "C" int cdlrm_interact_bwd(int device, const float* const* h_feat, int n_
         fp.p[i] = h_feat[i];
     }
     const bool fast8 = aligned_for(fp, n_feat, rs, 8) && ((uintptr_t)d_feat % 8 == 0) && (ld_dfeat % 2 == 0);
+    const bool fast16 = aligned_for(fp, n_feat, rs, 16) && ((uintptr_t)d_feat % 16 == 0) && (ld_dfeat % 4 == 0);
     bool done = false;
+    BWD_MMA_CASE(27, 128) BWD_MMA_CASE(27, 64) BWD_MMA_CASE(27, 32) BWD_MMA_CASE(9, 128) BWD_MMA_CASE(9, 64) BWD_MMA_CASE(9, 32)
     BWD_CASE(27, 128) BWD_CASE(27, 64) BWD_CASE(27, 32) BWD_CASE(27, 16)
     BWD_CASE(9, 128) BWD_CASE(9, 64) BWD_CASE(9, 32) BWD_CASE(9, 16)
     if (!done)

@@ -463,6 +463,77 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ sr
     }
 }
 
+// all weight matrices of one MLP in ONE launch (they change together, at the optimizer step)
+constexpr int MAX_LAYERS = 8;
+struct SplitJob {
+    const float* src; int64_t lds; int rows, cols;
+    float *hi, *lo; int64_t ld_o;
+    float *thi, *tlo; int64_t ld_t;
+    int tiles_x, tile0;          // 32 x 32 tiles per row of tiles, first global tile of this job
+};
+struct SplitBatch {
+    SplitJob job[MAX_LAYERS];
+    int n;
+};
+__global__ void __launch_bounds__(256) split_batch_kernel(const __grid_constant__ SplitBatch sb) {
+    __shared__ float s_hi[32][33], s_lo[32][33];
+    int j = 0;
+#pragma unroll 1
+    while (j + 1 < sb.n && (int)blockIdx.x >= sb.job[j + 1].tile0) ++j;
+    const SplitJob& jb = sb.job[j];
+    const int tile = blockIdx.x - jb.tile0;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = (tile / jb.tiles_x) * 32, c0 = (tile % jb.tiles_x) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        float h = 0.f, l = 0.f;
+        if (r < jb.rows && c < jb.cols) {
+            const float v = jb.src[(int64_t)r * jb.lds + c];
+            h = tf32_hi(v);
+            l = tf32_lo(v, h);
+            jb.hi[(int64_t)r * jb.ld_o + c] = h;
+            jb.lo[(int64_t)r * jb.ld_o + c] = l;
+        }
+        s_hi[ty + 8 * i][tx] = h;
+        s_lo[ty + 8 * i][tx] = l;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        if (r < jb.rows && c < jb.cols) {
+            jb.thi[(int64_t)c * jb.ld_t + r] = s_hi[tx][ty + 8 * i];
+            jb.tlo[(int64_t)c * jb.ld_t + r] = s_lo[tx][ty + 8 * i];
+        }
+    }
+}
+
+// dW [N, K] and db [N] of every layer out of the padded split-K accumulators, ONE launch
+struct UnpackJob {
+    const float* acc; int64_t ldp; int N, K;
+    float *dW, *db;
+    int64_t e0;                  // first global element of this job
+};
+struct UnpackBatch {
+    UnpackJob job[MAX_LAYERS];
+    int n;
+    int64_t total;
+};
+__global__ void __launch_bounds__(256) unpack_batch_kernel(const __grid_constant__ UnpackBatch ub) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ub.total; i += (int64_t)gridDim.x * blockDim.x) {
+        int j = 0;
+#pragma unroll 1
+        while (j + 1 < ub.n && i >= ub.job[j + 1].e0) ++j;
+        const UnpackJob& jb = ub.job[j];
+        const int64_t e = i - jb.e0;
+        const int n = (int)(e / (jb.K + 1)), k = (int)(e - (int64_t)n * (jb.K + 1));
+        const float v = jb.acc[(int64_t)n * jb.ldp + k];
+        if (k < jb.K) jb.dW[(int64_t)n * jb.K + k] = v;
+        else jb.db[n] = v;
+    }
+}
+
 __global__ void fill_kernel(float* p, int64_t n, float v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -612,18 +683,6 @@ int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* 
     return CDLRM_OK;
 }
 
-// dW [N, K] and db [N] out of the padded split-K accumulator [N, ldp] (column K = bias gradient)
-__global__ void unpack_wgrad_kernel(const float* __restrict__ acc, int64_t ldp, int N, int K, float* __restrict__ dW,
-                                    float* __restrict__ db) {
-    const int64_t total = (int64_t)N * (K + 1);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int n = (int)(i / (K + 1)), k = (int)(i - (int64_t)n * (K + 1));
-        const float v = acc[(int64_t)n * ldp + k];
-        if (k < K) dW[(int64_t)n * K + k] = v;
-        else db[n] = v;
-    }
-}
-
 int launch_split(const float* src, int64_t lds, int rows, int cols, const float* y, int64_t ldy, int dmode, float* hi,
                  float* lo, int64_t ld_o, float* thi, float* tlo, int64_t ld_t, cudaStream_t s) {
     if (rows <= 0 || cols <= 0) return CDLRM_OK;
@@ -655,6 +714,7 @@ struct cdlrm_mlp {
     std::vector<float*> x_hi, x_lo, xt_hi, xt_lo, g_hi, g_lo, gt_hi, gt_lo;
     std::vector<float*> dwp;     // per layer: split-K accumulator [N_l, pad4(K_l + 1)]
     float* y_out = nullptr;
+    int64_t dwp_bytes = 0;       // the dwp regions are carved back to back
     int last_batch = 0;
     bool ones_set = false;
     int num_sms = 148;
@@ -690,12 +750,14 @@ static int64_t mlp_carve(cdlrm_mlp* m, char* base) {
     }
     m->y_out = take(cap * pad4(m->D[L]));
     m->dwp.assign(L, nullptr);
+    const int64_t dwp0 = off;
     for (int l = 0; l < L; ++l) m->dwp[l] = take((int64_t)m->D[l + 1] * pad4(m->D[l] + 1));
+    m->dwp_bytes = off - dwp0;
     return off;
 }
 
 extern "C" int64_t cdlrm_mlp_workspace_bytes(int n_layers, const int32_t* h_dims, int32_t batch_cap) {
-    if (n_layers < 1 || !h_dims || batch_cap < 1) return -1;
+    if (n_layers < 1 || n_layers > MAX_LAYERS || !h_dims || batch_cap < 1) return -1;
     cdlrm_mlp m;
     m.L = n_layers;
     m.cap = batch_cap;
@@ -708,7 +770,7 @@ extern "C" int64_t cdlrm_mlp_workspace_bytes(int n_layers, const int32_t* h_dims
 extern "C" int cdlrm_mlp_create(cdlrm_mlp** out, int device, int n_layers, const int32_t* h_dims, int32_t batch_cap,
                                 int sigmoid_layer, void* workspace, int64_t workspace_bytes) {
     ARG_CHECK(out && h_dims && workspace);
-    ARG_CHECK(n_layers >= 1 && batch_cap >= 1);
+    ARG_CHECK(n_layers >= 1 && n_layers <= MAX_LAYERS && batch_cap >= 1);
     ARG_CHECK(((uintptr_t)workspace & 255) == 0);
     CU_CHECK(cudaSetDevice(device));
     cdlrm_mlp* m = new cdlrm_mlp();
@@ -783,11 +845,23 @@ extern "C" int cdlrm_mlp_forward(cdlrm_mlp* m, const float* x, int64_t ldx, int3
         CU_CHECK(cudaGetLastError());
         m->ones_set = true;
     }
-    // weights: W [N,K] -> hi/lo K-major and transposed (the dgrad operand)
-    for (int l = 0; l < L; ++l) {
-        ARG_CHECK(h_W[l] && h_b[l]);
-        const int K = m->D[l], N = m->D[l + 1];
-        if ((rc = launch_split(h_W[l], K, N, K, nullptr, 0, ACT_NONE, m->w_hi[l], m->w_lo[l], pad4(K), m->wt_hi[l], m->wt_lo[l], pad4(N), s))) return rc;
+    // weights: W [N,K] -> hi/lo K-major and transposed (the dgrad operand), all layers in one launch
+    {
+        SplitBatch sb;
+        int tiles = 0;
+        for (int l = 0; l < L; ++l) {
+            ARG_CHECK(h_W[l] && h_b[l]);
+            const int K = m->D[l], N = m->D[l + 1];
+            SplitJob& jb = sb.job[l];
+            jb.src = h_W[l]; jb.lds = K; jb.rows = N; jb.cols = K;
+            jb.hi = m->w_hi[l]; jb.lo = m->w_lo[l]; jb.ld_o = pad4(K);
+            jb.thi = m->wt_hi[l]; jb.tlo = m->wt_lo[l]; jb.ld_t = pad4(N);
+            jb.tiles_x = (K + 31) / 32; jb.tile0 = tiles;
+            tiles += jb.tiles_x * ((N + 31) / 32);
+        }
+        sb.n = L;
+        LAUNCH(K_MLP_SPLIT, s, (split_batch_kernel<<<tiles, 256, 0, s>>>(sb)));
+        CU_CHECK(cudaGetLastError());
     }
     // input
     if ((rc = launch_split(x, ldx, batch, m->D[0], nullptr, 0, ACT_NONE, m->x_hi[0], m->x_lo[0], pad4(m->D[0]), m->xt_hi[0], m->xt_lo[0], capp, s))) return rc;
@@ -829,6 +903,7 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
     const int last_act = (L - 1 == m->sigmoid_layer) ? ACT_SIGMOID : (m->sigmoid_layer == -2 ? ACT_NONE : ACT_RELU);
     if ((rc = launch_split(dy, lddy, batch, m->D[L], m->y_out, pad4(m->D[L]), last_act, m->g_hi[L], m->g_lo[L], pad4(m->D[L]),
                            m->gt_hi[L], m->gt_lo[L], capp, s))) return rc;
+    CU_CHECK(cudaMemsetAsync(m->dwp[0], 0, (size_t)m->dwp_bytes, s));      // every layer's split-K accumulator
     for (int l = L - 1; l >= 0; --l) {
         const int K = m->D[l], N = m->D[l + 1];
         ARG_CHECK(h_dW[l] && h_db[l]);
@@ -836,17 +911,11 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
         // padded accumulator, then unpacked into the dense dW / db the optimizer sees
         {
             const int64_t ldp = pad4(K + 1);
-            CU_CHECK(cudaMemsetAsync(m->dwp[l], 0, (size_t)N * ldp * 4, s));
             Epi ep = {};
             Out o;
             ep.M = N; ep.N = K + 1; ep.K = batch;
             o.c = m->dwp[l]; o.ldc = ldp; o.reduce = true;
             if ((rc = launch_gemm(m->gt_hi[l + 1], m->gt_lo[l + 1], capp, m->xt_hi[l], m->xt_lo[l], capp, ep, o, 0 /*auto split-K*/, s))) return rc;
-            const int64_t total = (int64_t)N * (K + 1);
-            int blocks = (int)((total + 255) / 256);
-            if (blocks > 1184) blocks = 1184;
-            LAUNCH(K_MLP_SPLIT, s, (unpack_wgrad_kernel<<<blocks, 256, 0, s>>>(m->dwp[l], ldp, N, K, h_dW[l], h_db[l])));
-            CU_CHECK(cudaGetLastError());
         }
         // dgrad: dX = dZ W, then the ReLU mask of the layer below -> its dZ (split, both layouts)
         if (l > 0) {
@@ -864,6 +933,23 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
             o.c = dx; o.ldc = lddx;
             if ((rc = launch_gemm(m->g_hi[l + 1], m->g_lo[l + 1], pad4(N), m->wt_hi[l], m->wt_lo[l], pad4(N), ep, o, 1, s))) return rc;
         }
+    }
+    // the dense dW / db the optimizer sees, all layers in one launch
+    {
+        UnpackBatch ub;
+        int64_t total = 0;
+        for (int l = 0; l < L; ++l) {
+            UnpackJob& jb = ub.job[l];
+            jb.acc = m->dwp[l]; jb.ldp = pad4(m->D[l] + 1); jb.N = m->D[l + 1]; jb.K = m->D[l];
+            jb.dW = h_dW[l]; jb.db = h_db[l]; jb.e0 = total;
+            total += (int64_t)jb.N * (jb.K + 1);
+        }
+        ub.n = L;
+        ub.total = total;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 1184) blocks = 1184;
+        LAUNCH(K_MLP_SPLIT, s, (unpack_batch_kernel<<<blocks, 256, 0, s>>>(ub)));
+        CU_CHECK(cudaGetLastError());
     }
     return CDLRM_OK;
 }

@@ -115,6 +115,9 @@ int cdlrm_embed_bwd_sgd(cdlrm_ctx* ctx, int table_begin, int table_count,
  * float32 [B, dim] matrices with row stride feat_row_stride (elements).
  * out[b] = [x[b], <T_i, T_j> for i in 0..n_feat-1 for j in 0..i-1 (+ j == i if itself)]
  * out row stride ld_out >= dim + n_pairs. */
+/* kernel variant (process-wide): key 0, value 0 = CUDA-core kernels (default), 1 = mma.sync 3xTF32 tensor-core
+ * kernels (measured slower on B200, kept for the comparison), 2 = the first CUDA-core forward (shuffle butterfly) */
+int cdlrm_interact_set_option(int key, int value);
 int cdlrm_interact_fwd(int device, const float* const* h_feat, int n_feat, int64_t feat_row_stride,
                        int32_t batch, int dim, int itself, float* out, int64_t ld_out,
                        cdlrm_stream stream);

@@ -140,8 +140,26 @@ def test_interaction_matches_reference_golden(case):
     util.assert_close_fp32(torch.stack([t.grad for t in ly]).cpu().numpy(), g[f"{case}_dly"])
 
 
-@pytest.mark.parametrize("shape", [(2048, 27, 128), (4099, 27, 16), (777, 9, 16), (513, 27, 64), (100, 3, 2)])
+@pytest.mark.parametrize("shape", [(2048, 27, 128), (4099, 27, 16), (777, 9, 16), (513, 27, 64), (100, 3, 2),
+                                   (8192, 27, 128), (301, 9, 32), (65, 27, 32), (130, 9, 128)])
 def test_interaction_matches_oracle_at_size(shape):
+    _interaction_at_size(shape)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("shape", [(2048, 27, 128), (513, 27, 64), (301, 9, 32), (130, 9, 128)])
+def test_interaction_other_kernel_variants(shape, variant):
+    """The mma.sync 3xTF32 kernels (1) and the first CUDA-core forward (2) stay correct (they are
+    selectable through cdlrm_interact_set_option and quoted in DESIGN.md as the comparison)."""
+    from cdlrm_b200._lib import check, lib
+    check(lib.cdlrm_interact_set_option(0, variant))
+    try:
+        _interaction_at_size(shape)
+    finally:
+        check(lib.cdlrm_interact_set_option(0, 0))
+
+
+def _interaction_at_size(shape):
     from oracle import oracle as O
     _, _, M = _mods()
     B, nf, d = shape

@@ -260,8 +260,12 @@ def gpu_run(a, wl, ln_emb):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # training runs on a high-priority stream: the look-ahead planner's kernels (side stream, default
+    # priority) then only take the SM slots the training step leaves free
+    torch.cuda.set_stream(torch.cuda.Stream(dev, priority=-1))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib
     args, ln_bot, ln_top = model_args(wl, ln_emb, world)
@@ -374,12 +378,18 @@ def gpu_run(a, wl, ln_emb):
     cuprof = os.environ.get("CDLRM_BENCH_CUPROF", "0") == "1"   # ncu --profile-from-start off: timed region only
     if cuprof:
         torch.cuda.profiler.start()
+    seg = max(1, K // 24)                 # per-segment device times: shows what the planner / boundaries cost
+    marks = []
     ev0.record()
-    for _ in range(K):
+    for i in range(K):
         if j % L == 0:
             n_boundaries += 1
         one_step(j)
         j += 1
+        if (i + 1) % seg == 0 and i + 1 < K:
+            m = torch.cuda.Event(enable_timing=True)
+            m.record()
+            marks.append((i + 1, m))
     ev1.record()
     torch.cuda.synchronize(dev)
     if cuprof:
@@ -388,6 +398,10 @@ def gpu_run(a, wl, ln_emb):
     if getattr(tr, "_graph", None) is not None:
         launches += K * tr.graph_launches      # graph replays re-issue the captured launches
     ms = ev0.elapsed_time(ev1)
+    series, prev_i, prev_e = [], 0, ev0
+    for i, m in marks + [(K, ev1)]:
+        series.append(round(prev_e.elapsed_time(m) / (i - prev_i), 4))
+        prev_i, prev_e = i, m
     if world > 1:
         dist.barrier()
         t = torch.tensor([ms], device=dev)
@@ -547,6 +561,7 @@ def gpu_run(a, wl, ln_emb):
                        "setup_s": round(setup_s, 1), "master_host_gb": round(sum(ln_emb) * d * 4 / 1e9, 1)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
             "caching_overhead_ms_per_window": [round(1000 * x, 2) for x in tr.caching_overhead[-3:]],
+            "ms_per_step_series": {"steps_per_segment": seg, "ms_per_step": series},
         }
     if world > 1:
         dist.barrier()

@@ -115,6 +115,44 @@ void cdlrm_prof_mark(int id, cudaStream_t s, int end);
 
 static inline int ceil_div_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// The per-step kernels are short (3-60 us) and run as one dependent chain, so the launch latency
+// between two of them is a visible share of the step.  Every kernel launched through LAUNCH_PDL
+// calls pdl_enter() first: it releases its dependents (they may be scheduled while this grid is still
+// running -- they block in their own griddepcontrol.wait until this grid has completed and its
+// writes are visible) and then waits for its own prerequisite grid.  A kernel launched WITH the
+// attribute but WITHOUT pdl_enter() would race with its predecessor: only use LAUNCH_PDL with kernels
+// that call it.  cdlrm_set_pdl(0) / CDLRM_PDL=0 switches the attribute off (plain stream order).
+extern int g_cdlrm_pdl;
+
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline void cdlrm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_cdlrm_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// kern may be a parenthesised template-id: LAUNCH_PDL(id, s, (k<A, B>), grid, block, smem, args...)
+#define LAUNCH_PDL(id, stream, kern, grid, block, smem, ...)                           \
+    do {                                                                               \
+        cdlrm_prof_mark((id), (stream), 0);                                            \
+        cdlrm_launch_pdl(kern, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__); \
+        cdlrm_prof_mark((id), (stream), 1);                                            \
+    } while (0)
+
 __device__ __forceinline__ int64_t set_index(int64_t id, int64_t S) {
     // torch.remainder semantics (non-negative result for S > 0)
     if ((uint64_t)id < 0x100000000ull && (uint64_t)S < 0x100000000ull)

@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -241,6 +243,17 @@ void cdlrm_prof_mark(int id, cudaStream_t s, int end) {
                 break;
             }
     }
+}
+
+// programmatic dependent launch of the per-step kernels (common.cuh); CDLRM_PDL=0 disables it
+int g_cdlrm_pdl = [] {
+    const char* e = getenv("CDLRM_PDL");
+    return (e && e[0] == '0') ? 0 : 1;
+}();
+
+extern "C" int cdlrm_set_pdl(int on) {
+    g_cdlrm_pdl = on ? 1 : 0;
+    return CDLRM_OK;
 }
 
 extern "C" int cdlrm_prof_enable(int on) {

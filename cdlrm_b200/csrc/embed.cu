@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(FWD_NT) fwd_fused_kernel(const TableDesc* __re
                                                             int32_t* __restrict__ slots, int64_t ld_slots,
                                                             uint32_t* __restrict__ missmap, int words,
                                                             float* __restrict__ out, int64_t ld_out, int dim, int ways) {
+    pdl_enter();
     const int t = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (FWD_NT / 32) + (threadIdx.x >> 5);
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(MISS_NT) fwd_miss_kernel(const TableDesc* __re
                                                             float* __restrict__ out, int64_t ld_out,
                                                             int32_t* __restrict__ n_miss, uint32_t* __restrict__ flags,
                                                             int dim, int ways, int64_t aux_rows) {
+    pdl_enter();
     using V = typename VecT<VEC>::type;
     constexpr int NW = MISS_NT / 32;
     __shared__ int s_red[2][NW];
@@ -359,6 +361,7 @@ __device__ __forceinline__ int block_excl_maxscan_1024(int v, int* s_warp) {
 __global__ void __launch_bounds__(PLAN_NT, 1) bwd_plan_kernel(const TableDesc* __restrict__ tabs, int tb,
                                                               const int32_t* __restrict__ slots, int64_t ld_slots,
                                                               int n_idx, int j0, int n, PlanView pv) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem[];
     // layout: keyA[n] keyB[n] (u32) | valA[n] valB[n] (u16) | cnt[8192] (u16) | scratch[40] (int)
     const int npad = (n + 7) & ~7;
@@ -479,6 +482,7 @@ __global__ void __launch_bounds__(APPLY_NT, 2) bwd_sgd_apply_kernel(const TableD
                                                                      const int32_t* __restrict__ bag_ids, int64_t ld_bag,
                                                                      const float* __restrict__ d_out, int64_t ld_dout,
                                                                      int64_t row_stride, float lr, int dim) {
+    pdl_enter();
     constexpr int NGW = 32 / G;               // lane groups per warp
     constexpr int EPG = G;                    // sorted entries per group (32 / NGW)
     constexpr int NB = EPG < CHB ? EPG : CHB; // entries per batch
@@ -649,7 +653,7 @@ extern "C" int cdlrm_embed_fwd(cdlrm_ctx* c, int tb, int tc, const int64_t* ids,
     const int words = (n_idx + 31) / 32;
     dim3 grid((words + FWD_NT / 32 - 1) / (FWD_NT / 32), tc);
     const int wsel = !tags16 ? 0 : (c->ways == 16 ? 16 : c->ways == 8 ? 8 : c->ways == 4 ? 4 : c->ways == 2 ? 2 : 0);
-#define LAUNCH_FUSED(WW, GG, CP) LAUNCH(K_PROBE, s, (fwd_fused_kernel<WW, GG, CP><<<grid, FWD_NT, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_missmap, words, out, ld_out, c->dim, c->ways)))
+#define LAUNCH_FUSED(WW, GG, CP) LAUNCH_PDL(K_PROBE, s, (fwd_fused_kernel<WW, GG, CP>), grid, FWD_NT, 0, c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_missmap, words, out, ld_out, c->dim, c->ways)
 #define FUSED_G(WW)                                             \
     if (!copy) { LAUNCH_FUSED(WW, 32, false); }                 \
     else switch (G) {                                           \
@@ -676,7 +680,7 @@ extern "C" int cdlrm_embed_fwd(cdlrm_ctx* c, int tb, int tc, const int64_t* ids,
     if (mctas > 256) mctas = 256;
     const int wpc = (words + mctas - 1) / mctas;
     dim3 mgrid(mctas, tc);
-#define LAUNCH_MISS(VEC, CP) LAUNCH(K_GATHER, s, (fwd_miss_kernel<VEC, CP><<<mgrid, MISS_NT, 0, s>>>(c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_missmap, words, wpc, c->d_losers, out, ld_out, n_miss, c->d_flags, c->dim, c->ways, c->aux)))
+#define LAUNCH_MISS(VEC, CP) LAUNCH_PDL(K_GATHER, s, (fwd_miss_kernel<VEC, CP>), mgrid, MISS_NT, 0, c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_missmap, words, wpc, c->d_losers, out, ld_out, n_miss, c->d_flags, c->dim, c->ways, c->aux)
     if (copy) LAUNCH_MISS(4, true);
     else if (vec == 4) LAUNCH_MISS(4, false);
     else if (vec == 2) LAUNCH_MISS(2, false);
@@ -724,7 +728,7 @@ extern "C" int cdlrm_embed_bwd_plan(cdlrm_ctx* c, int tb, int tc, const int32_t*
         const int n = n_idx - j0 < CDLRM_SORT_MAX ? n_idx - j0 : CDLRM_SORT_MAX;
         const int npad = (n + 7) & ~7;
         const int smem = npad * 12 + 8192 * 2 + 64 * 4;
-        LAUNCH(K_BWD_PLAN, s, bwd_plan_kernel<<<tc, PLAN_NT, smem, s>>>(c->d_tabs, tb, slots, ld_slots, n_idx, j0, n, pv));
+        LAUNCH_PDL(K_BWD_PLAN, s, bwd_plan_kernel, tc, PLAN_NT, smem, c->d_tabs, tb, slots, ld_slots, n_idx, j0, n, pv);
     }
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
@@ -754,7 +758,7 @@ extern "C" int cdlrm_embed_bwd_sgd(cdlrm_ctx* c, int tb, int tc, const void* pla
         if (vec == 4 && cpr <= 32) {
             dim3 grid((n + APPLY_NT - 1) / APPLY_NT, tc);     // a warp per 32 sorted entries
 #define LAUNCH_SGD(GG)                                                                                         \
-    LAUNCH(K_BWD_SGD, s, (bwd_sgd_apply_kernel<GG><<<grid, APPLY_NT, 0, s>>>(c->d_tabs, tb, pv, n_idx, j0, n, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim)))
+    LAUNCH_PDL(K_BWD_SGD, s, (bwd_sgd_apply_kernel<GG>), grid, APPLY_NT, 0, c->d_tabs, tb, pv, n_idx, j0, n, bag_ids, ld_bag, d_out, ld_dout, row_stride, lr, c->dim)
             switch (G) {
                 case 1: LAUNCH_SGD(1); break;
                 case 2: LAUNCH_SGD(2); break;

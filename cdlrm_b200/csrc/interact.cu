@@ -80,6 +80,7 @@ __device__ __forceinline__ float butterfly(float (&v)[LPS], int sub) {
 template <int F, int LPS, bool ITSELF>
 __global__ void __launch_bounds__(128) interact_fwd_kernel(FeatPtrs fp, int64_t row_stride, int B,
                                                            float* __restrict__ out, int64_t ld_out) {
+    pdl_enter();
     constexpr int DIM = LPS * 4;
     constexpr int SPW = 32 / LPS;  // samples per warp
     constexpr int NP = Pairs<F, ITSELF>::N;
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(128) interact_fwd_kernel(FeatPtrs fp, int64_t 
 template <int F, bool ITSELF>
 __global__ void __launch_bounds__(128, 4) interact_fwd_tr_kernel(FeatPtrs fp, int64_t row_stride, int B,
                                                               float* __restrict__ out, int64_t ld_out) {
+    pdl_enter();
     constexpr int DIM = 128, PITCH = 36;
     constexpr int NP = Pairs<F, ITSELF>::N;
     __shared__ __align__(16) float s_part[4][2][32 * PITCH];
@@ -185,6 +187,7 @@ template <int F, int TPS, bool ITSELF>
 __global__ void __launch_bounds__(128, 4) interact_bwd_kernel(FeatPtrs fp, int64_t row_stride, int B,
                                                            const float* __restrict__ d_out, int64_t ld_dout,
                                                            float* __restrict__ d_feat, int64_t ld_dfeat) {
+    pdl_enter();
     // TPS threads per sample, each owning a float2 column slice: dim = 2*TPS.  The NP pair
     // coefficients of a sample are staged once in shared memory (coalesced) and read back as
     // broadcast float4 loads -- one LDS.128 per four pairs instead of one shuffle per pair.
@@ -471,13 +474,13 @@ void launch_fwd(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_ou
     constexpr int SPW = 32 / LPS;
     const int warps = (B + SPW - 1) / SPW;
     const int blocks = (warps + 3) / 4;
-    LAUNCH(K_INT_FWD, s, (interact_fwd_kernel<F, LPS, ITSELF><<<blocks, 128, 0, s>>>(fp, rs, B, out, ld_out)));
+    LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_kernel<F, LPS, ITSELF>), blocks, 128, 0, fp, rs, B, out, ld_out);
 }
 
 template <int F, bool ITSELF>
 void launch_fwd_tr(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_out, cudaStream_t s) {
     const int blocks = (B + 3) / 4;                       // one warp per sample
-    LAUNCH(K_INT_FWD, s, (interact_fwd_tr_kernel<F, ITSELF><<<blocks, 128, 0, s>>>(fp, rs, B, out, ld_out)));
+    LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_tr_kernel<F, ITSELF>), blocks, 128, 0, fp, rs, B, out, ld_out);
 }
 
 template <int F, int TPS, bool ITSELF>
@@ -485,7 +488,7 @@ void launch_bwd(const FeatPtrs& fp, int64_t rs, int B, const float* d_out, int64
                 int64_t ld_dfeat, cudaStream_t s) {
     const int64_t threads = (int64_t)B * TPS;
     const int blocks = (int)((threads + 127) / 128);
-    LAUNCH(K_INT_BWD, s, (interact_bwd_kernel<F, TPS, ITSELF><<<blocks, 128, 0, s>>>(fp, rs, B, d_out, ld_dout, d_feat, ld_dfeat)));
+    LAUNCH_PDL(K_INT_BWD, s, (interact_bwd_kernel<F, TPS, ITSELF>), blocks, 128, 0, fp, rs, B, d_out, ld_dout, d_feat, ld_dfeat);
 }
 
 int g_variant = 0;       // cdlrm_interact_set_option(0, .): 0 CUDA cores (default), 1 mma.sync 3xTF32, 2 first CUDA-core version

@@ -224,6 +224,7 @@ gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_enter();            // everything above (barriers, TMEM, tensor-map prefetch) overlaps the previous kernel's tail
     if (threadIdx.x == 0) TRACE(3, 0);
 
     if (warp == 0) {
@@ -433,6 +434,7 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ sr
                                                     const float* __restrict__ y, int64_t ldy, int dmode,
                                                     float* __restrict__ hi, float* __restrict__ lo, int64_t ld_o,
                                                     float* __restrict__ thi, float* __restrict__ tlo, int64_t ld_t) {
+    pdl_enter();
     __shared__ float s_hi[32][33], s_lo[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -476,6 +478,7 @@ struct SplitBatch {
     int n;
 };
 __global__ void __launch_bounds__(256) split_batch_kernel(const __grid_constant__ SplitBatch sb) {
+    pdl_enter();
     __shared__ float s_hi[32][33], s_lo[32][33];
     int j = 0;
 #pragma unroll 1
@@ -521,6 +524,7 @@ struct UnpackBatch {
     int64_t total;
 };
 __global__ void __launch_bounds__(256) unpack_batch_kernel(const __grid_constant__ UnpackBatch ub) {
+    pdl_enter();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ub.total; i += (int64_t)gridDim.x * blockDim.x) {
         int j = 0;
 #pragma unroll 1
@@ -531,6 +535,136 @@ __global__ void __launch_bounds__(256) unpack_batch_kernel(const __grid_constant
         const float v = jb.acc[(int64_t)n * jb.ldp + k];
         if (k < jb.K) jb.dW[(int64_t)n * jb.K + k] = v;
         else jb.db[n] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Narrow last layer (ONE output column: the click probability of the top MLP, 256 -> 1).
+// On the tensor-core path a 128 x 128 tile would carry one useful column (forward, data
+// gradient) or one useful row (weight gradient): three GEMM launches plus a split for 4 MFLOP.
+// Forward is a row-wise dot product, backward an outer product and a column reduction: SIMT,
+// HBM-bound on the activations, FP32 throughout (x = x_hi + x_lo to 2^-22).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_apply(float z, int act) {
+    if (act == ACT_RELU) return z > 0.f ? z : 0.f;
+    if (act == ACT_SIGMOID) return 1.f / (1.f + expf(-z));
+    return z;
+}
+__device__ __forceinline__ float act_grad(float dy, float y, int act) {
+    if (act == ACT_RELU) return y > 0.f ? dy : 0.f;
+    if (act == ACT_SIGMOID) return dy * y * (1.f - y);
+    return dy;
+}
+
+// y[r] = act(sum_k x[r, k] W[k] + bias); one warp per row; written to the workspace copy (backward reads it)
+// and to the caller's output
+__global__ void __launch_bounds__(256) narrow_fwd_kernel(const float* __restrict__ x_hi, const float* __restrict__ x_lo,
+                                                         int64_t ldx, int rows, int K, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, int act,
+                                                         float* __restrict__ y_ws, int64_t ld_ws,
+                                                         float* __restrict__ y, int64_t ldy) {
+    pdl_enter();
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const float* h = x_hi + (int64_t)r * ldx;
+    const float* l = x_lo + (int64_t)r * ldx;
+    float acc = 0.f;
+    const int K4 = ((uintptr_t)W & 15) == 0 ? (K & ~3) : 0;       // rows of x are 16-byte aligned (padded ld)
+    for (int k = lane * 4; k < K4; k += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(h + k), b = *reinterpret_cast<const float4*>(l + k);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W + k));
+        acc = fmaf(a.x + b.x, w.x, acc); acc = fmaf(a.y + b.y, w.y, acc);
+        acc = fmaf(a.z + b.z, w.z, acc); acc = fmaf(a.w + b.w, w.w, acc);
+    }
+    for (int k = K4 + lane; k < K; k += 32) acc = fmaf(h[k] + l[k], __ldg(W + k), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const float v = act_apply(acc + __ldg(bias), act);
+        y_ws[(int64_t)r * ld_ws] = v;
+        y[(int64_t)r * ldy] = v;
+    }
+}
+
+// g[r] = dy[r] * act'(y[r]);  dwp[k] += sum_r g[r] x[r, k],  dwp[K] += sum_r g[r]  (weight / bias gradient, split
+// over row chunks, atomics into the zeroed accumulator);  dZ[r, k] = g[r] W[k] * (x[r, k] > 0) as hi/lo split,
+// row-major and transposed (the operands of the layer below), or plain FP32 into dx when this is layer 0.
+// Block = 32 columns x 128 rows (four 32 x 32 sub-tiles), 32 x 8 threads.
+constexpr int NARROW_ROWS = 128;
+__global__ void __launch_bounds__(256) narrow_bwd_kernel(const float* __restrict__ dy, int64_t lddy,
+                                                         const float* __restrict__ y, int64_t ldy, int act,
+                                                         const float* __restrict__ x_hi, const float* __restrict__ x_lo,
+                                                         int64_t ldx, int rows, int K, const float* __restrict__ W,
+                                                         int relu_mask, float* __restrict__ g_hi, float* __restrict__ g_lo,
+                                                         int64_t ld_o, float* __restrict__ gt_hi, float* __restrict__ gt_lo,
+                                                         int64_t ld_t, float* __restrict__ dx, int64_t lddx,
+                                                         float* __restrict__ dwp) {
+    pdl_enter();
+    __shared__ float s_hi[32][33], s_lo[32][33], s_g[NARROW_ROWS];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * NARROW_ROWS;
+    if (threadIdx.x < NARROW_ROWS) {
+        const int r = r0 + threadIdx.x;
+        s_g[threadIdx.x] = r < rows ? act_grad(dy[(int64_t)r * lddy], y[(int64_t)r * ldy], act) : 0.f;
+    }
+    __syncthreads();
+    const int c = c0 + tx;
+    const float w = c < K ? __ldg(W + c) : 0.f;
+    float wsum = 0.f;
+#pragma unroll 1
+    for (int sub = 0; sub < NARROW_ROWS / 32; ++sub) {
+        const int rb = r0 + sub * 32;
+        if (rb >= rows) break;                                    // block-uniform
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rl = sub * 32 + ty + 8 * i, r = r0 + rl;
+            float h = 0.f, l = 0.f;
+            if (r < rows && c < K) {
+                const float g = s_g[rl];
+                const float xh = x_hi[(int64_t)r * ldx + c];
+                wsum = fmaf(g, xh + x_lo[(int64_t)r * ldx + c], wsum);
+                float v = g * w;
+                if (relu_mask) v = xh > 0.f ? v : 0.f;
+                if (dx) dx[(int64_t)r * lddx + c] = v;
+                if (g_hi) {
+                    h = tf32_hi(v);
+                    l = tf32_lo(v, h);
+                    g_hi[(int64_t)r * ld_o + c] = h;
+                    g_lo[(int64_t)r * ld_o + c] = l;
+                }
+            }
+            s_hi[ty + 8 * i][tx] = h;
+            s_lo[ty + 8 * i][tx] = l;
+        }
+        if (gt_hi) {                                              // kernel-uniform
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cc = c0 + ty + 8 * i, r = rb + tx;
+                if (r < rows && cc < K) {
+                    gt_hi[(int64_t)cc * ld_t + r] = s_hi[tx][ty + 8 * i];
+                    gt_lo[(int64_t)cc * ld_t + r] = s_lo[tx][ty + 8 * i];
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // column sums over the block's rows: reduce the 8 row groups through shared memory
+    __syncthreads();
+    s_hi[ty][tx] = wsum;
+    __syncthreads();
+    if (ty == 0 && c < K) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s_hi[i][tx];
+        atomicAdd(dwp + c, t);
+    }
+    if (blockIdx.x == 0 && ty == 1) {                             // bias gradient: one column block adds sum_r g[r]
+        float t = s_g[tx] + s_g[tx + 32] + s_g[tx + 64] + s_g[tx + 96];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (tx == 0) atomicAdd(dwp + K, t);
     }
 }
 
@@ -626,6 +760,7 @@ struct Out {
     int64_t ld_t = 0;
 };
 
+int g_narrow = 1;    // 1: a last layer with one output column runs on the SIMT narrow kernels; cdlrm_mlp_set_option(2, .)
 int g_seg_kb = 8;    // K segment (k-blocks of 32) per TMEM accumulation chain; cdlrm_mlp_set_option(1, .)
 int g_num_sms = 0;
 int g_dbg = 0;
@@ -678,7 +813,7 @@ int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* 
     ep.seg_kb = g_seg_kb > 0 ? g_seg_kb * (32 / BK) : num_kb;      // the option counts k-blocks of 32
     const int64_t units = tiles_n * tiles_m * splits;
     const int grid = (int)(units < g_num_sms ? units : g_num_sms);
-    LAUNCH(K_MLP_GEMM, s, (gemm3x_tf32_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(mp, ep)));
+    LAUNCH_PDL(K_MLP_GEMM, s, gemm3x_tf32_kernel, grid, GEMM_THREADS, GEMM_SMEM, mp, ep);
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
 }
@@ -687,7 +822,7 @@ int launch_split(const float* src, int64_t lds, int rows, int cols, const float*
                  float* lo, int64_t ld_o, float* thi, float* tlo, int64_t ld_t, cudaStream_t s) {
     if (rows <= 0 || cols <= 0) return CDLRM_OK;
     dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-    LAUNCH(K_MLP_SPLIT, s, (split_kernel<<<grid, 256, 0, s>>>(src, lds, rows, cols, y, ldy, dmode, hi, lo, ld_o, thi, tlo, ld_t)));
+    LAUNCH_PDL(K_MLP_SPLIT, s, split_kernel, grid, 256, 0, src, lds, rows, cols, y, ldy, dmode, hi, lo, ld_o, thi, tlo, ld_t);
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
 }
@@ -716,6 +851,8 @@ struct cdlrm_mlp {
     float* y_out = nullptr;
     int64_t dwp_bytes = 0;       // the dwp regions are carved back to back
     int last_batch = 0;
+    bool last_narrow = false;    // the last forward ran its final layer on the narrow kernels
+    const float* last_W = nullptr;   // FP32 weights of that layer (the narrow backward reads them)
     bool ones_set = false;
     int num_sms = 148;
 };
@@ -797,6 +934,7 @@ extern "C" int cdlrm_mlp_create(cdlrm_mlp** out, int device, int n_layers, const
     return CDLRM_OK;
 }
 
+// key 2: 1 (default) = a last layer with a single output column uses the SIMT narrow kernels, 0 = tensor-core GEMMs
 // key 0: split rounding (0 = round to nearest, 1 = truncate); key 1: k-blocks (of 32) chained into one TMEM
 // accumulator before the partial result is added in registers (0 = the whole K; default 8)
 extern "C" int cdlrm_mlp_set_option(int key, int value) {
@@ -806,6 +944,8 @@ extern "C" int cdlrm_mlp_set_option(int key, int value) {
     } else if (key == 1) {
         ARG_CHECK(value >= 0 && value <= 4096);
         g_seg_kb = value;
+    } else if (key == 2) {
+        g_narrow = value ? 1 : 0;
     } else if (key == 3) {
         g_dbg = value;
     } else {
@@ -860,7 +1000,7 @@ extern "C" int cdlrm_mlp_forward(cdlrm_mlp* m, const float* x, int64_t ldx, int3
             tiles += jb.tiles_x * ((N + 31) / 32);
         }
         sb.n = L;
-        LAUNCH(K_MLP_SPLIT, s, (split_batch_kernel<<<tiles, 256, 0, s>>>(sb)));
+        LAUNCH_PDL(K_MLP_SPLIT, s, split_batch_kernel, tiles, 256, 0, sb);
         CU_CHECK(cudaGetLastError());
     }
     // input
@@ -878,10 +1018,20 @@ extern "C" int cdlrm_mlp_forward(cdlrm_mlp* m, const float* x, int64_t ldx, int3
         } else {
             o.c = m->y_out; o.ldc = pad4(N);
         }
+        if (l == L - 1 && N == 1 && g_narrow) {      // narrow last layer: row-wise dot products, writes y_out and y
+            LAUNCH_PDL(K_MLP_SPLIT, s, narrow_fwd_kernel, (batch + 7) / 8, 256, 0, m->x_hi[l], m->x_lo[l], pad4(K), batch, K,
+                       h_W[l], h_b[l], ep.act, m->y_out, pad4(N), y, ldy);
+            CU_CHECK(cudaGetLastError());
+            m->last_batch = batch;
+            m->last_narrow = true;
+            m->last_W = h_W[l];
+            return CDLRM_OK;
+        }
         if ((rc = launch_gemm(m->x_hi[l], m->x_lo[l], pad4(K), m->w_hi[l], m->w_lo[l], pad4(K), ep, o, 1, s))) return rc;
     }
     CU_CHECK(cudaMemcpy2DAsync(y, ldy * 4, m->y_out, pad4(m->D[L]) * 4, (size_t)m->D[L] * 4, batch, cudaMemcpyDeviceToDevice, s));
     m->last_batch = batch;
+    m->last_narrow = false;
     return CDLRM_OK;
 }
 
@@ -901,12 +1051,25 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
     int rc;
     // gradient w.r.t. the last pre-activation: dy * act'(y), as hi/lo, row-major and transposed
     const int last_act = (L - 1 == m->sigmoid_layer) ? ACT_SIGMOID : (m->sigmoid_layer == -2 ? ACT_NONE : ACT_RELU);
-    if ((rc = launch_split(dy, lddy, batch, m->D[L], m->y_out, pad4(m->D[L]), last_act, m->g_hi[L], m->g_lo[L], pad4(m->D[L]),
-                           m->gt_hi[L], m->gt_lo[L], capp, s))) return rc;
+    const bool narrow = m->last_narrow;
+    if (!narrow && (rc = launch_split(dy, lddy, batch, m->D[L], m->y_out, pad4(m->D[L]), last_act, m->g_hi[L], m->g_lo[L], pad4(m->D[L]),
+                                      m->gt_hi[L], m->gt_lo[L], capp, s))) return rc;
     CU_CHECK(cudaMemsetAsync(m->dwp[0], 0, (size_t)m->dwp_bytes, s));      // every layer's split-K accumulator
     for (int l = L - 1; l >= 0; --l) {
         const int K = m->D[l], N = m->D[l + 1];
         ARG_CHECK(h_dW[l] && h_db[l]);
+        if (narrow && l == L - 1) {
+            // activation derivative, weight / bias gradient and the data gradient (masked + split for the layer
+            // below, or plain into dx for a one-layer MLP) of the single-column layer in one SIMT launch
+            dim3 grid((K + 31) / 32, (batch + NARROW_ROWS - 1) / NARROW_ROWS);
+            const bool below = l > 0;
+            LAUNCH_PDL(K_MLP_SPLIT, s, narrow_bwd_kernel, grid, 256, 0, dy, lddy, m->y_out, pad4(N), last_act, m->x_hi[l],
+                       m->x_lo[l], pad4(K), batch, K, m->last_W, below ? 1 : 0, below ? m->g_hi[l] : nullptr,
+                       below ? m->g_lo[l] : nullptr, pad4(K), below ? m->gt_hi[l] : nullptr, below ? m->gt_lo[l] : nullptr, capp,
+                       below ? nullptr : dx, lddx, m->dwp[l]);
+            CU_CHECK(cudaGetLastError());
+            continue;
+        }
         // wgrad: [dW | db] = dZ^T [X^T ; 1]: split-K over the batch, TMA reduce-add into a zeroed
         // padded accumulator, then unpacked into the dense dW / db the optimizer sees
         {
@@ -948,7 +1111,7 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
         ub.total = total;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 1184) blocks = 1184;
-        LAUNCH(K_MLP_SPLIT, s, (unpack_batch_kernel<<<blocks, 256, 0, s>>>(ub)));
+        LAUNCH_PDL(K_MLP_SPLIT, s, unpack_batch_kernel, blocks, 256, 0, ub);
         CU_CHECK(cudaGetLastError());
     }
     return CDLRM_OK;

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) rows_kernel(TableDesc T, const int64_t* _
                                                    int write_master, int average, float divisor, int dim, int ways,
                                                    int G) {
     using V = typename VT<VEC>::type;
-    const int gl = threadIdx.x % G, group = threadIdx.x / G, NG = 256 / G;
+    const int gl = threadIdx.x % G, group = threadIdx.x / G, NG = blockDim.x / G;
     const int cpr = dim / VEC;
     float* master = const_cast<float*>(T.master);
     constexpr int U = 4;
@@ -148,12 +148,19 @@ int launch_rows(cdlrm_ctx* c, int k, const int64_t* ids, const int32_t* slots, c
     const int vec = vec_for(c->dim, rows, uses_master ? T.master : nullptr);
     const int cpr = c->dim / vec;
     const int G = pow2_ceil(cpr) > 32 ? 32 : pow2_ceil(cpr);
-    const int NG = 256 / G;
+    // HBM<->HBM movers: full grid.  Movers that touch the host master are PCIe-bound (a few hundred rows in
+    // flight saturate the link) and run for tens of milliseconds on the planner stream beside the training
+    // step: one small CTA per SM (128 threads, ~9 K registers) so that every training kernel -- including the
+    // 1-CTA-per-SM tensor-core GEMM with its 54 K registers -- still fits next to it.  With a full-occupancy
+    // persistent grid the training step stalled for the whole prefetch (measured: 110 ms per window).
+    const int nt = uses_master ? 128 : 256;
+    const int NG = nt / G;
     int64_t blocks = (n + NG * 4 - 1) / (NG * 4);
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    if (vec == 4) LAUNCH(mode_kid(MODE), s, (rows_kernel<4, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G)));
-    else if (vec == 2) LAUNCH(mode_kid(MODE), s, (rows_kernel<2, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G)));
-    else LAUNCH(mode_kid(MODE), s, (rows_kernel<1, MODE><<<(int)blocks, 256, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G)));
+    const int64_t cap = uses_master ? c->num_sms : (int64_t)c->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    if (vec == 4) LAUNCH(mode_kid(MODE), s, (rows_kernel<4, MODE><<<(int)blocks, nt, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G)));
+    else if (vec == 2) LAUNCH(mode_kid(MODE), s, (rows_kernel<2, MODE><<<(int)blocks, nt, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G)));
+    else LAUNCH(mode_kid(MODE), s, (rows_kernel<1, MODE><<<(int)blocks, nt, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G)));
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
 }

@@ -299,13 +299,17 @@ class Trainer:
             self.loss_fn = torch.nn.BCELoss(reduction="none")
         else:
             sys.exit("ERROR: --loss-function=" + args.loss_function + " is not supported")
+        # dense parameters and their gradients in one flat bucket each (tensor-core MLP path only)
+        self.flat = self.dlrm.mlp_impl == "tcgen05" and os.environ.get("CDLRM_FLAT_MLP", "1") != "0"
+        if self.flat:
+            self.dlrm.flatten_parameters()
         self.optimizer_mlps = torch.optim.SGD(self.dlrm.parameters(), lr=args.learning_rate)
         self.optimizer_embeds = torch.optim.SGD(self.cache_group.parameters(), lr=args.lr_embeds)   # :376
         self.cache_group._ensure_ctx(emb_tables)
         self.cache_group.assume_one_id_per_bag = True              # Criteo batches (:390)
         self.side = torch.cuda.Stream(self.dev)
         # the lookup runs on its own stream beside the bottom MLP (joined before the interaction)
-        self.cache_group.forward_stream = torch.cuda.Stream(self.dev)
+        self.cache_group.forward_stream = torch.cuda.Stream(self.dev, priority=-1)
         self.dlrm.pre_interact = self.cache_group.join_forward
         self.planner = WindowPlanner(self.cache_group, emb_tables, args.lookahead * args.mini_batch_size,
                                      rng=VictimRngDevice(args.numpy_rand_seed, self.dev), stream=self.side,
@@ -371,6 +375,20 @@ class Trainer:
         lookups, _idxs = self.cache_group(lS_o, lS_i, self.emb_tables, self.dev.index)
         Z = self.dlrm(X, lookups)
         E = loss_fn_wrap(Z, T, self.loss_fn, self.args, self.loss_ws)
+        if self.flat:
+            # the MLP backward writes dW / db into the flat bucket; weights (not biases: the reference's
+            # aggregate_gradients never reduces them, :234-247) are averaged by ONE in-place all-reduce
+            E.backward()
+            work = None
+            if self.world > 1:
+                gw = self.dlrm.flat_grads[:self.dlrm.flat_weight_elems]
+                gw /= self.world
+                work = dist.all_reduce(gw, async_op=True)
+            self.optimizer_embeds.step()      # applies the fused sparse update (pre-step hook)
+            if work is not None:
+                work.wait()
+            self.dlrm.flat_sgd_step(self.optimizer_mlps.param_groups[0]["lr"])
+            return E, Z
         self.optimizer_mlps.zero_grad(set_to_none=True)
         E.backward()
         reqs = aggregate_gradients(self.dlrm)
@@ -423,6 +441,9 @@ def Run(rank, m_spa, ln_emb, ln_bot, ln_top, train_ld, test_ld, batch_fifo, evic
         dist.init_process_group("nccl", rank=rank, world_size=args.world_size)
     tr = Trainer(args, m_spa, ln_emb, ln_bot, ln_top, emb_tables, rank=rank, world=args.world_size)
     dev, lb = tr.dev, tr.local_batch
+    # training on a high-priority stream: the look-ahead planner (side stream, default priority) only
+    # takes the SM slots the training step leaves free
+    torch.cuda.set_stream(torch.cuda.Stream(dev, priority=-1))
     share_occupancy_tables(tr.cache_group, occupancy_tables_fifos, rank)
     total_time = total_loss = total_accu = 0.0
     total_iter = total_samp = 0

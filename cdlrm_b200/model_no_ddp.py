@@ -592,6 +592,7 @@ class _MlpState:
         self.cap = 0
         self.ws = None
         self.fwd_id = 0
+        self.flat_grads = None     # ([dW views], [db views]) into DLRM_Net's flat gradient bucket, or None
 
     def ensure(self, batch, dev):
         if self.handle is not None and batch <= self.cap and self.ws.device == dev:
@@ -651,8 +652,11 @@ class _MlpFn(torch.autograd.Function):
         if dy.stride(1) != 1 or dy.dtype != torch.float32:
             dy = dy.contiguous().float()
         B = ctx.batch
-        dWs = [torch.empty(st.dims[i + 1], st.dims[i], dtype=torch.float32, device=dev) for i in range(len(st.linears))]
-        dbs = [torch.empty(st.dims[i + 1], dtype=torch.float32, device=dev) for i in range(len(st.linears))]
+        if st.flat_grads is not None:      # DLRM_Net.flatten_parameters: dW / db land in the flat gradient bucket
+            dWs, dbs = st.flat_grads
+        else:
+            dWs = [torch.empty(st.dims[i + 1], st.dims[i], dtype=torch.float32, device=dev) for i in range(len(st.linears))]
+            dbs = [torch.empty(st.dims[i + 1], dtype=torch.float32, device=dev) for i in range(len(st.linears))]
         dx = None
         dx_ptr, lddx = None, 0
         if ctx.need_dx:
@@ -662,6 +666,8 @@ class _MlpFn(torch.autograd.Function):
         check(lib.cdlrm_mlp_backward(st.handle, _vp(dy.data_ptr()), dy.stride(0), _vp(dx_ptr), lddx,
                                      _lib.ptr_array([t.data_ptr() for t in dWs]),
                                      _lib.ptr_array([t.data_ptr() for t in dbs]), _stream_ptr(dev)))
+        if st.flat_grads is not None:      # the bucket already holds them (p.grad is a view of it): nothing for autograd
+            return (None, dx) + (None,) * (2 * len(dWs))
         grads = []
         for w, b in zip(dWs, dbs):
             grads += [w, b]
@@ -717,6 +723,45 @@ class DLRM_Net(nn.Module):
         else:
             sys.exit("ERROR: --arch-interaction-op=" + self.arch_interaction_op + " is not supported")
 
+    def flatten_parameters(self):
+        """Flat-bucket mode for the dense parameters (the reference all-reduces the Linear
+        weight gradients one tensor at a time, main_no_ddp.py:234-247, and steps a per-tensor SGD, :413).
+        Every nn.Linear parameter of bot_l / top_l is re-pointed at one flat FP32 buffer -- all weights first,
+        then all biases, each 16-byte aligned -- and a gradient bucket of the same layout is allocated.  The
+        tensor-core MLP backward then writes dW / db straight into the bucket (no autograd accumulation), the
+        weight part is ONE all-reduce operand with no flatten / unflatten copies, and SGD is ONE axpy over
+        the bucket (``flat_sgd_step``).  ``p.grad`` of every parameter is a view of the bucket."""
+        lin = [m for seq in (self.bot_l, self.top_l) for m in seq if isinstance(m, nn.Linear)]
+        params = [m.weight for m in lin] + [m.bias for m in lin]
+        dev = params[0].device
+        offs, o = [], 0
+        for q in params:
+            offs.append(o)
+            o += (q.numel() + 3) & ~3
+            if q is lin[-1].weight:
+                n_w = o
+        flat_p = torch.zeros(o, dtype=torch.float32, device=dev)
+        flat_g = torch.zeros(o, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for q, off in zip(params, offs):
+                v = flat_p[off:off + q.numel()].view_as(q)
+                v.copy_(q.data)
+                q.data = v
+                q.grad = flat_g[off:off + q.numel()].view_as(q)
+        self.flat_params, self.flat_grads, self.flat_weight_elems = flat_p, flat_g, n_w
+        for which, seq in (("bot", self.bot_l), ("top", self.top_l)):
+            st = self._mlp_state.get(which)
+            if st is None:
+                st = self._mlp_state[which] = _MlpState(seq, getattr(self, "_sigmoid", {}).get(which, -1))
+            st.flat_grads = ([m.weight.grad for m in st.linears], [m.bias.grad for m in st.linears])
+        self.flat_mode = True
+        return flat_p, flat_g
+
+    @torch.no_grad()
+    def flat_sgd_step(self, lr):
+        """p -= lr * g over the whole flat bucket: one launch for all dense parameters."""
+        self.flat_params.add_(self.flat_grads, alpha=-float(lr))
+
     def apply_mlp(self, which, x):
         """bot_l / top_l (:306-309).  On CUDA with mlp_impl == "tcgen05" the whole Sequential runs
         in cdlrm_mlp_forward/_backward; the nn.Linear parameters stay the trainable state."""
@@ -727,7 +772,7 @@ class DLRM_Net(nn.Module):
         if st is None:
             st = self._mlp_state[which] = _MlpState(seq, getattr(self, "_sigmoid", {}).get(which, -1))
         params = []
-        for m in st.linears:
+        for m in st.linears:       # (flat mode: the backward fills the gradient bucket and returns None for these)
             params += [m.weight, m.bias]
         return _MlpFn.apply(st, x, *params)
 

@@ -266,6 +266,9 @@ int cdlrm_host_unregister(void* h_ptr);
 
 /* ---- measurement: every kernel launch of the library is counted; with profiling enabled
  *      each launch is additionally bracketed by CUDA events on its own stream ------------- */
+/* Programmatic dependent launch of the per-step kernels (on by default; environment CDLRM_PDL=0 or
+ * cdlrm_set_pdl(0) falls back to plain stream order).  No reference counterpart: launch plumbing. */
+int cdlrm_set_pdl(int on);
 int cdlrm_prof_enable(int on);
 int64_t cdlrm_prof_launches(int reset);          /* launches since the last reset */
 int cdlrm_prof_num_kernels(void);

@@ -139,3 +139,28 @@ def test_dlrm_step_same_loss_and_grads_both_mlp_paths():
             scale = float(b.abs().max())
             bad_rows = ((a - b).abs().amax(dim=1) > 2e-5 * scale).float().mean().item()
             assert bad_rows <= 5e-3, f"{nm}: {bad_rows:.2%} of the rows off by more than 2e-5 of the scale"
+
+
+def test_flat_bucket_mode_same_gradients_and_sgd_step():
+    """DLRM_Net.flatten_parameters (one flat parameter buffer + one gradient bucket, one-launch SGD) against the
+    per-tensor autograd path + torch.optim.SGD (main_no_ddp.py:375,413) on the same inputs."""
+    ln_bot, ln_top = [13, 512, 256, 128], [479, 512, 512, 256, 1]
+    B, d, T, lr = 1024, 128, 26, 0.1
+    g = torch.Generator(device=DEV).manual_seed(3)
+    X = torch.randn(B, 13, device=DEV, generator=g)
+    ly = [torch.randn(B, d, device=DEV, generator=g) * 0.05 for _ in range(T)]
+    Y = (torch.rand(B, 1, device=DEV, generator=g) < 0.25).float()
+    ref, flat = _net(ln_bot, ln_top, "tcgen05"), _net(ln_bot, ln_top, "tcgen05")
+    flat.flatten_parameters()
+    opt = torch.optim.SGD(ref.parameters(), lr=lr)
+    for step in range(2):
+        opt.zero_grad(set_to_none=True)
+        torch.nn.functional.binary_cross_entropy(ref(X, ly), Y).backward()
+        torch.nn.functional.binary_cross_entropy(flat(X, ly), Y).backward()
+        for (n, a), b in zip(ref.named_parameters(), flat.parameters()):
+            assert b.grad.data_ptr() >= flat.flat_grads.data_ptr()
+            util.assert_close_fp32(b.grad.cpu().numpy(), a.grad.cpu().numpy(), err_msg=f"step {step} grad {n}")
+        opt.step()
+        flat.flat_sgd_step(lr)
+        for (n, a), b in zip(ref.named_parameters(), flat.parameters()):
+            util.assert_close_fp32(b.detach().cpu().numpy(), a.detach().cpu().numpy(), err_msg=f"step {step} param {n}")

@@ -114,7 +114,7 @@ class PlanRecord:
     __slots__ = ("uniq", "hits", "dropped", "rows", "E", "F", "off", "evict_ids", "evict_slots",
                  "evict_primary", "fill_ids", "fill_slots", "event",
                  # look-ahead staging (WindowPlanner.stage / install_staged)
-                 "L", "loser_off", "loser_ids", "loser_stage", "fill_stage", "fill_soff", "evict_stage",
+                 "L", "loser_off", "loser_soff", "loser_ids", "loser_stage", "fill_stage", "fill_soff", "evict_stage",
                  "staged", "wb_done")
 
     def loser_list(self, k):
@@ -157,6 +157,11 @@ class WindowPlanner:
         self.plan_tags = None
         if lookahead_tags:
             self.enable_lookahead_tags()
+
+    @property
+    def loser_cap_rows(self):
+        gb = float(os.environ.get("CDLRM_LOSER_STORE_GB", "20"))
+        return int(gb * 1e9 / (4 * self.dim))
 
     def enable_lookahead_tags(self):
         """Give the planner its own evolving copy of the tags so that it can run one or more
@@ -248,6 +253,12 @@ class WindowPlanner:
                                             _vp(rec.loser_ids.data_ptr()), _vp(self._h_counts3.data_ptr()), _sp(s)))
                 s.synchronize()
                 rec.L = self._h_counts3.clone().tolist()
+                # HBM budget of the loser store (two of them alternate): beyond the cap only a prefix of each
+                # table's ascending loser ids is staged; the forward serves the others zero-copy from the host
+                # master (fwd_miss_kernel falls back when the binary search misses) -- same rows either way
+                tot = sum(rec.L)
+                if tot > self.loser_cap_rows:
+                    rec.L = [int(x * self.loser_cap_rows // tot) for x in rec.L]
             self.last_timing = {"phase_a_s": round(t_b - t_a, 4), "rng_s": round(t_c - t_b, 4),
                                 "phase_b_s": round(_t.perf_counter() - t_c, 4)}
         rec.event = None
@@ -288,12 +299,15 @@ class WindowPlanner:
             if rec.L is not None:
                 # two loser stores alternate: the previous window's is read by the forward until the boundary
                 self._stage_no += 1
-                rec.loser_stage = self._buf("loser%d" % (self._stage_no & 1), max(rec.loser_off[-1] + rec.L[-1], 1))
+                rec.loser_soff = [0] * self.T          # rows are packed by the (possibly capped) counts
+                for k in range(1, self.T):
+                    rec.loser_soff[k] = rec.loser_soff[k - 1] + rec.L[k - 1]
+                rec.loser_stage = self._buf("loser%d" % (self._stage_no & 1), max(sum(rec.L), 1))
                 for k in range(self.T):
                     if rec.L[k]:
                         o = rec.loser_off[k]
                         check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(rec.loser_ids[o:].data_ptr()), rec.L[k],
-                                                           _vp(rec.loser_stage[o:].data_ptr()), _sp(s)))
+                                                           _vp(rec.loser_stage[rec.loser_soff[k]:].data_ptr()), _sp(s)))
             rec.staged = torch.cuda.Event()
             rec.staged.record(s)
         return rec
@@ -334,7 +348,7 @@ class WindowPlanner:
                     self.ctx,
                     _lib.ptr_array([rec.loser_ids[rec.loser_off[k]:].data_ptr() if rec.L[k] else 0
                                     for k in range(self.T)]),
-                    _lib.ptr_array([rec.loser_stage[rec.loser_off[k]:].data_ptr() if rec.L[k] else 0
+                    _lib.ptr_array([rec.loser_stage[rec.loser_soff[k]:].data_ptr() if rec.L[k] else 0
                                     for k in range(self.T)]),
                     _lib.i64_array(rec.L), _sp(s)))
             else:

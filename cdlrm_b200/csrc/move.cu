@@ -150,10 +150,11 @@ int launch_rows(cdlrm_ctx* c, int k, const int64_t* ids, const int32_t* slots, c
     const int G = pow2_ceil(cpr) > 32 ? 32 : pow2_ceil(cpr);
     // HBM<->HBM movers: full grid.  Movers that touch the host master are PCIe-bound (a few hundred rows in
     // flight saturate the link) and run for tens of milliseconds on the planner stream beside the training
-    // step: one small CTA per SM (128 threads, ~9 K registers) so that every training kernel -- including the
-    // 1-CTA-per-SM tensor-core GEMM with its 54 K registers -- still fits next to it.  With a full-occupancy
+    // step: one small CTA per SM (64 threads, 4.6 K registers, 600 KB in flight over the whole GPU) so that every
+    // training kernel -- including the 1-CTA-per-SM tensor-core GEMM with its 54 K registers and the
+    // register-limited interaction / update kernels -- keeps (nearly) its occupancy next to it.  With a full-occupancy
     // persistent grid the training step stalled for the whole prefetch (measured: 110 ms per window).
-    const int nt = uses_master ? 128 : 256;
+    const int nt = uses_master ? 64 : 256;
     const int NG = nt / G;
     int64_t blocks = (n + NG * 4 - 1) / (NG * 4);
     const int64_t cap = uses_master ? c->num_sms : (int64_t)c->num_sms * 32;

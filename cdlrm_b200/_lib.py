@@ -70,6 +70,7 @@ SIGNATURES = {
     "cdlrm_agg_pack": (C.c_int, [vp, vp, c_i64p, C.c_float, vp, vp]),
     "cdlrm_agg_unpack": (C.c_int, [vp, vp, c_i64p, vp, C.c_int, vp]),
     "cdlrm_set_pdl": (C.c_int, [C.c_int]),
+    "cdlrm_bce_mean": (C.c_int, [C.c_int, vp, C.c_int64, vp, C.c_int64, C.c_int32, vp, vp, vp]),
     "cdlrm_prof_enable": (C.c_int, [C.c_int]),
     "cdlrm_prof_launches": (C.c_int64, [C.c_int]),
     "cdlrm_prof_num_kernels": (C.c_int, []),

@@ -1116,3 +1116,46 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
     }
     return CDLRM_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// Loss of the training step (main_no_ddp.py:355-369,403-405: torch.nn.BCELoss(reduction="mean") on the
+// sigmoid output of the top MLP) fused with its own derivative: stock PyTorch spends five launches on
+// 8192 numbers (loss, mean, ones, backward, scale).  One CTA:
+//   loss = mean( -(t log p + (1 - t) log(1 - p)) ), logs clamped at -100 as torch does,
+//   dz   = (p - t) / max(p (1 - p), 1e-12) / n          (d loss / d p)
+// ------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(1024) bce_mean_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ t,
+                                                        int64_t ldt, int n, float* __restrict__ loss, float* __restrict__ dz) {
+    pdl_enter();
+    __shared__ float s_red[32];
+    const float inv_n = 1.f / (float)n;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const float p = z[(int64_t)i * ldz], y = t[(int64_t)i * ldt];
+        const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(log1pf(-p), -100.f);
+        acc += (y - 1.f) * lq - y * lp;
+        dz[i] = (p - y) / fmaxf((1.f - p) * p, 1e-12f) * inv_n;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = s_red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) *loss = acc * inv_n;
+    }
+}
+}  // namespace
+
+extern "C" int cdlrm_bce_mean(int device, const float* z, int64_t ldz, const float* t, int64_t ldt, int32_t n, float* loss,
+                              float* dz, cdlrm_stream stream) {
+    ARG_CHECK(z && t && loss && dz && n > 0 && ldz >= 1 && ldt >= 1);
+    CU_CHECK(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH_PDL(K_MISC, s, bce_mean_kernel, 1, 1024, 0, z, ldz, t, ldt, (int)n, loss, dz);
+    CU_CHECK(cudaGetLastError());
+    return CDLRM_OK;
+}

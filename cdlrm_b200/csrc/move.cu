@@ -7,6 +7,8 @@
 // The master pointers are device-visible addresses of pinned host memory: the gathers
 // and the write-back are zero-copy PCIe reads/writes issued by the SMs, so scattered
 // 512-byte rows move without any host-side staging or CPU work.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "compact.cuh"
 
@@ -148,16 +150,21 @@ int launch_rows(cdlrm_ctx* c, int k, const int64_t* ids, const int32_t* slots, c
     const int vec = vec_for(c->dim, rows, uses_master ? T.master : nullptr);
     const int cpr = c->dim / vec;
     const int G = pow2_ceil(cpr) > 32 ? 32 : pow2_ceil(cpr);
-    // HBM<->HBM movers: full grid.  Movers that touch the host master are PCIe-bound (a few hundred rows in
-    // flight saturate the link) and run for tens of milliseconds on the planner stream beside the training
-    // step: one small CTA per SM (64 threads, 4.6 K registers, 600 KB in flight over the whole GPU) so that every
-    // training kernel -- including the 1-CTA-per-SM tensor-core GEMM with its 54 K registers and the
-    // register-limited interaction / update kernels -- keeps (nearly) its occupancy next to it.  With a full-occupancy
-    // persistent grid the training step stalled for the whole prefetch (measured: 110 ms per window).
-    const int nt = uses_master ? 64 : 256;
+    // HBM<->HBM movers: full grid.  Movers that touch the host master are PCIe-bound and run for ~0.1 s per
+    // window on the planner stream beside the training step.  What they cost the step is set by how many
+    // system-memory reads they keep in flight, not by their SM footprint (B200, Terabyte shape, 7 GB prefetch):
+    //     4736 CTAs x 256 thr (full occupancy)   training stalled outright, 110 ms per window
+    //      148 CTAs x  64 thr (600 KB in flight)  step 2-4x slower while it runs,  ~87 ms lost per window
+    //       16 CTAs x 256 thr (260 KB in flight)  step 1.15-1.3x slower,           ~25 ms lost, same PCIe rate
+    //        8 CTAs x 256 thr (130 KB in flight)  step 1.1x slower but the prefetch takes 1.5x longer
+    // Default: 32 CTAs x 128 threads (260 KB in flight; 9 K registers per CTA, so the 1-CTA-per-SM tensor-core
+    // GEMM with its 54 K registers still fits beside it).  CDLRM_PCIE_CTAS / CDLRM_PCIE_THREADS override.
+    static const int pcie_ctas = [] { const char* e = getenv("CDLRM_PCIE_CTAS"); return e ? atoi(e) : 32; }();
+    static const int pcie_threads = [] { const char* e = getenv("CDLRM_PCIE_THREADS"); return e ? atoi(e) : 128; }();
+    const int nt = uses_master ? (pcie_threads >= G && pcie_threads <= 256 ? pcie_threads : 128) : 256;
     const int NG = nt / G;
     int64_t blocks = (n + NG * 4 - 1) / (NG * 4);
-    const int64_t cap = uses_master ? c->num_sms : (int64_t)c->num_sms * 32;
+    const int64_t cap = uses_master ? (pcie_ctas > 0 ? pcie_ctas : 32) : (int64_t)c->num_sms * 32;
     if (blocks > cap) blocks = cap;
     if (vec == 4) LAUNCH(mode_kid(MODE), s, (rows_kernel<4, MODE><<<(int)blocks, nt, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G)));
     else if (vec == 2) LAUNCH(mode_kid(MODE), s, (rows_kernel<2, MODE><<<(int)blocks, nt, 0, s>>>(T, ids, slots, primary, n, rows, src_index, write_master, average, divisor, c->dim, c->ways, G)));

@@ -23,7 +23,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import check, lib
 from .cache_manager import Prefetcher, TorchGlobalRng, VictimRng, VictimRngDevice, WindowPlanner
-from .model_no_ddp import DLRM_Net, Embedding_Table_Cache_Group, Embedding_Table_Group
+from .model_no_ddp import DLRM_Net, Embedding_Table_Cache_Group, Embedding_Table_Group, bce_mean
 
 _vp = ctypes.c_void_p
 
@@ -374,7 +374,10 @@ class Trainer:
     def _step_eager(self, X, lS_o, lS_i, T):
         lookups, _idxs = self.cache_group(lS_o, lS_i, self.emb_tables, self.dev.index)
         Z = self.dlrm(X, lookups)
-        E = loss_fn_wrap(Z, T, self.loss_fn, self.args, self.loss_ws)
+        if self.args.loss_function == "bce" and os.environ.get("CDLRM_FUSED_LOSS", "1") != "0":
+            E = bce_mean(Z, T)                 # BCELoss(mean) and its derivative in one launch
+        else:
+            E = loss_fn_wrap(Z, T, self.loss_fn, self.args, self.loss_ws)
         if self.flat:
             # the MLP backward writes dW / db into the flat bucket; weights (not biases: the reference's
             # aggregate_gradients never reduces them, :234-247) are averaged by ONE in-place all-reduce

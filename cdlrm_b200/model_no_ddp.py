@@ -574,6 +574,38 @@ class _InteractFn(torch.autograd.Function):
         return (None,) + tuple(dfeat.unbind(0))
 
 
+class _BceMeanFn(torch.autograd.Function):
+    """torch.nn.BCELoss(reduction="mean")(Z, T) (main_no_ddp.py:355-369,403-405) with its derivative computed
+    in the same launch (cdlrm_bce_mean): two launches per step instead of PyTorch's five."""
+
+    @staticmethod
+    def forward(ctx, Z, T):
+        dev = Z.device
+        n = Z.numel()
+        Zc = Z if (Z.dim() == 2 and Z.shape[1] == 1) or Z.is_contiguous() else Z.contiguous()
+        Tc = T if (T.dim() == 2 and T.shape[1] == 1) or T.is_contiguous() else T.contiguous()
+        ldz = Zc.stride(0) if Zc.dim() == 2 and Zc.shape[1] == 1 else 1
+        ldt = Tc.stride(0) if Tc.dim() == 2 and Tc.shape[1] == 1 else 1
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dz = torch.empty(Z.shape, dtype=torch.float32, device=dev)
+        check(lib.cdlrm_bce_mean(dev.index, _vp(Zc.data_ptr()), ldz, _vp(Tc.data_ptr()), ldt, n, _vp(loss.data_ptr()),
+                                 _vp(dz.data_ptr()), _stream_ptr(dev)))
+        ctx.save_for_backward(dz)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return dz * g, None
+
+
+def bce_mean(Z, T):
+    """Fused BCELoss(mean) + derivative for float32 CUDA tensors; anything else goes to torch."""
+    if Z.is_cuda and Z.dtype == torch.float32 and T.dtype == torch.float32 and Z.shape == T.shape and Z.numel() > 0:
+        return _BceMeanFn.apply(Z, T)
+    return torch.nn.functional.binary_cross_entropy(Z, T)
+
+
 # ------------------------------------------------------------------------------------
 # dense MLPs on the tensor cores (cdlrm_mlp_*: 3xTF32 split GEMMs, FP32 accuracy)
 # ------------------------------------------------------------------------------------

@@ -266,6 +266,13 @@ int cdlrm_host_unregister(void* h_ptr);
 
 /* ---- measurement: every kernel launch of the library is counted; with profiling enabled
  *      each launch is additionally bracketed by CUDA events on its own stream ------------- */
+/* ---- loss of the training step: torch.nn.BCELoss(reduction="mean") (main_no_ddp.py:355-369, 403-405) and its
+ *      derivative in one launch: loss[0] = mean(-(t log z + (1-t) log(1-z))) (logs clamped at -100 as torch
+ *      does), dz[i] = (z_i - t_i) / max(z_i (1 - z_i), 1e-12) / n.  z, t: n float32 values with element strides
+ *      ldz / ldt; dz: n contiguous float32. */
+int cdlrm_bce_mean(int device, const float* z, int64_t ldz, const float* t, int64_t ldt, int32_t n, float* loss,
+                   float* dz, cdlrm_stream stream);
+
 /* Programmatic dependent launch of the per-step kernels (on by default; environment CDLRM_PDL=0 or
  * cdlrm_set_pdl(0) falls back to plain stream order).  No reference counterpart: launch plumbing. */
 int cdlrm_set_pdl(int on);

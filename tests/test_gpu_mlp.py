@@ -164,3 +164,22 @@ def test_flat_bucket_mode_same_gradients_and_sgd_step():
         flat.flat_sgd_step(lr)
         for (n, a), b in zip(ref.named_parameters(), flat.parameters()):
             util.assert_close_fp32(b.detach().cpu().numpy(), a.detach().cpu().numpy(), err_msg=f"step {step} param {n}")
+
+
+@pytest.mark.parametrize("B", [1, 77, 8192, 65536])
+def test_fused_bce_mean_matches_torch(B):
+    """cdlrm_bce_mean (loss + derivative in one launch) against torch.nn.BCELoss(reduction="mean")
+    (main_no_ddp.py:355-369), including saturated probabilities (log clamp at -100, derivative floor)."""
+    from cdlrm_b200 import model_no_ddp as M
+    g = torch.Generator(device=DEV).manual_seed(B)
+    z = torch.sigmoid(torch.randn(B, 1, device=DEV, generator=g) * 4)
+    if B > 4:
+        z[0], z[1], z[2] = 0.0, 1.0, 1e-30
+    t = (torch.rand(B, 1, device=DEV, generator=g) < 0.25).float()
+    z1, z2 = z.clone().requires_grad_(), z.clone().requires_grad_()
+    l1 = torch.nn.BCELoss(reduction="mean")(z1, t)
+    l2 = M.bce_mean(z2, t)
+    (l1 * 3.0).backward()
+    (l2 * 3.0).backward()
+    assert abs(l1.item() - l2.item()) <= 1e-5 * abs(l1.item())
+    util.assert_close_fp32(z2.grad.cpu().numpy(), z1.grad.cpu().numpy())

@@ -72,6 +72,7 @@ SIGNATURES = {
     "cdlrm_set_pdl": (C.c_int, [C.c_int]),
     "cdlrm_bce_mean": (C.c_int, [C.c_int, vp, C.c_int64, vp, C.c_int64, C.c_int32, vp, vp, vp]),
     "cdlrm_prof_enable": (C.c_int, [C.c_int]),
+    "cdlrm_prof_null": (C.c_int, [vp]),
     "cdlrm_prof_launches": (C.c_int64, [C.c_int]),
     "cdlrm_prof_num_kernels": (C.c_int, []),
     "cdlrm_prof_kernel_name": (C.c_char_p, [C.c_int]),

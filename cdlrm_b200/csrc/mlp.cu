@@ -62,6 +62,7 @@ struct Epi {
     int kb_per_split;            // k-blocks per K split
     int splits;                  // K splits (units = tiles x splits)
     int seg_kb;                  // k-blocks chained into one TMEM accumulator before the register add
+    int cluster;                 // CTAs per cluster along M (1 or 2): the pair shares every B tile (TMA multicast)
     long long* trace;            // measurement only (cdlrm_mlp_set_trace): CTA 0 writes %globaltimer stamps, [4][128]
     int dbg;                     // measurement only (cdlrm_mlp_set_option(3, .)): 1 no result stores, 4 no MMAs
     const float* bias;           // [N] added per column (or null)
@@ -77,6 +78,7 @@ struct Epi {
 // maps (box 32 x 32: row-major ones with the 128-byte swizzle, transposed ones dense)
 struct Maps {
     CUtensorMap a, b;            // operands: {K, rows, 2}: the hi and lo tensors are one 3-D tensor
+    CUtensorMap b_half;          // B again with a {BK, BN/2, 1} box: one CTA's share of a multicast B tile
     CUtensorMap c, c_hi, c_lo, t_hi, t_lo;
 };
 
@@ -119,6 +121,19 @@ __device__ __forceinline__ void tma_load_pair(uint32_t dst, const CUtensorMap* m
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(0), "r"(smem_u32(bar))
         : "memory");
 }
+// one half (BN/2 rows) of the hi (c2 = 0) or lo (c2 = 1) B tile, written to the same shared-memory offset of
+// every CTA in `mask`; each destination CTA's barrier (same offset) receives the byte count
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
@@ -131,6 +146,11 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same arrive on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -205,12 +225,22 @@ gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_n = (ep.N + BN - 1) / BN, tiles_m = (ep.M + BM - 1) / BM;
+    const int tiles_n = (ep.N + BN - 1) / BN;
     const int num_kb_total = (ep.K + BK - 1) / BK;
+    // Cluster mode (ep.cluster == 2, launched with cluster dims {2,1,1}): CTAs 2p and 2p+1 walk the same unit
+    // list; a unit then covers TWO adjacent m tiles (one per CTA) of one n tile, so both need the same B tile:
+    // each loads half of it and multicasts it into both shared memories.  The stage is free again when BOTH
+    // CTAs' MMAs have read it (empty barrier count 2, multicast tcgen05.commit).
+    const int cl = ep.cluster;                                   // 1 or 2
+    const int cr = cl == 2 ? (int)(blockIdx.x & 1u) : 0;         // rank in the cluster
+    const int u_first = cl == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int u_step = cl == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int tiles_m = ((ep.M + BM - 1) / BM + cl - 1) / cl;    // m tiles per unit column (pairs in cluster mode)
     const int units = tiles_n * tiles_m * ep.splits;
+    const uint16_t cl_mask = (uint16_t)((1u << cl) - 1u);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)cl); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a) : "memory");
@@ -222,6 +252,7 @@ gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
     }
     tc_fence_before();
     __syncthreads();
+    if (cl == 2) cluster_sync_all();        // the peer's barriers exist before anything of mine can arrive on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_enter();            // everything above (barriers, TMEM, tensor-map prefetch) overlaps the previous kernel's tail
@@ -231,8 +262,8 @@ gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t it = 0;                       // k-blocks issued so far (ring position)
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int n0 = (u % tiles_n) * BN, m0 = ((u / tiles_n) % tiles_m) * BM;
+            for (int u = u_first; u < units; u += u_step) {
+                const int n0 = (u % tiles_n) * BN, m0 = (((u / tiles_n) % tiles_m) * cl + cr) * BM;
                 const int kb0 = (u / (tiles_n * tiles_m)) * ep.kb_per_split;
                 const int num_kb = min(num_kb_total, kb0 + ep.kb_per_split) - kb0;
                 for (int i = 0; i < num_kb; ++i, ++it) {
@@ -241,9 +272,15 @@ gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
                     TRACE(0, it);
                     const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
                     const int k = (kb0 + i) * BK;
-                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);      // A + the whole B tile (own half + the peer's)
                     tma_load_pair(base, &maps.a, k, m0, &full_bar[s]);
-                    tma_load_pair(base + 2 * TILE_BYTES, &maps.b, k, n0, &full_bar[s]);
+                    if (cl == 2) {
+                        const uint32_t off = (uint32_t)cr * (TILE_BYTES / 2);
+                        tma_load_3d_mc(base + 2 * TILE_BYTES + off, &maps.b_half, k, n0 + cr * (BN / 2), 0, &full_bar[s], cl_mask);
+                        tma_load_3d_mc(base + 3 * TILE_BYTES + off, &maps.b_half, k, n0 + cr * (BN / 2), 1, &full_bar[s], cl_mask);
+                    } else {
+                        tma_load_pair(base + 2 * TILE_BYTES, &maps.b, k, n0, &full_bar[s]);
+                    }
                 }
             }
         }
@@ -251,7 +288,7 @@ gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
             uint32_t it = 0, seg = 0;              // ring position; K segments issued so far (TMEM buffer)
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            for (int u = u_first; u < units; u += u_step) {
                 const int kb0 = (u / (tiles_n * tiles_m)) * ep.kb_per_split;
                 const int num_kb = min(num_kb_total, kb0 + ep.kb_per_split) - kb0;
                 for (int i0 = 0; i0 < num_kb; i0 += ep.seg_kb, ++seg) {
@@ -277,7 +314,9 @@ gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
                             tc_mma_tf32(d_big, a_hi + adv, b_hi + adv, idesc_tf32(2 * BN), acc);
                             tc_mma_tf32(d_small, a_lo + adv, b_hi + adv, idesc_tf32(BN), 1u);
                         }
-                        tc_commit(&empty_bar[s]);      // the stage is free once these MMAs have read it
+                        // the stage is free once these MMAs have read it -- in cluster mode the peer must know too
+                        if (cl == 2) tc_commit_mc(&empty_bar[s], cl_mask);
+                        else tc_commit(&empty_bar[s]);
                     }
                     tc_commit(&tfull_bar[buf]);        // this segment's accumulators are complete
                 }
@@ -293,8 +332,8 @@ gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
         const int sw = lane & 7;                                  // swizzle phase of this thread's row
         uint32_t seg = 0;
         bool store_pending = false;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int n0 = (u % tiles_n) * BN, m0 = ((u / tiles_n) % tiles_m) * BM;
+        for (int u = u_first; u < units; u += u_step) {
+            const int n0 = (u % tiles_n) * BN, m0 = (((u / tiles_n) % tiles_m) * cl + cr) * BM;
             const int kb0 = (u / (tiles_n * tiles_m)) * ep.kb_per_split;
             const int num_kb = min(num_kb_total, kb0 + ep.kb_per_split) - kb0;
             float v[NCH][32];
@@ -423,6 +462,7 @@ gemm3x_tf32_kernel(const __grid_constant__ Maps maps, const Epi ep) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+    if (cl == 2) cluster_sync_all();        // the peer's last commits arrive on my barriers: stay until it is done too
 }
 
 // ------------------------------------------------------------------------------------
@@ -695,7 +735,8 @@ EncodeTiledFn get_encode() {
 // box elements read as zero and are not written
 // operand pair: hi at `hi`, lo at `lo` (same shape and row stride, lo behind hi) as one {inner, rows, 2} tensor;
 // box = BK x box_rows x 2, swizzle width = one BK row
-int make_pair_map(CUtensorMap* m, const float* hi, const float* lo, int64_t inner, int64_t rows, int64_t ld, int box_rows) {
+int make_pair_map(CUtensorMap* m, const float* hi, const float* lo, int64_t inner, int64_t rows, int64_t ld, int box_rows,
+                  int box_depth = 2) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         cdlrm_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -709,7 +750,7 @@ int make_pair_map(CUtensorMap* m, const float* hi, const float* lo, int64_t inne
     }
     cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, 2};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)gap};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)box_depth};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)hi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -761,6 +802,11 @@ struct Out {
 };
 
 int g_narrow = 1;    // 1: a last layer with one output column runs on the SIMT narrow kernels; cdlrm_mlp_set_option(2, .)
+// 2: CTA pairs share their B tiles through TMA multicast where the m tile count is even (cdlrm_mlp_set_option(4, .)).
+// Parity-green but measured 5 % SLOWER on B200 (tools/gemm_cluster_ab.py: 34.7 vs 32.8 us for 8192 x 512 x 512, top MLP
+// 335 vs 323 us): the multicast cuts L2 -> SM traffic by 25 % but every CTA still receives its 64 KB per k-block, so the
+// shared-memory write + operand-read bandwidth that bounds the mainloop is unchanged and the pair now runs in lockstep.
+int g_cluster = 1;
 int g_seg_kb = 8;    // K segment (k-blocks of 32) per TMEM accumulation chain; cdlrm_mlp_set_option(1, .)
 int g_num_sms = 0;
 int g_dbg = 0;
@@ -811,9 +857,21 @@ int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* 
     ep.dbg = g_dbg;
     ep.trace = g_trace;
     ep.seg_kb = g_seg_kb > 0 ? g_seg_kb * (32 / BK) : num_kb;      // the option counts k-blocks of 32
-    const int64_t units = tiles_n * tiles_m * splits;
-    const int grid = (int)(units < g_num_sms ? units : g_num_sms);
-    LAUNCH_PDL(K_MLP_GEMM, s, gemm3x_tf32_kernel, grid, GEMM_THREADS, GEMM_SMEM, mp, ep);
+    // optional: CTA pairs along M share the B tile of every k-block (half each, multicast): 25 % less L2 -> SM traffic
+    ep.cluster = (g_cluster == 2 && tiles_m % 2 == 0 && g_num_sms >= 2) ? 2 : 1;
+    int grid;
+    if (ep.cluster == 2) {
+        if ((rc = make_pair_map(&mp.b_half, b_hi, b_lo, ep.K, ep.N, ldb, BN / 2, 1))) return rc;
+        const int64_t pair_units = tiles_n * (tiles_m / 2) * splits;
+        const int64_t pairs = pair_units < g_num_sms / 2 ? pair_units : g_num_sms / 2;
+        grid = (int)(2 * pairs);
+    } else {
+        const int64_t units = tiles_n * tiles_m * splits;
+        grid = (int)(units < g_num_sms ? units : g_num_sms);
+    }
+    cdlrm_prof_mark(K_MLP_GEMM, s, 0);
+    cdlrm_launch_pdl_cluster(gemm3x_tf32_kernel, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM, s, ep.cluster, mp, ep);
+    cdlrm_prof_mark(K_MLP_GEMM, s, 1);
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
 }
@@ -934,6 +992,7 @@ extern "C" int cdlrm_mlp_create(cdlrm_mlp** out, int device, int n_layers, const
     return CDLRM_OK;
 }
 
+// key 4: CTAs per cluster along M (2 = pairs multicast their shared B tiles; 1 = no clusters, default: faster)
 // key 2: 1 (default) = a last layer with a single output column uses the SIMT narrow kernels, 0 = tensor-core GEMMs
 // key 0: split rounding (0 = round to nearest, 1 = truncate); key 1: k-blocks (of 32) chained into one TMEM
 // accumulator before the partial result is added in registers (0 = the whole K; default 8)
@@ -946,6 +1005,9 @@ extern "C" int cdlrm_mlp_set_option(int key, int value) {
         g_seg_kb = value;
     } else if (key == 2) {
         g_narrow = value ? 1 : 0;
+    } else if (key == 4) {
+        ARG_CHECK(value == 1 || value == 2);
+        g_cluster = value;
     } else if (key == 3) {
         g_dbg = value;
     } else {

@@ -277,6 +277,9 @@ int cdlrm_bce_mean(int device, const float* z, int64_t ldz, const float* t, int6
  * cdlrm_set_pdl(0) falls back to plain stream order).  No reference counterpart: launch plumbing. */
 int cdlrm_set_pdl(int on);
 int cdlrm_prof_enable(int on);
+/* launches an empty kernel through the same accounting: its reported duration ("null") is the overhead the
+ * event pair adds to every measured launch */
+int cdlrm_prof_null(cdlrm_stream stream);
 int64_t cdlrm_prof_launches(int reset);          /* launches since the last reset */
 int cdlrm_prof_num_kernels(void);
 const char* cdlrm_prof_kernel_name(int id);

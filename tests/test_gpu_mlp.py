@@ -183,3 +183,15 @@ def test_fused_bce_mean_matches_torch(B):
     (l2 * 3.0).backward()
     assert abs(l1.item() - l2.item()) <= 1e-5 * abs(l1.item())
     util.assert_close_fp32(z2.grad.cpu().numpy(), z1.grad.cpu().numpy())
+
+
+def test_mlp_cluster_multicast_mode_matches_fp64_reference():
+    """The optional CTA-pair mode of the GEMM (cdlrm_mlp_set_option(4, 2): the two CTAs of a cluster share every
+    B tile through TMA multicast, stage release through a multicast tcgen05.commit) must give the same results."""
+    from cdlrm_b200._lib import check, lib
+    check(lib.cdlrm_mlp_set_option(4, 2))
+    try:
+        _check_mlp("top", [479, 512, 512, 256, 1], 8192)
+        _check_mlp("bot", [13, 512, 256, 128], 1000)       # 8 m tiles: pairs; ragged last tile
+    finally:
+        check(lib.cdlrm_mlp_set_option(4, 1))

@@ -242,6 +242,233 @@ __global__ void __launch_bounds__(128, 4) interact_bwd_kernel(FeatPtrs fp, int64
     }
 }
 
+// ---- backward, dim 128, software-pipelined through shared memory -----------------------------------
+// ncu on interact_bwd_kernel (B200, 27 x 128, B = 8192): 60 us, issue slots 33 % busy, DRAM 40 %, the top stall
+// is long_scoreboard (4.9 stall cycles per issued instruction): with 128 registers only four 128-thread CTAs fit on an
+// SM, every CTA loads its rows, waits a full HBM round trip, computes, stores -- and the four of them do that
+// nearly in phase, so neither the memory system nor the issue slots stay busy.
+// Here a CTA is persistent and owns a two-stage shared-memory ring: while the 128 threads work on the two samples
+// of stage s, the 27 feature rows and the gradient rows of the next pair are already in flight into stage s^1 as
+// bulk async copies (cp.async.bulk, completion on an mbarrier: no registers, no LSU slots held).  The arithmetic is
+// the same as interact_bwd_kernel's (same order, same FFMA2s): results are bit-identical.
+namespace pipe {
+constexpr int SPB = 2;                       // samples per iteration (64 threads each)
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (++spins > (1u << 26)) __trap();       // a protocol error becomes a launch failure, never a hung GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+}
+}  // namespace pipe
+
+template <int F>
+struct BwdPipe {
+    static constexpr int DIM = 128, TPS = 64;
+    static constexpr int NP = Pairs<F, false>::N;
+    static constexpr int ROWF = (DIM + NP + 3) & ~3;                   // floats copied per gradient row
+    static constexpr int T_BYTES = F * pipe::SPB * DIM * 4;            // [F][SPB][DIM]
+    static constexpr int C_BYTES = pipe::SPB * ROWF * 4;               // [SPB][ROWF]
+    static constexpr int STAGE_BYTES = T_BYTES + C_BYTES;
+    static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 16;
+};
+
+template <int F>
+__global__ void __launch_bounds__(128, 3) interact_bwd_pipe_kernel(FeatPtrs fp, int64_t row_stride, int B,
+                                                                   const float* __restrict__ d_out, int64_t ld_dout,
+                                                                   float* __restrict__ d_feat, int64_t ld_dfeat) {
+    using P = BwdPipe<F>;
+    constexpr int DIM = P::DIM, TPS = P::TPS, SPB = pipe::SPB, NP = P::NP, ROWF = P::ROWF;
+    extern __shared__ __align__(128) unsigned char pipe_smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pipe_smem + 2 * P::STAGE_BYTES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ls = tid / TPS, col = tid % TPS;
+    const int items = (B + SPB - 1) / SPB;
+    if (tid == 0) {
+        pipe::bar_init(&bars[0], 1);
+        pipe::bar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_enter();
+
+    // warp 0 issues the copies of one item: lane i < F moves feature i (both samples in one copy when the rows
+    // are dense), lanes F .. F+SPB-1 the gradient rows
+    auto issue = [&](int stage, int item) {
+        unsigned char* base = pipe_smem + stage * P::STAGE_BYTES;
+        const int b0 = item * SPB;
+        const int ns = min(SPB, B - b0);
+        if (lane == 0) pipe::bar_expect(&bars[stage], (uint32_t)(ns * (F * DIM * 4 + ROWF * 4)));
+        __syncwarp();
+        if (lane < F) {
+            float* dst = reinterpret_cast<float*>(base) + lane * SPB * DIM;
+            const float* src = fp.p[lane] + (int64_t)b0 * row_stride;
+            if (row_stride == DIM) {
+                pipe::bulk_g2s(dst, src, (uint32_t)(ns * DIM * 4), &bars[stage]);
+            } else {
+                for (int q = 0; q < ns; ++q) pipe::bulk_g2s(dst + q * DIM, src + (int64_t)q * row_stride, DIM * 4, &bars[stage]);
+            }
+        } else if (lane < F + ns) {
+            const int q = lane - F;
+            pipe::bulk_g2s(base + P::T_BYTES + q * ROWF * 4, d_out + (int64_t)(b0 + q) * ld_dout, ROWF * 4, &bars[stage]);
+        }
+    };
+    if (warp == 0) {
+        if ((int)blockIdx.x < items) issue(0, blockIdx.x);
+        if ((int)(blockIdx.x + gridDim.x) < items) issue(1, blockIdx.x + gridDim.x);
+    }
+
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const int st = it & 1;
+        pipe::bar_wait(&bars[st], (uint32_t)((it >> 1) & 1));
+        const unsigned char* base = pipe_smem + st * P::STAGE_BYTES;
+        const float* T = reinterpret_cast<const float*>(base);                         // [F][SPB][DIM]
+        const float* crow = reinterpret_cast<const float*>(base + P::T_BYTES) + ls * ROWF;
+        const int b = item * SPB + ls;
+        const bool live = b < B;
+        float2 t[F], g[F];
+        static_for<F>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            t[i] = live ? reinterpret_cast<const float2*>(T + (i * SPB + ls) * DIM)[col] : make_float2(0.f, 0.f);
+            g[i] = make_float2(0.f, 0.f);
+        });
+        if (live) g[0] = reinterpret_cast<const float2*>(crow)[col];     // d/dx of the pass-through
+        const float4* c4p = reinterpret_cast<const float4*>(crow + DIM);
+        float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
+        static_for<F>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            constexpr int p0 = i * (i - 1) / 2;
+            static_for<i>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                constexpr int p = p0 + j;
+                if constexpr (p % 4 == 0) cq = c4p[p / 4];      // (a dead tail sample reads stale shared memory: never stored)
+                const float c = (p % 4 == 0) ? cq.x : (p % 4 == 1) ? cq.y : (p % 4 == 2) ? cq.z : cq.w;
+                const float2 cc = make_float2(c, c);
+                g[i] = __ffma2_rn(cc, t[j], g[i]);
+                g[j] = __ffma2_rn(cc, t[i], g[j]);
+            });
+        });
+        if (live) {
+            static_for<F>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                reinterpret_cast<float2*>(d_feat + (int64_t)i * ld_dfeat + (int64_t)b * DIM)[col] = g[i];
+            });
+        }
+        __syncthreads();                                     // every thread is done with this stage
+        const int nxt = item + 2 * (int)gridDim.x;
+        if (warp == 0 && nxt < items) issue(st, nxt);
+    }
+}
+
+// ---- forward, dim 128, software-pipelined through shared memory ------------------------------------
+// Same diagnosis as the backward (ncu on interact_fwd_tr_kernel: 40 us, issue slots 44 % busy, DRAM 37 %, 16 resident
+// warps per SM that all wait for their 27 rows at the same time).  Every warp is persistent and owns a private
+// two-stage ring [2][F][128] floats + two mbarriers: lane i issues the bulk async copy of feature row i of the sample
+// after next as soon as the current sample's rows sit in registers, so a full sample of work (about 2 000 warp
+// instructions) hides each load.  Arithmetic and reduction order are interact_fwd_tr_kernel's: results are
+// bit-identical.  Two warps per CTA, three CTAs per SM (2 x (27.6 KB ring + 9.2 KB transpose buffers) each).
+template <int F>
+struct FwdPipe {
+    static constexpr int DIM = 128, PITCH = 36, WARPS = 2;
+    static constexpr int RING_BYTES = 2 * F * DIM * 4;                 // per warp
+    static constexpr int PART_BYTES = 2 * 32 * PITCH * 4;              // per warp
+    static constexpr int SMEM_BYTES = WARPS * (RING_BYTES + PART_BYTES) + WARPS * 2 * 8;
+};
+
+template <int F>
+__global__ void __launch_bounds__(64, 3) interact_fwd_pipe_kernel(FeatPtrs fp, int64_t row_stride, int B,
+                                                                  float* __restrict__ out, int64_t ld_out) {
+    using P = FwdPipe<F>;
+    constexpr int DIM = P::DIM, PITCH = P::PITCH;
+    constexpr int NP = Pairs<F, false>::N;
+    extern __shared__ __align__(128) unsigned char pipe_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* ring = reinterpret_cast<float*>(pipe_smem + wib * P::RING_BYTES);                                  // [2][F][DIM]
+    float* part = reinterpret_cast<float*>(pipe_smem + P::WARPS * P::RING_BYTES + wib * P::PART_BYTES);        // [2][32 * PITCH]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pipe_smem + P::WARPS * (P::RING_BYTES + P::PART_BYTES)) + wib * 2;
+    if (lane == 0) {
+        pipe::bar_init(&bars[0], 1);
+        pipe::bar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    pdl_enter();
+    const int gw = blockIdx.x * P::WARPS + wib, nw = gridDim.x * P::WARPS;
+    auto issue = [&](int stage, int b) {
+        if (lane == 0) pipe::bar_expect(&bars[stage], (uint32_t)(F * DIM * 4));
+        __syncwarp();
+        if (lane < F) pipe::bulk_g2s(ring + (stage * F + lane) * DIM, fp.p[lane] + (int64_t)b * row_stride, DIM * 4, &bars[stage]);
+    };
+    if (gw < B) issue(0, gw);
+    if (gw + nw < B) issue(1, gw + nw);
+    int it = 0;
+    for (int b = gw; b < B; b += nw, ++it) {
+        const int st = it & 1;
+        pipe::bar_wait(&bars[st], (uint32_t)((it >> 1) & 1));
+        float4 t[F];
+        static_for<F>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            t[i] = reinterpret_cast<const float4*>(ring + (st * F + i) * DIM)[lane];
+        });
+        __syncwarp();                                          // the stage is in registers: refill it right away
+        if (b + 2 * nw < B) issue(st, b + 2 * nw);
+        float* orow = out + (int64_t)b * ld_out;
+        orow[lane * 4 + 0] = t[0].x; orow[lane * 4 + 1] = t[0].y;      // dense features pass through (model_no_ddp.py:293)
+        orow[lane * 4 + 2] = t[0].z; orow[lane * 4 + 3] = t[0].w;
+        float v[32];
+        static_for<F>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            constexpr int p0 = i * (i - 1) / 2;                        // row-major triangle offset
+            static_for<i>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                constexpr int p = p0 + j;
+                v[p % 32] = dot4_packed(t[i], t[j]);
+                if constexpr ((p + 1) % 32 == 0 || p + 1 == NP) {
+                    constexpr int blk = p / 32;
+                    constexpr int cnt = p + 1 - blk * 32;
+                    float* buf = part + (blk & 1) * 32 * PITCH;
+                    float4* wr = reinterpret_cast<float4*>(buf + lane * PITCH);
+                    static_for<(cnt + 3) / 4>([&](auto Q) {
+                        constexpr int q = decltype(Q)::value;
+                        wr[q] = make_float4(v[4 * q], 4 * q + 1 < cnt ? v[4 * q + 1] : 0.f, 4 * q + 2 < cnt ? v[4 * q + 2] : 0.f,
+                                            4 * q + 3 < cnt ? v[4 * q + 3] : 0.f);
+                    });
+                    __syncwarp();
+                    if (lane < cnt) {
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                        for (int r = 0; r < 32; r += 4) {
+                            a0 += buf[(r + 0) * PITCH + lane];
+                            a1 += buf[(r + 1) * PITCH + lane];
+                            a2 += buf[(r + 2) * PITCH + lane];
+                            a3 += buf[(r + 3) * PITCH + lane];
+                        }
+                        orow[DIM + blk * 32 + lane] = (a0 + a1) + (a2 + a3);
+                    }
+                }
+            });
+        });
+        __syncwarp();     // the last blocks' transpose buffers are read before the next sample overwrites them
+    }
+}
+
 // ---- tensor-core path (F <= 32, dim % 32 == 0, no self-interaction) -----------------------------
 // ncu on the CUDA-core kernels above: issue-bound (3048 / 3864 warp instructions per sample, FMA pipe
 // 36 %, DRAM 35 %), because the K reduction costs one shuffle + add per pair on top of the FMAs.
@@ -491,6 +718,11 @@ void launch_bwd(const FeatPtrs& fp, int64_t rs, int B, const float* d_out, int64
     LAUNCH_PDL(K_INT_BWD, s, (interact_bwd_kernel<F, TPS, ITSELF>), blocks, 128, 0, fp, rs, B, d_out, ld_dout, d_feat, ld_dfeat);
 }
 
+int g_bwd_pipe = 1;      // cdlrm_interact_set_option(1, .): software-pipelined backward for dim 128
+// cdlrm_interact_set_option(2, .): software-pipelined forward for dim 128.  Bit-identical, but measured SLOWER than
+// interact_fwd_tr_kernel on B200 (52 vs 46 us, tools/interact_pipe_time.py): its rings leave room for only 6 warps
+// per SM and the forward needs the issue slots of 16; the backward (12 warps, 2x the bytes per sample) gains 25 %.
+int g_fwd_pipe = 0;
 int g_variant = 0;       // cdlrm_interact_set_option(0, .): 0 CUDA cores (default), 1 mma.sync 3xTF32, 2 first CUDA-core version
 bool use_simt_only() { return g_variant != 1; }
 
@@ -504,6 +736,47 @@ int interact_grid(int B) {
     const int need = (B + 3) / 4;                 // one warp per sample, 4 warps per block
     const int cap = sms * 3 * 4;                  // 3 resident blocks per SM, a few samples per warp
     return need < cap ? need : cap;
+}
+
+template <int F>
+bool launch_fwd_pipe(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_out, cudaStream_t s) {
+    using P = FwdPipe<F>;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        if (cudaFuncSetAttribute(interact_fwd_pipe_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES) != cudaSuccess) {
+            cudaGetLastError();
+            sms = -1;
+        }
+    }
+    if (sms < 0) return false;
+    const int need = (B + P::WARPS - 1) / P::WARPS;
+    const int grid = need < sms * 3 ? need : sms * 3;            // persistent: three 2-warp CTAs per SM
+    LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_pipe_kernel<F>), grid, 32 * P::WARPS, P::SMEM_BYTES, fp, rs, B, out, ld_out);
+    return true;
+}
+
+template <int F>
+bool launch_bwd_pipe(const FeatPtrs& fp, int64_t rs, int B, const float* d_out, int64_t ld_dout, float* d_feat,
+                     int64_t ld_dfeat, cudaStream_t s) {
+    using P = BwdPipe<F>;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        if (cudaFuncSetAttribute(interact_bwd_pipe_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES) != cudaSuccess) {
+            cudaGetLastError();
+            sms = -1;
+        }
+    }
+    if (sms < 0) return false;
+    const int items = (B + pipe::SPB - 1) / pipe::SPB;
+    const int grid = items < sms * 3 ? items : sms * 3;          // persistent: three CTAs per SM (63 KB of smem each)
+    LAUNCH_PDL(K_INT_BWD, s, (interact_bwd_pipe_kernel<F>), grid, 128, P::SMEM_BYTES, fp, rs, B, d_out, ld_dout, d_feat, ld_dfeat);
+    return true;
 }
 
 template <int F, int DIM>
@@ -540,10 +813,20 @@ bool aligned_for(const FeatPtrs& fp, int n, int64_t rs, int bytes) {
         launch_fwd_tr<F_, false>(fp, rs, batch, out, ld_out, s);                          \
         done = true;                                                                      \
     }
+#define FWD_PIPE_CASE(F_)                                                                                   \
+    if (!done && n_feat == F_ && dim == 128 && !itself && fast16 && g_fwd_pipe && g_variant == 0) {          \
+        done = launch_fwd_pipe<F_>(fp, rs, batch, out, ld_out, s);                                          \
+    }
 #define FWD_CASE(F_, D_)                                                                  \
     if (!done && n_feat == F_ && dim == D_ && !itself && fast16) {                        \
         launch_fwd<F_, D_ / 4, false>(fp, rs, batch, out, ld_out, s);                      \
         done = true;                                                                      \
+    }
+// pipelined backward: dim 128, 16-byte aligned rows everywhere, gradient rows padded to a multiple of 4 floats
+#define BWD_PIPE_CASE(F_)                                                                                   \
+    if (!done && n_feat == F_ && dim == 128 && !itself && fast16 && g_bwd_pipe && g_variant == 0 &&         \
+        ((uintptr_t)d_out % 16 == 0) && (ld_dout % 4 == 0) && ld_dout >= BwdPipe<F_>::ROWF) {                 \
+        done = launch_bwd_pipe<F_>(fp, rs, batch, d_out, ld_dout, d_feat, ld_dfeat, s);                      \
     }
 #define BWD_CASE(F_, D_)                                                                  \
     if (!done && n_feat == F_ && dim == D_ && !itself && fast8) {                         \
@@ -554,7 +837,13 @@ bool aligned_for(const FeatPtrs& fp, int n, int64_t rs, int bytes) {
 // key 0: kernel variant (0 = CUDA cores with the shared-memory transpose reduction, the default and the fastest
 // measured; 1 = mma.sync.m16n8k8 3xTF32, kept as the evidence for "tensor cores do not pay off here":
 // 78 / 93 us against 51 / 73 us forward / backward at B = 8192, 27 x 128 on B200; 2 = the butterfly version)
+// key 1: software-pipelined backward for dim 128 (interact_bwd_pipe_kernel; default 1), 0 = interact_bwd_kernel
+// key 2: software-pipelined forward (interact_fwd_pipe_kernel; default 0: measured slower), 0 = interact_fwd_tr_kernel
 extern "C" int cdlrm_interact_set_option(int key, int value) {
+    if (key == 1 || key == 2) {
+        (key == 1 ? g_bwd_pipe : g_fwd_pipe) = value ? 1 : 0;
+        return CDLRM_OK;
+    }
     ARG_CHECK(key == 0 && value >= 0 && value <= 2);
     g_variant = value;
     return CDLRM_OK;
@@ -577,6 +866,7 @@ extern "C" int cdlrm_interact_fwd(int device, const float* const* h_feat, int n_
     const bool fast16 = aligned_for(fp, n_feat, rs, 16);
     bool done = false;
     FWD_MMA_CASE(27, 128) FWD_MMA_CASE(27, 64) FWD_MMA_CASE(27, 32) FWD_MMA_CASE(9, 128) FWD_MMA_CASE(9, 64) FWD_MMA_CASE(9, 32)
+    FWD_PIPE_CASE(27) FWD_PIPE_CASE(9)
     FWD_TR_CASE(27) FWD_TR_CASE(9)
     FWD_CASE(27, 128) FWD_CASE(27, 64) FWD_CASE(27, 32) FWD_CASE(27, 16)
     FWD_CASE(9, 128) FWD_CASE(9, 64) FWD_CASE(9, 32) FWD_CASE(9, 16)
@@ -604,6 +894,7 @@ extern "C" int cdlrm_interact_bwd(int device, const float* const* h_feat, int n_
     const bool fast16 = aligned_for(fp, n_feat, rs, 16) && ((uintptr_t)d_feat % 16 == 0) && (ld_dfeat % 4 == 0);
     bool done = false;
     BWD_MMA_CASE(27, 128) BWD_MMA_CASE(27, 64) BWD_MMA_CASE(27, 32) BWD_MMA_CASE(9, 128) BWD_MMA_CASE(9, 64) BWD_MMA_CASE(9, 32)
+    BWD_PIPE_CASE(27) BWD_PIPE_CASE(9)
     BWD_CASE(27, 128) BWD_CASE(27, 64) BWD_CASE(27, 32) BWD_CASE(27, 16)
     BWD_CASE(9, 128) BWD_CASE(9, 64) BWD_CASE(9, 32) BWD_CASE(9, 16)
     if (!done)

@@ -187,6 +187,58 @@ def _interaction_at_size(shape):
     util.assert_close_fp32(torch.stack([t.grad for t in lyt]).cpu().numpy(), np.stack(dly))
 
 
+@pytest.mark.parametrize("shape", [(8192, 27, 128), (2049, 27, 128), (1, 27, 128), (131, 9, 128)])
+@pytest.mark.parametrize("strided_feats", [False, True])
+def test_interaction_pipelined_kernels(shape, strided_feats):
+    """The software-pipelined kernels for dim 128 (interact_fwd_pipe_kernel / interact_bwd_pipe_kernel: persistent
+    warps / CTAs, bulk async copies into two-stage shared-memory rings).  The backward one is taken when the gradient
+    rows are padded to a multiple of 4 floats (what the top MLP's backward hands over).  Both must match the oracle
+    and be BIT-identical to the plain kernels (same arithmetic order); odd batch sizes exercise the half-filled last
+    item, strided features the per-row copies."""
+    from oracle import oracle as O
+    from cdlrm_b200._lib import check, lib
+    _, _, M = _mods()
+    B, nf, d = shape
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((B, d)).astype(np.float32)
+    ly = [rng.standard_normal((B, d)).astype(np.float32) for _ in range(nf - 1)]
+    npair = nf * (nf - 1) // 2
+    ld = (d + npair + 3) & ~3
+    dR = rng.standard_normal((B, d + npair)).astype(np.float32)
+    dRp = torch.full((B, ld), float("nan"), device=DEV)[:, :d + npair]      # padded rows, poison in the padding
+    dRp.copy_(torch.from_numpy(dR))
+    net = M.DLRM_Net.__new__(M.DLRM_Net)
+    torch.nn.Module.__init__(net)
+    net.arch_interaction_op, net.arch_interaction_itself = "dot", False
+
+    def feats():
+        if not strided_feats:
+            return [torch.from_numpy(a).to(DEV).requires_grad_() for a in [x] + ly]
+        big = torch.zeros(nf, B, d + 4, device=DEV)          # row stride d + 4: not dense
+        big[:, :, :d] = torch.from_numpy(np.stack([x] + ly))
+        return [big[i, :, :d].detach().requires_grad_() for i in range(nf)]
+
+    grads, outs = {}, {}
+    for pipe in (1, 0):
+        check(lib.cdlrm_interact_set_option(1, pipe))      # backward
+        check(lib.cdlrm_interact_set_option(2, pipe))      # forward
+        try:
+            f = feats()
+            R = net.interact_features(f[0], f[1:])
+            R.backward(dRp)
+            outs[pipe] = R.detach().cpu().numpy()
+            grads[pipe] = torch.stack([t.grad for t in f]).cpu().numpy()
+        finally:
+            check(lib.cdlrm_interact_set_option(1, 1))      # defaults: pipelined backward, plain forward
+            check(lib.cdlrm_interact_set_option(2, 0))
+    dx, dly = O.interact_bwd(x, ly, dR)
+    util.assert_close_fp32(outs[1], O.interact_fwd(x, ly))
+    util.assert_close_fp32(grads[1][0], dx)
+    util.assert_close_fp32(grads[1][1:], np.stack(dly))
+    assert np.array_equal(outs[1], outs[0])
+    assert np.array_equal(grads[1], grads[0])
+
+
 @pytest.mark.parametrize("mlp_impl", ["tcgen05", "torch"])
 def test_dlrm_tiny_loss_matches_reference_golden(mlp_impl):
     """End to end: cache + interaction kernels + MLPs (tensor-core path and stock PyTorch), BCE

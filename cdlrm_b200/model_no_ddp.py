@@ -172,6 +172,7 @@ class _LookupFn(torch.autograd.Function):
         # stream so that it overlaps the MLP forward instead of sitting on the critical path
         ctx.plan = group._early_plan(tb, slots, n_idx) if group.early_plan else None
         ctx.mark_non_differentiable(slots)
+        ctx.set_materialize_grads(False)      # no zero tensor for the (integer) slots output on every backward
         return (slots,) + tuple(out.unbind(0))
 
     @staticmethod

@@ -546,7 +546,7 @@ def gpu_run(a, wl, ln_emb):
             g["useful_TFLOP/s"] = round(fl / (t_us * 1e-6) / 1e12, 1)
             g["tf32_TFLOP/s"] = round(3 * fl / (t_us * 1e-6) / 1e12, 1)
         traffic = {}
-        tpath = os.path.join(ROOT, "profiles", "r1c_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r1d_traffic.json")
         if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch, one ncu --set full capture
             traffic = json.load(open(tpath))["kernels"]
         for nm in kernels:

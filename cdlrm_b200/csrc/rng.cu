@@ -12,6 +12,8 @@
 #include <thread>
 
 #include "common.cuh"
+#define MT_JUMP_QUAL __constant__
+#include "mt_jump_table.h"
 
 struct cdlrm_rng {
     std::mt19937 gen;
@@ -99,7 +101,8 @@ extern "C" int cdlrm_rng_exponential(cdlrm_rng* r, float* out, int64_t n, int th
 
 struct cdlrm_rngdev {
     int device = 0;
-    uint32_t* d_state = nullptr;  // x[624], pos
+    uint32_t* d_state = nullptr;   // x[624], pos
+    uint32_t* d_states = nullptr;  // [MT_MAX_CHUNKS][624]: start states of the chunks of one parallel generation
     uint64_t draws = 0;
 };
 
@@ -118,6 +121,97 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= (y << 15) & 0xefc60000u;
     y ^= y >> 18;
     return y;
+}
+
+// next block of 624 words in place (three dependent phases of up to 227 independent words); every thread of the
+// 256-thread CTA calls it; all reads of the old block by the caller must be complete (barrier) before the call
+__device__ __forceinline__ void mt_regen(uint32_t* x, int tid) {
+    uint32_t v = 0;
+    if (tid < 227) v = mt_twist(x[tid], x[tid + 1], x[tid + MT_M]);
+    __syncthreads();
+    if (tid < 227) x[tid] = v;
+    __syncthreads();
+    if (tid < 227) v = mt_twist(x[227 + tid], x[228 + tid], x[tid]);
+    __syncthreads();
+    if (tid < 227) x[227 + tid] = v;
+    __syncthreads();
+    if (tid < 170) v = mt_twist(x[454 + tid], x[tid == 169 ? 0 : 455 + tid], x[227 + tid]);
+    __syncthreads();
+    if (tid < 170) x[454 + tid] = v;
+    __syncthreads();
+}
+
+// ---- parallel generation of ONE sequential stream: jump-ahead ----------------------------------------------
+// mt19937 is sequential by construction (0.75 G words/s on one CTA: 0.4 s per Terabyte window on one GPU, 3.6 s
+// for the 8-GPU global window -- longer than the window trains).  The state J words ahead is a fixed GF(2)-linear
+// function of the state: with g(x) = x^J mod phi(x) (tools/gen_mt_jump.py derives phi and the g's, and checks them
+// against sequential generation),   s[n + J] = XOR_{i : g_i = 1} s[n + i]   word-wise.  A long request is cut into
+// chunks of MT_JUMP_BLOCKS_PER_CHUNK blocks; the start state of chunk j comes from chunk j - 2^m by the level-m
+// polynomial (log2(chunks) launches, all chunks of a level in parallel), then every chunk is generated by its own
+// CTA.  Output and final state are bit-identical to the sequential kernel (tests/test_gpu_parity.py).
+constexpr int MT_SEQ_BLOCKS = 33;                 // s[0 .. 33 * 624) covers i + k <= 19936 + 623
+constexpr int MT_MAX_CHUNKS = 1 << MT_JUMP_LEVELS;
+
+// states[lo + b] = states[b] advanced by MT_JUMP_CHUNK_WORDS * 2^level words, b = blockIdx.x.  (The low 31 bits of the
+// first word of a state are not state -- the recurrence only reads its top bit -- and come out arbitrary: a chunk's
+// start state is only ever the PREDECESSOR of the first block that is output.)
+__global__ void __launch_bounds__(256) mt_jump_kernel(uint32_t* __restrict__ states, int lo, int level) {
+    extern __shared__ uint32_t seq[];              // [MT_SEQ_BLOCKS * 624]
+    const int tid = threadIdx.x;
+    const uint32_t* src = states + (size_t)blockIdx.x * MT_N;
+    for (int i = tid; i < MT_N; i += 256) seq[i] = src[i];
+    __syncthreads();
+    for (int b = 1; b < MT_SEQ_BLOCKS; ++b) {
+        uint32_t* nb = seq + b * MT_N;
+        for (int i = tid; i < MT_N; i += 256) nb[i] = nb[i - MT_N];
+        __syncthreads();
+        mt_regen(nb, tid);
+    }
+    uint32_t a0 = 0, a1 = 0, a2 = 0;
+    const bool third = tid + 512 < MT_N;
+    for (int w = 0; w < MT_JUMP_POLY_WORDS; ++w) {
+        uint32_t bits = mt_jump_poly[level][w];       // uniform: constant cache
+        while (bits) {
+            const int i = w * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            a0 ^= seq[i + tid];
+            a1 ^= seq[i + tid + 256];
+            if (third) a2 ^= seq[i + tid + 512];
+        }
+    }
+    uint32_t* dst = states + (size_t)(lo + blockIdx.x) * MT_N;
+    dst[tid] = a0;
+    dst[tid + 256] = a1;
+    if (third) dst[tid + 512] = a2;
+}
+
+// chunk j = blockIdx.x: the pending words of the current block (chunk 0 only), then blocks j*CB + 1 .. (j+1)*CB after
+// it, tempered, at their position in the stream; the chunk that produces the last block leaves the generator state
+__global__ void __launch_bounds__(256) mt_chunks_kernel(const uint32_t* __restrict__ states, uint32_t* __restrict__ state,
+                                                        uint32_t* __restrict__ out, int pos, long long n_words, long long nb) {
+    __shared__ uint32_t x[MT_N];
+    const int tid = threadIdx.x;
+    const long long j = blockIdx.x;
+    for (int i = tid; i < MT_N; i += 256) x[i] = states[(size_t)j * MT_N + i];
+    __syncthreads();
+    const int r0 = MT_N - pos;
+    if (j == 0)
+        for (int i = tid; i < r0; i += 256) out[i] = mt_temper(x[pos + i]);
+    __syncthreads();
+    const long long q0 = j * MT_JUMP_BLOCKS_PER_CHUNK + 1;
+    const long long q1 = (j + 1) * MT_JUMP_BLOCKS_PER_CHUNK < nb ? (j + 1) * MT_JUMP_BLOCKS_PER_CHUNK : nb;
+    for (long long q = q0; q <= q1; ++q) {
+        mt_regen(x, tid);
+        const long long base = r0 + (q - 1) * MT_N;
+        const long long left = n_words - base;
+        const int cnt = left < MT_N ? (int)left : MT_N;
+        for (int i = tid; i < cnt; i += 256) out[base + i] = mt_temper(x[i]);
+        __syncthreads();
+    }
+    if (q1 == nb && q0 <= q1) {
+        for (int i = tid; i < MT_N; i += 256) state[i] = x[i];
+        if (tid == 0) state[MT_N] = (uint32_t)(n_words - (r0 + (nb - 1) * MT_N));
+    }
 }
 
 __global__ void __launch_bounds__(256) mt_generate_kernel(uint32_t* __restrict__ state, uint32_t* __restrict__ out,
@@ -164,6 +258,8 @@ __global__ void exp_from_raw_kernel(const uint2* __restrict__ raw, float* __rest
 
 }  // namespace
 
+static long long g_mt_parallel_min_words = 0;     // requests of two or more chunks (5.1 M words) go parallel
+
 extern "C" int cdlrm_rngdev_create(cdlrm_rngdev** out, int device, uint64_t seed) {
     ARG_CHECK(out);
     CU_CHECK(cudaSetDevice(device));
@@ -175,6 +271,9 @@ extern "C" int cdlrm_rngdev_create(cdlrm_rngdev** out, int device, uint64_t seed
     h[MT_N] = MT_N;  // first use regenerates
     CU_CHECK(cudaMalloc(&r->d_state, sizeof(h)));
     CU_CHECK(cudaMemcpy(r->d_state, h, sizeof(h), cudaMemcpyHostToDevice));
+    CU_CHECK(cudaMalloc(&r->d_states, (size_t)MT_MAX_CHUNKS * MT_N * sizeof(uint32_t)));
+    CU_CHECK(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  MT_SEQ_BLOCKS * MT_N * (int)sizeof(uint32_t)));
     *out = r;
     return CDLRM_OK;
 }
@@ -183,6 +282,7 @@ extern "C" int cdlrm_rngdev_destroy(cdlrm_rngdev* r) {
     if (!r) return CDLRM_OK;
     cudaSetDevice(r->device);
     cudaFree(r->d_state);
+    cudaFree(r->d_states);
     delete r;
     return CDLRM_OK;
 }
@@ -195,9 +295,32 @@ extern "C" int cdlrm_rngdev_raw(cdlrm_rngdev* r, uint32_t* d_out, int64_t n_draw
     ARG_CHECK(d_out && ((uintptr_t)d_out & 7) == 0);
     CU_CHECK(cudaSetDevice(r->device));
     cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH(K_RNG_MT, s, mt_generate_kernel<<<1, 256, 0, s>>>(r->d_state, d_out, (long long)n_draws * 2));
+    const long long n_words = (long long)n_draws * 2;
+    // the host knows where the stream stands: `pos` words of the current block are used up
+    const uint64_t before = r->draws * 2;
+    const int pos = before == 0 ? MT_N : (int)((before - 1) % MT_N) + 1;
+    const int r0 = MT_N - pos;
+    const long long nb = n_words > r0 ? (n_words - r0 + MT_N - 1) / MT_N : 0;          // blocks after the current one
+    const long long n_chunks = (nb + MT_JUMP_BLOCKS_PER_CHUNK - 1) / MT_JUMP_BLOCKS_PER_CHUNK;
+    if (g_mt_parallel_min_words >= 0 && n_words >= g_mt_parallel_min_words && n_chunks >= 2 && n_chunks <= MT_MAX_CHUNKS) {
+        CU_CHECK(cudaMemcpyAsync(r->d_states, r->d_state, MT_N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        for (int m = 0; (1LL << m) < n_chunks; ++m) {
+            const long long lo = 1LL << m, hi = (2LL << m) < n_chunks ? (2LL << m) : n_chunks;
+            LAUNCH(K_RNG_MT, s, (mt_jump_kernel<<<(int)(hi - lo), 256, MT_SEQ_BLOCKS * MT_N * sizeof(uint32_t), s>>>(r->d_states, (int)lo, m)));
+        }
+        LAUNCH(K_RNG_MT, s, (mt_chunks_kernel<<<(int)n_chunks, 256, 0, s>>>(r->d_states, r->d_state, d_out, pos, n_words, nb)));
+    } else {
+        LAUNCH(K_RNG_MT, s, mt_generate_kernel<<<1, 256, 0, s>>>(r->d_state, d_out, n_words));
+    }
     CU_CHECK(cudaGetLastError());
     r->draws += (uint64_t)n_draws;
+    return CDLRM_OK;
+}
+
+// key 0: smallest request (in 32-bit words) that is generated chunk-parallel with jump-ahead; -1 = always sequential
+extern "C" int cdlrm_rngdev_set_option(int key, int64_t value) {
+    ARG_CHECK(key == 0);
+    g_mt_parallel_min_words = (long long)value;
     return CDLRM_OK;
 }
 

@@ -309,6 +309,9 @@ int cdlrm_rngdev_raw(cdlrm_rngdev* rng, uint32_t* d_out, int64_t n_draws, cdlrm_
 int cdlrm_rngdev_exponential(cdlrm_rngdev* rng, float* d_out, int64_t n, uint32_t* d_raw_scratch,
                              cdlrm_stream stream);
 uint64_t cdlrm_rngdev_draws(const cdlrm_rngdev* rng);
+/* key 0: smallest request (32-bit words) generated chunk-parallel by mt19937 jump-ahead (default 0: every request of
+ * two or more chunks of 2.56 M words); -1 = always the sequential single-CTA kernel.  Same stream either way. */
+int cdlrm_rngdev_set_option(int key, int64_t value);
 /* d_out[i] = exponential draw of the raw word pair {d_raw[2i], d_raw[2i+1]} (the transform alone) */
 int cdlrm_exp_from_raw(const uint32_t* d_raw, float* d_out, int64_t n, cdlrm_stream stream);
 

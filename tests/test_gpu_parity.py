@@ -351,6 +351,47 @@ def test_device_victim_stream_equals_host_stream():
     assert np.array_equal(want.view(np.int32), got.view(np.int32))
 
 
+def test_device_victim_stream_jump_ahead_equals_sequential():
+    """Chunk-parallel generation of the mt19937 stream (jump-ahead polynomials, csrc/mt_jump_table.h) against the
+    sequential single-CTA kernel: same words, same final state, over request sizes that start mid-block, end on and
+    off block / chunk boundaries and need up to 8 jump levels (340 M words)."""
+    import ctypes
+    import time
+    from cdlrm_b200._lib import check, lib
+    vp = ctypes.c_void_p
+    CH = 2555904                                  # words per chunk (MT_JUMP_CHUNK_WORDS), 2 words per draw
+    sizes = [1000, 3_000_000, 77, CH, 5, 45_000_000, 700_000, (CH * 3) // 2 + 312 - 1077 // 2, 170_000_000, 11]
+    outs = {}
+    stream = vp(torch.cuda.current_stream().cuda_stream)
+    for mode in ("seq", "par"):
+        check(lib.cdlrm_rngdev_set_option(0, -1 if mode == "seq" else 0))
+        h = vp()
+        check(lib.cdlrm_rngdev_create(ctypes.byref(h), 0, 4242))
+        try:
+            digests, t_big = [], None
+            for n in sizes:
+                buf = torch.empty(2 * n, dtype=torch.int32, device=DEV)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                check(lib.cdlrm_rngdev_raw(h, vp(buf.data_ptr()), n, stream))
+                torch.cuda.synchronize()
+                if n == max(sizes):
+                    t_big = time.perf_counter() - t0
+                # order-sensitive digest + head / tail words
+                w = buf.to(torch.int64) & 0xffffffff
+                k = torch.arange(1, w.numel() + 1, device=DEV, dtype=torch.int64)
+                digests.append((int(w.sum()), int((w * (k % 65521)).sum() % (1 << 61)), buf[:4].tolist(), buf[-4:].tolist()))
+                del buf, w, k
+            outs[mode] = (digests, int(lib.cdlrm_rngdev_draws(h)), t_big)
+        finally:
+            lib.cdlrm_rngdev_destroy(h)
+            check(lib.cdlrm_rngdev_set_option(0, 0))
+    assert outs["seq"][0] == outs["par"][0]
+    assert outs["seq"][1] == outs["par"][1] == sum(sizes)
+    print(f"340 M words: sequential {outs['seq'][2] * 1e3:.1f} ms, jump-ahead {outs['par'][2] * 1e3:.1f} ms")
+    assert outs["par"][2] < outs["seq"][2]
+
+
 def _device_exp_from_raw(raw_u64):
     """Runs csrc/expdraw.cuh on given 53-bit integers through the select kernel's twin
     (cdlrm_rngdev_exponential's transform) by planting them as a fake raw stream."""

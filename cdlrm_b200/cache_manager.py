@@ -160,7 +160,9 @@ class WindowPlanner:
 
     @property
     def loser_cap_rows(self):
-        gb = float(os.environ.get("CDLRM_LOSER_STORE_GB", "20"))
+        # two stores alternate; at 8 GPUs (global window of 197 M ids per table, 14 M un-cacheable ids per big table)
+        # the uncapped store would need 2 x 42 GB next to 41 GB of window ids
+        gb = float(os.environ.get("CDLRM_LOSER_STORE_GB", "12"))
         return int(gb * 1e9 / (4 * self.dim))
 
     def enable_lookahead_tags(self):
@@ -272,7 +274,9 @@ class WindowPlanner:
         if b is None or b.shape[0] < rows:
             b = None
             self._bufs[name] = None
-            b = torch.empty(int(rows * 1.25) + 16, self.dim, dtype=torch.float32, device=self.dev)
+            # head-room so that the next, slightly larger window does not re-allocate: 25 %, at most 1 GB
+            extra = min(int(rows * 0.25), (1 << 30) // (4 * self.dim))
+            b = torch.empty(int(rows) + extra + 16, self.dim, dtype=torch.float32, device=self.dev)
             self._bufs[name] = b
         return b
 

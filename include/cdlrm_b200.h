@@ -119,7 +119,8 @@ int cdlrm_embed_bwd_sgd(cdlrm_ctx* ctx, int table_begin, int table_count,
  * kernels (measured slower on B200, kept for the comparison), 2 = the first CUDA-core forward (shuffle butterfly) */
 /* key 1: 1 (default) = software-pipelined backward for dim 128 (persistent CTAs, bulk async copies into a two-stage
  * shared-memory ring; taken when d_out rows are 16-byte aligned, ld_dout % 4 == 0), 0 = the plain kernel;
- * key 2: the same for the forward (default 0: measured slower than the plain kernel on B200) */
+ * key 2: pipelined forward variants (1 = two-stage rings, 2 = one-stage rings; default 0 = plain kernel: neither
+ * variant is faster on B200) */
 int cdlrm_interact_set_option(int key, int value);
 int cdlrm_interact_fwd(int device, const float* const* h_feat, int n_feat, int64_t feat_row_stride,
                        int32_t batch, int dim, int itself, float* out, int64_t ld_out,

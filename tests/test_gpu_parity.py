@@ -219,9 +219,9 @@ def test_interaction_pipelined_kernels(shape, strided_feats):
         return [big[i, :, :d].detach().requires_grad_() for i in range(nf)]
 
     grads, outs = {}, {}
-    for pipe in (1, 0):
-        check(lib.cdlrm_interact_set_option(1, pipe))      # backward
-        check(lib.cdlrm_interact_set_option(2, pipe))      # forward
+    for pipe in (1, 0, 2):                                 # forward variants 1 and 2 (two- / one-stage rings), 0 = plain
+        check(lib.cdlrm_interact_set_option(1, min(pipe, 1)))      # backward
+        check(lib.cdlrm_interact_set_option(2, pipe))              # forward
         try:
             f = feats()
             R = net.interact_features(f[0], f[1:])
@@ -235,8 +235,8 @@ def test_interaction_pipelined_kernels(shape, strided_feats):
     util.assert_close_fp32(outs[1], O.interact_fwd(x, ly))
     util.assert_close_fp32(grads[1][0], dx)
     util.assert_close_fp32(grads[1][1:], np.stack(dly))
-    assert np.array_equal(outs[1], outs[0])
-    assert np.array_equal(grads[1], grads[0])
+    assert np.array_equal(outs[1], outs[0]) and np.array_equal(outs[2], outs[0])
+    assert np.array_equal(grads[1], grads[0]) and np.array_equal(grads[2], grads[0])
 
 
 @pytest.mark.parametrize("mlp_impl", ["tcgen05", "torch"])

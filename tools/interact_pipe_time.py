@@ -22,8 +22,8 @@ sets = [(torch.randn(B, d, device=dev).requires_grad_(), [torch.randn(B, d, devi
         for _ in range(12)]
 npair = F * (F - 1) // 2
 dR = torch.randn(B, 480, device=dev)[:, :d + npair]
-for pipe in (1, 0, 1, 0):
-    check(lib.cdlrm_interact_set_option(1, pipe))
+for pipe in (2, 0, 1, 2, 0):
+    check(lib.cdlrm_interact_set_option(1, min(pipe, 1)))
     check(lib.cdlrm_interact_set_option(2, pipe))
     for rep in range(2):
         if rep == 1:
@@ -40,6 +40,6 @@ for pipe in (1, 0, 1, 0):
     for nm in ("interact_fwd", "interact_bwd", "null"):
         i = names.index(nm)
         out.append(f"{nm}: {ms[i] * 1e3 / max(calls[i], 1):.1f} us")
-    print("pipelined" if pipe else "plain    ", "  ".join(out), flush=True)
+    print({0: "plain              ", 1: "pipelined (2-stage)", 2: "pipelined (1-stage)"}[pipe], "  ".join(out), flush=True)
 check(lib.cdlrm_interact_set_option(1, 1))
 check(lib.cdlrm_interact_set_option(2, 0))

@@ -6,8 +6,8 @@ Terabyte-shape synthetic data (BASELINE.json metric), one process per GPU.
   python bench.py --impl reference --gpus N --steps K --warmup W
 
 A step = one full training iteration over one global batch: cache forward (probe + gather +
-pool), bottom/top MLPs (stock PyTorch fp32), pairwise-dot interaction fwd/bwd, BCE loss,
-de-duplicated sparse SGD on the cache, MLP SGD; window install every `lookahead` steps with
+pool), bottom/top MLPs (tcgen05 3xTF32 GEMMs, FP32 accuracy), pairwise-dot interaction fwd/bwd, BCE loss,
+de-duplicated sparse SGD on the cache, dense SGD; window install every `lookahead` steps with
 the next window planned concurrently on a side stream; table aggregation every
 `table_agg_freq` steps when N > 1.  Prints ONE JSON line (rank 0).
 """

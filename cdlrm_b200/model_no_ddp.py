@@ -708,7 +708,9 @@ class _MlpFn(torch.autograd.Function):
 
 
 class DLRM_Net(nn.Module):
-    """model_no_ddp.py:215-316.  MLPs and loss stay stock PyTorch (cuBLAS); the pairwise-dot
+    """model_no_ddp.py:215-316.  bot_l / top_l are the reference's nn.Sequential stacks (same parameters, same
+    numpy-RNG initialisation); on CUDA they execute through cdlrm_mlp_* (TMA + tcgen05 3xTF32 GEMMs, FP32
+    accuracy; ``mlp_impl = "torch"`` / CDLRM_MLP=torch runs the stock modules).  The pairwise-dot
     interaction (:272-293) runs in cdlrm_interact_fwd/_bwd."""
 
     def __init__(self, ln_bot=None, ln_top=None, arch_interaction_op=None, arch_interaction_itself=False,

@@ -14,6 +14,7 @@ import ctypes
 import math
 import os
 import threading
+import time
 
 import numpy as np
 import torch
@@ -187,8 +188,7 @@ class WindowPlanner:
         ascending-unique int64 tensors (the reference-API path)."""
         s = self.stream
         rec = PlanRecord()
-        import time as _t
-        t_a = _t.perf_counter()
+        t_a = time.perf_counter()
         with torch.cuda.stream(s):
             if uniq_lists is not None:
                 lens = [int(u.numel()) for u in uniq_lists]
@@ -216,10 +216,10 @@ class WindowPlanner:
             for k in range(1, self.T):
                 rec.off[k] = rec.off[k - 1] + rec.rows[k - 1]
             # q for table 0..T-1 in one draw: the stream is split-invariant
-            t_b = _t.perf_counter()
+            t_b = time.perf_counter()
             dev_rng = getattr(self.rng, "on_device", False)
             q_host = None if dev_rng else self.rng.exponential(total * self.ways)
-            t_c = _t.perf_counter()
+            t_c = time.perf_counter()
             if not dev_rng:
                 q = q_host.to(self.dev, non_blocking=True) if total else torch.empty(0, device=self.dev)
             n = max(total, 1)
@@ -262,7 +262,7 @@ class WindowPlanner:
                 if tot > self.loser_cap_rows:
                     rec.L = [int(x * self.loser_cap_rows // tot) for x in rec.L]
             self.last_timing = {"phase_a_s": round(t_b - t_a, 4), "rng_s": round(t_c - t_b, 4),
-                                "phase_b_s": round(_t.perf_counter() - t_c, 4)}
+                                "phase_b_s": round(time.perf_counter() - t_c, 4)}
         rec.event = None
         rec.staged = rec.wb_done = rec.fill_stage = rec.loser_stage = rec.evict_stage = None
         return rec

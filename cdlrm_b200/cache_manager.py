@@ -161,10 +161,22 @@ class WindowPlanner:
 
     @property
     def loser_cap_rows(self):
-        # two stores alternate; at 8 GPUs (global window of 197 M ids per table, 14 M un-cacheable ids per big table)
-        # the uncapped store would need 2 x 42 GB next to 41 GB of window ids
-        gb = float(os.environ.get("CDLRM_LOSER_STORE_GB", "12"))
-        return int(gb * 1e9 / (4 * self.dim))
+        """HBM budget (rows) of ONE loser store; two alternate.  ``CDLRM_LOSER_STORE_GB`` fixes it; otherwise it is
+        sized once, at the first plan, from the HBM that is free then: half of (free - 70 GB), within [8, 32] GB.
+        The 70 GB are what a Terabyte-shape window still allocates afterwards (fill / evict staging up to the
+        cache size, plan records, the next window's inputs).  1-4 GPUs: the whole store fits (5 / 13 / 25 GB); at
+        8 GPUs (14 M un-cacheable ids per big table, 42 GB) about half of it does."""
+        cap = getattr(self, "_loser_cap_rows", None)
+        if cap is None:
+            env = os.environ.get("CDLRM_LOSER_STORE_GB")
+            if env:
+                gb = float(env)
+            else:
+                free, _total = torch.cuda.mem_get_info(self.dev)
+                cached = torch.cuda.memory_reserved(self.dev) - torch.cuda.memory_allocated(self.dev)
+                gb = min(32.0, max(8.0, ((free + cached) / 1e9 - 70.0) / 2))
+            cap = self._loser_cap_rows = int(gb * 1e9 / (4 * self.dim))
+        return cap
 
     def enable_lookahead_tags(self):
         """Give the planner its own evolving copy of the tags so that it can run one or more

@@ -177,8 +177,24 @@ def aggregate_gradients(dlrm, include_bias=False):
 # ------------------------------------------------------------------------------------
 
 
+class _DistComm:
+    """The two collectives of the table aggregation over torch.distributed (NCCL on the GPU box).
+    Tests substitute an in-process transport with the same three members to run W > 1 replicas
+    of ``broadcast_and_aggregate`` on one device (tests/test_gpu_aggregate.py)."""
+
+    @property
+    def world(self):
+        return _world()
+
+    def all_gather_into(self, out, inp):
+        dist.all_gather_into_tensor(out, inp)
+
+    def all_reduce(self, buf, op):
+        dist.all_reduce(buf, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+
+
 @torch.no_grad()
-def broadcast_and_aggregate(cache_group, cache_group_idxs, rank, reduce_op="mean"):
+def broadcast_and_aggregate(cache_group, cache_group_idxs, rank, reduce_op="mean", comm=None):
     """Every ``table_agg_freq`` steps: union over ranks of the touched slots per table,
     ``weight[u] = sum_r weight_r[u] / W`` (mean) or sum / max.  ``cache_group_idxs`` is the
     reference's int32 ``[T, n]`` slot tensor; pass ``None`` to use the dirty bitmaps that the
@@ -188,25 +204,28 @@ def broadcast_and_aggregate(cache_group, cache_group_idxs, rank, reduce_op="mean
     ctx = cg._ensure_ctx(None)
     dev = cg.device
     s = _vp(torch.cuda.current_stream(dev).cuda_stream)
-    W = _world()
+    comm = comm if comm is not None else _DistComm()
+    W = comm.world
+    if reduce_op not in ("mean", "sum", "max"):
+        raise ValueError(reduce_op)
     if cache_group_idxs is not None:
         idx = cache_group_idxs.to(dev, dtype=torch.int32)
         if idx.stride(1) != 1:
             idx = idx.contiguous()
         check(lib.cdlrm_agg_mark(ctx, _vp(idx.data_ptr()), idx.stride(0), idx.shape[1], s))
     dirty = cg.dirty_bitmap()
-    if W > 1:
-        gathered = torch.empty(W, dirty.numel(), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(gathered.view(-1), dirty)
-        check(lib.cdlrm_agg_or_bitmaps(ctx, _vp(gathered.data_ptr()), W, dirty.numel(), s))
     T = len(cg.emb_l)
     bufs = getattr(cg, "_agg_bufs", None)
-    if bufs is None:
+    if bufs is None or bufs[3].shape[0] != W:
         cap = int(sum(cg._cache_rows))
         bufs = (torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(T, dtype=torch.int64, device=dev),
-                torch.zeros(T, dtype=torch.int64).pin_memory())
+                torch.zeros(T, dtype=torch.int64).pin_memory(),
+                torch.empty(W, dirty.numel(), dtype=torch.int32, device=dev))
         cg._agg_bufs = bufs
-    slot_list, d_counts, h_counts = bufs
+    slot_list, d_counts, h_counts, gathered = bufs
+    if W > 1:
+        comm.all_gather_into(gathered.view(-1), dirty)
+        check(lib.cdlrm_agg_or_bitmaps(ctx, _vp(gathered.data_ptr()), W, dirty.numel(), s))
     check(lib.cdlrm_agg_collect(ctx, _vp(slot_list.data_ptr()), _vp(d_counts.data_ptr()), _vp(h_counts.data_ptr()), s))
     torch.cuda.current_stream(dev).synchronize()
     counts = h_counts.tolist()
@@ -214,18 +233,15 @@ def broadcast_and_aggregate(cache_group, cache_group_idxs, rank, reduce_op="mean
     carr = _lib.i64_array(counts)
     if total == 0:
         return
-    buf = torch.empty(total, cg.dim, dtype=torch.float32, device=dev)
-    if reduce_op == "mean":
-        div, op = float(W), dist.ReduceOp.SUM
-    elif reduce_op == "sum":
-        div, op = 1.0, dist.ReduceOp.SUM
-    elif reduce_op == "max":
-        div, op = 1.0, dist.ReduceOp.MAX
-    else:
-        raise ValueError(reduce_op)
+    rows = getattr(cg, "_agg_rows", None)          # packed row buffer: grown, never shrunk
+    if rows is None or rows.shape[0] < total:
+        cg._agg_rows = None
+        rows = cg._agg_rows = torch.empty(int(total * 1.25) + 16, cg.dim, dtype=torch.float32, device=dev)
+    buf = rows[:total]
+    div = float(W) if reduce_op == "mean" else 1.0
     check(lib.cdlrm_agg_pack(ctx, _vp(slot_list.data_ptr()), carr, div, _vp(buf.data_ptr()), s))
     if W > 1:
-        dist.all_reduce(buf, op=op)
+        comm.all_reduce(buf, reduce_op)
     check(lib.cdlrm_agg_unpack(ctx, _vp(slot_list.data_ptr()), carr, _vp(buf.data_ptr()), 1, s))
 
 

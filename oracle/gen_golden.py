@@ -323,6 +323,87 @@ def gen_dlrm_tiny():
     np.savez_compressed(os.path.join(OUT, "dlrm_tiny.npz"), **out)
 
 
+TRAINER = dict(name="dlrm_trainer", ln_emb=[3000, 37, 800, 5, 12000], dim=16, cache_size=50, num_ways=4, batch=64,
+               lookahead=6, n_windows=4, lr_embeds=0.3, lr_mlp=0.1, seed=123, data_seed=23, dist="zipf", zipf_a=1.1)
+
+
+def gen_dlrm_trainer():
+    """The reference's Run loop body (main_no_ddp.py:393-415: window install every `lookahead`
+    steps, forward, BCE loss, backward, both SGD steps) on an undersized cache (drops, duplicate
+    claims, evictions, forward misses through the aux rows), with the victim generator re-armed
+    right before the first window (as run_trace does).  Pins tests/test_gpu_trainer.py: the
+    benchmarked Trainer / CUDA-graph path must reproduce the loss curve, the tags after every
+    window, the final dense parameters, cache rows and master rows."""
+    cfg = dict(TRAINER)
+    seed = cfg["seed"]
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    ln_emb = np.asarray(cfg["ln_emb"])
+    d, B, L = cfg["dim"], cfg["batch"], cfg["lookahead"]
+    T = len(ln_emb)
+    ln_bot = np.asarray([13, 32, d])
+    nf = T + 1
+    ln_top = np.asarray([d + nf * (nf - 1) // 2, 32, 1])
+    master = M.Embedding_Table_Group(d, ln_emb)
+    cg = M.Embedding_Table_Cache_Group(d, ln_emb, max_cache_size=cfg["cache_size"],
+                                       aux_table_size=B, num_ways=cfg["num_ways"])
+    for e in cg.emb_l:
+        e.weight.data.zero_()
+    np.random.seed(seed)                                 # Run re-seeds (main :335)
+    torch.manual_seed(seed)
+    dlrm = M.DLRM_Net(ln_bot, ln_top, arch_interaction_op="dot", arch_interaction_itself=False,
+                      sigmoid_bot=-1, sigmoid_top=ln_top.size - 2)
+    loss_fn = torch.nn.BCELoss(reduction="mean")
+    opt_m = torch.optim.SGD(dlrm.parameters(), lr=cfg["lr_mlp"])
+    opt_e = torch.optim.SGD(cg.parameters(), lr=cfg["lr_embeds"])
+    rank = CpuRank("cpu")
+    evq = queue.Queue()
+    ids = make_ids(cfg)
+    drng = np.random.default_rng(cfg["data_seed"] + 2)
+    nsteps = cfg["n_windows"] * L
+    X = np.log1p(drng.integers(0, 100, size=(nsteps, B, 13))).astype(np.float32)
+    Y = (drng.random((nsteps, B, 1)) < 0.25).astype(np.float32)
+    out = {"X": X, "Y": Y, "cfg_json": np.array(json.dumps(cfg)), "ln_bot": ln_bot, "ln_top": ln_top}
+    for i, p in enumerate(dlrm.parameters()):
+        out[f"mlp_init_{i}"] = p.detach().numpy().copy()
+    lS_o = torch.arange(B).reshape(1, -1).repeat(T, 1)
+    torch.manual_seed(seed)                              # victim stream starts here
+    losses, n_miss = [], []
+    step = 0
+    for w in range(cfg["n_windows"]):
+        win = torch.from_numpy(ids[:, w * L * B:(w + 1) * L * B])
+        rows, uniq, maps = C.Prefetcher.process_batch_slice(win, master)
+        R.CacheEmbeddings(rows, uniq, maps, cg, evq, rank)
+        ev = evq.get()
+        for k, (ix, emb) in enumerate(ev):
+            master.emb_l[k].weight.data[ix] = emb
+        out[f"w{w}_tags"] = np.concatenate([t.numpy().ravel() for t in cg.occupancy_tables])
+        out[f"w{w}_evict_len"] = np.asarray([e[0].numel() for e in ev], dtype=np.int64)
+        for b in range(L):
+            lS_i = win[:, b * B:(b + 1) * B]
+            ly, _ = cg(lS_o, lS_i, master, rank)
+            n_miss.append([cg.victim_cache_entries[k][0].numel() for k in range(T)])
+            Z = dlrm(torch.from_numpy(X[step]), ly)
+            E = loss_fn(Z, torch.from_numpy(Y[step]))
+            opt_m.zero_grad()
+            opt_e.zero_grad()
+            E.backward()
+            opt_e.step()
+            opt_m.step()
+            losses.append(E.item())
+            step += 1
+    out["losses"] = np.asarray(losses, dtype=np.float64)
+    out["n_miss"] = np.asarray(n_miss, dtype=np.int64)
+    for i, p in enumerate(dlrm.parameters()):
+        out[f"mlp_final_{i}"] = p.detach().numpy().copy()
+    for k in range(T):
+        out[f"final_weight_{k}"] = cg.emb_l[k].weight.data.numpy().copy()
+        out[f"final_master_{k}"] = master.emb_l[k].weight.data.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "dlrm_trainer.npz"), **out)
+    print("dlrm_trainer: misses/step", out["n_miss"].sum(1).tolist(), "evictions",
+          [out[f"w{w}_evict_len"].tolist() for w in range(cfg["n_windows"])])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gen_geometry()
@@ -334,9 +415,14 @@ def main():
         print(cfg["name"], "done",
               {k: res[k].tolist() for k in res if k.endswith("evict_len") or k.endswith("uniq_len")})
     gen_dlrm_tiny()
+    gen_dlrm_trainer()
     gen_aggregate()
     print("golden vectors written to", os.path.abspath(OUT))
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:          # e.g. `gen_golden.py gen_dlrm_trainer`: regenerate one fixture
+        for fn in sys.argv[1:]:
+            globals()[fn]()
+    else:
+        main()

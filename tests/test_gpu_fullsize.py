@@ -33,7 +33,24 @@ def _setup(ln_emb, d, B, L, ways, csz, seed, losers):
 
 @pytest.mark.parametrize("losers", [False, True])
 def test_terabyte_shape_steps_match_oracle(losers):
-    ln_emb, d, B, L, ways, csz, lr = [3, 36, 155, 5000, 400_000, 1_000_000], 128, 8192, 3, 16, 150000, 0.5
+    _steps_vs_oracle([3, 36, 155, 5000, 400_000, 1_000_000], 128, 8192, 3, 16, 150000, 0.5, losers)
+
+
+def test_kaggle_shape_steps_match_oracle():
+    """BASELINE.json configs[1]: 26 Kaggle tables (largest ones capped at 3 M rows so that the numpy oracle's
+    master copy stays small), dim 16, batch 2048, cache 150000 x 16 ways."""
+    from cdlrm_b200.synthetic import KAGGLE_ROWS
+    _steps_vs_oracle([min(n, 3_000_000) for n in KAGGLE_ROWS], 16, 2048, 3, 16, 150000, 0.8, True)
+
+
+@pytest.mark.parametrize("csz,ways", [(50000, 4), (600000, 8), (150000, 4), (300000, 16)])
+def test_cache_geometry_sweep_matches_oracle(csz, ways):
+    """BASELINE.json configs[3] geometries: num_sets 50021 / 600011 / 150001 / 300002 (the quirky non-prime) with
+    4 / 8 / 16 ways, Terabyte step size."""
+    _steps_vs_oracle([4, 155, 5000, 700_000, 2_500_000], 128, 8192, 2, ways, csz, 0.5, True)
+
+
+def _steps_vs_oracle(ln_emb, d, B, L, ways, csz, lr, losers):
     T = len(ln_emb)
     C, M, O, master, master_np, cg, planner, oc, gen = _setup(ln_emb, d, B, L, ways, csz, 11, losers)
     rng = np.random.default_rng(5)

@@ -103,3 +103,27 @@ def test_fast_variants_equal_reference_variants():
         a, sa, ma = O.forward_table(cache, k, np.arange(32), ids[k], master[k])
         b, sb, mb = O.forward_table_fast(cache, k, ids[k], master[k])
         assert np.array_equal(sa, sb) and ma == mb and np.array_equal(a, b)
+
+
+def test_trainer_golden_decisions_match_oracle():
+    """dlrm_trainer.npz (the reference's Run loop body end to end): the tag evolution and the
+    forward miss counts depend on the index stream and the victim generator only, so the oracle
+    must reproduce them without the MLPs."""
+    g = util.load_golden("dlrm_trainer.npz")
+    cfg = util.golden_cfg(g)
+    master = util.master_init(cfg)
+    T, B, L, d = len(cfg["ln_emb"]), cfg["batch"], cfg["lookahead"], cfg["dim"]
+    cache = O.OracleCache(d, cfg["ln_emb"], cfg["cache_size"], B, cfg["num_ways"])
+    gen = O.TorchCpuGenerator(cfg["seed"])
+    ids = util.make_ids(cfg)
+    off = np.arange(B, dtype=np.int64)
+    n_miss = []
+    for w in range(cfg["n_windows"]):
+        win = ids[:, w * L * B:(w + 1) * L * B]
+        ev, _plans, _uniq = O.install_window(cache, master, win, gen)
+        assert np.array_equal(np.concatenate([t.ravel() for t in cache.tags]), g[f"w{w}_tags"])
+        assert [len(e[0]) for e in ev] == g[f"w{w}_evict_len"].tolist()
+        for b in range(L):
+            _ly, _slots, nm = O.forward(cache, [off] * T, win[:, b * B:(b + 1) * B], master)
+            n_miss.append(nm)
+    assert np.array_equal(np.asarray(n_miss, dtype=np.int64), g["n_miss"])

@@ -182,6 +182,7 @@ class WindowPlanner:
         """Give the planner its own evolving copy of the tags so that it can run one or more
         windows ahead of the live tags (which are patched by ``install``)."""
         self.plan_tags = [t.clone() for t in self.cg.occupancy_tables]
+        self.cg._plan_tags = self.plan_tags     # kept bound across re-binds of the cache group (_ensure_ctx)
         check(lib.cdlrm_ctx_bind_plan_tags(self.ctx, _lib.ptr_array([t.data_ptr() for t in self.plan_tags])))
 
     def unique_ptr(self, k):

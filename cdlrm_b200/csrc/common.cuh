@@ -97,6 +97,10 @@ struct cdlrm_ctx {
 
 int cdlrm_sync_tabs(cdlrm_ctx* ctx, cudaStream_t s);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: opt `func` in for `bytes` on the current
+// device once per (function, device), thread-safe.  Returns cudaSuccess or the error of the attribute call.
+cudaError_t cdlrm_smem_optin(const void* func, int bytes);
+
 // ---- launch accounting / optional per-kernel event timing (see cdlrm_prof_* in the header) ----
 enum KernelId {
     K_PROBE = 0, K_GATHER, K_POOL, K_BWD_PLAN, K_BWD_SGD, K_BWD_SGD_MULTI, K_INT_FWD, K_INT_BWD,

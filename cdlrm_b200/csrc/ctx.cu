@@ -6,7 +6,26 @@
 
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
+
+cudaError_t cdlrm_smem_optin(const void* func, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> done;     // (function, device) -> bytes opted in
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(func, dev);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done[key] = bytes;
+    return e;
+}
 
 static thread_local char g_err[1024] = "";
 

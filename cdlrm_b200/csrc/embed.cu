@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(FWD_NT) fwd_fused_kernel(const TableDesc* __re
                                                             const int64_t* __restrict__ ids, int64_t ld_ids, int n_idx,
                                                             int32_t* __restrict__ slots, int64_t ld_slots,
                                                             uint32_t* __restrict__ missmap, int words,
-                                                            float* __restrict__ out, int64_t ld_out, int dim, int ways) {
+                                                            float* __restrict__ out, int64_t ld_out, int dim, int ways,
+                                                            uint32_t* __restrict__ flags) {
     pdl_enter();
     const int t = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -93,9 +94,13 @@ __global__ void __launch_bounds__(FWD_NT) fwd_fused_kernel(const TableDesc* __re
     const int64_t S = T.num_sets;
     const int j0 = w * 32, j = j0 + lane;
     const bool valid = j < n_idx;
-    const int64_t id = valid ? __ldg(ids + (int64_t)t * ld_ids + j) : 0;
-    const int64_t s = set_index(id, S);
-    const int way = probe_line<WAYS>(T.tags, s, id, ways);
+    int64_t id = valid ? __ldg(ids + (int64_t)t * ld_ids + j) : 0;
+    if ((uint64_t)id >= (uint64_t)T.n_rows) {     // IndexError in the reference (master.weight[missing], :176)
+        atomicOr(flags, 2u);                      // sticky; K2 gives the position a zero row and slot -1
+        id = -1;                                  // matches no live tag that could be read as a hit of a real id
+    }
+    const int64_t s = set_index(id < 0 ? 0 : id, S);
+    const int way = id < 0 ? -1 : probe_line<WAYS>(T.tags, s, id, ways);
     const bool miss = valid && way < 0;
     const int32_t slot = (valid && way >= 0) ? (int32_t)(S * way + s) : -1;
     if (valid) slots[(int64_t)t * ld_slots + j] = slot;
@@ -195,11 +200,18 @@ __global__ void __launch_bounds__(MISS_NT) fwd_miss_kernel(const TableDesc* __re
         const float* src_l = nullptr;
         int64_t aux_l = -1;
         if (mine) {
-            if (ord >= aux_rows) {
-                atomicOr(flags, 1u);                 // IndexError in the reference
+            const int64_t id = __ldg(ids + (int64_t)t * ld_ids + j);
+            const bool bad_id = (uint64_t)id >= (uint64_t)T.n_rows;       // flag 2 was raised by K1
+            if (ord >= aux_rows || bad_id) {
+                // IndexError in the reference.  Here: sticky flag (check_device_flags raises it on the host),
+                // the position keeps slot -1 (skipped by the pooling and by the backward) and pools a zero row.
+                if (!bad_id) atomicOr(flags, 1u);
+                if (COPY) {
+                    float* orow = out + (int64_t)t * ld_out + (int64_t)j * dim;
+                    for (int c = 0; c < dim; ++c) orow[c] = 0.f;
+                }
             } else {
                 aux_l = aux_base + ord;
-                const int64_t id = __ldg(ids + (int64_t)t * ld_ids + j);
                 int64_t lo = 0, hi = l_n;              // first index with l_ids[idx] >= id
                 while (lo < hi) {
                     const int64_t mid = (lo + hi) >> 1;
@@ -267,7 +279,7 @@ __global__ void __launch_bounds__(256) pool_kernel(const TableDesc* __restrict__
         V acc;
         vzero(acc);
         for (int64_t j = lo; j < hi; ++j)
-            acc = vadd(acc, reinterpret_cast<const V*>(weight + (int64_t)tsl[j] * dim)[c]);
+            if (tsl[j] >= 0) acc = vadd(acc, reinterpret_cast<const V*>(weight + (int64_t)tsl[j] * dim)[c]);
         reinterpret_cast<V*>(out + (int64_t)t * ld_out + (int64_t)b * dim)[c] = acc;
     }
 }
@@ -375,12 +387,15 @@ __global__ void __launch_bounds__(PLAN_NT, 1) bwd_plan_kernel(const TableDesc* _
     const int t = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t* tsl = slots + (int64_t)t * ld_slots + j0;
+    const int64_t rows = tabs[tb + t].cache_rows;
     for (int i = tid; i < n; i += PLAN_NT) {
-        keyA[i] = (uint32_t)tsl[i];
+        // unresolved positions (slot -1: aux overflow / id out of range, flagged by the forward) sort behind
+        // every real slot under the key `rows`; the apply kernel skips them
+        const uint32_t k = (uint32_t)tsl[i];
+        keyA[i] = k < (uint32_t)rows ? k : (uint32_t)rows;
         valA[i] = (uint16_t)i;
     }
-    const int64_t rows = tabs[tb + t].cache_rows;
-    const int bits = 64 - __clzll((unsigned long long)(rows > 1 ? rows - 1 : 1));
+    const int bits = 64 - __clzll((unsigned long long)(rows > 1 ? rows : 1));   // the key `rows` must be representable
     const int passes = (bits + 7) / 8;
     const int per_warp = (((n + 31) / 32) + 31) & ~31;  // keys per warp, multiple of 32
     const int rounds = per_warp / 32;                   // <= PLAN_MAX_ROUNDS
@@ -495,8 +510,9 @@ __global__ void __launch_bounds__(APPLY_NT, 2) bwd_sgd_apply_kernel(const TableD
     const float* gbase = d_out + (int64_t)t * ld_dout;
     const int64_t obase = (int64_t)t * n_idx + j0;
     const uint32_t* keys = pv.sorted_key + obase;
-    const bool valid_l = e0 + lane < n;
-    const uint32_t key_l = valid_l ? keys[e0 + lane] : 0xffffffffu;
+    const uint32_t nkeys = (uint32_t)T.cache_rows;       // keys >= nkeys: unresolved positions, at the end of the run
+    const uint32_t key_l = e0 + lane < n ? keys[e0 + lane] : 0xffffffffu;
+    const bool valid_l = key_l < nkeys;
     int pos_l = valid_l ? pv.sorted_pos[obase + e0 + lane] : 0;
     if (bag_ids && valid_l) pos_l = bag_ids[(int64_t)t * ld_bag + pos_l];
     // neighbours across the warp's range
@@ -539,7 +555,7 @@ __global__ void __launch_bounds__(APPLY_NT, 2) bwd_sgd_apply_kernel(const TableD
             key[q] = __shfl_sync(0xffffffffu, key_l, src);
             pos[q] = __shfl_sync(0xffffffffu, pos_l, src);
             fl[q] = __shfl_sync(0xffffffffu, flags_l, src);
-            if (e0 + src >= n) fl[q] = -1;                            // past the end of the run
+            if (e0 + src >= n || key[q] >= nkeys) fl[q] = -1;         // past the end of the run / unresolved
         }
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
@@ -580,6 +596,7 @@ __global__ void __launch_bounds__(256) bwd_sgd_kernel(const TableDesc* __restric
     int p0 = pv.sorted_pos[obase + e];
     if (bag_ids) p0 = bag_ids[(int64_t)t * ld_bag + p0];
     const TableDesc& T = tabs[tb + t];
+    if (slot >= (uint32_t)T.cache_rows) return;          // unresolved position (see bwd_plan_kernel)
     const float* g = d_out + (int64_t)t * ld_dout + (int64_t)p0 * row_stride;
     float* wrow = T.weight + (int64_t)slot * dim;
     const int cpr = dim / VEC;
@@ -653,7 +670,7 @@ extern "C" int cdlrm_embed_fwd(cdlrm_ctx* c, int tb, int tc, const int64_t* ids,
     const int words = (n_idx + 31) / 32;
     dim3 grid((words + FWD_NT / 32 - 1) / (FWD_NT / 32), tc);
     const int wsel = !tags16 ? 0 : (c->ways == 16 ? 16 : c->ways == 8 ? 8 : c->ways == 4 ? 4 : c->ways == 2 ? 2 : 0);
-#define LAUNCH_FUSED(WW, GG, CP) LAUNCH_PDL(K_PROBE, s, (fwd_fused_kernel<WW, GG, CP>), grid, FWD_NT, 0, c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_missmap, words, out, ld_out, c->dim, c->ways)
+#define LAUNCH_FUSED(WW, GG, CP) LAUNCH_PDL(K_PROBE, s, (fwd_fused_kernel<WW, GG, CP>), grid, FWD_NT, 0, c->d_tabs, tb, ids, ld_ids, n_idx, slots, ld_slots, c->d_missmap, words, out, ld_out, c->dim, c->ways, c->d_flags)
 #define FUSED_G(WW)                                             \
     if (!copy) { LAUNCH_FUSED(WW, 32, false); }                 \
     else switch (G) {                                           \
@@ -717,12 +734,8 @@ extern "C" int cdlrm_embed_bwd_plan(cdlrm_ctx* c, int tb, int tc, const int32_t*
     if (rc) return rc;
     PlanView pv = plan_view(plan, tc, n_idx);
     const int nsub = plan_nsub(n_idx);
-    static bool attr_done = false;
     const int max_smem = CDLRM_SORT_MAX * 12 + 8192 * 2 + 64 * 4;
-    if (!attr_done) {
-        CU_CHECK(cudaFuncSetAttribute(bwd_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_done = true;
-    }
+    CU_CHECK(cdlrm_smem_optin((const void*)bwd_plan_kernel, max_smem));
     for (int sub = 0; sub < nsub; ++sub) {
         const int j0 = sub * CDLRM_SORT_MAX;
         const int n = n_idx - j0 < CDLRM_SORT_MAX ? n_idx - j0 : CDLRM_SORT_MAX;

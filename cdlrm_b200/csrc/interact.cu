@@ -755,13 +755,11 @@ bool launch_fwd_pipe(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t 
         int dev = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-        if (cudaFuncSetAttribute(interact_fwd_pipe_kernel<F, STAGES, WARPS, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 P::SMEM_BYTES) != cudaSuccess) {
-            cudaGetLastError();
-            sms = -1;
-        }
     }
-    if (sms < 0) return false;
+    if (cdlrm_smem_optin((const void*)interact_fwd_pipe_kernel<F, STAGES, WARPS, PB>, P::SMEM_BYTES) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
     const int need = (B + WARPS - 1) / WARPS;
     const int grid = need < sms * P::CTAS_PER_SM ? need : sms * P::CTAS_PER_SM;      // persistent warps
     LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_pipe_kernel<F, STAGES, WARPS, PB>), grid, 32 * WARPS, P::SMEM_BYTES, fp, rs, B, out, ld_out);
@@ -777,12 +775,11 @@ bool launch_bwd_pipe(const FeatPtrs& fp, int64_t rs, int B, const float* d_out, 
         int dev = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-        if (cudaFuncSetAttribute(interact_bwd_pipe_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES) != cudaSuccess) {
-            cudaGetLastError();
-            sms = -1;
-        }
     }
-    if (sms < 0) return false;
+    if (cdlrm_smem_optin((const void*)interact_bwd_pipe_kernel<F>, P::SMEM_BYTES) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
     const int items = (B + pipe::SPB - 1) / pipe::SPB;
     const int grid = items < sms * 3 ? items : sms * 3;          // persistent: three CTAs per SM (63 KB of smem each)
     LAUNCH_PDL(K_INT_BWD, s, (interact_bwd_pipe_kernel<F>), grid, 128, P::SMEM_BYTES, fp, rs, B, d_out, ld_dout, d_feat, ld_dfeat);

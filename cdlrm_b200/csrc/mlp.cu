@@ -820,9 +820,9 @@ int launch_gemm(const float* a_hi, const float* a_lo, int64_t lda, const float* 
         int dev = 0, n = 0;
         CU_CHECK(cudaGetDevice(&dev));
         CU_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-        CU_CHECK(cudaFuncSetAttribute(gemm3x_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         g_num_sms = n > 0 ? n : 148;
     }
+    CU_CHECK(cdlrm_smem_optin((const void*)gemm3x_tf32_kernel, GEMM_SMEM));
     const int64_t tiles_m = (ep.M + BM - 1) / BM, tiles_n = (ep.N + BN - 1) / BN;
     if (splits == 0) splits = (int)(g_num_sms / (tiles_m * tiles_n));      // split-K sized to one round of the persistent grid
     Maps mp;

@@ -375,6 +375,10 @@ class Trainer:
         rec = self._plan_q.get()
         if isinstance(rec, Exception):
             raise rec
+        if self._installed is not None:
+            # conditions the reference raises on the host (IndexError: aux overflow, id outside its table,
+            # model_no_ddp.py:176-179) are sticky device flags here: surface them once per window
+            self.cache_group.check_device_flags()
         if self.world > 1:
             broadcast_and_aggregate(self.cache_group, None, self.rank, self.args.table_agg_op)
             self.steps_since_agg = 0

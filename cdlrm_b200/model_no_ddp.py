@@ -296,9 +296,18 @@ class Embedding_Table_Cache_Group(nn.Module):
         if key != self._bound_key:
             check(lib.cdlrm_ctx_bind_cache(self._ctx, _lib.ptr_array([e.weight.data_ptr() for e in self.emb_l]),
                                            _lib.ptr_array([t.data_ptr() for t in self.occupancy_tables])))
-            check(lib.cdlrm_ctx_bind_plan_tags(self._ctx, _lib.ptr_array([t.data_ptr() for t in self.occupancy_tables])))
+            # a planner running ahead of the live tags owns a separate copy (WindowPlanner.enable_lookahead_tags):
+            # a re-bind (module moved, state dict assigned) must not point the planner back at the live tags
+            ptags = getattr(self, "_plan_tags", None)
+            if ptags is not None:
+                ptags[:] = [t if t.device == dev else t.to(dev) for t in ptags]
+            check(lib.cdlrm_ctx_bind_plan_tags(self._ctx, _lib.ptr_array(
+                [t.data_ptr() for t in (ptags if ptags is not None else self.occupancy_tables)])))
             words = [(r + 31) // 32 for r in self._cache_rows]
-            self._dirty = torch.zeros(sum(words), dtype=torch.int32, device=dev)
+            if self._dirty is None or self._dirty.numel() != sum(words):
+                self._dirty = torch.zeros(sum(words), dtype=torch.int32, device=dev)
+            elif self._dirty.device != dev:      # pending dirty bits survive the move (rows touched since the last aggregation)
+                self._dirty = self._dirty.to(dev)
             offs = np.concatenate([[0], np.cumsum(words)[:-1]])
             check(lib.cdlrm_ctx_bind_dirty(self._ctx, _lib.ptr_array(
                 [self._dirty.data_ptr() + 4 * int(o) for o in offs])))

@@ -274,7 +274,7 @@ def gpu_run(a, wl, ln_emb):
     torch.cuda.set_device(dev)
     # training runs on a high-priority stream: the look-ahead planner's kernels (side stream, default
     # priority) then only take the SM slots the training step leaves free
-    torch.cuda.set_stream(torch.cuda.Stream(dev, priority=-1))
+    torch.cuda.set_stream(_lib.new_stream(dev, priority=-1))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")

@@ -69,6 +69,8 @@ SIGNATURES = {
     "cdlrm_agg_collect": (C.c_int, [vp, vp, vp, vp, vp]),
     "cdlrm_agg_pack": (C.c_int, [vp, vp, c_i64p, C.c_float, vp, vp]),
     "cdlrm_agg_unpack": (C.c_int, [vp, vp, c_i64p, vp, C.c_int, vp]),
+    "cdlrm_stream_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp)]),
+    "cdlrm_stream_destroy": (C.c_int, [C.c_int, vp]),
     "cdlrm_set_pdl": (C.c_int, [C.c_int]),
     "cdlrm_bce_mean": (C.c_int, [C.c_int, vp, C.c_int64, vp, C.c_int64, C.c_int32, vp, vp, vp]),
     "cdlrm_prof_enable": (C.c_int, [C.c_int]),
@@ -131,3 +133,21 @@ def i64_array(vals):
     for i, v in enumerate(vals):
         arr[i] = int(v)
     return arr
+
+
+def new_stream(device, priority=0):
+    """A torch.cuda.ExternalStream over a stream of the library's own (cdlrm_stream_create): never one of
+    PyTorch's pooled streams, so it cannot alias another torch.cuda.Stream of the process (in particular
+    the stream a training-step CUDA graph is captured on).  Destroyed with the returned object."""
+    import weakref
+
+    import torch
+    dev = torch.device(device)
+    h = vp()
+    check(lib.cdlrm_stream_create(dev.index, int(priority), C.byref(h)))
+    st = torch.cuda.ExternalStream(h.value, device=dev)
+    try:
+        weakref.finalize(st, lib.cdlrm_stream_destroy, dev.index, vp(h.value))
+    except TypeError:       # stream objects without weak-reference support: the handle lives until exit
+        pass
+    return st

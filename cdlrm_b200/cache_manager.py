@@ -559,9 +559,41 @@ class Prefetcher(threading.Thread):
             if acc:
                 yield torch.cat(acc, dim=1)
 
-    def run(self):
+    @property
+    def fifo_payload(self):
+        """What ``run`` puts on ``batch_fifo`` per window.  "tuples" (default -- the reference's contract,
+        cache_manager.py:102-104): ``process_batch_slice``'s ``(rows, uniq, maps)``, consumed by
+        ``load_caches_and_broadcast`` / ``CacheEmbeddings``.  "ids": the raw window ids [T, n] -- all the
+        GPU-resident ``WindowPlanner`` needs (it finds the unique ids itself and reads the master rows at
+        install time), without the per-window gather of every unique row.  Chosen by ``args.fifo_payload``
+        (flag ``--fifo-payload`` of this package's main); the consumers accept either."""
+        return getattr(self.args, "fifo_payload", None) or "tuples"
+
+    def payloads(self):
+        """Generator of the FIFO entries in training order (what ``run`` puts)."""
+        mode = self.fifo_payload
+        if mode not in ("tuples", "ids"):
+            raise ValueError("fifo_payload must be 'tuples' or 'ids', got %r" % (mode,))
         for win in self.windows():
-            self.batch_fifo.put(win)
-        self.batch_fifo.put(None)
+            if mode == "ids":
+                yield win
+            else:
+                a = Prefetcher.process_batch_slice(win, self.emb_tables_cpu)
+                yield (a[0], a[1], a[2])                                   # cache_manager.py:102-104
+
+    def run(self):
+        """cache_manager.py:66-115: start the eviction manager, then feed ``batch_fifo`` window by window (the
+        bounded queue is the back-pressure, as in the reference), then wait for ``finish_event``."""
+        ev = threading.Thread(target=Prefetcher.eviction_manager, daemon=True,
+                              args=(self.emb_tables_cpu, self.eviction_fifo, self.args.average_on_writeback,
+                                    self.args.main_start_core + 2, self.args.eviction_fifo_timeout))
+        if self.eviction_fifo is not None:
+            ev.start()
+        try:
+            for item in self.payloads():
+                self.batch_fifo.put(item)
+        except Exception as e:          # surfaced by the consumer instead of a silent hang on an empty queue
+            self.batch_fifo.put(e)
+            raise
         if self.finish_event is not None:
             self.finish_event.wait()

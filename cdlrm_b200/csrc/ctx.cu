@@ -171,6 +171,24 @@ extern "C" int cdlrm_ctx_bind_dirty(cdlrm_ctx* c, uint32_t* const* d) {
     return CDLRM_OK;
 }
 
+extern "C" int cdlrm_stream_create(int device, int priority, cdlrm_stream* out) {
+    ARG_CHECK(out);
+    CU_CHECK(cudaSetDevice(device));
+    int lo = 0, hi = 0;                     // numerically lowest = highest priority
+    CU_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t s = nullptr;
+    CU_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, priority < 0 ? hi : lo));
+    *out = (cdlrm_stream)s;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_stream_destroy(int device, cdlrm_stream stream) {
+    if (!stream) return CDLRM_OK;
+    CU_CHECK(cudaSetDevice(device));
+    CU_CHECK(cudaStreamDestroy((cudaStream_t)stream));
+    return CDLRM_OK;
+}
+
 int cdlrm_sync_tabs(cdlrm_ctx* c, cudaStream_t s) {
     if (!c->tabs_dirty) return CDLRM_OK;
     // Synchronous copy on purpose: bindings change only at set-up time, and a

@@ -57,8 +57,16 @@ _FLAGS = [
 ]
 # additions of this implementation (not in the reference)
 _EXTRA_FLAGS = [
-    ("strict-reference", "flag", False),   # reproduce rank-0 install + overwrite of the other ranks
-    ("synthetic-dist", str, "zipf"), ("synthetic-zipf-a", float, 1.05), ("synthetic-steps", int, 0),
+    # Run executes the reference's literal loop: rank-0 CacheEmbeddings + full-cache broadcast at every window
+    # (load_caches_and_broadcast), explicit slot windows for broadcast_and_aggregate, torch's global CPU
+    # generator as the victim stream (consumed in the reference's order, so the cache decisions are those of the
+    # reference program run with the same seed), no look-ahead overlap, no CUDA graph
+    ("strict-reference", "flag", False),
+    # index distribution of --data-generation synthetic|random (cdlrm_b200/synthetic.py)
+    ("synthetic-dist", str, "zipf"), ("synthetic-zipf-a", float, 1.05),
+    # what Prefetcher.run puts on batch_fifo: "tuples" = the reference's (rows, uniq, maps); "ids" = raw window ids
+    ("fifo-payload", str, ""),
+    ("no-cuda-graph", "flag", False),
 ]
 
 
@@ -252,13 +260,30 @@ def share_occupancy_tables(cache_group, occupancy_tables_fifos, rank):
     cache_group._ensure_ctx(None)
 
 
+def _fifo_get(batch_fifo):
+    item = batch_fifo.get()
+    if isinstance(item, Exception):          # the Prefetcher thread died: say so instead of hanging
+        raise item
+    return item
+
+
 @torch.no_grad()
 def load_caches_and_broadcast(cache_group, batch_fifo, eviction_fifo, rank):
-    """main_no_ddp.py:309-321, reference semantics: rank 0 installs the window, then every
-    table's full cache weight (and, here, the HBM tags) is broadcast from rank 0."""
+    """main_no_ddp.py:309-321, reference semantics: rank 0 pops the next window off ``batch_fifo`` and installs
+    it (``CacheEmbeddings``), then every table's full cache weight (and, here, the HBM tags, which the reference
+    shares through host memory, :295-306) is broadcast from rank 0.  The FIFO entry is the reference's
+    ``(rows, uniq, maps)`` tuple (cache_manager.py:102-104) or a raw window id tensor [T, n], which is put
+    through ``Prefetcher.process_batch_slice`` first."""
     dist_req_objs = []
     if rank == 0:
-        cached_entries_per_table, lists_of_unique_idxs, unique_indices_maps = batch_fifo.get()
+        item = _fifo_get(batch_fifo)
+        if isinstance(item, torch.Tensor):
+            master = getattr(cache_group, "_emb_tables", lambda: None)()
+            if master is None:
+                raise _lib.CdlrmError("a raw id window needs the master tables: call cache_group(...) or "
+                                      "cache_group._ensure_ctx(emb_tables) once before the first install")
+            item = Prefetcher.process_batch_slice(item, master)
+        cached_entries_per_table, lists_of_unique_idxs, unique_indices_maps = item
         CacheEmbeddings(cached_entries_per_table, lists_of_unique_idxs, unique_indices_maps, cache_group,
                         eviction_fifo, rank)
     if _world() > 1:
@@ -289,8 +314,13 @@ class Trainer:
     touched rows are averaged first, so rank 0 writes back the cross-rank mean.
     """
 
-    def __init__(self, args, m_spa, ln_emb, ln_bot, ln_top, emb_tables, rank=0, world=1, device=None):
+    def __init__(self, args, m_spa, ln_emb, ln_bot, ln_top, emb_tables, rank=0, world=1, device=None,
+                 strict_reference=False):
+        """``strict_reference``: objects are built in the reference's order with the reference's consumption
+        of the global generators (Run, main_no_ddp.py:335-376), and no look-ahead planner is created -- windows
+        are installed with ``load_caches_and_broadcast`` by the caller."""
         self.args = args
+        self.strict = bool(strict_reference)
         self.rank, self.world = rank, world
         self.dev = device if device is not None else torch.device("cuda", rank)
         torch.cuda.set_device(self.dev)
@@ -301,7 +331,8 @@ class Trainer:
         self.emb_tables = emb_tables
         self.cache_group = Embedding_Table_Cache_Group(m_spa, ln_emb, max_cache_size=args.cache_size,
                                                        aux_table_size=args.mini_batch_size,
-                                                       num_ways=args.num_ways, device=self.dev)
+                                                       num_ways=args.num_ways, device=self.dev,
+                                                       init="reference" if self.strict else "zeros")
         self.dlrm = DLRM_Net(ln_bot, ln_top, arch_interaction_op=args.arch_interaction_op,
                              arch_interaction_itself=args.arch_interaction_itself,
                              sync_dense_params=args.sync_dense_params, sigmoid_bot=-1,
@@ -323,26 +354,39 @@ class Trainer:
         self.optimizer_embeds = torch.optim.SGD(self.cache_group.parameters(), lr=args.lr_embeds)   # :376
         self.cache_group._ensure_ctx(emb_tables)
         self.cache_group.assume_one_id_per_bag = True              # Criteo batches (:390)
-        self.side = torch.cuda.Stream(self.dev)
+        # streams of the library's own: a pooled torch.cuda.Stream may alias the stream a graph is captured on
+        self.side = _lib.new_stream(self.dev)
+        self._capture_stream = _lib.new_stream(self.dev, priority=-1)
         # the lookup runs on its own stream beside the bottom MLP (joined before the interaction)
-        self.cache_group.forward_stream = torch.cuda.Stream(self.dev, priority=-1)
+        self.cache_group.forward_stream = _lib.new_stream(self.dev, priority=-1)
         self.dlrm.pre_interact = self.cache_group.join_forward
-        self.planner = WindowPlanner(self.cache_group, emb_tables, args.lookahead * args.mini_batch_size,
-                                     rng=VictimRngDevice(args.numpy_rand_seed, self.dev), stream=self.side,
-                                     lookahead_tags=True)
-        self.planner.collect_losers = True     # un-cached ids of a window are served from an HBM loser store
+        self.planner = None
+        if not self.strict:
+            self.planner = WindowPlanner(self.cache_group, emb_tables, args.lookahead * args.mini_batch_size,
+                                         rng=VictimRngDevice(args.numpy_rand_seed, self.dev), stream=self.side,
+                                         lookahead_tags=True)
+            self.planner.collect_losers = True     # un-cached ids of a window are served from an HBM loser store
         self._host_group = dist.new_group(backend="gloo") if world > 1 else None   # plan-thread barrier
         self._installed = None
         self._plan_q = queue.Queue()
         self._plan_thread = None
         self.steps_since_agg = 0
         self.caching_overhead = []
+        self.keep_losses = False         # tests: keep every step's loss tensor (no sync) in loss_history
+        self.loss_history = []
 
     # -- look-ahead -------------------------------------------------------------------------
     def submit_window(self, win_ids):
-        """Start planning a window (int64 [T, n] device tensor of the GLOBAL batch ids) in the
-        background; windows must be submitted in training order."""
+        """Start planning a window in the background; windows must be submitted in training order.
+        ``win_ids``: int64 [T, n] tensor of the GLOBAL batch ids of the window, or the reference's FIFO entry
+        ``(rows, uniq, maps)`` (cache_manager.py:102-104), of which the ascending unique id lists are what the
+        plan needs (the rows are read from the master at install time: sequential schedule)."""
         import threading
+        uniq_lists = None
+        if isinstance(win_ids, (tuple, list)):
+            uniq_lists = [u.to(self.dev, non_blocking=True) for u in win_ids[1]]
+        else:
+            win_ids = win_ids.to(self.dev, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))   # ids produced on the current stream are ready
         prev = self._plan_thread
@@ -353,7 +397,8 @@ class Trainer:
             torch.cuda.set_device(self.dev)
             self.side.wait_event(ev)
             try:
-                rec = self.planner.plan(win_ids=win_ids)
+                rec = (self.planner.plan(uniq_lists=uniq_lists) if uniq_lists is not None
+                       else self.planner.plan(win_ids=win_ids))
                 if self.world > 1:
                     # the prefetch below reads master rows: rank 0's write-back of the previous
                     # boundary (asynchronous, on its planner stream) must have landed first
@@ -423,8 +468,11 @@ class Trainer:
     def capture_graph(self, X, lS_o, lS_i, T):
         """Capture one whole training step (forward, backward, both optimizers, the MLP-grad
         all-reduce) into a CUDA graph.  The captured step is NOT executed by the capture; the
-        caller replays it through ``step``.  Call while no window plan is running."""
+        caller replays it through ``step``.  A look-ahead plan running on the side stream is waited
+        for first: its stream waits, allocations and frees may not interleave with a capture."""
         dev = self.dev
+        if self._plan_thread is not None:
+            self._plan_thread.join()
         self._g_in = (torch.empty_like(X, device=dev), torch.empty(tuple(lS_i.shape), dtype=torch.int64, device=dev),
                       torch.empty_like(T, device=dev))
         self._g_lso = lS_o
@@ -433,7 +481,7 @@ class Trainer:
         torch.cuda.synchronize(dev)
         self._graph = torch.cuda.CUDAGraph()
         n0 = lib.cdlrm_prof_launches(0)
-        with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
+        with torch.cuda.graph(self._graph, stream=self._capture_stream, capture_error_mode="thread_local"):
             self._g_out = self._step_eager(self._g_in[0], lS_o, self._g_in[1], self._g_in[2])
         self.graph_launches = int(lib.cdlrm_prof_launches(0) - n0)   # library kernels per replay
         return self._graph
@@ -448,57 +496,169 @@ class Trainer:
             return self._g_out
         return self._step_eager(X, lS_o, lS_i, T)
 
+    def step_reference(self, X, lS_o, lS_i, T):
+        """The reference's step, call for call (main_no_ddp.py:401-415); returns (E, Z, cache_group_idxs)."""
+        lookups, cache_group_idxs = self.cache_group(lS_o, lS_i, self.emb_tables, self.dev.index)
+        Z = self.dlrm(X, lookups)
+        E = loss_fn_wrap(Z, T, self.loss_fn, self.args, self.loss_ws)
+        self.optimizer_mlps.zero_grad()
+        self.optimizer_embeds.zero_grad()
+        E.backward()
+        if self.flat:
+            work = None
+            if self.world > 1:
+                gw = self.dlrm.flat_grads[:self.dlrm.flat_weight_elems]
+                gw /= self.world
+                work = dist.all_reduce(gw, async_op=True)
+            self.optimizer_embeds.step()
+            if work is not None:
+                work.wait()
+            self.dlrm.flat_sgd_step(self.optimizer_mlps.param_groups[0]["lr"])
+        else:
+            reqs = aggregate_gradients(self.dlrm)
+            self.optimizer_embeds.step()
+            wait_wrap(reqs)
+            self.optimizer_mlps.step()
+        return E, Z, cache_group_idxs
+
+    def finish(self):
+        """Wait for the look-ahead thread and the last asynchronous write-back; raise pending device flags."""
+        if self._plan_thread is not None:
+            self._plan_thread.join()
+        if self._installed is not None and self._installed.wb_done is not None:
+            self._installed.wb_done.synchronize()
+        torch.cuda.synchronize(self.dev)
+        self.cache_group.check_device_flags()
+
     def maybe_aggregate(self, j):
         if self.world > 1 and j > 0 and j % self.args.table_agg_freq == 0:     # :418-420
             broadcast_and_aggregate(self.cache_group, None, self.rank, self.args.table_agg_op)
             self.steps_since_agg = 0
 
 
+def _bcast_fifo_entry(item, rank, dev):
+    """One shared ``batch_fifo`` read by rank 0 only (the reference's wiring, main_no_ddp.py:624,638-643): rank 0
+    ships the window to the other ranks, which need it to run the same deterministic plan.  Raw id windows go as
+    one int64 [T, n] tensor, ``(rows, uniq, maps)`` tuples as their unique-id lists (padded to one tensor)."""
+    hdr = [None]
+    if rank == 0:
+        if isinstance(item, torch.Tensor):
+            hdr[0] = ("ids", tuple(item.shape))
+        else:
+            hdr[0] = ("uniq", [int(u.numel()) for u in item[1]])
+    dist.broadcast_object_list(hdr, src=0)
+    kind, meta = hdr[0]
+    if kind == "ids":
+        t = item.to(dev) if rank == 0 else torch.empty(meta, dtype=torch.int64, device=dev)
+        dist.broadcast(t, src=0)
+        return t
+    ld = max(max(meta), 1)
+    buf = torch.zeros(len(meta), ld, dtype=torch.int64, device=dev)
+    if rank == 0:
+        for k, u in enumerate(item[1]):
+            buf[k, :meta[k]].copy_(u)
+    dist.broadcast(buf, src=0)
+    return (None, [buf[k, :meta[k]] for k in range(len(meta))], None)
+
+
+def slice_batch(rank, local_batch_size, X, lS_o, lS_i, T):
+    """main_no_ddp.py:388-391: rank r trains on samples [r*lb, (r+1)*lb) of the global batch every rank loads;
+    the offsets are cut to the first lb columns, which assumes one id per bag (P = 1, Criteo)."""
+    lo, hi = rank * local_batch_size, (rank + 1) * local_batch_size
+    return X[lo:hi, :], lS_o[:, :local_batch_size], lS_i[:, lo:hi], T[lo:hi, :]
+
+
 def Run(rank, m_spa, ln_emb, ln_bot, ln_top, train_ld, test_ld, batch_fifo, eviction_fifo, occupancy_tables_fifos,
         emb_tables, args):
-    """main_no_ddp.py:324-502.  ``batch_fifo`` carries raw window id tensors [T, n] in training
-    order (what this package's ``Prefetcher.run`` produces)."""
+    """main_no_ddp.py:324-502.  ``batch_fifo`` carries one entry per window in training order: the reference's
+    ``(rows, uniq, maps)`` tuples or raw window id tensors [T, n] (``Prefetcher.fifo_payload``).
+
+    Default: every rank plans the window itself one window ahead on a side stream (``Trainer``), the step is a
+    CUDA graph, metrics are read every ``print_freq`` steps only.  With one ``batch_fifo`` shared by the ranks
+    (the reference's wiring) rank 0 reads it and ships the window to the others; ``args.fifo_per_rank`` (set by
+    this package's ``__main__``, where every rank runs its own Prefetcher on the deterministic loader) makes
+    every rank read its own.
+
+    ``--strict-reference``: the reference's literal loop (:393-425) on the same-named functions --
+    ``load_caches_and_broadcast`` + ``wait_wrap`` at every window, ``cache_group(...)``, ``dlrm(...)``,
+    ``aggregate_gradients``, both optimizers, ``broadcast_and_aggregate`` on explicit slot windows."""
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", str(args.master_port))
     if args.world_size > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", rank=rank, world_size=args.world_size)
-    tr = Trainer(args, m_spa, ln_emb, ln_bot, ln_top, emb_tables, rank=rank, world=args.world_size)
-    dev, lb = tr.dev, tr.local_batch
+    strict = bool(getattr(args, "strict_reference", False))
+    tr = Trainer(args, m_spa, ln_emb, ln_bot, ln_top, emb_tables, rank=rank, world=args.world_size,
+                 strict_reference=strict)
+    dev, lb, L = tr.dev, tr.local_batch, args.lookahead
     # training on a high-priority stream: the look-ahead planner (side stream, default priority) only
     # takes the SM slots the training step leaves free
-    torch.cuda.set_stream(torch.cuda.Stream(dev, priority=-1))
+    torch.cuda.set_stream(_lib.new_stream(dev, priority=-1))
     share_occupancy_tables(tr.cache_group, occupancy_tables_fifos, rank)
+    shared_fifo = args.world_size > 1 and not getattr(args, "fifo_per_rank", False)
+    n_windows = args.nepochs * math.ceil(len(train_ld) / L)
+    popped = 0
+
+    def next_entry():
+        nonlocal popped
+        if popped >= n_windows:
+            return None
+        popped += 1
+        item = _fifo_get(batch_fifo) if (rank == 0 or not shared_fifo) else None
+        return _bcast_fifo_entry(item, rank, dev) if shared_fifo else item
+
+    use_graph = not strict and not getattr(args, "no_cuda_graph", False)
     total_time = total_loss = total_accu = 0.0
     total_iter = total_samp = 0
-    first = batch_fifo.get()
-    if first is not None:
-        tr.submit_window(first.to(dev, non_blocking=True))
+    idxs_window = []
+    if not strict:
+        tr.submit_window(next_entry())
+    step_no = 0
     for epoch in range(args.nepochs):
         for j, (X, lS_o, lS_i, T) in enumerate(train_ld):
-            X = X[rank * lb:(rank + 1) * lb, :].to(dev, non_blocking=True)          # :388-391
-            lS_i = lS_i[:, rank * lb:(rank + 1) * lb].to(dev, non_blocking=True)
-            lS_o = lS_o[:, :lb]
-            T = T[rank * lb:(rank + 1) * lb, :].to(dev, non_blocking=True)
-            if j % args.lookahead == 0:
-                tr.install_window()
-                nxt = batch_fifo.get()
-                if nxt is not None:
-                    tr.submit_window(nxt.to(dev, non_blocking=True))
+            X, lS_o, lS_i, T = slice_batch(rank, lb, X, lS_o, lS_i, T)               # :388-391
+            X, lS_i, T = (t.to(dev, non_blocking=True) for t in (X, lS_i, T))
+            if j % L == 0:                                                           # :393-399
+                t0 = time.perf_counter()
+                if strict:
+                    popped += 1
+                    wait_wrap(load_caches_and_broadcast(tr.cache_group, batch_fifo, eviction_fifo, rank))
+                    tr.caching_overhead.append(time.perf_counter() - t0)
+                else:
+                    tr.install_window()
+                    nxt = next_entry()
+                    if nxt is not None:
+                        tr.submit_window(nxt)
+            if use_graph and step_no == 2 and tuple(lS_i.shape) == (len(ln_emb), lb):
+                tr.capture_graph(X, lS_o, lS_i, T)           # after two eager steps (lazy initialisation)
             t1 = time.perf_counter()
-            E, Z = tr.step(X, lS_o, lS_i, T)
-            tr.maybe_aggregate(j)
+            if strict:
+                E, Z, idxs = tr.step_reference(X, lS_o, lS_i, T)
+                if args.world_size > 1:
+                    if j > 0 and j % args.table_agg_freq == 0:                       # :418-423
+                        broadcast_and_aggregate(tr.cache_group, torch.cat(idxs_window + [torch.stack(idxs)], dim=1),
+                                                rank, args.table_agg_op)
+                        idxs_window = []
+                    else:
+                        idxs_window.append(torch.stack(idxs))
+            else:
+                E, Z = tr.step(X, lS_o, lS_i, T)
+                tr.maybe_aggregate(j)
+            step_no += 1
+            if tr.keep_losses:
+                tr.loss_history.append(E.detach().clone())
             if rank == 0 and j > 0 and j % args.print_freq == 0:
                 torch.cuda.synchronize(dev)
+                tr.cache_group.check_device_flags()
                 total_time += time.perf_counter() - t1
-                L = E.item()
+                L_ = E.item()
                 A = float(((Z.detach().round() == T).sum()).item())
                 mbs = T.shape[0]
                 total_iter += 1
                 gT = 1000.0 * total_time / max(total_iter, 1)
-                ovh = 1000 * (np.mean(tr.caching_overhead) / args.lookahead) if tr.caching_overhead else 0.0
+                ovh = 1000 * (np.mean(tr.caching_overhead) / L) if tr.caching_overhead else 0.0
                 tr.caching_overhead = []
                 print('Epoch {}: Finished {}/{} in {} ms/it. Caching overhead = {}. Loss = {}, Train Acc = {}'.format(
-                    epoch, j, len(train_ld), gT, ovh, L, A / mbs))
+                    epoch, j, len(train_ld), gT, ovh, L_, A / mbs))
                 total_time, total_iter = 0.0, 0
             if rank == 0 and test_ld is not None and ((args.test_freq > 0 and j > 0 and j % args.test_freq == 0)
                                                       or j == len(train_ld) - 1):
@@ -510,5 +670,118 @@ def Run(rank, m_spa, ln_emb, ln_bot, ln_top, train_ld, test_ld, batch_fifo, evic
                         Zt = tr.dlrm(Xt.to(dev), lookups)
                         total_test_acc += int((Zt.round().cpu() == Tt).sum())
                         test_samp += Tt.shape[0]
+                # a test batch larger than the aux region raises IndexError in the reference (:176-179)
+                tr.cache_group.check_device_flags()
                 print('Test accuracy = {}%'.format(100 * (total_test_acc / max(test_samp, 1))))
+    torch.cuda.synchronize(dev)
+    tr.finish()
     return tr
+
+
+# ------------------------------------------------------------------------------------
+# __main__ -- main_no_ddp.py:505-646
+# ------------------------------------------------------------------------------------
+
+
+def _derive_topology(args):
+    """:525-616: table sizes, MLP shapes and the reference's sanity checks (same messages)."""
+    ln_bot = np.fromstring(args.arch_mlp_bot, dtype=int, sep="-")
+    if args.data_generation == "dataset":
+        sys.exit("ERROR: --data-generation=dataset needs the Criteo loaders (dlrm_data_pytorch.py), which are outside "
+                 "the cache hot path this package implements; use --data-generation=synthetic")
+    ln_emb = np.fromstring(args.arch_embedding_size, dtype=int, sep="-")
+    m_den = ln_bot[0]
+    m_spa = args.arch_sparse_feature_size
+    num_fea = ln_emb.size + 1
+    m_den_out = ln_bot[ln_bot.size - 1]
+    if args.arch_interaction_op == "dot":
+        if args.arch_interaction_itself:
+            num_int = (num_fea * (num_fea + 1)) // 2 + m_den_out
+        else:
+            num_int = (num_fea * (num_fea - 1)) // 2 + m_den_out
+    elif args.arch_interaction_op == "cat":
+        num_int = num_fea * m_den_out
+    else:
+        sys.exit("ERROR: --arch-interaction-op=" + args.arch_interaction_op + " is not supported")
+    ln_top = np.fromstring(str(num_int) + "-" + args.arch_mlp_top, dtype=int, sep="-")
+    if m_spa != m_den_out:
+        sys.exit("ERROR: arch-sparse-feature-size " + str(m_spa) + " does not match last dim of bottom mlp "
+                 + str(m_den_out))
+    if num_int != ln_top[0]:
+        sys.exit("ERROR: # of feature interactions " + str(num_int) + " does not match first dimension of top mlp "
+                 + str(ln_top[0]))
+    if args.qr_flag or args.md_flag:
+        sys.exit("ERROR: QR / mixed-dimension embeddings are outside the cache hot path (unreachable from the "
+                 "reference's own Run as well)")
+    return ln_emb, ln_bot, ln_top, m_spa, m_den
+
+
+def _rank_main(rank, args, shm_prefix=None):
+    """One trainer process: its own loaders, Prefetcher thread and FIFOs over the deterministic synthetic
+    stream (every rank sees the same windows), master tables shared through /dev/shm when world_size > 1."""
+    import threading
+    from .synthetic import make_synthetic_data_and_loaders
+    ln_emb, ln_bot, ln_top, m_spa, m_den = _derive_topology(args)
+    np.random.seed(args.numpy_rand_seed)
+    torch.manual_seed(args.numpy_rand_seed)
+    train_ld, test_ld, cache_ld = make_synthetic_data_and_loaders(args, ln_emb, m_den)
+    torch.cuda.set_device(rank)
+    if args.world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", str(args.master_port))
+        dist.init_process_group("nccl", rank=rank, world_size=args.world_size, device_id=torch.device("cuda", rank))
+        if rank == 0:
+            emb_tables = Embedding_Table_Group(m_spa, ln_emb, init=f"shm:{shm_prefix}:create")
+        dist.barrier()
+        if rank != 0:
+            emb_tables = Embedding_Table_Group(m_spa, ln_emb, init=f"shm:{shm_prefix}:attach")
+    else:
+        big = int(np.sum(ln_emb)) * int(m_spa) > (1 << 28)
+        emb_tables = Embedding_Table_Group(m_spa, ln_emb, init="device" if big else "reference")    # :621
+    batch_fifo = queue.Queue(maxsize=args.batch_fifo_size)                                           # :624-626
+    eviction_fifo = queue.Queue(maxsize=args.eviction_fifo_size)
+    finish_event = threading.Event()
+    args.fifo_per_rank = True
+    if not args.fifo_payload:
+        args.fifo_payload = "tuples" if args.strict_reference else "ids"
+    cm = Prefetcher(args, emb_tables, batch_fifo, eviction_fifo, finish_event, cache_ld)             # :630
+    cm.start()
+    try:
+        tr = Run(rank, m_spa, ln_emb, ln_bot, ln_top, train_ld, test_ld, batch_fifo, eviction_fifo, [], emb_tables,
+                 args)
+    finally:
+        finish_event.set()
+        if args.world_size > 1:
+            dist.barrier()
+            if rank == 0:
+                for k in range(len(ln_emb)):
+                    try:
+                        os.unlink(f"{shm_prefix}_{k}.bin")
+                    except OSError:
+                        pass
+    cm.join(timeout=5)
+    return tr
+
+
+def main(argv=None):
+    """python -m cdlrm_b200.main_no_ddp [the reference's flags] -- README.md:7 of the reference, with
+    ``--data-generation synthetic`` (Criteo-shaped synthetic batches, cdlrm_b200/synthetic.py)."""
+    args = ProcessArgs(argv)
+    np.set_printoptions(precision=args.print_precision)
+    torch.set_printoptions(precision=args.print_precision)
+    if args.test_mini_batch_size < 0:                    # :517-522
+        args.test_mini_batch_size = args.mini_batch_size
+    if args.test_num_workers < 0:
+        args.test_num_workers = args.num_workers
+    _derive_topology(args)                               # argument errors before any process is spawned
+    if args.world_size <= 1:
+        args.world_size = 1
+        return _rank_main(0, args)
+    import torch.multiprocessing as mp
+    prefix = f"/dev/shm/cdlrm_master_{os.getpid()}"
+    mp.spawn(_rank_main, args=(args, prefix), nprocs=args.world_size, join=True)    # :638-643
+    return None
+
+
+if __name__ == "__main__":
+    main()

@@ -209,8 +209,14 @@ class Embedding_Table_Cache_Group(nn.Module):
     with the module), ``victim_cache_entries``.
     """
 
-    def __init__(self, m_spa, ln_emb, max_cache_size, aux_table_size, num_ways, device=None):
+    def __init__(self, m_spa, ln_emb, max_cache_size, aux_table_size, num_ways, device=None, init="zeros"):
+        """``init="reference"``: build every ``nn.EmbeddingBag`` exactly as model_no_ddp.py:138 does (N(0,1)
+        rows drawn from torch's global CPU generator, then moved to ``device``).  The rows are never read before
+        a fill, but the draws advance the generator that ``Categorical.sample()`` later consumes for the victim
+        ways (main_no_ddp.py:183-185): ``--strict-reference`` needs the same offset to reproduce the reference
+        program's cache decisions.  Default "zeros": no draws, rows zeroed on the device."""
         super().__init__()
+        self._init_mode = init
         self.ln_emb = np.asarray(ln_emb)
         self.dim = int(m_spa)
         self.num_ways = int(num_ways)
@@ -252,6 +258,10 @@ class Embedding_Table_Cache_Group(nn.Module):
             n = int(ln[i])
             num_rows = n if n < max_cache_size else max_cache_size
             cache_sizes.append(num_rows)
+            if getattr(self, "_init_mode", "zeros") == "reference":
+                EE = nn.EmbeddingBag(num_ways * num_rows + aux_table_size, m, mode="sum", sparse=True)   # :138
+                emb_l.append(EE.to(device) if device is not None else EE)
+                continue
             # rows are only ever read after a fill: skip the N(0,1) init of nn.EmbeddingBag
             w = torch.zeros(num_ways * num_rows + aux_table_size, m, dtype=torch.float32, device=device)
             emb_l.append(nn.EmbeddingBag(num_ways * num_rows + aux_table_size, m, mode="sum", sparse=True,
@@ -317,6 +327,7 @@ class Embedding_Table_Cache_Group(nn.Module):
             if getattr(self, "_master_key", None) != mkey:
                 check(lib.cdlrm_ctx_bind_master(self._ctx, _lib.ptr_array(emb_tables.device_pointers(dev.index))))
                 self._master_key = mkey
+                self._emb_tables = weakref.ref(emb_tables)
         return self._ctx
 
     def __del__(self):
@@ -458,7 +469,7 @@ class Embedding_Table_Cache_Group(nn.Module):
             ps = self.forward_stream           # stream order after the lookup that produced the slots
         else:
             if self._plan_stream is None:
-                self._plan_stream = torch.cuda.Stream(dev)
+                self._plan_stream = _lib.new_stream(dev)
             ps = self._plan_stream
             ps.wait_stream(cur)
         T = slots.shape[0]

@@ -50,3 +50,65 @@ class SyntheticStream:
         X = torch.log1p(torch.randint(0, 101, (N, self.dense_dim), generator=g, device=self.dev).float())
         T = (torch.rand(N, 1, generator=g, device=self.dev) < 0.25).float()
         return X, T
+
+
+# ------------------------------------------------------------------------------------------
+# host-side loaders: the role of dlrm_data_pytorch.make_criteo_data_and_loaders (:386-547),
+# which hands main_no_ddp.py a (train_ld, test_ld, cache_ld) triple.  cache_ld is the
+# Prefetcher's look-ahead twin of train_ld: it yields the SAME batches in the SAME order
+# (cache_manager.py:87 reads only the sparse ids), which is the invariant the window FIFO
+# relies on.
+# ------------------------------------------------------------------------------------------
+
+
+class SyntheticCriteoLoader:
+    """Iterable of ``(X, lS_o, lS_i, T)`` CPU batches in the collate format of
+    data_loader_terabyte.py:68-87.  Batch j is a pure function of (seed, split, j): any number
+    of loaders built with the same arguments replay the same stream, whole epochs repeat it."""
+
+    def __init__(self, ln_emb, batch, num_batches, dense_dim=13, dist="zipf", zipf_a=1.05, seed=123, split=0):
+        self.ln = [int(n) for n in ln_emb]
+        self.B, self.n = int(batch), int(num_batches)
+        self.dense_dim, self.dist, self.a, self.seed, self.split = int(dense_dim), dist, float(zipf_a), int(seed), split
+        self.lS_o = torch.arange(self.B).reshape(1, -1).repeat(len(self.ln), 1)
+
+    def __len__(self):
+        return self.n
+
+    def sparse_ids(self, j, rng=None):
+        rng = rng if rng is not None else np.random.default_rng([self.seed, self.split, j, 1])
+        out = np.empty((len(self.ln), self.B), dtype=np.int64)
+        for k, n in enumerate(self.ln):
+            u = rng.random(self.B)
+            if self.dist == "uniform" or n == 1:
+                r = np.minimum((u * n).astype(np.int64), n - 1)
+            else:  # inverse CDF of the continuous power law on [1, n+1), as SyntheticStream
+                e = 1.0 - self.a
+                r = np.clip((((n + 1.0) ** e - 1.0) * u + 1.0) ** (1.0 / e) - 1, 0, n - 1).astype(np.int64)
+            out[k] = (r * 2654435761 + 40503 * k) % n
+        return out
+
+    def batch(self, j):
+        ids = self.sparse_ids(j)
+        rng = np.random.default_rng([self.seed, self.split, j, 2])
+        X = np.log1p(rng.integers(0, 101, size=(self.B, self.dense_dim))).astype(np.float32)
+        T = (rng.random((self.B, 1)) < 0.25).astype(np.float32)
+        return torch.from_numpy(X), self.lS_o, torch.from_numpy(ids), torch.from_numpy(T)
+
+    def __iter__(self):
+        for j in range(self.n):
+            yield self.batch(j)
+
+
+def make_synthetic_data_and_loaders(args, ln_emb, m_den):
+    """(train_ld, test_ld, cache_ld) for ``--data-generation synthetic`` (and ``random``: the reference's own
+    random branch, main_no_ddp.py:539-547, builds no cache_ld / test_ld and cannot run).  Number of train
+    batches: ``--num-batches`` or ``--data-size // --mini-batch-size`` (dlrm_data_pytorch.py:575)."""
+    nb = int(args.num_batches) if args.num_batches > 0 else max(1, int(args.data_size) // int(args.mini_batch_size))
+    kw = dict(dense_dim=int(m_den), dist=getattr(args, "synthetic_dist", "zipf"),
+              zipf_a=getattr(args, "synthetic_zipf_a", 1.05), seed=int(args.numpy_rand_seed))
+    train_ld = SyntheticCriteoLoader(ln_emb, args.mini_batch_size, nb, split=0, **kw)
+    cache_ld = SyntheticCriteoLoader(ln_emb, args.mini_batch_size, nb, split=0, **kw)
+    tb = args.test_mini_batch_size if getattr(args, "test_mini_batch_size", -1) > 0 else args.mini_batch_size
+    test_ld = SyntheticCriteoLoader(ln_emb, tb, max(1, min(4, nb)), split=1, **kw)
+    return train_ld, test_ld, cache_ld

@@ -277,6 +277,13 @@ int cdlrm_host_unregister(void* h_ptr);
 int cdlrm_bce_mean(int device, const float* z, int64_t ldz, const float* t, int64_t ldt, int32_t n, float* loss,
                    float* dz, cdlrm_stream stream);
 
+/* A CUDA stream of the library's own (cudaStreamNonBlocking; priority 0 = default, -1 = highest).  PyTorch hands out
+ * streams from a round-robin pool of 32 per priority, so two torch.cuda.Stream objects can be the SAME stream: the
+ * look-ahead planner's side stream must never alias the stream a training-step graph is captured on.  The host
+ * mirror wraps these with torch.cuda.ExternalStream.  No reference counterpart: stream plumbing. */
+int cdlrm_stream_create(int device, int priority, cdlrm_stream* out);
+int cdlrm_stream_destroy(int device, cdlrm_stream stream);
+
 /* Programmatic dependent launch of the per-step kernels (on by default; environment CDLRM_PDL=0 or
  * cdlrm_set_pdl(0) falls back to plain stream order).  No reference counterpart: launch plumbing. */
 int cdlrm_set_pdl(int on);

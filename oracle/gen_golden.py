@@ -404,6 +404,79 @@ def gen_dlrm_trainer():
           [out[f"w{w}_evict_len"].tolist() for w in range(cfg["n_windows"])])
 
 
+def gen_run_strict():
+    """The reference PROGRAM's order of generator consumption (main_no_ddp.py:509-512,621 then Run :335-376):
+    seeds -> master tables (numpy) -> [Run] seeds again -> cache group (nn.EmbeddingBag N(0,1) init draws from
+    torch's global CPU generator, NOT re-armed afterwards) -> DLRM_Net (nn.Linear default init draws, numpy
+    weights) -> windows.  So the victim stream starts at the offset the real program would see.  Pins
+    tests/test_gpu_run.py::test_run_strict_reference_matches_reference_program (Run with --strict-reference)."""
+    cfg = dict(TRAINER, name="run_strict")
+    seed = cfg["seed"]
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    ln_emb = np.asarray(cfg["ln_emb"])
+    d, B, L = cfg["dim"], cfg["batch"], cfg["lookahead"]
+    T = len(ln_emb)
+    ln_bot = np.asarray([13, 32, d])
+    nf = T + 1
+    ln_top = np.asarray([d + nf * (nf - 1) // 2, 32, 1])
+    master = M.Embedding_Table_Group(d, ln_emb)                                   # main :621
+    np.random.seed(seed)                                                          # Run :335-337
+    torch.manual_seed(seed)
+    cg = M.Embedding_Table_Cache_Group(d, ln_emb, max_cache_size=cfg["cache_size"],
+                                       aux_table_size=B, num_ways=cfg["num_ways"])   # :346 (draws N(0,1) rows)
+    dlrm = M.DLRM_Net(ln_bot, ln_top, arch_interaction_op="dot", arch_interaction_itself=False,
+                      sigmoid_bot=-1, sigmoid_top=ln_top.size - 2)                # :351
+    loss_fn = torch.nn.BCELoss(reduction="mean")
+    opt_m = torch.optim.SGD(dlrm.parameters(), lr=cfg["lr_mlp"])
+    opt_e = torch.optim.SGD(cg.parameters(), lr=cfg["lr_embeds"])
+    rank = CpuRank("cpu")
+    evq = queue.Queue()
+    ids = make_ids(cfg)
+    drng = np.random.default_rng(cfg["data_seed"] + 2)
+    nsteps = cfg["n_windows"] * L
+    X = np.log1p(drng.integers(0, 100, size=(nsteps, B, 13))).astype(np.float32)
+    Y = (drng.random((nsteps, B, 1)) < 0.25).astype(np.float32)
+    out = {"X": X, "Y": Y, "cfg_json": np.array(json.dumps(cfg)), "ln_bot": ln_bot, "ln_top": ln_top}
+    lS_o = torch.arange(B).reshape(1, -1).repeat(T, 1)
+    losses, n_miss = [], []
+    step = 0
+    for w in range(cfg["n_windows"]):
+        win = torch.from_numpy(ids[:, w * L * B:(w + 1) * L * B])
+        rows, uniq, maps = C.Prefetcher.process_batch_slice(win, master)
+        R.CacheEmbeddings(rows, uniq, maps, cg, evq, rank)                        # :309-316 on rank 0
+        for k, (ix, emb) in enumerate(evq.get()):
+            master.emb_l[k].weight.data[ix] = emb
+        out[f"w{w}_tags"] = np.concatenate([t.numpy().ravel() for t in cg.occupancy_tables])
+        for b in range(L):
+            lS_i = win[:, b * B:(b + 1) * B]
+            ly, _ = cg(lS_o, lS_i, master, rank)
+            n_miss.append([cg.victim_cache_entries[k][0].numel() for k in range(T)])
+            Z = dlrm(torch.from_numpy(X[step]), ly)
+            E = loss_fn(Z, torch.from_numpy(Y[step]))
+            opt_m.zero_grad()
+            opt_e.zero_grad()
+            E.backward()
+            opt_e.step()
+            opt_m.step()
+            losses.append(E.item())
+            step += 1
+    out["losses"] = np.asarray(losses, dtype=np.float64)
+    out["n_miss"] = np.asarray(n_miss, dtype=np.int64)
+    for i, p in enumerate(dlrm.parameters()):
+        out[f"mlp_final_{i}"] = p.detach().numpy().copy()
+    for k in range(T):
+        nc = cg.cache_sizes[k] * cfg["num_ways"]
+        live = (cg.occupancy_tables[k].t().reshape(-1) >= 0).numpy()             # way-major slot order
+        out[f"final_live_{k}"] = live
+        out[f"final_weight_live_{k}"] = cg.emb_l[k].weight.data.numpy()[:nc][live].copy()
+        out[f"final_master_{k}"] = master.emb_l[k].weight.data.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "run_strict.npz"), **out)
+    g0 = np.load(os.path.join(OUT, "dlrm_trainer.npz"))
+    print("run_strict: tags differ from the re-armed-seed golden in window 0:",
+          bool((g0["w0_tags"] != out["w0_tags"]).any()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gen_geometry()
@@ -416,6 +489,7 @@ def main():
               {k: res[k].tolist() for k in res if k.endswith("evict_len") or k.endswith("uniq_len")})
     gen_dlrm_tiny()
     gen_dlrm_trainer()
+    gen_run_strict()
     gen_aggregate()
     print("golden vectors written to", os.path.abspath(OUT))
 

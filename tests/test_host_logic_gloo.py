@@ -45,9 +45,51 @@ def test_aggregate_gradients_two_ranks_gloo():
 
 
 def test_batch_slicing_contract():
+    """main_no_ddp.slice_batch (:388-391), the function Run cuts every batch with: the ranks' slices tile the
+    global batch in rank order; offsets are the first local_batch columns."""
     import math
-    B, W = 10, 4
+
+    from cdlrm_b200.main_no_ddp import slice_batch
+    B, W, Tn = 10, 4, 3
     lb = math.ceil(B / W)
-    ids = torch.arange(3 * B).reshape(3, B)
-    got = torch.cat([ids[:, r * lb:(r + 1) * lb] for r in range(W)], dim=1)
-    assert torch.equal(got, ids)
+    X = torch.arange(B * 13, dtype=torch.float32).reshape(B, 13)
+    ids = torch.arange(Tn * B).reshape(Tn, B)
+    lS_o = torch.arange(B).reshape(1, -1).repeat(Tn, 1)
+    Y = torch.arange(B, dtype=torch.float32).reshape(B, 1)
+    parts = [slice_batch(r, lb, X, lS_o, ids, Y) for r in range(W)]
+    assert torch.equal(torch.cat([p[0] for p in parts]), X)
+    assert torch.equal(torch.cat([p[2] for p in parts], dim=1), ids)
+    assert torch.equal(torch.cat([p[3] for p in parts]), Y)
+    for r, (x, o, i, y) in enumerate(parts):
+        n = max(0, min(lb, B - r * lb))
+        assert x.shape[0] == i.shape[1] == y.shape[0] == n
+        assert torch.equal(o, lS_o[:, :lb])                      # :390: offsets are NOT re-based (P = 1)
+
+
+def test_prefetcher_window_slicing_contract():
+    """Prefetcher.windows (cache_manager.py:75,85-110): FIFO entry w covers exactly the training steps
+    [w*lookahead, (w+1)*lookahead) of the epoch (main_no_ddp.py:393), the last one may be short, and every
+    epoch starts a new window; cache_ld is a twin of train_ld (same ids in the same order)."""
+    import argparse
+
+    from cdlrm_b200.cache_manager import Prefetcher
+    from cdlrm_b200.synthetic import make_synthetic_data_and_loaders
+    ln_emb = [50, 7, 3000]
+    args = argparse.Namespace(lookahead=4, nepochs=2, mini_batch_size=8, num_batches=10, data_size=1,
+                              numpy_rand_seed=5, test_mini_batch_size=-1, cache_workers=1, main_start_core=0,
+                              average_on_writeback=False, eviction_fifo_timeout=1)
+    train_ld, test_ld, cache_ld = make_synthetic_data_and_loaders(args, ln_emb, 13)
+    assert len(train_ld) == len(cache_ld) == 10
+    cm = Prefetcher(args, None, None, None, None, cache_ld)
+    assert cm.fifo_payload == "tuples"                           # the reference's contract is the default
+    wins = list(cm.windows())
+    assert [w.shape[1] for w in wins] == [32, 32, 16] * 2
+    steps = [b[2] for b in train_ld]
+    for e in range(2):
+        for w in range(3):
+            want = torch.cat(steps[w * 4:(w + 1) * 4], dim=1)
+            assert torch.equal(wins[e * 3 + w], want)
+    for k, n in enumerate(ln_emb):
+        assert int(wins[0][k].min()) >= 0 and int(wins[0][k].max()) < n
+    x, o, i, t = next(iter(test_ld))
+    assert x.shape == (8, 13) and i.shape == (3, 8) and t.shape == (8, 1) and torch.equal(o[0], torch.arange(8))

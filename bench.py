@@ -27,7 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # BASELINE.json configs[2] (the configuration the metric is quoted on)
+    # BASELINE.json configs[2] (the configuration the metric is quoted on); configs[3] / [4] are this workload with
+    # --cache-size / --num-ways / --dist and --batch / --table-agg-freq overridden
     "terabyte": dict(rows="terabyte", dim=128, bot="13-512-256-128", top="512-512-256-1", batch=8192,
                      cache=150000, ways=16, lookahead=3000, agg=100),
     # configs[1]
@@ -37,6 +38,7 @@ WORKLOADS = {
     "small": dict(rows=[100000] * 8, dim=16, bot="13-64-16", top="64-1", batch=128, cache=10000, ways=16,
                   lookahead=100, agg=100),
 }
+METRIC = "samples/sec (Terabyte-shape synthetic) at 1/2/4/8 B200; cache-op HBM GB/s"
 
 
 def log(msg):
@@ -48,17 +50,25 @@ def log(msg):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=0)       # 0: one full window (lookahead steps)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20)      # 0: one full window (lookahead steps)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="cdlrm_b200")
     ap.add_argument("--workload", type=str, default="terabyte")
     ap.add_argument("--dist", type=str, default="zipf")
     ap.add_argument("--zipf-a", type=float, default=1.05)
     ap.add_argument("--row-cap", type=int, default=40_000_000)
     ap.add_argument("--lookahead", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
+    ap.add_argument("--cache-size", type=int, default=0)
+    ap.add_argument("--num-ways", type=int, default=0)
+    ap.add_argument("--table-agg-freq", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0)          # per-GPU batch
+    # end-to-end leg: 0 = one whole look-ahead window starting at a window boundary (one install, the next window
+    # planned and prefetched beside training, lookahead / table_agg_freq aggregations); n > 0 = n steps; -1 = skip
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=4)
+    ap.add_argument("--ref-window-steps", type=int, default=0)   # reference arm: steps per installed window (0: auto)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-prof", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     return ap.parse_args()
 
@@ -259,11 +269,31 @@ def cpu_reference_run(wl, ln_emb, steps, warmup, budget_s, dist, zipf_a):
 # GPU arm
 # ------------------------------------------------------------------------------------------
 
+def pcie_peaks(torch, dev, nbytes=256 << 20, reps=5):
+    """Measured cudaMemcpyAsync peaks between pinned host memory and this GPU (the denominator north_star asks
+    for next to the prefetch rate): best of `reps`, CUDA events."""
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, (dst, src) in {"h2d": (d, h), "d2h": (h, d)}.items():
+        best = 1e9
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out[name + "_GB/s"] = round(nbytes / (best * 1e-3) / 1e9, 1)
+    del h, d
+    return out
+
+
 def gpu_run(a, wl, ln_emb):
     import torch
     import torch.distributed as dist
     from cdlrm_b200 import _lib
-    from cdlrm_b200.main_no_ddp import Trainer
+    from cdlrm_b200.main_no_ddp import Trainer, broadcast_and_aggregate
     from cdlrm_b200.model_no_ddp import Embedding_Table_Group
     from cdlrm_b200.synthetic import SyntheticStream
 
@@ -274,7 +304,7 @@ def gpu_run(a, wl, ln_emb):
     torch.cuda.set_device(dev)
     # training runs on a high-priority stream: the look-ahead planner's kernels (side stream, default
     # priority) then only take the SM slots the training step leaves free
-    torch.cuda.set_stream(_lib.new_stream(dev, priority=-1))
+    torch.cuda.set_stream(torch.cuda.Stream(dev, priority=-1))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
@@ -311,12 +341,13 @@ def gpu_run(a, wl, ln_emb):
                 except OSError:
                     pass
     setup_s = time.time() - t0
+    pcie = pcie_peaks(torch, dev)
 
     Bg = lb * world                     # weak scaling: the per-GPU batch stays at the configured size
     stream_g = SyntheticStream(ln_emb, Bg, dev, dist=a.dist, zipf_a=a.zipf_a, seed=123)
     stream_l = SyntheticStream(ln_emb, lb, dev, dist=a.dist, zipf_a=a.zipf_a, seed=777 + rank)
-    n_e2e = max(0, a.e2e_steps)
     data = {}
+    recs = {}                           # window -> PlanRecord (prefetch timing)
 
     def prepare(w):
         """Generate window w on the side stream (overlaps training), start its plan, keep this
@@ -341,10 +372,27 @@ def gpu_run(a, wl, ln_emb):
 
     lS_o = torch.arange(lb).reshape(1, -1).repeat(T, 1)
     torch.cuda.synchronize(dev)
+    bound_log, agg_log = [], []        # (host seconds, event pair) per boundary / aggregation of the e2e leg
+    logging_on = [False]
+
+    def timed_call(fn, sink):
+        if not logging_on[0]:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0 = time.perf_counter()
+        e0.record()
+        r = fn()
+        e1.record()
+        sink.append((time.perf_counter() - h0, e0, e1))
+        return r
 
     def boundary(j):
-        tr.install_window()
+        recs[j // L] = timed_call(tr.install_window, bound_log)
         prepare(j // L + 1)
+
+    def aggregate(j):
+        if world > 1 and j > 0 and j % args.table_agg_freq == 0:
+            timed_call(lambda: tr.maybe_aggregate(j), agg_log)
 
     def one_step(j, host=None):
         w, b = divmod(j, L)
@@ -354,19 +402,22 @@ def gpu_run(a, wl, ln_emb):
         if host is None:
             ids, X, Y = window(w)
             E, _ = tr.step(X[lo:lo + lb], lS_o, ids[:, lo:lo + lb], Y[lo:lo + lb])
-        else:   # end-to-end: inputs come from pinned host memory, result goes back to the host
-            hX, hI, hY = host
-            E, _ = tr.step(hX.to(dev, non_blocking=True), lS_o, hI.to(dev, non_blocking=True),
-                           hY.to(dev, non_blocking=True))
-            tr.maybe_aggregate(j)
-            return E.item()
-        tr.maybe_aggregate(j)
-        return E
+            aggregate(j)
+            return E
+        # end-to-end: inputs come from pinned host memory, the result goes back to the host
+        hX, hI, hY = host
+        E, _ = tr.step(hX[b].to(dev, non_blocking=True), lS_o, hI[b].to(dev, non_blocking=True),
+                       hY[b].to(dev, non_blocking=True))
+        aggregate(j)
+        return E.item()
 
     # first window: plan + install (untimed set-up), look-ahead plan of window 1 starts
+    t_w0 = time.perf_counter()
     prepare(0)
-    tr.install_window()
-    log("window 0 installed")
+    recs[0] = tr.install_window()
+    torch.cuda.synchronize(dev)
+    first_install_ms = 1000 * (time.perf_counter() - t_w0)
+    log(f"window 0 planned + installed in {first_install_ms:.0f} ms (not overlapped with anything)")
     j = 0
     for _ in range(3):                 # eager steps: lazy initialisation (cuBLAS handles, scratch)
         one_step(j)
@@ -377,27 +428,27 @@ def gpu_run(a, wl, ln_emb):
     log("graph captured" if not a.no_graph else "eager mode")
     prepare(1)
     if world > 1:
-        # lazy initialisation of the aggregation path (NCCL connections for the all-gather / large all-reduce,
-        # pinned count buffers, the packed row buffer): one untimed table aggregation; measured 0.6 s when it
-        # fell into the timed region
-        from cdlrm_b200.main_no_ddp import broadcast_and_aggregate
+        # lazy initialisation of the aggregation path (NCCL connections, pinned count buffers, the packed row
+        # buffer): one untimed table aggregation; measured 0.6 s when it fell into a timed region
         broadcast_and_aggregate(tr.cache_group, None, rank, args.table_agg_op)
     for _ in range(max(W - 3, 0)):
         one_step(j)
         j += 1
-    # A run of a whole window or more (the default) carries that window's share of look-ahead planning inside
-    # the timed region.  A SHORT run would otherwise sit entirely inside the planner's burst (the plan and PCIe
-    # prefetch of the next window take ~0.15 s right after a boundary and slow the step 1.2-1.3x while they run,
-    # 2.5 % averaged over the 2.2 s window): let the burst finish first so that the short run measures the steady
-    # state; config.lookahead_plan says which case applied.
+    # A SHORT run would otherwise sit entirely inside the planner's burst (the plan and PCIe prefetch of the next
+    # window take ~0.15 s right after a boundary and slow the step 1.2-1.3x while they run, 2.5 % averaged over the
+    # 2.2 s window): let the burst finish first so that the short run measures the steady state.  The end-to-end
+    # leg below covers a whole window with its boundary, plan, prefetch and aggregations inside the timed region.
     plan_inside = K >= L
     if not plan_inside and tr._plan_thread is not None:
         tr._plan_thread.join()
+    # the clock sampler forks nvidia-smi: start it BEFORE the barrier so that every rank enters the timed region
+    # together, and keep it running through the end-to-end leg (seconds, not milliseconds, of samples)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize(dev)
     log("warm-up done, timing")
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     lib.cdlrm_prof_launches(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_boundaries = 0
@@ -433,48 +484,167 @@ def gpu_run(a, wl, ln_emb):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    clocks = sampler.stop() if sampler else None
     log(f"timed region done: {ms / K:.3f} ms/step")
     value = K * lb * world / (ms / 1000.0)
 
     # -- end to end through the public API with host buffers ---------------------------------------
-    e2e = None
-    if n_e2e:
-        hosts = []
-        for i in range(n_e2e):
-            w, b = divmod(j + i, L)
-            if w not in data:
-                break
-            ids, X, Y = window(w)
-            lo = b * lb
-            hosts.append((X[lo:lo + lb].cpu().pin_memory(), ids[:, lo:lo + lb].contiguous().cpu().pin_memory(),
-                          Y[lo:lo + lb].cpu().pin_memory()))
+    e2e = full_window = None
+    if a.e2e_steps >= 0:
+        whole = a.e2e_steps == 0
+        n_e2e = L if whole else a.e2e_steps
+        if whole:
+            # run (untimed) up to the next window boundary, so that the leg is exactly one window: its install
+            # first, then the plan + PCIe prefetch of the following window beside the steps, every aggregation
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_fill = (-j) % L
+            f0.record()
+            for _ in range(n_fill):
+                one_step(j)
+                j += 1
+            f1.record()
+        w_e, b_e = divmod(j, L)
+        if not whole:
+            n_e2e = min(n_e2e, L - b_e)
+        ids, X, Y = window(w_e)
+        torch.cuda.synchronize(dev)
+        filler_ms = f0.elapsed_time(f1) / max(n_fill, 1) if whole and n_fill else None
+        # this window's inputs in pinned host memory, one contiguous block per step
+        hI = torch.empty(n_e2e, T, lb, dtype=torch.int64, pin_memory=True)
+        hX = torch.empty(n_e2e, lb, X.shape[1], dtype=torch.float32, pin_memory=True)
+        hY = torch.empty(n_e2e, lb, 1, dtype=torch.float32, pin_memory=True)
+        lo = b_e * lb
+        hI.copy_(ids[:, lo:lo + n_e2e * lb].view(T, n_e2e, lb).permute(1, 0, 2))
+        hX.copy_(X[lo:lo + n_e2e * lb].view(n_e2e, lb, -1))
+        hY.copy_(Y[lo:lo + n_e2e * lb].view(n_e2e, lb, 1))
+        hosts = (hX, hI, hY)
+        del ids, X, Y
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
+            torch.cuda.synchronize(dev)
+        log(f"end-to-end leg: {n_e2e} steps from pinned host inputs ({(hI.nbytes + hX.nbytes + hY.nbytes) / 1e9:.1f} GB)")
+        logging_on[0] = True
+        lib.cdlrm_prof_launches(1)
+        seg2 = max(1, n_e2e // 24)
+        marks2 = []
         t0 = time.perf_counter()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        n_e2e = len(hosts)
         for i in range(n_e2e):
-            one_step(j, hosts[i])
+            # (one_step indexes the host block by the step's position in its window)
+            w_, b_ = divmod(j, L)
+            if b_ == 0 and j > 0:
+                boundary(j)
+            E, _ = tr.step(hX[i].to(dev, non_blocking=True), lS_o, hI[i].to(dev, non_blocking=True),
+                           hY[i].to(dev, non_blocking=True))
+            aggregate(j)
+            loss_host = E.item()                       # device -> host read of the step's result
             j += 1
+            if (i + 1) % seg2 == 0 and i + 1 < n_e2e:
+                m = torch.cuda.Event(enable_timing=True)
+                m.record()
+                marks2.append((i + 1, m))
         e1.record()
         torch.cuda.synchronize(dev)
+        wall_ms = 1000 * (time.perf_counter() - t0)
+        logging_on[0] = False
+        e2e_launches = int(lib.cdlrm_prof_launches(0)) + (n_e2e * tr.graph_launches if getattr(tr, "_graph", None) else 0)
         ems = e0.elapsed_time(e1)
+        series2, prev_i, prev_e = [], 0, e0
+        for i, m in marks2 + [(n_e2e, e1)]:
+            series2.append(round(prev_e.elapsed_time(m) / (i - prev_i), 4))
+            prev_i, prev_e = i, m
         if world > 1:
             t = torch.tensor([ems], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
-        hb = sum(x.numel() * x.element_size() for x in hosts[0])
+        hb = (hI[0].nbytes + hX[0].nbytes + hY[0].nbytes)
         e2e = {"value": n_e2e * lb * world / (ems / 1000.0), "unit": "samples/s", "h2d_bytes_per_step": hb * world,
-               "d2h_bytes_per_step": 4 * world, "steps": n_e2e,
-               "wall_ms_per_step": 1000 * (time.perf_counter() - t0) / n_e2e}
+               "d2h_bytes_per_step": 4 * world, "steps": n_e2e, "ms_per_step": ems / n_e2e,
+               "wall_ms_per_step": wall_ms / n_e2e, "last_loss": loss_host,
+               "whole_window": whole, "gpu_launches": e2e_launches}
+        # what the leg contained
+        rec_next = None
+        if tr._plan_thread is not None:
+            tr._plan_thread.join()
+        try:
+            rec_next = tr._plan_q.queue[0] if tr._plan_q.qsize() else None
+        except Exception:
+            rec_next = None
+        torch.cuda.synchronize(dev)
+        full_window = {
+            "ms_per_step": round(ems / n_e2e, 4), "steps": n_e2e, "window_boundaries": len(bound_log),
+            "boundary_ms": [round(1000 * h, 3) for h, _, _ in bound_log],
+            "boundary_device_ms": [round(b0.elapsed_time(b1), 3) for _, b0, b1 in bound_log],
+            "aggregations": len(agg_log),
+            "agg_ms_per_call": round(float(np.mean([1000 * h for h, _, _ in agg_log])), 4) if agg_log else None,
+            "agg_device_ms_per_call": round(float(np.mean([b0.elapsed_time(b1) for _, b0, b1 in agg_log])), 4) if agg_log else None,
+            "agg_ms_per_step_amortised": round(float(np.sum([b0.elapsed_time(b1) for _, b0, b1 in agg_log])) / n_e2e, 5) if agg_log else 0.0,
+            "ms_per_step_series": {"steps_per_segment": seg2, "ms_per_step": series2},
+            "steady_ms_per_step_before": round(filler_ms, 4) if filler_ms else None,
+        }
+        if rec_next is not None and not isinstance(rec_next, Exception) and getattr(rec_next, "stage_begin", None) is not None:
+            st_ms = rec_next.stage_begin.elapsed_time(rec_next.staged)
+            full_window["planner_ms"] = {k: round(1000 * v, 1) for k, v in tr.planner.last_timing.items()}
+            full_window["planner_ms"]["prefetch"] = round(st_ms, 1)
+            pcie["prefetch_bytes"] = int(rec_next.stage_bytes)
+            pcie["prefetch_ms"] = round(st_ms, 2)
+            pcie["prefetch_GB/s"] = round(rec_next.stage_bytes / (st_ms * 1e-3) / 1e9, 2) if st_ms > 0 else None
+            pcie["prefetch_frac_of_h2d_peak"] = round(pcie["prefetch_GB/s"] / pcie["h2d_GB/s"], 3) if st_ms > 0 else None
+            pcie["prefetch_how"] = ("SM-driven zero-copy row gathers from the pinned master (32 CTAs), beside the "
+                                    "training steps of the end-to-end leg, all ranks at once")
+        del hosts, hI, hX, hY
+    clocks = sampler.stop() if sampler else None
 
     # -- per-kernel durations (CUDA events around every launch of the library) ------------------
     roof = kernels = None
-    # every rank takes these steps (they contain collectives); rank 0 reports
+    res = None
+    if not a.no_kernel_prof:
+        kernels, roof, step_bytes = kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, j, L, lb, T,
+                                                   d, dev, ln_bot, ln_top)
+        j += 20
+    if rank == 0:
+        peak, _src = measured_peak()
+        res = {
+            "metric": METRIC,
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_string(a, wl, T, world),
+                       "global_batch": Bg, "local_batch": lb, "parallelism": f"dp{world} (replicated cache)",
+                       "window_boundaries_in_timed_region": n_boundaries,
+                       "l2_policy": "inputs larger than L2: every step reads a fresh 26x8192-row slice of a "
+                                    "10+ GB cache and a new batch of the 5 GB window",
+                       "lookahead_plan": "planned inside the timed region" if plan_inside else
+                                         "next window planned before the timed region (steps < lookahead); the e2e leg "
+                                         "is a whole window with its boundary, plan, prefetch and aggregations inside",
+                       "cuda_graph": getattr(tr, "_graph", None) is not None,
+                       "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1),
+                       "setup_s": round(setup_s, 1), "master_host_gb": round(sum(ln_emb) * d * 4 / 1e9, 1),
+                       "first_window_install_ms": round(first_install_ms, 1)},
+            "e2e": e2e, "full_window": full_window, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "pcie": pcie, "kernels": kernels,
+            "caching_overhead_ms_per_window": [round(1000 * x, 2) for x in tr.caching_overhead[-3:]],
+            "ms_per_step_series": {"steps_per_segment": seg, "ms_per_step": series},
+        }
+        if kernels is not None:
+            # whole-step roofline: algorithmic bytes of the cache path + interaction per step over the step time
+            res["step_roofline"] = {
+                "algo_bytes_per_step": int(step_bytes), "ms_per_step": round(ms / K, 4),
+                "GB/s": round(step_bytes / (ms / K * 1e-3) / 1e9, 1), "peak": peak,
+                "frac": round(step_bytes / (ms / K * 1e-3) / 1e9 / peak, 3),
+                "note": "HBM-bound kernels only (cache forward / miss / update, interaction fwd / bwd); the rest of the "
+                        "step is the 3xTF32 MLP GEMMs (tensor-bound, kernels.mlp_gemm)"}
+    if world > 1:
+        dist.barrier()
+    tr.finish()
+    return res, rank
+
+
+def kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, j, L, lb, T, d, dev, ln_bot, ln_top):
+    """Eager steps with every library launch bracketed by CUDA events on its own stream (every rank takes these
+    steps: they contain collectives).  Returns (kernels, roofline, algorithmic bytes per step)."""
     NK = lib.cdlrm_prof_num_kernels()
     lib.cdlrm_prof_enable(1)
     nprof = 0
@@ -499,8 +669,7 @@ def gpu_run(a, wl, ln_emb):
     calls = (ctypes.c_int64 * NK)()
     _lib.check(lib.cdlrm_prof_report(msv, calls, NK))
     lib.cdlrm_prof_enable(0)
-    n_miss = tr.cache_group.last_n_miss.sum().item()
-    miss_per_step = int(n_miss)
+    n_miss = int(tr.cache_group.last_n_miss.sum().item())
     w, b = divmod(j - 1, L)
     lo = b * lb
     ids = window(w)[0][:, lo:lo + lb]
@@ -516,7 +685,7 @@ def gpu_run(a, wl, ln_emb):
     algo = {   # ALGORITHMIC bytes per launch
         # id + tag line + slot + miss-bitmap word per id; row read + out write per hit
         "embed_fwd": n * (8 + 8 * wl["ways"] + 4) + n // 8 + (n - n_miss) * 8 * d,
-        # bitmap read; per miss: id + slot + master row (PCIe) + aux row + out row
+        # bitmap read; per miss: id + slot + row read (HBM loser store or PCIe) + aux row + out row
         "embed_miss": n // 8 + n_miss * (8 + 4 + 12 * d),
         "bwd_plan": n * (4 + 8),
         # per id: sorted (slot, position) pair + its gradient row; per distinct slot: weight row read + write
@@ -527,9 +696,14 @@ def gpu_run(a, wl, ln_emb):
     peak, peak_src = measured_peak()
     kernels = {}
     names = [lib.cdlrm_prof_kernel_name(i).decode() for i in range(NK)]
-    # what the event pair itself adds (an empty kernel measured the same way); durations below are net of it
+    # what the event pair itself adds (an empty kernel measured the same way): reported next to the raw time
     i_null = names.index("null")
     null_us = 1000.0 * msv[i_null] / calls[i_null] if calls[i_null] else 0.0
+    traffic, traffic_src = {}, None
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tpath) and a.workload == "terabyte" and not (a.cache_size or a.num_ways or a.batch):
+        tj = json.load(open(tpath))    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full
+        traffic, traffic_src = tj["kernels"], tj.get("source", "profiles/r2_traffic.json")
     for i in range(NK):
         if calls[i] and i != i_null:
             nm = names[i]
@@ -541,9 +715,15 @@ def gpu_run(a, wl, ln_emb):
                 kernels[nm]["algo_bytes"] = int(algo[nm])
                 kernels[nm]["GB/s"] = round(algo[nm] / (us * 1e-6) / 1e9, 1)
                 kernels[nm]["frac_of_peak"] = round(algo[nm] / (us * 1e-6) / 1e9 / peak, 3)
-            if nm == "embed_miss":   # bounded by zero-copy PCIe reads of the master rows, not by HBM
-                kernels[nm]["misses_per_step"] = miss_per_step
-                kernels[nm]["pcie_GB/s"] = round(miss_per_step * 4 * d / (us * 1e-6) / 1e9, 1)
+                kernels[nm]["frac_of_peak_raw_event_pair"] = round(algo[nm] / (raw * 1e-6) / 1e9 / peak, 3)
+            if nm in traffic:
+                db = int(traffic[nm]["dram_bytes_per_launch"])
+                kernels[nm]["ncu_dram_bytes_static_profile"] = db
+                # the Zipf head and the tiny tables are served by L2: DRAM traffic, not algorithmic bytes, is what
+                # an HBM fraction has to be quoted on when the two differ
+                kernels[nm]["dram_frac_of_peak"] = round(db / (us * 1e-6) / 1e9 / peak, 3)
+            if nm == "embed_miss":
+                kernels[nm]["misses_per_step"] = n_miss
     # useful FP32 flops of the MLP GEMMs (forward + data gradient + weight gradient); the tcgen05 kernel
     # spends 3 TF32 products per FP32 product (3xTF32 split)
     if "mlp_gemm" in kernels:
@@ -556,51 +736,28 @@ def gpu_run(a, wl, ln_emb):
         g = kernels["mlp_gemm"]
         t_us = g["us_per_launch"] * g["launches_per_step"]
         g["fp32_flops_per_step"] = int(fl)
+        g["us_per_step"] = round(t_us, 1)
         g["useful_TFLOP/s"] = round(fl / (t_us * 1e-6) / 1e12, 1)
         g["tf32_TFLOP/s"] = round(3 * fl / (t_us * 1e-6) / 1e12, 1)
-    traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r1d_traffic.json")
-    if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch, one ncu --set full capture
-        traffic = json.load(open(tpath))["kernels"]
-    for nm in kernels:
-        if nm in traffic:
-            kernels[nm]["ncu_dram_bytes"] = int(traffic[nm]["dram_bytes_per_launch"])
+    roof = None
     cand = [k for k in kernels if "GB/s" in kernels[k] and k != "embed_miss"]
     if cand:
         top = max(cand, key=lambda k: kernels[k]["us_per_launch"] * kernels[k]["launches_per_step"])
         roof = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["GB/s"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[top]["frac_of_peak"], "traffic": kernels[top].get("ncu_dram_bytes"),
+                "frac": kernels[top]["frac_of_peak"],
+                "traffic": kernels[top].get("ncu_dram_bytes_static_profile"),
+                "traffic_source": traffic_src if kernels[top].get("ncu_dram_bytes_static_profile") else None,
                 "peak_source": peak_src,
                 "algo_bytes_per_launch": kernels[top]["algo_bytes"],
                 "us_per_launch": kernels[top]["us_per_launch"],
+                "us_raw_event_pair": kernels[top]["us_raw_event_pair"],
+                "frac_raw_event_pair": kernels[top]["frac_of_peak_raw_event_pair"],
                 "event_pair_overhead_us": round(null_us, 2),
-                "note": "dominant HBM-bound kernel of the cache path; the MLP GEMMs (tensor-bound, section "
-                        "8f of the survey) are listed under kernels.mlp_gemm"}
-
-    res = None
-    if rank == 0:
-        res = {
-            "metric": "samples/sec (Terabyte-shape synthetic) at 1/2/4/8 B200; cache-op HBM GB/s",
-            "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_string(a, wl, T, world),
-                       "global_batch": Bg, "local_batch": lb, "parallelism": f"dp{world} (replicated cache)",
-                       "window_boundaries_in_timed_region": n_boundaries,
-                       "l2_policy": "inputs larger than L2: every step reads a fresh 26x8192-row slice of a "
-                                    "10+ GB cache and a new batch of the 5 GB window",
-                       "lookahead_plan": "planned inside the timed region" if plan_inside else
-                                         "next window planned before the timed region (steps < lookahead)",
-                       "cuda_graph": getattr(tr, "_graph", None) is not None,
-                       "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1),
-                       "setup_s": round(setup_s, 1), "master_host_gb": round(sum(ln_emb) * d * 4 / 1e9, 1)},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
-            "caching_overhead_ms_per_window": [round(1000 * x, 2) for x in tr.caching_overhead[-3:]],
-            "ms_per_step_series": {"steps_per_segment": seg, "ms_per_step": series},
-        }
-    if world > 1:
-        dist.barrier()
-    return res, rank
+                "note": "dominant HBM-bound kernel of the cache path; us_per_launch is net of the event-pair overhead "
+                        "(an empty kernel through the same pair), frac_raw_event_pair is the same fraction without that "
+                        "subtraction; the MLP GEMMs (tensor-bound) are under kernels.mlp_gemm"}
+    step_bytes = sum(algo[k] for k in algo if k in kernels)
+    return kernels, roof, step_bytes
 
 
 def main():
@@ -615,26 +772,54 @@ def main():
         real_stdout.flush()
 
 
+def cpu_arm(a, wl, ln_emb, steps, warmup, window_steps):
+    """The reference's CPU path on this box's host cores: the reference's OWN code from baseline/_ref
+    (kind "reference", baseline/ref_arm.py) when the copy made by __graft_entry__.install_reference travelled with
+    the snapshot, else the numpy oracle port (kind "port")."""
+    sys.path.insert(0, ROOT)
+    from baseline import ref_arm
+    if ref_arm.available():
+        r = ref_arm.run(wl, ln_emb, steps, warmup, window_steps, dist=a.dist, zipf_a=a.zipf_a, log=log)
+        r["kind"] = "reference"
+        return r
+    log("baseline/_ref is missing: timing the numpy oracle port instead of the reference's own code")
+    r = cpu_reference_run(wl, ln_emb, steps, warmup, 60.0, a.dist, a.zipf_a)
+    r["kind"] = "port"
+    return r
+
+
 def _main(a, out):
     wl = dict(WORKLOADS[a.workload])
-    if a.lookahead:
-        wl["lookahead"] = a.lookahead
+    for key, val in (("lookahead", a.lookahead), ("cache", a.cache_size), ("ways", a.num_ways),
+                     ("agg", a.table_agg_freq), ("batch", a.batch)):
+        if val:
+            wl[key] = val
     ln_emb = table_rows(wl, a.row_cap)
     rank = int(os.environ.get("RANK", "0"))
+    world = max(a.gpus, 1)
     if a.impl == "reference":
         if rank != 0:
             return
         K = a.steps if a.steps > 0 else 20
-        r = cpu_reference_run(wl, ln_emb, K, max(a.warmup, 0) if a.warmup < 5 else 2, 120.0, a.dist, a.zipf_a)
-        line = {"impl": "reference", "metric": "samples/sec (Terabyte-shape synthetic) at 1/2/4/8 B200; cache-op HBM GB/s",
+        W = max(a.warmup, 0)
+        # a window long enough to hold the warm-up and the timed steps, at least 32 steps (bounded: the install of
+        # a 3000-step window takes the reference minutes)
+        Lp = a.ref_window_steps or max(32, min(wl["lookahead"], K + W))
+        r = cpu_arm(a, wl, ln_emb, K, W, Lp)
+        cb = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        for k in ("step_ms", "step_ms_median", "install_s", "window_steps", "lookahead", "batch", "installs"):
+            if k in r:
+                cb[k] = r[k]
+        line = {"impl": "reference", "metric": METRIC,
                 "value": r["value"], "unit": "samples/s", "n_gpus": a.gpus, "steps": K, "warmup": a.warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_string(a, wl, len(ln_emb), max(a.gpus, 1)),
-                           "note": "CPU arm: the reference's algorithm (oracle port) on the host cores, on a bounded "
-                                   "sample of this workload (cpu_baseline.sample)"},
-                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                                 "sample": r["sample"]},
+                "config": {"workload": workload_string(a, wl, len(ln_emb), world),
+                           "note": "CPU arm on the box's host cores (no GPU work, nothing of cdlrm_b200 loaded): the "
+                                   "reference's own functions at the full batch of ONE trainer; a CPU run does not "
+                                   "scale with --gpus, the same figure stands beside every N (cpu_baseline.sample "
+                                   "says what was run)"},
+                "cpu_baseline": cb,
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         out.write(json.dumps(line) + "\n")
@@ -642,9 +827,11 @@ def _main(a, out):
     res, rank = gpu_run(a, wl, ln_emb)
     if rank == 0:
         if not a.no_cpu_baseline and int(os.environ.get("WORLD_SIZE", "1")) == 1:
-            r = cpu_reference_run(wl, ln_emb, 6, 1, a.cpu_baseline_seconds, a.dist, a.zipf_a)
-            res["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+            r = cpu_arm(a, wl, ln_emb, max(a.cpu_baseline_steps, 1), 1, 8)
+            res["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
                                    "sample": r["sample"]}
+            if "step_ms" in r:
+                res["cpu_baseline"].update(step_ms=round(r["step_ms"], 2), install_s=[round(x, 2) for x in r["install_s"]])
         out.write(json.dumps(res) + "\n")
 
 

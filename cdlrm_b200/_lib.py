@@ -137,17 +137,16 @@ def i64_array(vals):
 
 def new_stream(device, priority=0):
     """A torch.cuda.ExternalStream over a stream of the library's own (cdlrm_stream_create): never one of
-    PyTorch's pooled streams, so it cannot alias another torch.cuda.Stream of the process (in particular
-    the stream a training-step CUDA graph is captured on).  Destroyed with the returned object."""
-    import weakref
-
+    PyTorch's pooled streams (32 per priority, handed out round-robin), so it cannot alias another
+    torch.cuda.Stream of the process -- in particular not the stream a training-step CUDA graph is captured
+    on.  Meant for SIDE streams (planner, lookup): work is sent to it through the C ABI, event record / wait and
+    ``with torch.cuda.stream(...)`` allocations.  Do not make it the current stream of autograd work or of a graph
+    capture: the engine falls back to the legacy default stream for streams it does not own.  The handful of
+    streams a process creates live until it exits."""
     import torch
     dev = torch.device(device)
+    if os.environ.get("CDLRM_POOL_STREAMS", "0") == "1":        # A/B switch: PyTorch's pooled streams
+        return torch.cuda.Stream(dev, priority=int(priority))
     h = vp()
     check(lib.cdlrm_stream_create(dev.index, int(priority), C.byref(h)))
-    st = torch.cuda.ExternalStream(h.value, device=dev)
-    try:
-        weakref.finalize(st, lib.cdlrm_stream_destroy, dev.index, vp(h.value))
-    except TypeError:       # stream objects without weak-reference support: the handle lives until exit
-        pass
-    return st
+    return torch.cuda.ExternalStream(h.value, device=dev)

@@ -116,7 +116,7 @@ class PlanRecord:
                  "evict_primary", "fill_ids", "fill_slots", "event",
                  # look-ahead staging (WindowPlanner.stage / install_staged)
                  "L", "loser_off", "loser_soff", "loser_ids", "loser_stage", "fill_stage", "fill_soff", "evict_stage",
-                 "staged", "wb_done")
+                 "staged", "wb_done", "stage_begin", "stage_bytes")
 
     def loser_list(self, k):
         o, n = self.loser_off[k], self.L[k]
@@ -278,6 +278,7 @@ class WindowPlanner:
                                 "phase_b_s": round(time.perf_counter() - t_c, 4)}
         rec.event = None
         rec.staged = rec.wb_done = rec.fill_stage = rec.loser_stage = rec.evict_stage = None
+        rec.stage_begin, rec.stage_bytes = None, 0
         return rec
 
     def _buf(self, name, rows):
@@ -304,6 +305,8 @@ class WindowPlanner:
         s = self.stream
         d = self.dim
         with torch.cuda.stream(s):
+            rec.stage_begin = torch.cuda.Event(enable_timing=True)
+            rec.stage_begin.record(s)
             rec.fill_soff = [0] * self.T
             for k in range(1, self.T):
                 rec.fill_soff[k] = rec.fill_soff[k - 1] + rec.F[k - 1]
@@ -325,8 +328,10 @@ class WindowPlanner:
                         o = rec.loser_off[k]
                         check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(rec.loser_ids[o:].data_ptr()), rec.L[k],
                                                            _vp(rec.loser_stage[rec.loser_soff[k]:].data_ptr()), _sp(s)))
-            rec.staged = torch.cuda.Event()
+            rec.staged = torch.cuda.Event(enable_timing=True)
             rec.staged.record(s)
+            # host-master rows pulled over PCIe by this prefetch (bench.py: prefetch GB/s = bytes / event time)
+            rec.stage_bytes = 4 * d * (sum(rec.F) + (sum(rec.L) if rec.L is not None else 0))
         return rec
 
     def install_staged(self, rec, write_master=True, average_on_writeback=False, stream=None):

@@ -356,7 +356,6 @@ class Trainer:
         self.cache_group.assume_one_id_per_bag = True              # Criteo batches (:390)
         # streams of the library's own: a pooled torch.cuda.Stream may alias the stream a graph is captured on
         self.side = _lib.new_stream(self.dev)
-        self._capture_stream = _lib.new_stream(self.dev, priority=-1)
         # the lookup runs on its own stream beside the bottom MLP (joined before the interaction)
         self.cache_group.forward_stream = _lib.new_stream(self.dev, priority=-1)
         self.dlrm.pre_interact = self.cache_group.join_forward
@@ -481,7 +480,7 @@ class Trainer:
         torch.cuda.synchronize(dev)
         self._graph = torch.cuda.CUDAGraph()
         n0 = lib.cdlrm_prof_launches(0)
-        with torch.cuda.graph(self._graph, stream=self._capture_stream, capture_error_mode="thread_local"):
+        with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
             self._g_out = self._step_eager(self._g_in[0], lS_o, self._g_in[1], self._g_in[2])
         self.graph_launches = int(lib.cdlrm_prof_launches(0) - n0)   # library kernels per replay
         return self._graph
@@ -592,7 +591,7 @@ def Run(rank, m_spa, ln_emb, ln_bot, ln_top, train_ld, test_ld, batch_fifo, evic
     dev, lb, L = tr.dev, tr.local_batch, args.lookahead
     # training on a high-priority stream: the look-ahead planner (side stream, default priority) only
     # takes the SM slots the training step leaves free
-    torch.cuda.set_stream(_lib.new_stream(dev, priority=-1))
+    torch.cuda.set_stream(torch.cuda.Stream(dev, priority=-1))
     share_occupancy_tables(tr.cache_group, occupancy_tables_fifos, rank)
     shared_fifo = args.world_size > 1 and not getattr(args, "fifo_per_rank", False)
     n_windows = args.nepochs * math.ceil(len(train_ld) / L)

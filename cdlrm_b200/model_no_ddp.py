@@ -237,7 +237,6 @@ class Embedding_Table_Cache_Group(nn.Module):
         self.last_n_miss = None
         self._ctx = None
         self._bound_key = None
-        self._anchor = None
         self._pending = []
         self._plan_buf = None
         self._dirty = None
@@ -300,7 +299,6 @@ class Embedding_Table_Cache_Group(nn.Module):
             check(lib.cdlrm_ctx_geometry(self._ctx, sets, rows))
             assert list(sets) == [int(s) for s in self.cache_sizes]
             self._cache_rows = list(rows)
-            self._anchor = torch.zeros(1, device=dev, requires_grad=True)
         self.occupancy_tables = [t if t.device == dev else t.to(dev) for t in self.occupancy_tables]
         key = tuple(e.weight.data_ptr() for e in self.emb_l) + tuple(t.data_ptr() for t in self.occupancy_tables)
         if key != self._bound_key:
@@ -440,7 +438,13 @@ class Embedding_Table_Cache_Group(nn.Module):
             offsets = lS_o.to(dev, dtype=torch.int64, non_blocking=True).contiguous()
         # (overflow of the aux region is detected on the device: check_device_flags)
         if torch.is_grad_enabled():
-            res = _LookupFn.apply(self._anchor, self, ids, offsets, n_idx, n_bags, tb)
+            # A fresh zero-size leaf per call: autograd needs one differentiable input to call backward at all.  A
+            # long-lived leaf would do, except that its AccumulateGrad node is pinned to the stream of the step
+            # that created it for as long as ANY earlier graph is alive (a caller still holding last step's loss):
+            # the engine then syncs that stream at the end of every backward -- inside a CUDA-graph capture that is
+            # "dependency created on uncaptured work in another stream" and the capture dies.
+            anchor = torch.empty(0, device=dev, requires_grad=True)
+            res = _LookupFn.apply(anchor, self, ids, offsets, n_idx, n_bags, tb)
             slots, outs = res[0], res[1:]
         else:
             out, slots, _ = self._launch_forward(ids, offsets, n_idx, n_bags, tb)
@@ -675,11 +679,16 @@ class _MlpState:
 
 
 class _MlpFn(torch.autograd.Function):
-    """y = seq(x) for a create_mlp Sequential; params = W_0, b_0, W_1, b_1, ..."""
+    """y = seq(x) for a create_mlp Sequential; params = W_0, b_0, W_1, b_1, ... as autograd inputs, or none of
+    them in flat-bucket mode (the backward writes dW / db straight into the bucket: the parameters then stay out
+    of the graph -- see the note on long-lived leaves in Embedding_Table_Cache_Group._forward_uniform -- and a
+    fresh zero-size ``anchor`` leaf makes autograd call the backward)."""
 
     @staticmethod
-    def forward(ctx, state, x, *params):
+    def forward(ctx, state, x, anchor, *params):
         dev = x.device
+        if not params:
+            params = [p for m in state.linears for p in (m.weight, m.bias)]
         if x.dtype != torch.float32 or x.stride(1) != 1:
             x = x.contiguous().float()
         B = x.shape[0]
@@ -694,6 +703,7 @@ class _MlpFn(torch.autograd.Function):
         state.fwd_id += 1
         ctx.state, ctx.fwd_id, ctx.batch = state, state.fwd_id, B
         ctx.need_dx = ctx.needs_input_grad[1]
+        ctx.n_params = len(ctx.needs_input_grad) - 3
         return y
 
     @staticmethod
@@ -720,11 +730,11 @@ class _MlpFn(torch.autograd.Function):
                                      _lib.ptr_array([t.data_ptr() for t in dWs]),
                                      _lib.ptr_array([t.data_ptr() for t in dbs]), _stream_ptr(dev)))
         if st.flat_grads is not None:      # the bucket already holds them (p.grad is a view of it): nothing for autograd
-            return (None, dx) + (None,) * (2 * len(dWs))
+            return (None, dx, None) + (None,) * ctx.n_params
         grads = []
         for w, b in zip(dWs, dbs):
             grads += [w, b]
-        return (None, dx) + tuple(grads)
+        return (None, dx, None) + tuple(grads)
 
 
 class DLRM_Net(nn.Module):
@@ -826,10 +836,12 @@ class DLRM_Net(nn.Module):
         st = self._mlp_state.get(which)
         if st is None:
             st = self._mlp_state[which] = _MlpState(seq, getattr(self, "_sigmoid", {}).get(which, -1))
+        if st.flat_grads is not None and torch.is_grad_enabled():
+            return _MlpFn.apply(st, x, torch.empty(0, device=x.device, requires_grad=True))
         params = []
-        for m in st.linears:       # (flat mode: the backward fills the gradient bucket and returns None for these)
+        for m in st.linears:
             params += [m.weight, m.bias]
-        return _MlpFn.apply(st, x, *params)
+        return _MlpFn.apply(st, x, None, *params)
 
     def forward(self, dense_x, ly):
         x = self.apply_mlp("bot", dense_x)

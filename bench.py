@@ -349,18 +349,32 @@ def gpu_run(a, wl, ln_emb):
     data = {}
     recs = {}                           # window -> PlanRecord (prefetch timing)
 
+    mark_buf = {}
+
     def prepare(w):
-        """Generate window w on the side stream (overlaps training), start its plan, keep this
-        rank's slice of the ids plus its dense inputs/labels for the training steps."""
+        """Window w on the side stream (overlaps training): this rank's slice of the ids plus its dense inputs /
+        labels for the training steps, and the look-ahead plan over the GLOBAL window.  At N > 1 the global window
+        ([T, L x global batch] int64: 41 GB at 8 GPUs) is never materialised: the stream is counter-based, so the
+        planner's scan regenerates it chunk by chunk into one reused buffer (Trainer.submit_window(callable))."""
         with torch.cuda.stream(tr.side):
-            g = stream_g.window_ids(w, L)                                   # [T, L*Bg] global ids
-            loc = g if world == 1 else g.view(T, L, world, lb)[:, :, rank].reshape(T, L * lb).contiguous()
+            loc = stream_g.ids(w * L, L, b0=rank * lb, nb=lb, stream=tr.side)          # [T, L*lb]
             X, Y = stream_l.dense_and_labels(w, L)
             ready = torch.cuda.Event()
             ready.record(tr.side)
-            for t_ in (g, loc, X, Y):     # allocated on the side stream, read by the training stream
+            for t_ in (loc, X, Y):        # allocated on the side stream, read by the training stream
                 t_.record_stream(torch.cuda.current_stream(dev))
-        tr.submit_window(g)
+        if world == 1:
+            tr.submit_window(loc)
+        else:
+            def mark(planner):
+                cs = max(1, (1 << 22) // Bg)                 # ~4 M ids per table per chunk (0.9 GB for 26 tables)
+                if "b" not in mark_buf:
+                    mark_buf["b"] = torch.empty(T, cs * Bg, dtype=torch.int64, device=dev)
+                for s0 in range(0, L, cs):
+                    ns = min(cs, L - s0)
+                    planner.mark_ids(stream_g.ids(w * L + s0, ns, out=mark_buf["b"], stream=planner.stream))
+                return L * Bg
+            tr.submit_window(mark)
         data[w] = (loc, X, Y, ready)
         for old in [x for x in data if x < w - 1]:
             del data[old]
@@ -603,7 +617,6 @@ def gpu_run(a, wl, ln_emb):
     if not a.no_kernel_prof:
         kernels, roof, step_bytes = kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, j, L, lb, T,
                                                    d, dev, ln_bot, ln_top)
-        j += 20
     if rank == 0:
         peak, _src = measured_peak()
         res = {
@@ -646,6 +659,13 @@ def kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, 
     """Eager steps with every library launch bracketed by CUDA events on its own stream (every rank takes these
     steps: they contain collectives).  Returns (kernels, roofline, algorithmic bytes per step)."""
     NK = lib.cdlrm_prof_num_kernels()
+    if j % L == 0:              # at a window boundary (the whole-window e2e leg ends on one): take it first
+        one_step(j)
+        j += 1
+    if tr._plan_thread is not None:     # the look-ahead plan / prefetch of the next window must not run beside
+        tr._plan_thread.join()          # the kernels being timed
+    tr.side.synchronize()
+    torch.cuda.synchronize(dev)
     lib.cdlrm_prof_enable(1)
     nprof = 0
     graph, tr._graph = getattr(tr, "_graph", None), None     # eager launches so that events can bracket them

@@ -36,6 +36,7 @@ SIGNATURES = {
     "cdlrm_embed_bwd_plan": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int64, C.c_int32, vp, vp]),
     "cdlrm_embed_bwd_sgd": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int32, vp, C.c_int64, vp, C.c_int64,
                                       C.c_int64, C.c_float, vp]),
+    "cdlrm_embed_set_option": (C.c_int, [C.c_int, C.c_int]),
     "cdlrm_interact_set_option": (C.c_int, [C.c_int, C.c_int]),
     "cdlrm_interact_fwd": (C.c_int, [C.c_int, C.POINTER(vp), C.c_int, C.c_int64, C.c_int32, C.c_int, C.c_int,
                                      vp, C.c_int64, vp]),
@@ -51,6 +52,9 @@ SIGNATURES = {
     "cdlrm_plan_workspace_bytes": (C.c_int64, [vp, C.c_int64]),
     "cdlrm_plan_bind_workspace": (C.c_int, [vp, vp, C.c_int64, C.c_int64]),
     "cdlrm_plan_unique": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp, vp]),
+    "cdlrm_plan_mark_ids": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp]),
+    "cdlrm_synth_ids": (C.c_int, [C.c_int, C.c_int, C.c_int, c_i64p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32,
+                                  C.c_int64, C.c_int32, C.c_int, C.c_double, vp, C.c_int64, vp]),
     "cdlrm_plan_phase_a": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_i64p, vp, vp]),
     "cdlrm_plan_phase_b": (C.c_int, [vp, vp, c_i64p, vp, vp, vp, vp, vp, vp, vp]),
     "cdlrm_plan_unique_ptr": (vp, [vp, C.c_int]),

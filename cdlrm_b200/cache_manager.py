@@ -196,9 +196,16 @@ class WindowPlanner:
         return out
 
     # -- plan -----------------------------------------------------------------------------
-    def plan(self, win_ids=None, uniq_lists=None):
+    def mark_ids(self, ids):
+        """Chunked window scan: OR a chunk of window ids (int64 device tensor [T, n]) into the planner's id
+        bitmaps on the planner's stream; finish with ``plan(marked=total ids per table)``."""
+        assert ids.is_cuda and ids.dtype == torch.int64 and ids.stride(1) == 1 and ids.shape[0] == self.T
+        check(lib.cdlrm_plan_mark_ids(self.ctx, _vp(ids.data_ptr()), ids.stride(0), ids.shape[1], _sp(self.stream)))
+
+    def plan(self, win_ids=None, uniq_lists=None, marked=None):
         """win_ids: int64 device tensor [T, n] (raw window ids), or uniq_lists: list of T
-        ascending-unique int64 tensors (the reference-API path)."""
+        ascending-unique int64 tensors (the reference-API path), or marked: the number of ids per table
+        already scanned chunk by chunk with ``mark_ids``."""
         s = self.stream
         rec = PlanRecord()
         t_a = time.perf_counter()
@@ -214,6 +221,9 @@ class WindowPlanner:
                         buf[k, :lens[k]].copy_(u.to(self.dev, non_blocking=True))
                 check(lib.cdlrm_plan_phase_a(self.ctx, _vp(buf.data_ptr()), buf.stride(0), ld,
                                              _lib.i64_array(lens), _vp(self._h_counts.data_ptr()), _sp(s)))
+            elif marked is not None:
+                check(lib.cdlrm_plan_phase_a(self.ctx, None, 0, min(int(marked), self.window_len), None,
+                                             _vp(self._h_counts.data_ptr()), _sp(s)))
             else:
                 assert win_ids.is_cuda and win_ids.dtype == torch.int64 and win_ids.stride(1) == 1
                 check(lib.cdlrm_plan_phase_a(self.ctx, _vp(win_ids.data_ptr()), win_ids.stride(0),

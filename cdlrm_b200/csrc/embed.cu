@@ -3,6 +3,8 @@
 // de-duplicated sparse-SGD backward (EmbeddingBag backward + optimizer_embeds.step(),
 // main_no_ddp.py:376,409,413).  All tables of a call are covered by one launch per
 // stage (grid.y = table).  HBM-bound integer/row-copy work: no tensor cores.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -474,6 +476,168 @@ __global__ void __launch_bounds__(PLAN_NT, 1) bwd_plan_kernel(const TableDesc* _
 }
 
 // ------------------------------------------------------------------------------
+// Backward plan, cluster version: the same stable LSD radix sort, but one thread-block CLUSTER of C CTAs per
+// table instead of one CTA (26 CTAs on 148 SMs, 32 us, was the slowest stage of the cache path).  CTA c owns
+// positions [c*chunk, (c+1)*chunk) of the current order in its shared memory; per 8-bit pass
+//   1. ranks of its keys within (digit, warp)   (__match_any_sync, as above);
+//   2. per-digit totals published in shared memory;  cluster barrier;
+//   3. every CTA reads the C x 256 totals over DSMEM: global digit bases + what the CTAs before it hold;
+//   4. keys and positions are scattered to their destination CTA's other buffer with DSMEM stores;  cluster barrier.
+// Stable by construction (lane < round < warp < CTA order = position order), so the sorted run is bit-identical
+// to bwd_plan_kernel's.  Unresolved positions and the padding carry the key `rows` and sort to the end.
+// ------------------------------------------------------------------------------
+constexpr int CPL_NT = 512;
+constexpr int CPL_NW = CPL_NT / 32;
+constexpr int CPL_MAX_ROUNDS = 4;                 // keys per thread: chunk <= 4 * 512 = 2048
+constexpr int CPL_MAX_CHUNK = CPL_NT * CPL_MAX_ROUNDS;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory variable in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem, uint32_t rank) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(local_smem), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ uint32_t dsmem_ld_u32(uint32_t addr) {
+    uint32_t v; asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v;
+}
+__device__ __forceinline__ void dsmem_st_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void dsmem_st_u16(uint32_t addr, uint16_t v) { asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+
+__global__ void __launch_bounds__(CPL_NT, 1) bwd_plan_cluster_kernel(const TableDesc* __restrict__ tabs, int tb,
+                                                                     const int32_t* __restrict__ slots, int64_t ld_slots,
+                                                                     int n_idx, int j0, int n, int chunk, PlanView pv) {
+    pdl_enter();
+    extern __shared__ __align__(16) unsigned char smem[];
+    // layout: keyA[chunk] keyB[chunk] (u32) | valA[chunk] valB[chunk] (u16) | cnt[256][NW] (u16) | tot[256] base[256] (u32) | scratch
+    uint32_t* keyA = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* keyB = keyA + chunk;
+    uint16_t* valA = reinterpret_cast<uint16_t*>(keyB + chunk);
+    uint16_t* valB = valA + chunk;
+    uint16_t* cnt = valB + chunk;
+    uint32_t* tot = reinterpret_cast<uint32_t*>(cnt + 256 * CPL_NW);
+    uint32_t* base = tot + 256;
+    int* s_scr = reinterpret_cast<int*>(base + 256);
+
+    const int t = blockIdx.y;
+    const uint32_t crank = cluster_ctarank(), C = cluster_nctarank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t* tsl = slots + (int64_t)t * ld_slots + j0;
+    const int64_t rows = tabs[tb + t].cache_rows;
+    const int g0 = (int)crank * chunk;
+    for (int i = tid; i < chunk; i += CPL_NT) {
+        const int gp = g0 + i;
+        uint32_t k = (uint32_t)rows;
+        if (gp < n) {
+            const uint32_t sl = (uint32_t)tsl[gp];
+            if (sl < (uint32_t)rows) k = sl;
+        }
+        keyA[i] = k;
+        valA[i] = (uint16_t)gp;
+    }
+    const int bits = 64 - __clzll((unsigned long long)(rows > 1 ? rows : 1));
+    const int passes = (bits + 7) / 8;
+    const int per_warp = chunk / CPL_NW;                // multiple of 32 (chunk is a multiple of 512)
+    const int rounds = per_warp / 32;                   // <= CPL_MAX_ROUNDS
+    const uint32_t lt = (1u << lane) - 1u;
+    __syncthreads();
+
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = pass * 8;
+        for (int e = tid; e < 256 * CPL_NW / 2; e += CPL_NT) reinterpret_cast<uint32_t*>(cnt)[e] = 0;
+        __syncthreads();
+        uint16_t rk[CPL_MAX_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < CPL_MAX_ROUNDS; ++r) {
+            if (r < rounds) {
+                const int i = warp * per_warp + r * 32 + lane;
+                const uint32_t dg = (keyA[i] >> shift) & 255u;
+                const uint32_t peers = __match_any_sync(0xffffffffu, dg);
+                const int leader = __ffs(peers) - 1;
+                int old = 0;
+                if (lane == leader) {
+                    old = cnt[dg * CPL_NW + warp];
+                    cnt[dg * CPL_NW + warp] = (uint16_t)(old + __popc(peers));
+                }
+                old = __shfl_sync(0xffffffffu, old, leader);
+                rk[r] = (uint16_t)(old + __popc(peers & lt));
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (tid < 256) {        // digit tid: exclusive prefix over this CTA's warps, total of the CTA
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < CPL_NW; ++w) {
+                const uint32_t v = cnt[tid * CPL_NW + w];
+                cnt[tid * CPL_NW + w] = (uint16_t)run;
+                run += v;
+            }
+            tot[tid] = run;
+        }
+        cluster_sync_all();     // every CTA's totals are visible cluster-wide
+        {
+            uint32_t col = 0, mine = 0;
+            if (tid < 256) {
+                for (uint32_t cc = 0; cc < C; ++cc) {
+                    const uint32_t v = cc == crank ? tot[tid] : dsmem_ld_u32(dsmem_addr(tot + tid, cc));
+                    if (cc < crank) mine += v;
+                    col += v;
+                }
+            }
+            // exclusive scan of the digit totals over the first 256 threads (8 warps)
+            uint32_t inc = col;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += nb;
+            }
+            if (tid < 256 && lane == 31) s_scr[warp] = (int)inc;
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t woff = 0;
+                for (int w = 0; w < warp; ++w) woff += (uint32_t)s_scr[w];
+                base[tid] = woff + inc - col + mine;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < CPL_MAX_ROUNDS; ++r) {
+            if (r < rounds) {
+                const int i = warp * per_warp + r * 32 + lane;
+                const uint32_t k = keyA[i];
+                const uint32_t dg = (k >> shift) & 255u;
+                const uint32_t dst = base[dg] + cnt[dg * CPL_NW + warp] + rk[r];
+                const uint32_t dc = dst / (uint32_t)chunk, off = dst - dc * (uint32_t)chunk;
+                if (dc == crank) {
+                    keyB[off] = k;
+                    valB[off] = valA[i];
+                } else {
+                    dsmem_st_u32(dsmem_addr(keyB + off, dc), k);
+                    dsmem_st_u16(dsmem_addr(valB + off, dc), valA[i]);
+                }
+            }
+        }
+        cluster_sync_all();     // all scatters of the pass have landed; nobody reads tot / writes keyB any more
+        uint32_t* tk = keyA; keyA = keyB; keyB = tk;
+        uint16_t* tv = valA; valA = valB; valB = tv;
+    }
+
+    const int64_t obase = (int64_t)t * n_idx + j0;
+    for (int i = tid; i < chunk; i += CPL_NT) {
+        const int gp = g0 + i;
+        if (gp < n) {
+            pv.sorted_key[obase + gp] = keyA[i];
+            pv.sorted_pos[obase + gp] = j0 + (int)valA[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------
 // Backward apply over the sorted run (slot keys ascending, positions ascending within a
 // slot).  A warp owns 32 consecutive sorted entries of one table: one coalesced load
 // brings their (slot, position) pairs, everything after that is independent row traffic.
@@ -620,6 +784,14 @@ inline int pick_vec(int dim, const void* a, const void* b, int64_t s1, int64_t s
 
 }  // namespace
 
+static int g_plan_cluster = -1;
+
+extern "C" int cdlrm_embed_set_option(int key, int value) {
+    if (key == 0) { g_plan_cluster = value; return CDLRM_OK; }
+    cdlrm_set_error("cdlrm_embed_set_option: unknown key %d", key);
+    return CDLRM_ERR_ARG;
+}
+
 static int ensure_scratch(cdlrm_ctx* c, int64_t n_idx) {
     if (n_idx <= c->scratch_max_idx && c->d_missmap) return CDLRM_OK;
     return cdlrm_ctx_reserve(c, n_idx > 8192 ? n_idx : 8192);
@@ -735,13 +907,31 @@ extern "C" int cdlrm_embed_bwd_plan(cdlrm_ctx* c, int tb, int tc, const int32_t*
     PlanView pv = plan_view(plan, tc, n_idx);
     const int nsub = plan_nsub(n_idx);
     const int max_smem = CDLRM_SORT_MAX * 12 + 8192 * 2 + 64 * 4;
-    CU_CHECK(cdlrm_smem_optin((const void*)bwd_plan_kernel, max_smem));
+    // cluster size of the multi-CTA sort (cdlrm_embed_set_option(0, .) / CDLRM_PLAN_CLUSTER; 0 = one CTA per table)
+    static const int env_cluster = [] { const char* e = getenv("CDLRM_PLAN_CLUSTER"); return e ? atoi(e) : -1; }();
+    const int want = g_plan_cluster >= 0 ? g_plan_cluster : (env_cluster >= 0 ? env_cluster : 8);
     for (int sub = 0; sub < nsub; ++sub) {
         const int j0 = sub * CDLRM_SORT_MAX;
         const int n = n_idx - j0 < CDLRM_SORT_MAX ? n_idx - j0 : CDLRM_SORT_MAX;
-        const int npad = (n + 7) & ~7;
-        const int smem = npad * 12 + 8192 * 2 + 64 * 4;
-        LAUNCH_PDL(K_BWD_PLAN, s, bwd_plan_kernel, tc, PLAN_NT, smem, c->d_tabs, tb, slots, ld_slots, n_idx, j0, n, pv);
+        int C = 0;
+        if (want > 0) {         // smallest power of two <= want whose chunks fit a CTA, not more CTAs than 512-key chunks
+            C = 1;
+            while (C < want && C < 8 && (int64_t)C * 512 < n) C <<= 1;
+            if (((int64_t)n + C - 1) / C > CPL_MAX_CHUNK) C = 0;
+        }
+        if (C > 0) {
+            const int chunk = (int)((((int64_t)n + C - 1) / C + 511) / 512 * 512);
+            const int smem = chunk * 12 + 256 * CPL_NW * 2 + 512 * 4 + 64 * 4;
+            cdlrm_prof_mark(K_BWD_PLAN, s, 0);
+            cdlrm_launch_pdl_cluster(bwd_plan_cluster_kernel, dim3(C, tc), dim3(CPL_NT), smem, s, C, c->d_tabs, tb, slots,
+                                     ld_slots, n_idx, j0, n, chunk, pv);
+            cdlrm_prof_mark(K_BWD_PLAN, s, 1);
+        } else {
+            CU_CHECK(cdlrm_smem_optin((const void*)bwd_plan_kernel, max_smem));
+            const int npad = (n + 7) & ~7;
+            const int smem = npad * 12 + 8192 * 2 + 64 * 4;
+            LAUNCH_PDL(K_BWD_PLAN, s, bwd_plan_kernel, tc, PLAN_NT, smem, c->d_tabs, tb, slots, ld_slots, n_idx, j0, n, pv);
+        }
     }
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;

@@ -408,9 +408,28 @@ extern "C" int cdlrm_plan_phase_a(cdlrm_ctx* c, const int64_t* win_ids, int64_t 
     return plan_impl(c, win_ids, ld, n, h_uniq_len, h_counts, false, stream);
 }
 
+extern "C" int cdlrm_plan_mark_ids(cdlrm_ctx* c, const int64_t* ids, int64_t ld, int64_t n, cdlrm_stream stream) {
+    ARG_CHECK(c && n >= 0);
+    if (n == 0) return CDLRM_OK;
+    ARG_CHECK(ids);
+    if (c->ptabs.empty()) {
+        cdlrm_set_error("planner workspace not bound");
+        return CDLRM_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(c->device));
+    for (int k = 0; k < c->T; ++k) {
+        const int g1 = (int)((n + 1023) / 1024 < 148 * 16 ? (n + 1023) / 1024 : 148 * 16);
+        LAUNCH(K_PLAN_BITMAP_SET, s, bitmap_set_kernel<<<g1 > 0 ? g1 : 1, 256, 0, s>>>(ids + k * ld, n, c->ptabs[k].bitmap, c->tabs[k].n_rows, c->d_flags));
+    }
+    CU_CHECK(cudaGetLastError());
+    return CDLRM_OK;
+}
+
 static int plan_impl(cdlrm_ctx* c, const int64_t* win_ids, int64_t ld, int64_t n, const int64_t* h_uniq_len,
                      int64_t* h_counts, bool unique_only, cdlrm_stream stream) {
-    ARG_CHECK(c && win_ids && h_counts);
+    ARG_CHECK(c && h_counts);
+    ARG_CHECK(win_ids || !h_uniq_len);       // win_ids == NULL: the bitmaps were filled by cdlrm_plan_mark_ids
     ARG_CHECK(n >= 0);
     if (c->ptabs.empty()) {
         cdlrm_set_error("planner workspace not bound");
@@ -449,7 +468,7 @@ static int plan_impl(cdlrm_ctx* c, const int64_t* win_ids, int64_t ld, int64_t n
             if (n > 0) {
                 const int64_t nwords = (t.n_rows + 31) / 32;
                 int g1 = (int)((n + 1023) / 1024 < 148 * 16 ? (n + 1023) / 1024 : 148 * 16);
-                LAUNCH(K_PLAN_BITMAP_SET, s, bitmap_set_kernel<<<g1 > 0 ? g1 : 1, 256, 0, s>>>(win_ids + k * ld, n, p.bitmap, t.n_rows, c->d_flags));
+                if (win_ids) LAUNCH(K_PLAN_BITMAP_SET, s, bitmap_set_kernel<<<g1 > 0 ? g1 : 1, 256, 0, s>>>(win_ids + k * ld, n, p.bitmap, t.n_rows, c->d_flags));
                 const int nblk = (int)((nwords + TILE - 1) / TILE);
                 LAUNCH(K_PLAN_COMPACT, s, bitmap_count_kernel<<<nblk, 256, 0, s>>>(p.bitmap, nwords, c->p_blocksum));
                 LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(c->p_blocksum, nblk, ck + CNT_U));

@@ -381,8 +381,12 @@ class Trainer:
         ``(rows, uniq, maps)`` (cache_manager.py:102-104), of which the ascending unique id lists are what the
         plan needs (the rows are read from the master at install time: sequential schedule)."""
         import threading
-        uniq_lists = None
-        if isinstance(win_ids, (tuple, list)):
+        uniq_lists = marker = None
+        if callable(win_ids):
+            # chunked scan: ``win_ids(planner)`` feeds the window to ``planner.mark_ids`` chunk by chunk (on the
+            # planner's stream, from the plan thread) and returns the number of ids per table it marked
+            marker = win_ids
+        elif isinstance(win_ids, (tuple, list)):
             uniq_lists = [u.to(self.dev, non_blocking=True) for u in win_ids[1]]
         else:
             win_ids = win_ids.to(self.dev, non_blocking=True)
@@ -396,8 +400,14 @@ class Trainer:
             torch.cuda.set_device(self.dev)
             self.side.wait_event(ev)
             try:
-                rec = (self.planner.plan(uniq_lists=uniq_lists) if uniq_lists is not None
-                       else self.planner.plan(win_ids=win_ids))
+                if marker is not None:
+                    with torch.cuda.stream(self.side):
+                        n_marked = marker(self.planner)
+                    rec = self.planner.plan(marked=n_marked)
+                elif uniq_lists is not None:
+                    rec = self.planner.plan(uniq_lists=uniq_lists)
+                else:
+                    rec = self.planner.plan(win_ids=win_ids)
                 if self.world > 1:
                     # the prefetch below reads master rows: rank 0's write-back of the previous
                     # boundary (asynchronous, on its planner stream) must have landed first

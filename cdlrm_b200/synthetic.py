@@ -3,8 +3,7 @@ main).  Batch format of data_loader_terabyte.py:68-87:
 X[B,13] = log(1 + U{0..100}), lS_o[T,B] = arange(B), lS_i[T,B] int64, T[B,1] ~ Bernoulli(0.25).
 
 Index stream per table k: a bounded power law over ranks 1..n_k (exponent ``zipf_a``) or
-uniform, scrambled over the id space with a multiplicative hash; generated on the device
-in whole windows so that the look-ahead planner and the training steps read the same ids.
+uniform, scrambled over the id space with a multiplicative hash.
 """
 import numpy as np
 import torch
@@ -18,9 +17,15 @@ KAGGLE_ROWS = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683
 
 
 class SyntheticStream:
+    """Device-side twin of the loaders below for measurement at full size: ids come from cdlrm_synth_ids (one
+    counter-based stream per table, csrc/synth.cu), so the id of (table, global step, sample) is a pure function
+    of the seed.  ``ids`` generates any (step range x sample range) slice -- a rank's own training batches, or
+    chunks of the GLOBAL window for the look-ahead planner -- and no rank ever has to hold the whole
+    [T, lookahead x global batch] window."""
+
     def __init__(self, ln_emb, batch, device, dist="zipf", zipf_a=1.05, seed=123, dense_dim=13):
         self.ln = [int(n) for n in ln_emb]
-        self.B = int(batch)
+        self.B = int(batch)                  # samples per step of the stream (the GLOBAL batch)
         self.dev = torch.device(device)
         self.dist, self.a, self.seed, self.dense_dim = dist, float(zipf_a), int(seed), dense_dim
 
@@ -29,20 +34,25 @@ class SyntheticStream:
         g.manual_seed(self.seed * 1000003 + w)
         return g
 
+    def ids(self, step0, n_steps, b0=0, nb=None, out=None, stream=None):
+        """int64 [T, n_steps*nb] on the device: samples [b0, b0+nb) of steps [step0, step0+n_steps)."""
+        import ctypes
+
+        from ._lib import check, i64_array, lib
+        nb = self.B - b0 if nb is None else int(nb)
+        T, n = len(self.ln), int(n_steps) * nb
+        if out is None:
+            out = torch.empty(T, n, dtype=torch.int64, device=self.dev)
+        assert out.is_cuda and out.dtype == torch.int64 and out.shape[0] == T and out.stride(1) == 1 and out.shape[1] >= n
+        s = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        check(lib.cdlrm_synth_ids(self.dev.index, 0, T, i64_array(self.ln), self.seed, self.B, int(step0), int(n_steps),
+                                  int(b0), nb, int(self.dist == "uniform"), self.a, ctypes.c_void_p(out.data_ptr()),
+                                  out.stride(0), ctypes.c_void_p(s.cuda_stream)))
+        return out[:, :n]
+
     def window_ids(self, w, n_steps):
-        """int64 [T, n_steps*B] on the device: ids of steps [0, n_steps) of window w."""
-        N = n_steps * self.B
-        g = self._gen(w)
-        out = torch.empty(len(self.ln), N, dtype=torch.int64, device=self.dev)
-        for k, n in enumerate(self.ln):
-            u = torch.rand(N, generator=g, device=self.dev, dtype=torch.float64)
-            if self.dist == "uniform" or n == 1:
-                r = (u * n).long().clamp_(max=n - 1)
-            else:  # inverse CDF of the continuous power law on [1, n+1)
-                e = 1.0 - self.a
-                r = (((n + 1.0) ** e - 1.0) * u + 1.0).pow_(1.0 / e).long().sub_(1).clamp_(0, n - 1)
-            out[k] = (r * 2654435761 + 40503 * k) % n
-        return out
+        """int64 [T, n_steps*B] on the device: the whole batch of steps [w*n_steps, (w+1)*n_steps)."""
+        return self.ids(w * n_steps, n_steps)
 
     def dense_and_labels(self, w, n_steps):
         g = self._gen(10_000_000 + w)

@@ -104,6 +104,9 @@ int64_t cdlrm_embed_bwd_plan_bytes(int table_count, int32_t n_idx);
 int cdlrm_embed_bwd_plan(cdlrm_ctx* ctx, int table_begin, int table_count,
                          const int32_t* slots, int64_t ld_slots, int32_t n_idx,
                          void* plan, cdlrm_stream stream);
+/* key 0: thread-block cluster size of the backward plan's multi-CTA radix sort (1, 2, 4, 8; 0 = the one-CTA-per-table
+ * kernel; -1 = default: environment CDLRM_PLAN_CLUSTER, else 8).  Same sorted run either way. */
+int cdlrm_embed_set_option(int key, int value);
 int cdlrm_embed_bwd_sgd(cdlrm_ctx* ctx, int table_begin, int table_count,
                         const void* plan, int32_t n_idx,
                         const int32_t* bag_ids, int64_t ld_bag,
@@ -170,6 +173,10 @@ int cdlrm_plan_bind_workspace(cdlrm_ctx* ctx, void* workspace, int64_t bytes, in
  * h_counts[k*4] = number of unique ids of table k (other three entries 0). */
 int cdlrm_plan_unique(cdlrm_ctx* ctx, const int64_t* win_ids, int64_t ld, int64_t n,
                       int64_t* h_counts, cdlrm_stream stream);
+/* Chunked window scan: OR the ids of a chunk (int64 [num_tables][n], table k at ids + k*ld) into the planner's id
+ * bitmaps.  Any number of calls, in any order, then cdlrm_plan_phase_a with win_ids == NULL and n = the number of
+ * ids marked per table (an upper bound of the distinct ids): the window never has to exist as one tensor. */
+int cdlrm_plan_mark_ids(cdlrm_ctx* ctx, const int64_t* ids, int64_t ld, int64_t n, cdlrm_stream stream);
 /* phase A, all tables: unique ids of the window (ascending), probe against the plan
  * tags, pin hit ways, drop misses whose set is fully pinned, rank the survivors.
  * win_ids of table k at win_ids + k*ld (int64 [n]).  If h_uniq != NULL ids are taken
@@ -276,6 +283,16 @@ int cdlrm_host_unregister(void* h_ptr);
  *      ldz / ldt; dz: n contiguous float32. */
 int cdlrm_bce_mean(int device, const float* z, int64_t ldz, const float* t, int64_t ldt, int32_t n, float* loss,
                    float* dz, cdlrm_stream stream);
+
+/* ---- synthetic Criteo-shaped sparse ids (synthetic train_ld + cache_ld twin; replaces the role of
+ *      dlrm_data_pytorch.py:386-547 for measurement, the reference's random mode main_no_ddp.py:539-547 cannot run).
+ * out[(k - table_begin) * ld + s * nb + b] = id of table k, global step step0 + s, sample b0 + b of the global batch
+ * (batch_global samples per step): a pure function of (seed, k, step, sample), so the trainers' batches and the
+ * look-ahead planner's window scan can be generated independently, in chunks, on any rank.  uniform != 0: uniform
+ * over [0, n_k); else a bounded power law with exponent zipf_a over ranks 1..n_k, scrambled over the id space. */
+int cdlrm_synth_ids(int device, int table_begin, int table_count, const int64_t* h_n_rows, uint64_t seed,
+                    int64_t batch_global, int64_t step0, int32_t n_steps, int64_t b0, int32_t nb,
+                    int uniform, double zipf_a, int64_t* out, int64_t ld, cdlrm_stream stream);
 
 /* A CUDA stream of the library's own (cudaStreamNonBlocking; priority 0 = default, -1 = highest).  PyTorch hands out
  * streams from a round-robin pool of 32 per priority, so two torch.cuda.Stream objects can be the SAME stream: the

@@ -359,7 +359,7 @@ def gpu_run(a, wl, ln_emb):
         with torch.cuda.stream(tr.side):
             loc = stream_g.ids(w * L, L, b0=rank * lb, nb=lb, stream=tr.side)          # [T, L*lb]
             X, Y = stream_l.dense_and_labels(w, L)
-            ready = torch.cuda.Event()
+            ready = torch.cuda.Event(enable_timing=True)
             ready.record(tr.side)
             for t_ in (loc, X, Y):        # allocated on the side stream, read by the training stream
                 t_.record_stream(torch.cuda.current_stream(dev))
@@ -501,6 +501,12 @@ def gpu_run(a, wl, ln_emb):
     log(f"timed region done: {ms / K:.3f} ms/step")
     value = K * lb * world / (ms / 1000.0)
 
+    # -- per-kernel durations (CUDA events around every launch of the library) ------------------
+    roof = kernels = None
+    if not a.no_kernel_prof:
+        kernels, roof, step_bytes, j = kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, j, L,
+                                                      lb, T, d, dev, ln_bot, ln_top)
+
     # -- end to end through the public API with host buffers ---------------------------------------
     e2e = full_window = None
     if a.e2e_steps >= 0:
@@ -539,26 +545,40 @@ def gpu_run(a, wl, ln_emb):
         log(f"end-to-end leg: {n_e2e} steps from pinned host inputs ({(hI.nbytes + hX.nbytes + hY.nbytes) / 1e9:.1f} GB)")
         logging_on[0] = True
         lib.cdlrm_prof_launches(1)
-        seg2 = max(1, n_e2e // 24)
+        seg2 = max(1, n_e2e // 120)
         marks2 = []
         t0 = time.perf_counter()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
+        # Every step: its inputs come from pinned host memory (Trainer.stage_inputs: the copy of step i+1 runs on
+        # the copy stream beside step i) and its loss is read back to the host (asynchronous copy into a pinned
+        # ring, read one step later, so that the host can enqueue step i+1 while step i runs).
+        loss_pin = torch.zeros(2, dtype=torch.float32, pin_memory=True)
+        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        loss_host = float("nan")
         e0.record()
+        st = tr.stage_inputs(hX[0], hI[0], hY[0])
         for i in range(n_e2e):
             # (one_step indexes the host block by the step's position in its window)
             w_, b_ = divmod(j, L)
             if b_ == 0 and j > 0:
                 boundary(j)
-            E, _ = tr.step(hX[i].to(dev, non_blocking=True), lS_o, hI[i].to(dev, non_blocking=True),
-                           hY[i].to(dev, non_blocking=True))
+            nxt = tr.stage_inputs(hX[i + 1], hI[i + 1], hY[i + 1]) if i + 1 < n_e2e else None
+            E, _ = tr.step_staged(st, lS_o)
             aggregate(j)
-            loss_host = E.item()                       # device -> host read of the step's result
+            loss_pin[i & 1].copy_(E.detach().reshape(()), non_blocking=True)   # device -> host read of the result
+            loss_ev[i & 1].record()
+            if i:
+                loss_ev[(i - 1) & 1].synchronize()
+                loss_host = float(loss_pin[(i - 1) & 1])
+            st = nxt
             j += 1
             if (i + 1) % seg2 == 0 and i + 1 < n_e2e:
                 m = torch.cuda.Event(enable_timing=True)
                 m.record()
                 marks2.append((i + 1, m))
+        loss_ev[(n_e2e - 1) & 1].synchronize()
+        loss_host = float(loss_pin[(n_e2e - 1) & 1])
         e1.record()
         torch.cuda.synchronize(dev)
         wall_ms = 1000 * (time.perf_counter() - t0)
@@ -601,6 +621,11 @@ def gpu_run(a, wl, ln_emb):
         if rec_next is not None and not isinstance(rec_next, Exception) and getattr(rec_next, "stage_begin", None) is not None:
             st_ms = rec_next.stage_begin.elapsed_time(rec_next.staged)
             full_window["planner_ms"] = {k: round(1000 * v, 1) for k, v in tr.planner.last_timing.items()}
+            # when, after the start of the leg, each phase of the next window's look-ahead ended on the side stream
+            tl = {"ids_ready": data[max(data)][3]}
+            tl.update(rec_next.marks)
+            tl.update(stage_begin=rec_next.stage_begin, staged=rec_next.staged)
+            full_window["planner_timeline_ms"] = {k: round(e0.elapsed_time(v), 1) for k, v in tl.items()}
             full_window["planner_ms"]["prefetch"] = round(st_ms, 1)
             pcie["prefetch_bytes"] = int(rec_next.stage_bytes)
             pcie["prefetch_ms"] = round(st_ms, 2)
@@ -611,12 +636,7 @@ def gpu_run(a, wl, ln_emb):
         del hosts, hI, hX, hY
     clocks = sampler.stop() if sampler else None
 
-    # -- per-kernel durations (CUDA events around every launch of the library) ------------------
-    roof = kernels = None
     res = None
-    if not a.no_kernel_prof:
-        kernels, roof, step_bytes = kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, j, L, lb, T,
-                                                   d, dev, ln_bot, ln_top)
     if rank == 0:
         peak, _src = measured_peak()
         res = {
@@ -657,7 +677,7 @@ def gpu_run(a, wl, ln_emb):
 
 def kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, j, L, lb, T, d, dev, ln_bot, ln_top):
     """Eager steps with every library launch bracketed by CUDA events on its own stream (every rank takes these
-    steps: they contain collectives).  Returns (kernels, roofline, algorithmic bytes per step)."""
+    steps: they contain collectives).  Returns (kernels, roofline, algorithmic bytes per step, next step index)."""
     NK = lib.cdlrm_prof_num_kernels()
     if j % L == 0:              # at a window boundary (the whole-window e2e leg ends on one): take it first
         one_step(j)
@@ -688,6 +708,7 @@ def kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, 
     msv = (ctypes.c_double * NK)()
     calls = (ctypes.c_int64 * NK)()
     _lib.check(lib.cdlrm_prof_report(msv, calls, NK))
+    log(f"kernel profile over {nprof} eager steps: {lib.cdlrm_last_error().decode()}")
     lib.cdlrm_prof_enable(0)
     n_miss = int(tr.cache_group.last_n_miss.sum().item())
     w, b = divmod(j - 1, L)
@@ -777,7 +798,7 @@ def kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, 
                         "(an empty kernel through the same pair), frac_raw_event_pair is the same fraction without that "
                         "subtraction; the MLP GEMMs (tensor-bound) are under kernels.mlp_gemm"}
     step_bytes = sum(algo[k] for k in algo if k in kernels)
-    return kernels, roof, step_bytes
+    return kernels, roof, step_bytes, j
 
 
 def main():

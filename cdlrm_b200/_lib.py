@@ -64,6 +64,11 @@ SIGNATURES = {
     "cdlrm_move_scatter_master2": (C.c_int, [vp, C.c_int, vp, vp, C.c_int64, vp, C.c_int, vp]),
     "cdlrm_plan_losers": (C.c_int, [vp, c_i64p, c_i64p, vp, vp, vp]),
     "cdlrm_ctx_bind_losers": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), c_i64p, vp]),
+    "cdlrm_peer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(vp), vp]),
+    "cdlrm_peer_open": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
+    "cdlrm_peer_close": (C.c_int, [C.c_int, vp]),
+    "cdlrm_peer_free": (C.c_int, [C.c_int, vp]),
+    "cdlrm_ctx_bind_losers_sharded": (C.c_int, [vp, C.POINTER(vp), c_i64p, c_i64p, C.c_int, C.POINTER(vp), vp]),
     "cdlrm_host_register": (C.c_int, [C.c_int, vp, C.c_int64, C.POINTER(vp)]),
     "cdlrm_host_unregister": (C.c_int, [vp]),
     "cdlrm_agg_mark": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp]),

@@ -116,7 +116,8 @@ class PlanRecord:
                  "evict_primary", "fill_ids", "fill_slots", "event",
                  # look-ahead staging (WindowPlanner.stage / install_staged)
                  "L", "loser_off", "loser_soff", "loser_ids", "loser_stage", "fill_stage", "fill_soff", "evict_stage",
-                 "staged", "wb_done", "stage_begin", "stage_bytes")
+                 "staged", "wb_done", "stage_begin", "stage_bytes", "loser_shard", "loser_peers",
+                 "marks")
 
     def loser_list(self, k):
         o, n = self.loser_off[k], self.L[k]
@@ -155,6 +156,8 @@ class WindowPlanner:
         self.collect_losers = False      # also list the window's un-cached ids (for the HBM loser store)
         self._bufs = {}                  # persistent grow-only staging buffers (no cudaMalloc per window)
         self._stage_no = 0
+        self._shard = None               # (rank, world, host process group): loser store sharded over the node
+        self._peer_bufs = {}             # name -> (capacity rows, [device address of every rank's shard buffer])
         self.plan_tags = None
         if lookahead_tags:
             self.enable_lookahead_tags()
@@ -177,6 +180,74 @@ class WindowPlanner:
                 gb = min(32.0, max(8.0, ((free + cached) / 1e9 - 70.0) / 2))
             cap = self._loser_cap_rows = int(gb * 1e9 / (4 * self.dim))
         return cap
+
+    def _agreed_loser_cap(self):
+        """Rows one window's loser store may hold: ``loser_cap_rows`` on one rank; sharded, ``world`` times the
+        smallest per-rank budget (agreed once over the host group, the plans must stay identical)."""
+        if self._shard is None:
+            return self.loser_cap_rows
+        cap = getattr(self, "_loser_cap_agreed", None)
+        if cap is None:
+            import torch.distributed as dist
+            _rank, world, group = self._shard
+            caps = [int(self.loser_cap_rows)] * world
+            if group != "local":
+                dist.all_gather_object(caps, int(self.loser_cap_rows), group=group)
+            cap = self._loser_cap_agreed = min(caps) * world
+        return cap
+
+    def enable_sharded_losers(self, rank, world, group):
+        """Shard the loser store over the ``world`` ranks of ONE node (peer.cu): every rank runs the same plan, so
+        the un-cached ids of a window are the same everywhere; rank r prefetches rows [r * shard, (r + 1) * shard) of
+        each table's ascending loser list over its own PCIe link into a buffer its peers can read over NVLink, and
+        the forward reads a missing row from the rank that holds it.  ``group``: a host-side (gloo) process group
+        used to exchange the IPC handles and to agree on sizes; calls that touch it come from the plan thread of
+        every rank in the same order."""
+        if world > 1:
+            if world > 8:
+                raise _lib.CdlrmError("the sharded loser store spans the (at most 8) GPUs of one node")
+            self._shard = (int(rank), int(world), group)      # group "local": single-process emulation (tests)
+
+    def _peer_buf(self, name, rows):
+        """Peer-readable [rows, dim] fp32 buffer ``name`` of this rank plus the addresses of the same-named buffers
+        of every other rank (collective over the host group: every rank asks for the same ``rows``).  Grown (x1.25)
+        only when a window needs more."""
+        import torch.distributed as dist
+        rank, world, group = self._shard
+        ent = self._peer_bufs.get(name)
+        if ent is not None and ent[0] >= rows:
+            return ent
+        if group == "local":
+            # in-process emulation (tests on a one-GPU box): the shards of all `world` ranks live on this device
+            cap = int(rows) + 16
+            keep = [torch.empty(cap, self.dim, dtype=torch.float32, device=self.dev) for _ in range(world)]
+            ent = self._peer_bufs[name] = (cap, [t.data_ptr() for t in keep], keep)
+            return ent
+        dev = self.dev.index
+        if ent is not None:
+            # nobody reads this buffer any more (it served window w-1; every rank has installed window w: the plan
+            # barrier precedes the staging of window w+1): unmap the peers' copies everywhere, then free
+            for r, p in enumerate(ent[1]):
+                if r != rank:
+                    check(lib.cdlrm_peer_close(dev, _vp(p)))
+            dist.barrier(group=group)
+            check(lib.cdlrm_peer_free(dev, _vp(ent[1][rank])))
+        cap = int(rows) + min(int(rows * 0.25), (1 << 30) // (4 * self.dim)) + 16
+        mine = _vp()
+        handle = ctypes.create_string_buffer(64)
+        check(lib.cdlrm_peer_alloc(dev, cap * self.dim * 4, ctypes.byref(mine), handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        ptrs = []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(mine.value)
+            else:
+                p = _vp()
+                check(lib.cdlrm_peer_open(dev, ctypes.create_string_buffer(handles[r], 64), ctypes.byref(p)))
+                ptrs.append(p.value)
+        ent = self._peer_bufs[name] = (cap, ptrs)
+        return ent
 
     def enable_lookahead_tags(self):
         """Give the planner its own evolving copy of the tags so that it can run one or more
@@ -208,8 +279,15 @@ class WindowPlanner:
         already scanned chunk by chunk with ``mark_ids``."""
         s = self.stream
         rec = PlanRecord()
+        rec.marks = {}                   # phase name -> timing event on the planner's stream (bench.py: timeline)
+
+        def mark(name):
+            e = rec.marks[name] = torch.cuda.Event(enable_timing=True)
+            e.record(s)
+
         t_a = time.perf_counter()
         with torch.cuda.stream(s):
+            mark("plan_begin")
             if uniq_lists is not None:
                 lens = [int(u.numel()) for u in uniq_lists]
                 ld = max(max(lens), 1)
@@ -228,6 +306,7 @@ class WindowPlanner:
                 assert win_ids.is_cuda and win_ids.dtype == torch.int64 and win_ids.stride(1) == 1
                 check(lib.cdlrm_plan_phase_a(self.ctx, _vp(win_ids.data_ptr()), win_ids.stride(0),
                                              win_ids.shape[1], None, _vp(self._h_counts.data_ptr()), _sp(s)))
+            mark("phase_a_done")
             s.synchronize()
             cnt = self._h_counts.view(self.T, 4).clone()
             rec.uniq = cnt[:, 0].tolist()
@@ -262,6 +341,7 @@ class WindowPlanner:
             else:
                 check(lib.cdlrm_plan_phase_b(self.ctx, _vp(q.data_ptr()) if total else None,
                                              _lib.i64_array(rec.rows), *outs))
+            mark("phase_b_done")
             s.synchronize()
             c2 = self._h_counts2.view(self.T, 2).clone()
             rec.E = c2[:, 0].tolist()
@@ -282,12 +362,14 @@ class WindowPlanner:
                 # table's ascending loser ids is staged; the forward serves the others zero-copy from the host
                 # master (fwd_miss_kernel falls back when the binary search misses) -- same rows either way
                 tot = sum(rec.L)
-                if tot > self.loser_cap_rows:
-                    rec.L = [int(x * self.loser_cap_rows // tot) for x in rec.L]
+                cap_rows = self._agreed_loser_cap()
+                if tot > cap_rows:
+                    rec.L = [int(x * cap_rows // tot) for x in rec.L]
             self.last_timing = {"phase_a_s": round(t_b - t_a, 4), "rng_s": round(t_c - t_b, 4),
                                 "phase_b_s": round(time.perf_counter() - t_c, 4)}
         rec.event = None
         rec.staged = rec.wb_done = rec.fill_stage = rec.loser_stage = rec.evict_stage = None
+        rec.loser_shard = rec.loser_peers = None
         rec.stage_begin, rec.stage_bytes = None, 0
         return rec
 
@@ -326,7 +408,29 @@ class WindowPlanner:
                     ids, _slots = rec.fill_list(k)
                     check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(ids.data_ptr()), rec.F[k],
                                                        _vp(rec.fill_stage[rec.fill_soff[k]:].data_ptr()), _sp(s)))
-            if rec.L is not None:
+            rec.loser_shard = rec.loser_peers = None
+            n_loser_rows = 0
+            if rec.L is not None and self._shard is not None:
+                # sharded store: this rank pulls rows [rank * shard, (rank + 1) * shard) of every table's list
+                rank, world, _group = self._shard
+                self._stage_no += 1
+                rec.loser_shard = [(n + world - 1) // world for n in rec.L]
+                rec.loser_soff = [0] * self.T
+                for k in range(1, self.T):
+                    rec.loser_soff[k] = rec.loser_soff[k - 1] + rec.loser_shard[k - 1]
+                ptrs = self._peer_buf("loser%d" % (self._stage_no & 1), max(sum(rec.loser_shard), 1))[1]
+                row_b = 4 * d
+                rec.loser_peers = [[ptrs[r] + rec.loser_soff[k] * row_b for r in range(world)] for k in range(self.T)]
+                for k in range(self.T):
+                    for r in (range(world) if _group == "local" else (rank,)):
+                        lo = r * rec.loser_shard[k]
+                        n_k = min(rec.L[k], lo + rec.loser_shard[k]) - lo
+                        if n_k > 0:
+                            o = rec.loser_off[k] + lo
+                            check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(rec.loser_ids[o:].data_ptr()), n_k,
+                                                               _vp(rec.loser_peers[k][r]), _sp(s)))
+                            n_loser_rows += n_k
+            elif rec.L is not None:
                 # two loser stores alternate: the previous window's is read by the forward until the boundary
                 self._stage_no += 1
                 rec.loser_soff = [0] * self.T          # rows are packed by the (possibly capped) counts
@@ -338,10 +442,11 @@ class WindowPlanner:
                         o = rec.loser_off[k]
                         check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(rec.loser_ids[o:].data_ptr()), rec.L[k],
                                                            _vp(rec.loser_stage[rec.loser_soff[k]:].data_ptr()), _sp(s)))
+                n_loser_rows = sum(rec.L)
             rec.staged = torch.cuda.Event(enable_timing=True)
             rec.staged.record(s)
             # host-master rows pulled over PCIe by this prefetch (bench.py: prefetch GB/s = bytes / event time)
-            rec.stage_bytes = 4 * d * (sum(rec.F) + (sum(rec.L) if rec.L is not None else 0))
+            rec.stage_bytes = 4 * d * (sum(rec.F) + n_loser_rows)
         return rec
 
     def install_staged(self, rec, write_master=True, average_on_writeback=False, stream=None):
@@ -375,7 +480,15 @@ class WindowPlanner:
                     ids, slots = rec.fill_list(k)
                     check(lib.cdlrm_move_fill(self.ctx, k, _vp(ids.data_ptr()), _vp(slots.data_ptr()), rec.F[k],
                                               _vp(rec.fill_stage[rec.fill_soff[k]:].data_ptr()), None, _sp(s)))
-            if rec.L is not None:
+            if rec.L is not None and rec.loser_peers is not None:
+                world = self._shard[1]
+                check(lib.cdlrm_ctx_bind_losers_sharded(
+                    self.ctx,
+                    _lib.ptr_array([rec.loser_ids[rec.loser_off[k]:].data_ptr() if rec.L[k] else 0
+                                    for k in range(self.T)]),
+                    _lib.i64_array(rec.L), _lib.i64_array(rec.loser_shard), world,
+                    _lib.ptr_array([p for k in range(self.T) for p in rec.loser_peers[k]]), _sp(s)))
+            elif rec.L is not None:
                 check(lib.cdlrm_ctx_bind_losers(
                     self.ctx,
                     _lib.ptr_array([rec.loser_ids[rec.loser_off[k]:].data_ptr() if rec.L[k] else 0

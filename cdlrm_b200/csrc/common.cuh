@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 #include <vector>
 
@@ -57,10 +58,15 @@ struct PlanTable {
 // Loser store of one table: the window's ids that are NOT cached after the install (lost a
 // contested slot, or dropped because their set was fully pinned), ascending, with a copy of
 // their master rows staged in HBM; the forward serves these misses from HBM instead of PCIe.
+// Sharded over the ranks of a node (shard > 0): index i of the list lives on rank i / shard, at row i % shard of
+// that rank's shard (peer[r]: device address of rank r's shard of this table, readable over NVLink; peer[own
+// rank] is local HBM).
 struct LoserDesc {
     const int64_t* ids;
     const float* rows;
     int64_t n;
+    int64_t shard;                       // 0: the whole store is local (rows)
+    const float* peer[CDLRM_MAX_PEERS];
 };
 
 struct cdlrm_ctx {

@@ -321,16 +321,25 @@ extern "C" int cdlrm_prof_report(double* h_ms, int64_t* h_calls, int n) {
     CU_CHECK(cudaDeviceSynchronize());
     std::lock_guard<std::mutex> lk(g_prof_mu);
     for (int i = 0; i < n; ++i) { h_ms[i] = 0.0; h_calls[i] = 0; }
+    size_t failed = 0;
+    cudaError_t first = cudaSuccess;
     for (auto& r : g_prof) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, r.b, r.e) == cudaSuccess) {
+        const cudaError_t e = cudaEventElapsedTime(&ms, r.b, r.e);
+        if (e == cudaSuccess) {
             h_ms[r.id] += ms;
             h_calls[r.id] += 1;
+        } else {
+            if (!failed++) first = e;
+            cudaGetLastError();
         }
         cudaEventDestroy(r.b);
         cudaEventDestroy(r.e);
     }
     cudaGetLastError();
+    // not an error of the call: cdlrm_last_error() carries the tally for the caller's log
+    cdlrm_set_error("prof_report: %zu records, %zu without a duration (%s)", g_prof.size(), failed,
+                    failed ? cudaGetErrorString(first) : "-");
     g_prof.clear();
     return CDLRM_OK;
 }

@@ -183,10 +183,11 @@ __global__ void __launch_bounds__(MISS_NT) fwd_miss_kernel(const TableDesc* __re
     // loser store of the installed window: ascending ids + their master rows staged in HBM
     const int64_t* __restrict__ l_ids = nullptr;
     const float* __restrict__ l_rows = nullptr;
-    int64_t l_n = 0;
+    const LoserDesc* __restrict__ l_desc = nullptr;
+    int64_t l_n = 0, l_shard = 0;
     if (losers) {
-        const LoserDesc L = losers[tb + t];
-        l_ids = L.ids; l_rows = L.rows; l_n = L.n;
+        l_desc = losers + tb + t;
+        l_ids = l_desc->ids; l_rows = l_desc->rows; l_n = l_desc->n; l_shard = l_desc->shard;
     }
     // warp `warp` owns words w_lo + warp, w_lo + warp + NW, ... ; its running ordinal starts at the
     // popcount of the range's words that precede each of them, recomputed per word (ranges are short)
@@ -219,8 +220,16 @@ __global__ void __launch_bounds__(MISS_NT) fwd_miss_kernel(const TableDesc* __re
                     const int64_t mid = (lo + hi) >> 1;
                     if (__ldg(l_ids + mid) < id) lo = mid + 1; else hi = mid;
                 }
-                if (lo < l_n && __ldg(l_ids + lo) == id) src_l = l_rows + lo * dim;   // HBM
-                else src_l = master + id * dim;                                        // zero-copy PCIe
+                if (lo < l_n && __ldg(l_ids + lo) == id) {
+                    if (l_shard) {              // sharded store: the row is in the HBM of rank lo / shard (NVLink)
+                        const int64_t owner = lo / l_shard;
+                        src_l = l_desc->peer[owner] + (lo - owner * l_shard) * dim;
+                    } else {
+                        src_l = l_rows + lo * dim;                                     // local HBM
+                    }
+                } else {
+                    src_l = master + id * dim;                                         // zero-copy PCIe
+                }
                 slots[(int64_t)t * ld_slots + j] = (int32_t)aux_l;
             }
         }

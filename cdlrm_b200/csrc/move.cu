@@ -240,10 +240,39 @@ extern "C" int cdlrm_ctx_bind_losers(cdlrm_ctx* c, const int64_t* const* h_ids, 
     }
     LoserDesc* h = c->h_losers + (size_t)(c->losers_flip++ & 3) * c->T;   // 4 updates may be in flight
     for (int k = 0; k < c->T; ++k) {
+        memset(&h[k], 0, sizeof(LoserDesc));
         h[k].ids = h_ids ? h_ids[k] : nullptr;
         h[k].rows = h_rows ? h_rows[k] : nullptr;
         h[k].n = (h_ids && h_rows && h_n) ? h_n[k] : 0;
         ARG_CHECK(h[k].n >= 0 && (h[k].n == 0 || (h[k].ids && h[k].rows)));
+    }
+    CU_CHECK(cudaMemcpyAsync(c->d_losers, h, sizeof(LoserDesc) * c->T, cudaMemcpyHostToDevice, s));
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_ctx_bind_losers_sharded(cdlrm_ctx* c, const int64_t* const* h_ids, const int64_t* h_n,
+                                             const int64_t* h_shard, int world, const float* const* h_peer,
+                                             cdlrm_stream stream) {
+    ARG_CHECK(c && h_ids && h_n && h_shard && h_peer && world >= 1 && world <= CDLRM_MAX_PEERS);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(c->device));
+    if (!c->d_losers) {
+        CU_CHECK(cudaMalloc(&c->d_losers, sizeof(LoserDesc) * c->T));
+        CU_CHECK(cudaMemset(c->d_losers, 0, sizeof(LoserDesc) * c->T));
+        CU_CHECK(cudaHostAlloc(&c->h_losers, sizeof(LoserDesc) * c->T * 4, cudaHostAllocDefault));
+    }
+    LoserDesc* h = c->h_losers + (size_t)(c->losers_flip++ & 3) * c->T;
+    for (int k = 0; k < c->T; ++k) {
+        memset(&h[k], 0, sizeof(LoserDesc));
+        h[k].n = h_n[k];
+        if (h[k].n == 0) continue;
+        ARG_CHECK(h[k].n > 0 && h_ids[k] && h_shard[k] > 0 && h_shard[k] * world >= h[k].n);
+        h[k].ids = h_ids[k];
+        h[k].shard = h_shard[k];
+        for (int r = 0; r < world; ++r) {
+            h[k].peer[r] = h_peer[(size_t)k * world + r];
+            ARG_CHECK(h[k].peer[r] || (int64_t)r * h_shard[k] >= h[k].n);     // a rank without rows may pass NULL
+        }
     }
     CU_CHECK(cudaMemcpyAsync(c->d_losers, h, sizeof(LoserDesc) * c->T, cudaMemcpyHostToDevice, s));
     return CDLRM_OK;

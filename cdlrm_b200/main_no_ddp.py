@@ -366,6 +366,12 @@ class Trainer:
                                          lookahead_tags=True)
             self.planner.collect_losers = True     # un-cached ids of a window are served from an HBM loser store
         self._host_group = dist.new_group(backend="gloo") if world > 1 else None   # plan-thread barrier
+        # un-cached ids of a window (the same on every rank): one store sharded over the node's GPUs and read over
+        # NVLink instead of a full copy per rank (CDLRM_LOSER_SHARDED=0: one local store per rank)
+        self.sharded_losers = (world > 1 and self.planner is not None
+                               and os.environ.get("CDLRM_LOSER_SHARDED", "1") != "0")
+        if self.sharded_losers:
+            self.planner.enable_sharded_losers(rank, world, self._host_group)
         self._installed = None
         self._plan_q = queue.Queue()
         self._plan_thread = None
@@ -415,7 +421,13 @@ class Trainer:
                     if self.rank == 0 and prev_rec is not None and prev_rec.wb_done is not None:
                         prev_rec.wb_done.synchronize()
                     dist.barrier(group=self._host_group)
-                self._plan_q.put(self.planner.stage(rec))
+                rec = self.planner.stage(rec)
+                if self.sharded_losers:
+                    # a peer's forward reads this rank's shard right after ITS install: every rank's prefetch must
+                    # have landed before any rank is handed the record
+                    rec.staged.synchronize()
+                    dist.barrier(group=self._host_group)
+                self._plan_q.put(rec)
             except Exception as e:  # surfaced by install_window
                 self._plan_q.put(e)
 
@@ -504,6 +516,52 @@ class Trainer:
             self._graph.replay()
             return self._g_out
         return self._step_eager(X, lS_o, lS_i, T)
+
+    # -- host inputs: copy of step i+1 beside step i --------------------------------------------
+    class StagedInputs:
+        __slots__ = ("X", "lS_i", "T", "ready", "slot")
+
+    def stage_inputs(self, X, lS_i, T):
+        """Start the host->device copy of ONE step's inputs (pinned host tensors: dense features, ids [T, lb],
+        labels) on the trainer's copy stream and return a handle for ``step_staged``.  Two device-side slots
+        alternate, so the copy of step i+1 runs beside step i instead of in front of it on the training stream
+        (2.2 MB per step at the Terabyte shape: ~40 us of PCIe time per step otherwise serialised with the step)."""
+        if getattr(self, "_in_slots", None) is None:
+            self._copy_stream = _lib.new_stream(self.dev)
+            self._in_slots, self._in_no = [None, None], 0
+        k = self._in_no & 1
+        self._in_no += 1
+        sl = self._in_slots[k]
+        shapes = (tuple(X.shape), tuple(lS_i.shape), tuple(T.shape))
+        if sl is None or sl[0] != shapes:
+            if sl is not None:
+                torch.cuda.synchronize(self.dev)
+            st = Trainer.StagedInputs()
+            st.X = torch.empty(shapes[0], dtype=X.dtype, device=self.dev)
+            st.lS_i = torch.empty(shapes[1], dtype=torch.int64, device=self.dev)
+            st.T = torch.empty(shapes[2], dtype=T.dtype, device=self.dev)
+            st.ready, st.slot = torch.cuda.Event(), k
+            sl = self._in_slots[k] = (shapes, st, torch.cuda.Event())
+            sl[2].record(torch.cuda.current_stream(self.dev))
+        _shapes, st, free = sl
+        cs = self._copy_stream
+        cs.wait_event(free)                 # the step that last read this slot has taken its inputs
+        with torch.cuda.stream(cs):
+            st.X.copy_(X, non_blocking=True)
+            st.lS_i.copy_(lS_i, non_blocking=True)
+            st.T.copy_(T, non_blocking=True)
+            st.ready.record(cs)
+        return st
+
+    def step_staged(self, st, lS_o):
+        """``step`` on inputs staged by ``stage_inputs``."""
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(st.ready)
+        out = self.step(st.X, lS_o, st.lS_i, st.T)
+        # graph path: the replay begins with device-to-device copies into the captured input buffers, but the
+        # slot is only known to be free once the whole step is enqueued behind them -- record after the step
+        self._in_slots[st.slot][2].record(cur)
+        return out
 
     def step_reference(self, X, lS_o, lS_i, T):
         """The reference's step, call for call (main_no_ddp.py:401-415); returns (E, Z, cache_group_idxs)."""

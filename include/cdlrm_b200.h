@@ -34,6 +34,8 @@ extern "C" {
 
 #define CDLRM_ABI_VERSION 1
 #define CDLRM_MAX_WAYS 64          /* pin masks are 64-bit */
+#define CDLRM_MAX_PEERS 8          /* ranks of one node that can share a sharded loser store */
+#define CDLRM_IPC_HANDLE_BYTES 64  /* sizeof(cudaIpcMemHandle_t) */
 #define CDLRM_SORT_MAX 16384       /* ids per table sorted by one CTA in the backward plan */
 
 typedef struct cdlrm_ctx cdlrm_ctx;
@@ -283,6 +285,21 @@ int cdlrm_host_unregister(void* h_ptr);
  *      ldz / ldt; dz: n contiguous float32. */
 int cdlrm_bce_mean(int device, const float* z, int64_t ldz, const float* t, int64_t ldt, int32_t n, float* loss,
                    float* dz, cdlrm_stream stream);
+
+/* ---- peer-readable device buffers (CUDA IPC over NVLink / NVSwitch) and the SHARDED loser store ----------------
+ * No reference counterpart as code: the reference fetches every forward miss from the CPU master table
+ * (model_no_ddp.py:176-179).  Here the un-cacheable ids of a window (identical on every rank: same deterministic
+ * plan) are prefetched into HBM, 1/world of the rows per rank, and a missing row is read from the rank that holds it.
+ * alloc: cudaMalloc + IPC handle (CDLRM_IPC_HANDLE_BYTES bytes, to be sent to the peers); open / close: map / unmap a
+ * peer's buffer on `device`; free: release a buffer made by alloc. */
+int cdlrm_peer_alloc(int device, int64_t bytes, void** d_ptr, void* handle_out);
+int cdlrm_peer_open(int device, const void* handle, void** d_ptr);
+int cdlrm_peer_close(int device, void* d_ptr);
+int cdlrm_peer_free(int device, void* d_ptr);
+/* Sharded variant of cdlrm_ctx_bind_losers: table k has h_n[k] ascending ids at h_ids[k]; index i of that list is
+ * row i % h_shard[k] of rank i / h_shard[k], whose shard of table k starts at h_peer[k * world + rank]. */
+int cdlrm_ctx_bind_losers_sharded(cdlrm_ctx* ctx, const int64_t* const* h_ids, const int64_t* h_n,
+                                  const int64_t* h_shard, int world, const float* const* h_peer, cdlrm_stream stream);
 
 /* ---- synthetic Criteo-shaped sparse ids (synthetic train_ld + cache_ld twin; replaces the role of
  *      dlrm_data_pytorch.py:386-547 for measurement, the reference's random mode main_no_ddp.py:539-547 cannot run).

@@ -48,13 +48,16 @@ def _run_cuda_trace(cfg, mode):
     torch.manual_seed(seed)
     planner = None
     capped = mode == "staged_capped"      # tiny HBM budget for the loser store: most misses fall back to the host master
-    if capped:
+    sharded = mode == "staged_sharded"    # loser store cut into 3 per-"rank" shards (all on this device), peer.cu path
+    if capped or sharded:
         mode = "staged"
     if mode in ("fast", "fast_devrng", "staged"):
         cg._ensure_ctx(master)
         rng = C.VictimRng(seed) if mode == "fast" else C.VictimRngDevice(seed, DEV)
         planner = C.WindowPlanner(cg, master, L * B, rng=rng, lookahead_tags=True)
         planner.collect_losers = mode == "staged"
+        if sharded:
+            planner.enable_sharded_losers(1, 3, "local")
     step = 0
     for w in range(cfg["n_windows"]):
         win = torch.from_numpy(ids[:, w * L * B:(w + 1) * L * B])
@@ -119,7 +122,7 @@ def _run_cuda_trace(cfg, mode):
 
 @pytest.mark.parametrize("name", ["trace_tiny.npz", "trace_pressure.npz", "trace_pressure_avgwb.npz",
                                   "trace_cfg0_small.npz"])
-@pytest.mark.parametrize("mode", ["api", "fast", "fast_devrng", "staged", "staged_capped"])
+@pytest.mark.parametrize("mode", ["api", "fast", "fast_devrng", "staged", "staged_capped", "staged_sharded"])
 def test_trace_matches_reference_golden(name, mode, monkeypatch):
     g = util.load_golden(name)
     cfg = util.golden_cfg(g)

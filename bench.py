@@ -400,9 +400,14 @@ def gpu_run(a, wl, ln_emb):
         sink.append((time.perf_counter() - h0, e0, e1))
         return r
 
+    prep_log = []
+
     def boundary(j):
         recs[j // L] = timed_call(tr.install_window, bound_log)
+        h0 = time.perf_counter()
         prepare(j // L + 1)
+        if logging_on[0]:
+            prep_log.append((round(1e3 * (time.perf_counter() - h0), 2), dict(tr.boundary_breakdown_ms)))
 
     def aggregate(j):
         if world > 1 and j > 0 and j % args.table_agg_freq == 0:
@@ -573,7 +578,7 @@ def gpu_run(a, wl, ln_emb):
                 loss_host = float(loss_pin[(i - 1) & 1])
             st = nxt
             j += 1
-            if (i + 1) % seg2 == 0 and i + 1 < n_e2e:
+            if ((i + 1) % seg2 == 0 or i < 40) and i + 1 < n_e2e:
                 m = torch.cuda.Event(enable_timing=True)
                 m.record()
                 marks2.append((i + 1, m))
@@ -615,7 +620,10 @@ def gpu_run(a, wl, ln_emb):
             "agg_ms_per_call": round(float(np.mean([1000 * h for h, _, _ in agg_log])), 4) if agg_log else None,
             "agg_device_ms_per_call": round(float(np.mean([b0.elapsed_time(b1) for _, b0, b1 in agg_log])), 4) if agg_log else None,
             "agg_ms_per_step_amortised": round(float(np.sum([b0.elapsed_time(b1) for _, b0, b1 in agg_log])) / n_e2e, 5) if agg_log else 0.0,
-            "ms_per_step_series": {"steps_per_segment": seg2, "ms_per_step": series2},
+            "ms_per_step_series": {"steps_per_segment": seg2, "first_40_steps_ms": series2[:40],
+                                   "ms_per_step": series2[40:]},
+            "boundary_host_breakdown_ms": [b for _, b in prep_log],
+            "next_window_input_generation_host_ms": [p_ for p_, _ in prep_log],
             "steady_ms_per_step_before": round(filler_ms, 4) if filler_ms else None,
         }
         if rec_next is not None and not isinstance(rec_next, Exception) and getattr(rec_next, "stage_begin", None) is not None:
@@ -692,6 +700,7 @@ def kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, 
     # every kernel alone on one stream (no overlap with the MLPs), so that a duration is the kernel's own
     fstream, tr.cache_group.forward_stream = tr.cache_group.forward_stream, None
     eplan, tr.cache_group.early_plan = tr.cache_group.early_plan, False
+    lib.cdlrm_mlp_set_option(5, 0)      # weight-gradient GEMMs in line, not beside the data-gradient chain
     for _ in range(20):
         if j % L == 0:
             break
@@ -705,6 +714,7 @@ def kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, 
         nprof += 1
     tr._graph = graph
     tr.cache_group.forward_stream, tr.cache_group.early_plan = fstream, eplan
+    lib.cdlrm_mlp_set_option(5, int(os.environ.get("CDLRM_WGRAD_SIDE", "1") != "0"))
     msv = (ctypes.c_double * NK)()
     calls = (ctypes.c_int64 * NK)()
     _lib.check(lib.cdlrm_prof_report(msv, calls, NK))

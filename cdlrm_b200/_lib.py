@@ -47,6 +47,8 @@ SIGNATURES = {
     "cdlrm_mlp_destroy": (C.c_int, [vp]),
     "cdlrm_mlp_set_option": (C.c_int, [C.c_int, C.c_int]),
     "cdlrm_mlp_set_trace": (C.c_int, [vp]),
+    "cdlrm_mlp_set_defer_join": (C.c_int, [vp, C.c_int]),
+    "cdlrm_mlp_join": (C.c_int, [vp, vp]),
     "cdlrm_mlp_forward": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp]),
     "cdlrm_mlp_backward": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, C.POINTER(vp), C.POINTER(vp), vp]),
     "cdlrm_plan_workspace_bytes": (C.c_int64, [vp, C.c_int64]),

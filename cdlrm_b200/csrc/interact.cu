@@ -183,6 +183,84 @@ __global__ void __launch_bounds__(128, 4) interact_fwd_tr_kernel(FeatPtrs fp, in
     });
 }
 
+// Forward for dim = 128, HALF a warp per sample: lane h of a half-warp holds the float4 column slices h and h + 16
+// of the 27 rows (8 floats per row, 216 registers), so a partial dot product covers 8 columns (5 packed
+// instructions) and only 16 partials per pair have to be added up -- against interact_fwd_tr_kernel (a warp per
+// sample, 4 columns per lane, 32 partials per pair) that is 0.83x the multiply instructions and half of the
+// shared-memory transpose and of the adds per sample: ~1 150 instead of ~2 050 warp instructions per sample.
+// Blocks of 32 pairs: every lane stores its 32 partials as one row of a [32 lanes][36] tile (STS.128, conflict
+// free), then lane L adds up columns 2(L%16), 2(L%16)+1 over the 16 rows of its own half-warp (LDS.64); the tile is
+// double-buffered so that one __syncwarp per block is enough.  Two CTAs of four warps per SM (255 registers).
+template <int F>
+__global__ void __launch_bounds__(128, 2) interact_fwd_h_kernel(FeatPtrs fp, int64_t row_stride, int B,
+                                                                float* __restrict__ out, int64_t ld_out) {
+    pdl_enter();
+    constexpr int DIM = 128, PITCH = 36;
+    constexpr int NP = Pairs<F, false>::N;
+    __shared__ __align__(16) float s_part[4][2][32 * PITCH];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int h = lane & 15, half = lane >> 4;
+    const int b = (((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 1) + half;
+    const bool live = b < B;
+    const int bb = live ? b : B - 1;                      // a dead half-warp (odd B) recomputes the last sample, stores nothing
+    float4 ta[F], tb[F];
+    static_for<F>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const float4* row = reinterpret_cast<const float4*>(fp.p[i] + (int64_t)bb * row_stride);
+        ta[i] = __ldg(row + h);
+        tb[i] = __ldg(row + 16 + h);
+    });
+    float* orow = out + (int64_t)bb * ld_out;
+    if (live) {                                           // dense features pass through (model_no_ddp.py:293)
+        orow[h * 4 + 0] = ta[0].x; orow[h * 4 + 1] = ta[0].y; orow[h * 4 + 2] = ta[0].z; orow[h * 4 + 3] = ta[0].w;
+        orow[64 + h * 4 + 0] = tb[0].x; orow[64 + h * 4 + 1] = tb[0].y; orow[64 + h * 4 + 2] = tb[0].z; orow[64 + h * 4 + 3] = tb[0].w;
+    }
+    float v[8];
+    static_for<F>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        constexpr int p0 = i * (i - 1) / 2;               // row-major offset into the strict lower triangle
+        static_for<i>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            constexpr int p = p0 + j;
+            {
+                float2 q = __fmul2_rn(make_float2(ta[i].x, ta[i].y), make_float2(ta[j].x, ta[j].y));
+                q = __ffma2_rn(make_float2(ta[i].z, ta[i].w), make_float2(ta[j].z, ta[j].w), q);
+                q = __ffma2_rn(make_float2(tb[i].x, tb[i].y), make_float2(tb[j].x, tb[j].y), q);
+                q = __ffma2_rn(make_float2(tb[i].z, tb[i].w), make_float2(tb[j].z, tb[j].w), q);
+                v[p % 8] = q.x + q.y;
+            }
+            constexpr int blk = p / 32;
+            if constexpr ((p + 1) % 8 == 0 || p + 1 == NP) {      // 8 partials (or the tail) -> two STS.128
+                constexpr int c8 = (p % 32) / 8;                  // chunk of 8 within the block
+                constexpr int n8 = p % 8 + 1;                     // valid partials in this chunk
+                float4* wr = reinterpret_cast<float4*>(s_part[wib][blk & 1] + lane * PITCH + c8 * 8);
+                wr[0] = make_float4(v[0], n8 > 1 ? v[1] : 0.f, n8 > 2 ? v[2] : 0.f, n8 > 3 ? v[3] : 0.f);
+                if constexpr (n8 > 4) wr[1] = make_float4(v[4], n8 > 5 ? v[5] : 0.f, n8 > 6 ? v[6] : 0.f, n8 > 7 ? v[7] : 0.f);
+            }
+            if constexpr ((p + 1) % 32 == 0 || p + 1 == NP) {
+                constexpr int cnt = p + 1 - blk * 32;
+                const float* buf = s_part[wib][blk & 1];
+                __syncwarp();
+                const int c0 = 2 * h;
+                if (c0 < cnt) {
+                    const float* col = buf + (half * 16) * PITCH + c0;
+                    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int r = 0; r < 16; r += 2) {
+                        a0 = __fadd2_rn(a0, *reinterpret_cast<const float2*>(col + r * PITCH));
+                        a1 = __fadd2_rn(a1, *reinterpret_cast<const float2*>(col + (r + 1) * PITCH));
+                    }
+                    a0 = __fadd2_rn(a0, a1);
+                    if (live) {
+                        orow[DIM + blk * 32 + c0] = a0.x;
+                        if (c0 + 1 < cnt) orow[DIM + blk * 32 + c0 + 1] = a0.y;
+                    }
+                }
+            }
+        });
+    });
+}
+
 template <int F, int TPS, bool ITSELF>
 __global__ void __launch_bounds__(128, 4) interact_bwd_kernel(FeatPtrs fp, int64_t row_stride, int B,
                                                            const float* __restrict__ d_out, int64_t ld_dout,
@@ -717,6 +795,12 @@ void launch_fwd_tr(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld
     LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_tr_kernel<F, ITSELF>), blocks, 128, 0, fp, rs, B, out, ld_out);
 }
 
+template <int F>
+void launch_fwd_h(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_out, cudaStream_t s) {
+    const int blocks = (B + 7) / 8;                       // half a warp per sample, 8 samples per block
+    LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_h_kernel<F>), blocks, 128, 0, fp, rs, B, out, ld_out);
+}
+
 template <int F, int TPS, bool ITSELF>
 void launch_bwd(const FeatPtrs& fp, int64_t rs, int B, const float* d_out, int64_t ld_dout, float* d_feat,
                 int64_t ld_dfeat, cudaStream_t s) {
@@ -731,7 +815,12 @@ int g_bwd_pipe = 1;      // cdlrm_interact_set_option(1, .): software-pipelined 
 // neither faster on B200 (tools/interact_pipe_time.py, event-timed: 54 / 47-50 us against 46-48 us): hiding the row
 // loads does not help a kernel whose 2 050 instructions per sample are mostly dependent FADD / LDS chains of the
 // cross-lane reduction; the backward (independent FFMA2s, 2x the bytes per sample) gains 25 % from the same ring.
-int g_fwd_pipe = 0;
+// 3 = interact_fwd_h_kernel (half a warp per sample, not bit-identical to the others: 8-column partials); -1 = default
+constexpr int FWD_DEFAULT = 3;
+int g_fwd_pipe = [] {
+    const char* e = getenv("CDLRM_INTERACT_FWD");       // A/B switch for whole-step measurements
+    return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : FWD_DEFAULT;
+}();
 int g_variant = 0;       // cdlrm_interact_set_option(0, .): 0 CUDA cores (default), 1 mma.sync 3xTF32, 2 first CUDA-core version
 bool use_simt_only() { return g_variant != 1; }
 
@@ -821,6 +910,10 @@ bool aligned_for(const FeatPtrs& fp, int n, int64_t rs, int bytes) {
         done = true;                                                                      \
     }
 #define FWD_PIPE_CASE(F_)                                                                                   \
+    if (!done && n_feat == F_ && dim == 128 && !itself && fast16 && g_fwd_pipe == 3 && g_variant == 0) {     \
+        launch_fwd_h<F_>(fp, rs, batch, out, ld_out, s);                                                     \
+        done = true;                                                                                         \
+    }                                                                                                        \
     if (!done && n_feat == F_ && dim == 128 && !itself && fast16 && g_fwd_pipe && g_variant == 0) {          \
         done = g_fwd_pipe == 2 ? launch_fwd_pipe<F_, 1, 4, 1>(fp, rs, batch, out, ld_out, s)                 \
                                : launch_fwd_pipe<F_, 2, 2, 2>(fp, rs, batch, out, ld_out, s);                \
@@ -854,8 +947,8 @@ extern "C" int cdlrm_interact_set_option(int key, int value) {
         return CDLRM_OK;
     }
     if (key == 2) {
-        ARG_CHECK(value >= 0 && value <= 2);
-        g_fwd_pipe = value;
+        ARG_CHECK(value >= -1 && value <= 3);
+        g_fwd_pipe = value < 0 ? FWD_DEFAULT : value;
         return CDLRM_OK;
     }
     ARG_CHECK(key == 0 && value >= 0 && value <= 2);

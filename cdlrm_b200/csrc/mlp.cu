@@ -809,6 +809,7 @@ int g_narrow = 1;    // 1: a last layer with one output column runs on the SIMT 
 // 335 vs 323 us): the multicast cuts L2 -> SM traffic by 25 % but every CTA still receives its 64 KB per k-block, so the
 // shared-memory write + operand-read bandwidth that bounds the mainloop is unchanged and the pair now runs in lockstep.
 int g_cluster = 1;
+int g_wgrad_side = 1;   // 1: weight-gradient GEMMs run on a side stream beside the dgrad chain; cdlrm_mlp_set_option(5, .)
 int g_seg_kb = 8;    // K segment (k-blocks of 32) per TMEM accumulation chain; cdlrm_mlp_set_option(1, .)
 int g_num_sms = 0;
 int g_dbg = 0;
@@ -915,6 +916,11 @@ struct cdlrm_mlp {
     const float* last_W = nullptr;   // FP32 weights of that layer (the narrow backward reads them)
     bool ones_set = false;
     int num_sms = 148;
+    // weight-gradient GEMMs on a stream of their own beside the data-gradient chain (cdlrm_mlp_backward)
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev_g = nullptr, ev_done = nullptr;
+    bool defer_join = false;     // cdlrm_mlp_set_defer_join: the caller joins with cdlrm_mlp_join
+    bool pending_join = false;
 };
 
 static int64_t mlp_carve(cdlrm_mlp* m, char* base) {
@@ -990,6 +996,16 @@ extern "C" int cdlrm_mlp_create(cdlrm_mlp** out, int device, int n_layers, const
         return CDLRM_ERR_ARG;
     }
     if (cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || m->num_sms <= 0) m->num_sms = 148;
+    {   // side stream of the weight-gradient GEMMs (created here, not lazily: the first backward may be under capture)
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&m->s2, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_g, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            m->s2 = nullptr;        // no device (CPU-only build check) or out of resources: in-line weight gradients
+        }
+    }
     *out = m;
     return CDLRM_OK;
 }
@@ -1012,6 +1028,8 @@ extern "C" int cdlrm_mlp_set_option(int key, int value) {
         g_cluster = value;
     } else if (key == 3) {
         g_dbg = value;
+    } else if (key == 5) {
+        g_wgrad_side = value ? 1 : 0;
     } else {
         ARG_CHECK(false && "unknown option");
     }
@@ -1027,7 +1045,27 @@ extern "C" int cdlrm_mlp_set_trace(void* d_buf) {
 }
 
 extern "C" int cdlrm_mlp_destroy(cdlrm_mlp* m) {
+    if (m) {
+        if (m->s2) { cudaStreamSynchronize(m->s2); cudaStreamDestroy(m->s2); }
+        if (m->ev_g) cudaEventDestroy(m->ev_g);
+        if (m->ev_done) cudaEventDestroy(m->ev_done);
+    }
     delete m;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_mlp_set_defer_join(cdlrm_mlp* m, int on) {
+    ARG_CHECK(m);
+    m->defer_join = on != 0;
+    return CDLRM_OK;
+}
+
+extern "C" int cdlrm_mlp_join(cdlrm_mlp* m, cdlrm_stream stream) {
+    ARG_CHECK(m);
+    if (m->pending_join) {
+        CU_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, m->ev_done, 0));
+        m->pending_join = false;
+    }
     return CDLRM_OK;
 }
 
@@ -1041,6 +1079,10 @@ extern "C" int cdlrm_mlp_forward(cdlrm_mlp* m, const float* x, int64_t ldx, int3
     const int L = m->L;
     const int64_t capp = pad4(m->cap);
     int rc;
+    if (m->pending_join) {      // weight-gradient GEMMs of the last backward still read the transposed activations
+        CU_CHECK(cudaStreamWaitEvent(s, m->ev_done, 0));
+        m->pending_join = false;
+    }
     if (!m->ones_set) {     // the ones rows of the transposed activations (bias gradient); lo part = 0
         for (int i = 0; i < L; ++i) {
             LAUNCH(K_MLP_SPLIT, s, (fill_kernel<<<64, 256, 0, s>>>(m->xt_hi[i] + (int64_t)m->D[i] * capp, capp, 1.f)));
@@ -1113,6 +1155,15 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
     const int L = m->L;
     const int64_t capp = pad4(m->cap);
     int rc;
+    if (m->pending_join) {      // a deferred join nobody asked for: the previous backward's dW must be complete
+        CU_CHECK(cudaStreamWaitEvent(s, m->ev_done, 0));
+        m->pending_join = false;
+    }
+    // The weight-gradient GEMMs are leaves of the backward: they run on a stream of their own, each behind the
+    // event that marks its dZ ready, so that their CTAs fill the SMs the data-gradient chain (the critical path)
+    // leaves idle at its tile-count tails and launch gaps.  Legal inside a stream capture (fork / join by events).
+    const bool side = g_wgrad_side != 0 && m->s2 != nullptr;
+    cudaStream_t sw = side ? m->s2 : s;
     // gradient w.r.t. the last pre-activation: dy * act'(y), as hi/lo, row-major and transposed
     const int last_act = (L - 1 == m->sigmoid_layer) ? ACT_SIGMOID : (m->sigmoid_layer == -2 ? ACT_NONE : ACT_RELU);
     const bool narrow = m->last_narrow;
@@ -1142,7 +1193,11 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
             Out o;
             ep.M = N; ep.N = K + 1; ep.K = batch;
             o.c = m->dwp[l]; o.ldc = ldp; o.reduce = true;
-            if ((rc = launch_gemm(m->gt_hi[l + 1], m->gt_lo[l + 1], capp, m->xt_hi[l], m->xt_lo[l], capp, ep, o, 0 /*auto split-K*/, s))) return rc;
+            if (side) {         // dZ of this layer (and, the first time, the zeroed accumulators) are ready on s
+                CU_CHECK(cudaEventRecord(m->ev_g, s));
+                CU_CHECK(cudaStreamWaitEvent(sw, m->ev_g, 0));
+            }
+            if ((rc = launch_gemm(m->gt_hi[l + 1], m->gt_lo[l + 1], capp, m->xt_hi[l], m->xt_lo[l], capp, ep, o, 0 /*auto split-K*/, sw))) return rc;
         }
         // dgrad: dX = dZ W, then the ReLU mask of the layer below -> its dZ (split, both layouts)
         if (l > 0) {
@@ -1175,8 +1230,24 @@ extern "C" int cdlrm_mlp_backward(cdlrm_mlp* m, const float* dy, int64_t lddy, f
         ub.total = total;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 1184) blocks = 1184;
-        LAUNCH_PDL(K_MLP_SPLIT, s, unpack_batch_kernel, blocks, 256, 0, ub);
+        // the unpack reads the split-K accumulators of the narrow layer (written on s) and of the GEMMs (on sw)
+        const bool deferred = side && m->defer_join;
+        if (side) {
+            if (deferred) {
+                CU_CHECK(cudaEventRecord(m->ev_g, s));
+                CU_CHECK(cudaStreamWaitEvent(sw, m->ev_g, 0));
+            } else {
+                CU_CHECK(cudaEventRecord(m->ev_done, sw));
+                CU_CHECK(cudaStreamWaitEvent(s, m->ev_done, 0));
+            }
+        }
+        cudaStream_t su = deferred ? sw : s;
+        LAUNCH_PDL(K_MLP_SPLIT, su, unpack_batch_kernel, blocks, 256, 0, ub);
         CU_CHECK(cudaGetLastError());
+        if (deferred) {         // dW / db become visible to the caller's stream at cdlrm_mlp_join
+            CU_CHECK(cudaEventRecord(m->ev_done, sw));
+            m->pending_join = true;
+        }
     }
     return CDLRM_OK;
 }

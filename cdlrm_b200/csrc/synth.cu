@@ -25,16 +25,38 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
+// (r * 2654435761 + c) mod n without a 64-bit division: 32-bit arithmetic for small n, a double-precision quotient
+// estimate (off by at most one: x < 2^58, n >= 2^16) with an exact integer remainder otherwise
+__device__ __forceinline__ int64_t scramble_mod(uint64_t r, uint64_t c, uint64_t n, double inv_n) {
+    if (n < 65536ull) {
+        const uint32_t n32 = (uint32_t)n;
+        return (int64_t)(((uint32_t)r * (uint32_t)(2654435761ull % n) + (uint32_t)(c % n)) % n32);
+    }
+    const uint64_t x = r * 2654435761ull + c;
+    const uint64_t q = (uint64_t)((double)x * inv_n);
+    int64_t rem = (int64_t)(x - q * n);
+    if (rem < 0) rem += (int64_t)n;
+    else if (rem >= (int64_t)n) rem -= (int64_t)n;
+    return rem;
+}
+
+// One thread per (step, sample) element and SHORT CTAs (no grid-stride loop): the stream is generated on a side stream
+// beside training, and a low-priority grid of long-running CTAs keeps the SM slots it once got (a training kernel's
+// CTAs then wait for them), whereas short CTAs hand the slots back within microseconds.  blockIdx.y = step chunk,
+// blockIdx.z = table: no 64-bit division per element.
+constexpr int SYNTH_STEPS_PER_CTA = 4;
 __global__ void __launch_bounds__(256) synth_ids_kernel(SynthTables tb, int t0, uint64_t seed, int64_t batch_global,
                                                         int64_t step0, int n_steps, int64_t b0, int nb, int uniform,
                                                         double inv_e, int64_t* __restrict__ out, int64_t ld) {
-    const int k = t0 + blockIdx.y;
-    const int64_t total = (int64_t)n_steps * nb;
+    const int k = t0 + blockIdx.z;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
     const int64_t n = tb.n[k];
-    const double c0 = tb.c0[k];
+    const double c0 = tb.c0[k], inv_n = 1.0 / (double)n;
     const uint64_t key = splitmix64(seed ^ (0x51ed270b1f2d3a4full * (uint64_t)(k + 1)));
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t s = i / nb, b = i - s * nb;
+    const int s_lo = blockIdx.y * SYNTH_STEPS_PER_CTA;
+    const int s_hi = min(n_steps, s_lo + SYNTH_STEPS_PER_CTA);
+    for (int s = s_lo; s < s_hi; ++s) {
         const uint64_t ctr = (uint64_t)((step0 + s) * batch_global + b0 + b);
         const double u = (double)(splitmix64(key + ctr) >> 11) * (1.0 / 9007199254740992.0);
         int64_t r;
@@ -44,7 +66,7 @@ __global__ void __launch_bounds__(256) synth_ids_kernel(SynthTables tb, int t0, 
             r = (int64_t)pow(c0 * u + 1.0, inv_e) - 1;
         }
         r = r < 0 ? 0 : (r >= n ? n - 1 : r);
-        out[(int64_t)blockIdx.y * ld + i] = (int64_t)(((uint64_t)r * 2654435761ull + 40503ull * (uint64_t)k) % (uint64_t)n);
+        out[(int64_t)blockIdx.z * ld + (int64_t)s * nb + b] = scramble_mod((uint64_t)r, 40503ull * (uint64_t)k, (uint64_t)n, inv_n);
     }
 }
 
@@ -66,12 +88,16 @@ extern "C" int cdlrm_synth_ids(int device, int table_begin, int table_count, con
         tb.n[k] = h_n_rows[k - table_begin];
         tb.c0[k] = uniform ? 0.0 : pow((double)tb.n[k] + 1.0, e) - 1.0;
     }
-    const int64_t total = (int64_t)n_steps * nb;
-    int64_t gx = (total + 255) / 256;
-    if (gx > 148 * 8) gx = 148 * 8;
     cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH(K_MISC, s, synth_ids_kernel<<<dim3((unsigned)gx, table_count), 256, 0, s>>>(
-        tb, table_begin, seed, batch_global, step0, n_steps, b0, nb, uniform, uniform ? 0.0 : 1.0 / e, out, ld));
+    const int chunks = (n_steps + SYNTH_STEPS_PER_CTA - 1) / SYNTH_STEPS_PER_CTA;
+    for (int c0 = 0; c0 < chunks; c0 += 65535) {          // gridDim.y limit
+        const int cy = chunks - c0 < 65535 ? chunks - c0 : 65535;
+        const int s0 = c0 * SYNTH_STEPS_PER_CTA;
+        const int ns = n_steps - s0 < cy * SYNTH_STEPS_PER_CTA ? n_steps - s0 : cy * SYNTH_STEPS_PER_CTA;
+        LAUNCH(K_MISC, s, synth_ids_kernel<<<dim3((unsigned)((nb + 255) / 256), (unsigned)cy, (unsigned)table_count), 256, 0, s>>>(
+            tb, table_begin, seed, batch_global, step0 + s0, ns, b0, nb, uniform, uniform ? 0.0 : 1.0 / e,
+            out + (int64_t)s0 * nb, ld));
+    }
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;
 }

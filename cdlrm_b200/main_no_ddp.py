@@ -350,6 +350,9 @@ class Trainer:
         self.flat = self.dlrm.mlp_impl == "tcgen05" and os.environ.get("CDLRM_FLAT_MLP", "1") != "0"
         if self.flat:
             self.dlrm.flatten_parameters()
+            check(lib.cdlrm_mlp_set_option(5, int(os.environ.get("CDLRM_WGRAD_SIDE", "1") != "0")))
+            if os.environ.get("CDLRM_DEFER_WGRAD", "1") != "0":
+                self.dlrm.defer_wgrad_join(True)     # joined in the step, right before the gradients are used
         self.optimizer_mlps = torch.optim.SGD(self.dlrm.parameters(), lr=args.learning_rate)
         self.optimizer_embeds = torch.optim.SGD(self.cache_group.parameters(), lr=args.lr_embeds)   # :376
         self.cache_group._ensure_ctx(emb_tables)
@@ -359,6 +362,9 @@ class Trainer:
         # the lookup runs on its own stream beside the bottom MLP (joined before the interaction)
         self.cache_group.forward_stream = _lib.new_stream(self.dev, priority=-1)
         self.dlrm.pre_interact = self.cache_group.join_forward
+        # the sparse update runs on the lookup stream beside the bottom MLP's backward (joined by
+        # optimizer_embeds.step()); CDLRM_OVERLAP_UPDATE=0: from the optimizer hook, after the whole backward
+        self.overlap_update = not self.strict and os.environ.get("CDLRM_OVERLAP_UPDATE", "1") != "0"
         self.planner = None
         if not self.strict:
             self.planner = WindowPlanner(self.cache_group, emb_tables, args.lookahead * args.mini_batch_size,
@@ -441,23 +447,34 @@ class Trainer:
         rec = self._plan_q.get()
         if isinstance(rec, Exception):
             raise rec
+        t1 = time.perf_counter()
         if self._installed is not None:
             # conditions the reference raises on the host (IndexError: aux overflow, id outside its table,
             # model_no_ddp.py:176-179) are sticky device flags here: surface them once per window
             self.cache_group.check_device_flags()
+        t2 = time.perf_counter()
         if self.world > 1:
             broadcast_and_aggregate(self.cache_group, None, self.rank, self.args.table_agg_op)
             self.steps_since_agg = 0
+        t3 = time.perf_counter()
         # evict / fill are HBM->HBM against the staging buffers the plan thread filled during the
         # previous window; the host write-back runs on the planner stream beside the next steps
         self.planner.install_staged(rec, write_master=(self.rank == 0),
                                     average_on_writeback=self.args.average_on_writeback)
         self._installed = rec            # keeps the loser store of this window alive
-        self.caching_overhead.append(time.perf_counter() - t0)
+        t4 = time.perf_counter()
+        self.caching_overhead.append(t4 - t0)
+        # host milliseconds of the boundary: waiting for the plan, draining the stream for the device flags,
+        # aggregation, enqueueing evict / fill
+        self.boundary_breakdown_ms = {"wait_plan": round(1e3 * (t1 - t0), 2), "flags_sync": round(1e3 * (t2 - t1), 2),
+                                      "aggregate": round(1e3 * (t3 - t2), 2), "install": round(1e3 * (t4 - t3), 2)}
         return rec
 
     # -- one training step -------------------------------------------------------------------
     def _step_eager(self, X, lS_o, lS_i, T):
+        if self.overlap_update:
+            self.cache_group.overlap_update = True
+            self.cache_group.fused_lr = float(self.optimizer_embeds.param_groups[0]["lr"])
         lookups, _idxs = self.cache_group(lS_o, lS_i, self.emb_tables, self.dev.index)
         Z = self.dlrm(X, lookups)
         if self.args.loss_function == "bce" and os.environ.get("CDLRM_FUSED_LOSS", "1") != "0":
@@ -470,12 +487,14 @@ class Trainer:
             E.backward()
             work = None
             if self.world > 1:
+                self.dlrm.join_mlp_grads()
                 gw = self.dlrm.flat_grads[:self.dlrm.flat_weight_elems]
                 gw /= self.world
                 work = dist.all_reduce(gw, async_op=True)
             self.optimizer_embeds.step()      # applies the fused sparse update (pre-step hook)
             if work is not None:
                 work.wait()
+            self.dlrm.join_mlp_grads()        # weight-gradient GEMMs ran beside everything up to here
             self.dlrm.flat_sgd_step(self.optimizer_mlps.param_groups[0]["lr"])
             return E, Z
         self.optimizer_mlps.zero_grad(set_to_none=True)
@@ -565,6 +584,7 @@ class Trainer:
 
     def step_reference(self, X, lS_o, lS_i, T):
         """The reference's step, call for call (main_no_ddp.py:401-415); returns (E, Z, cache_group_idxs)."""
+        self.cache_group.overlap_update, self.cache_group.fused_lr = False, None   # update at optimizer_embeds.step()
         lookups, cache_group_idxs = self.cache_group(lS_o, lS_i, self.emb_tables, self.dev.index)
         Z = self.dlrm(X, lookups)
         E = loss_fn_wrap(Z, T, self.loss_fn, self.args, self.loss_ws)
@@ -573,6 +593,7 @@ class Trainer:
         E.backward()
         if self.flat:
             work = None
+            self.dlrm.join_mlp_grads()
             if self.world > 1:
                 gw = self.dlrm.flat_grads[:self.dlrm.flat_weight_elems]
                 gw /= self.world

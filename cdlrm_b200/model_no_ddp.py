@@ -152,6 +152,7 @@ class Embedding_Table_Group(nn.Module):
 # ------------------------------------------------------------------------------------
 
 _GROUPS = weakref.WeakSet()      # cache groups with a pending fused update (optimizer hook)
+_GRAD_READY = {}                 # data_ptr of the interaction backward's gradient planes -> event recorded behind it
 
 
 class _LookupFn(torch.autograd.Function):
@@ -232,6 +233,11 @@ class Embedding_Table_Cache_Group(nn.Module):
         self.fused_lr = None               # set to apply the SGD update inside backward
         self.early_plan = True             # build the backward plan during forward, on a side stream
         self.forward_stream = None         # set: lookup kernels run on this stream; consumers call join_forward()
+        # with fused_lr and forward_stream set: the sparse update is launched from backward on forward_stream, behind
+        # the event that marks the lookups' gradients ready, beside the rest of the backward (the bottom MLP);
+        # optimizer_embeds.step() (pre-step hook) joins it
+        self.overlap_update = False
+        self._upd_done = None
         self._fwd_done = None
         self._plan_stream = None
         self.last_n_miss = None
@@ -492,6 +498,8 @@ class Embedding_Table_Cache_Group(nn.Module):
         item = (tb, slots, bag_ids, n_idx, dbase, ld, rs, keep, plan)
         if self.fused_lr is not None:
             self._apply_update(item, float(self.fused_lr))
+            if self._upd_done is not None:
+                _GROUPS.add(self)
         else:
             self._pending.append(item)
             _GROUPS.add(self)
@@ -503,6 +511,19 @@ class Embedding_Table_Cache_Group(nn.Module):
         dev = self.device
         T = slots.shape[0]
         cur = torch.cuda.current_stream(dev)
+        us = self.forward_stream if (self.overlap_update and self.forward_stream is not None) else None
+        if us is not None:
+            # not wait_stream(cur): autograd has usually enqueued the bottom MLP's backward on `cur` already, and
+            # the point is to run beside it -- wait for the producer of the gradients only
+            ready = _GRAD_READY.pop(dbase.data_ptr(), None)
+            if ready is not None:
+                us.wait_event(ready)
+            else:
+                us.wait_stream(cur)
+            for t in (dbase, slots, bag_ids):
+                if t is not None:
+                    t.record_stream(us)
+            cur = us
         s = _vp(cur.cuda_stream)
         if plan is not None:
             buf, base, done = plan
@@ -519,6 +540,15 @@ class Embedding_Table_Cache_Group(nn.Module):
                                       _vp(bag_ids.data_ptr()) if bag_ids is not None else None,
                                       bag_ids.stride(0) if bag_ids is not None else 0,
                                       _vp(dbase.data_ptr()), ld, rs, lr, s))
+        if us is not None:
+            self._upd_done = torch.cuda.Event()
+            self._upd_done.record(us)
+
+    def join_update(self):
+        """Make the current stream wait for a sparse update launched on ``forward_stream`` (``overlap_update``)."""
+        if self._upd_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._upd_done)
+            self._upd_done = None
 
     def apply_pending_updates(self, lr):
         """Apply the sparse SGD updates queued by backward (called by the optimizer hook
@@ -535,12 +565,14 @@ def _optimizer_pre_step(optimizer, args, kwargs):
     if not _GROUPS:
         return
     for group in list(_GROUPS):
-        if not group._pending:
+        if not group._pending and group._upd_done is None:
             continue
         mine = {id(e.weight) for e in group.emb_l}
         for pg in optimizer.param_groups:
             if any(id(p) in mine for p in pg["params"]):
-                group.apply_pending_updates(float(pg["lr"]))
+                if group._pending:
+                    group.apply_pending_updates(float(pg["lr"]))
+                group.join_update()      # an update launched from backward on the lookup stream is complete here
                 break
 
 
@@ -596,6 +628,13 @@ class _InteractFn(torch.autograd.Function):
         check(lib.cdlrm_interact_bwd(dev.index, _lib.ptr_array([f.data_ptr() for f in feats]), nf, ctx.rs, B, d,
                                      int(ctx.itself), _vp(dR.data_ptr()), dR.stride(0), _vp(dfeat.data_ptr()),
                                      dfeat.stride(0), _stream_ptr(dev)))
+        if nf > 1:
+            # the lookups' gradients (planes 1..) are ready here: a cache group that overlaps its sparse update with
+            # the rest of the backward waits for this event instead of the whole stream (Embedding_Table_Cache_Group)
+            _GRAD_READY.clear()
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            _GRAD_READY[dfeat[1].data_ptr()] = ev
         return (None,) + tuple(dfeat.unbind(0))
 
 
@@ -650,6 +689,7 @@ class _MlpState:
         self.ws = None
         self.fwd_id = 0
         self.flat_grads = None     # ([dW views], [db views]) into DLRM_Net's flat gradient bucket, or None
+        self.defer_join = False    # cdlrm_mlp_set_defer_join: dW / db complete only after DLRM_Net.join_mlp_grads()
 
     def ensure(self, batch, dev):
         if self.handle is not None and batch <= self.cap and self.ws.device == dev:
@@ -665,6 +705,13 @@ class _MlpState:
         h = ctypes.c_void_p()
         check(lib.cdlrm_mlp_create(ctypes.byref(h), dev.index, L, dims, batch, self.sigmoid_layer, _vp(base), need))
         self.handle, self.cap = h, batch
+        if self.defer_join:
+            check(lib.cdlrm_mlp_set_defer_join(self.handle, 1))
+
+    def set_defer_join(self, on):
+        self.defer_join = bool(on)
+        if self.handle is not None:
+            check(lib.cdlrm_mlp_set_defer_join(self.handle, int(self.defer_join)))
 
     def close(self):
         if self.handle is not None:
@@ -821,6 +868,21 @@ class DLRM_Net(nn.Module):
             st.flat_grads = ([m.weight.grad for m in st.linears], [m.bias.grad for m in st.linears])
         self.flat_mode = True
         return flat_p, flat_g
+
+    def defer_wgrad_join(self, on=True):
+        """Flat-bucket mode only: let the weight-gradient GEMMs of an MLP backward (side stream, csrc/mlp.cu) keep
+        running after ``cdlrm_mlp_backward`` returns -- beside the interaction backward and the bottom MLP -- and
+        make the caller responsible for ``join_mlp_grads()`` before it reads the gradient bucket."""
+        if not getattr(self, "flat_mode", False):
+            raise _lib.CdlrmError("defer_wgrad_join needs flatten_parameters(): autograd consumes dW / db otherwise")
+        for st in self._mlp_state.values():
+            st.set_defer_join(on)
+
+    def join_mlp_grads(self):
+        """Make the dW / db written by the last MLP backwards visible to the current stream."""
+        for st in self._mlp_state.values():
+            if st.handle is not None:
+                check(lib.cdlrm_mlp_join(st.handle, _stream_ptr(self.flat_params.device)))
 
     @torch.no_grad()
     def flat_sgd_step(self, lr):

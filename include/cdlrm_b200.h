@@ -155,8 +155,15 @@ int cdlrm_mlp_destroy(cdlrm_mlp* mlp);
  * Numerics knobs (process-wide; defaults are the accurate settings): key 0 = operand split
  * rounding (0 nearest, 1 truncate), key 1 = k-blocks of 32 chained into one TMEM accumulator
  * before the partial sum is added in registers (0 = whole K, default 8), key 2 = tile width
- * (0: 128 x 128, 1: 128 x 256, 2: by shape), key 3 = measurement switches (results invalid). */
+ * (0: 128 x 128, 1: 128 x 256, 2: by shape), key 3 = measurement switches (results invalid), key 5 = weight-gradient
+ * GEMMs of the backward on a side stream beside the data-gradient chain (1, default) or in line (0). */
 int cdlrm_mlp_set_option(int key, int value);
+/* With key 5 on, cdlrm_mlp_backward joins the side stream before it returns, unless defer_join is set on the
+ * object: then dW / db are complete on the caller's stream only after cdlrm_mlp_join(mlp, stream) -- which lets
+ * the weight gradients of the top MLP run beside the interaction backward and the bottom MLP.  A forward or
+ * backward of the same object joins implicitly. */
+int cdlrm_mlp_set_defer_join(cdlrm_mlp* mlp, int on);
+int cdlrm_mlp_join(cdlrm_mlp* mlp, cdlrm_stream stream);
 /* measurement hook: CTA 0 of every following GEMM writes %globaltimer stamps into d_buf (4 x 128 int64); NULL = off */
 int cdlrm_mlp_set_trace(void* d_buf);
 int cdlrm_mlp_forward(cdlrm_mlp* mlp, const float* x, int64_t ldx, int32_t batch,

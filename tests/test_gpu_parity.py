@@ -169,6 +169,19 @@ def test_interaction_other_kernel_variants(shape, variant):
         check(lib.cdlrm_interact_set_option(0, 0))
 
 
+@pytest.mark.parametrize("fwd", [0, 3])
+@pytest.mark.parametrize("shape", [(8192, 27, 128), (2049, 27, 128), (1, 27, 128), (7, 27, 128), (131, 9, 128)])
+def test_interaction_forward_kernels_dim128(shape, fwd):
+    """Both dim-128 forward kernels against the oracle whichever is the default: 0 = interact_fwd_tr_kernel (a warp
+    per sample), 3 = interact_fwd_h_kernel (half a warp per sample; odd batches leave a dead half-warp)."""
+    from cdlrm_b200._lib import check, lib
+    check(lib.cdlrm_interact_set_option(2, fwd))
+    try:
+        _interaction_at_size(shape)
+    finally:
+        check(lib.cdlrm_interact_set_option(2, -1))
+
+
 def _interaction_at_size(shape):
     from oracle import oracle as O
     _, _, M = _mods()
@@ -232,8 +245,8 @@ def test_interaction_pipelined_kernels(shape, strided_feats):
             outs[pipe] = R.detach().cpu().numpy()
             grads[pipe] = torch.stack([t.grad for t in f]).cpu().numpy()
         finally:
-            check(lib.cdlrm_interact_set_option(1, 1))      # defaults: pipelined backward, plain forward
-            check(lib.cdlrm_interact_set_option(2, 0))
+            check(lib.cdlrm_interact_set_option(1, 1))      # defaults: pipelined backward, the library's forward
+            check(lib.cdlrm_interact_set_option(2, -1))
     dx, dly = O.interact_bwd(x, ly, dR)
     util.assert_close_fp32(outs[1], O.interact_fwd(x, ly))
     util.assert_close_fp32(grads[1][0], dx)

@@ -71,6 +71,7 @@ def main():
 
     g = sg.window_ids(0, L)
     tr.submit_window(g)
+    checked_losers = 0
     j = 0
     losses = []
     for w in range(n_windows):
@@ -79,6 +80,24 @@ def main():
         for k in range(T):                       # (1) tags identical on every rank
             for other in gathered(cg.occupancy_tables[k]):
                 assert torch.equal(other, cg.occupancy_tables[k]), f"tags of table {k} differ across ranks"
+        # (1b) the loser store (sharded over the ranks, read over NVLink): a forward over un-cached ids of this window
+        # returns exactly their master rows, whichever rank holds them
+        if rec.L is not None:
+            probe = torch.zeros(T, lb, dtype=torch.int64, device=dev)
+            for k in range(T):
+                lo = rec.loser_list(k)
+                if rec.L[k]:
+                    probe[k] = lo[torch.arange(lb, device=dev) * max(rec.L[k] // lb, 1) % rec.L[k]]
+            with torch.no_grad():
+                outs, _ = cg(lS_o, probe, master, dev.index)
+                cg.join_forward()
+            torch.cuda.synchronize()
+            for k in range(T):
+                if rec.L[k]:
+                    want = master.emb_l[k].weight.data[probe[k].cpu()]
+                    assert torch.equal(outs[k].cpu(), want), f"window {w}: loser rows of table {k} differ from the master"
+            checked_losers += sum(1 for k in range(T) if rec.L[k])
+        dist.barrier()
         nxt = sg.window_ids(w + 1, L)
         tr.submit_window(nxt)
         loc = g.view(T, L, world, lb)[:, :, rank].reshape(T, L * lb).contiguous()
@@ -138,7 +157,9 @@ def main():
     cg.check_device_flags()
     dist.barrier()
     if rank == 0:
-        print(f"mgpu_check OK: world={world}, {n_windows} windows x {L} steps, loss {losses[0]:.4f} -> {losses[-1]:.4f}")
+        print(f"mgpu_check OK: world={world}, {n_windows} windows x {L} steps, loss {losses[0]:.4f} -> {losses[-1]:.4f}; "
+              f"loser store {'sharded over the ranks' if tr.sharded_losers else 'per rank'}, {checked_losers} table probes, "
+              f"loss digest {hash(tuple(losses)) & 0xffffffff:08x}")
     dist.destroy_process_group()
 
 

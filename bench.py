@@ -70,6 +70,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-prof", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    # measurement only: at a third of the timed region, enqueue this many GB of copy-engine host-to-device copies
+    # (256 MB pinned chunks, side stream) beside the steps: what a cudaMemcpyAsync prefetch would cost the step
+    ap.add_argument("--ce-probe-gb", type=float, default=0.0)
     return ap.parse_args()
 
 
@@ -350,19 +353,27 @@ def gpu_run(a, wl, ln_emb):
     recs = {}                           # window -> PlanRecord (prefetch timing)
 
     mark_buf = {}
+    win_bufs = []
 
     def prepare(w):
         """Window w on the side stream (overlaps training): this rank's slice of the ids plus its dense inputs /
         labels for the training steps, and the look-ahead plan over the GLOBAL window.  At N > 1 the global window
         ([T, L x global batch] int64: 41 GB at 8 GPUs) is never materialised: the stream is counter-based, so the
         planner's scan regenerates it chunk by chunk into one reused buffer (Trainer.submit_window(callable))."""
+        # three rotating sets of persistent buffers (window w-1 may still be read when w+1 is generated): no
+        # allocation beside training (a cudaMalloc of gigabytes stalls the host thread that enqueues the steps)
+        if not win_bufs:
+            for _ in range(3):
+                win_bufs.append((torch.empty(T, L * lb, dtype=torch.int64, device=dev),
+                                 torch.empty(L * lb, 13, dtype=torch.float32, device=dev),
+                                 torch.empty(L * lb, 1, dtype=torch.float32, device=dev)))
+        b_loc, b_X, b_Y = win_bufs[w % 3]
+        # (the steps that read this set belong to window w-3: finished at least a whole window ago)
         with torch.cuda.stream(tr.side):
-            loc = stream_g.ids(w * L, L, b0=rank * lb, nb=lb, stream=tr.side)          # [T, L*lb]
-            X, Y = stream_l.dense_and_labels(w, L)
+            loc = stream_g.ids(w * L, L, b0=rank * lb, nb=lb, out=b_loc, stream=tr.side)          # [T, L*lb]
+            X, Y = stream_l.dense_and_labels(w, L, out=(b_X, b_Y))
             ready = torch.cuda.Event(enable_timing=True)
             ready.record(tr.side)
-            for t_ in (loc, X, Y):        # allocated on the side stream, read by the training stream
-                t_.record_stream(torch.cuda.current_stream(dev))
         if world == 1:
             tr.submit_window(loc)
         else:
@@ -370,8 +381,11 @@ def gpu_run(a, wl, ln_emb):
                 cs = max(1, (1 << 22) // Bg)                 # ~4 M ids per table per chunk (0.9 GB for 26 tables)
                 if "b" not in mark_buf:
                     mark_buf["b"] = torch.empty(T, cs * Bg, dtype=torch.int64, device=dev)
-                for s0 in range(0, L, cs):
-                    ns = min(cs, L - s0)
+                r_, w_ = planner.scan_shard              # sharded scan: this rank marks steps [lo, hi) only
+                per = (L + w_ - 1) // w_
+                lo_s, hi_s = r_ * per, min(L, (r_ + 1) * per)
+                for s0 in range(lo_s, hi_s, cs):
+                    ns = min(cs, hi_s - s0)
                     planner.mark_ids(stream_g.ids(w * L + s0, ns, out=mark_buf["b"], stream=planner.stream))
                 return L * Bg
             tr.submit_window(mark)
@@ -476,10 +490,21 @@ def gpu_run(a, wl, ln_emb):
         torch.cuda.profiler.start()
     seg = max(1, K // 24)                 # per-segment device times: shows what the planner / boundaries cost
     marks = []
+    probe = None
+    if a.ce_probe_gb > 0:
+        probe = (torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True),
+                 torch.empty(256 << 20, dtype=torch.uint8, device=dev), _lib.new_stream(dev),
+                 torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     ev0.record()
     for i in range(K):
         if j % L == 0:
             n_boundaries += 1
+        if probe is not None and i == K // 3:
+            with torch.cuda.stream(probe[2]):
+                probe[3].record()
+                for _ in range(int(a.ce_probe_gb * 4)):
+                    probe[1].copy_(probe[0], non_blocking=True)
+                probe[4].record()
         one_step(j)
         j += 1
         if (i + 1) % seg == 0 and i + 1 < K:
@@ -504,6 +529,9 @@ def gpu_run(a, wl, ln_emb):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     log(f"timed region done: {ms / K:.3f} ms/step")
+    if probe is not None:
+        log(f"copy-engine probe: {a.ce_probe_gb} GB host-to-device in {probe[3].elapsed_time(probe[4]):.1f} ms, started "
+            f"{ev0.elapsed_time(probe[3]):.1f} ms into the timed region; per-segment ms/step: {series}")
     value = K * lb * world / (ms / 1000.0)
 
     # -- per-kernel durations (CUDA events around every launch of the library) ------------------
@@ -558,32 +586,39 @@ def gpu_run(a, wl, ln_emb):
         # Every step: its inputs come from pinned host memory (Trainer.stage_inputs: the copy of step i+1 runs on
         # the copy stream beside step i) and its loss is read back to the host (asynchronous copy into a pinned
         # ring, read one step later, so that the host can enqueue step i+1 while step i runs).
-        loss_pin = torch.zeros(2, dtype=torch.float32, pin_memory=True)
-        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        # The host runs AHEAD steps in front of the device (a data-parallel rank that may not run ahead stalls its
+        # peers in every step's all-reduce whenever its host thread hiccups): inputs of step i+AHEAD are staged while
+        # step i is enqueued, the loss of step i-AHEAD is read while step i runs.
+        AHEAD = tr.input_slots - 2
+        loss_pin = torch.zeros(AHEAD + 1, dtype=torch.float32, pin_memory=True)
+        loss_ev = [torch.cuda.Event() for _ in range(AHEAD + 1)]
         loss_host = float("nan")
         e0.record()
-        st = tr.stage_inputs(hX[0], hI[0], hY[0])
+        staged = [tr.stage_inputs(hX[q], hI[q], hY[q]) for q in range(min(AHEAD, n_e2e))]
         for i in range(n_e2e):
             # (one_step indexes the host block by the step's position in its window)
             w_, b_ = divmod(j, L)
             if b_ == 0 and j > 0:
                 boundary(j)
-            nxt = tr.stage_inputs(hX[i + 1], hI[i + 1], hY[i + 1]) if i + 1 < n_e2e else None
-            E, _ = tr.step_staged(st, lS_o)
+            if i + AHEAD < n_e2e:
+                staged.append(tr.stage_inputs(hX[i + AHEAD], hI[i + AHEAD], hY[i + AHEAD]))
+            E, _ = tr.step_staged(staged.pop(0), lS_o)
             aggregate(j)
-            loss_pin[i & 1].copy_(E.detach().reshape(()), non_blocking=True)   # device -> host read of the result
-            loss_ev[i & 1].record()
-            if i:
-                loss_ev[(i - 1) & 1].synchronize()
-                loss_host = float(loss_pin[(i - 1) & 1])
-            st = nxt
+            q = i % (AHEAD + 1)
+            loss_pin[q].copy_(E.detach().reshape(()), non_blocking=True)   # device -> host read of the result
+            loss_ev[q].record()
+            if i >= AHEAD:
+                q = (i - AHEAD) % (AHEAD + 1)
+                loss_ev[q].synchronize()
+                loss_host = float(loss_pin[q])
             j += 1
             if ((i + 1) % seg2 == 0 or i < 40) and i + 1 < n_e2e:
                 m = torch.cuda.Event(enable_timing=True)
                 m.record()
                 marks2.append((i + 1, m))
-        loss_ev[(n_e2e - 1) & 1].synchronize()
-        loss_host = float(loss_pin[(n_e2e - 1) & 1])
+        for i in range(max(n_e2e - AHEAD, 0), n_e2e):          # the last AHEAD losses
+            loss_ev[i % (AHEAD + 1)].synchronize()
+            loss_host = float(loss_pin[i % (AHEAD + 1)])
         e1.record()
         torch.cuda.synchronize(dev)
         wall_ms = 1000 * (time.perf_counter() - t0)
@@ -633,14 +668,19 @@ def gpu_run(a, wl, ln_emb):
             tl = {"ids_ready": data[max(data)][3]}
             tl.update(rec_next.marks)
             tl.update(stage_begin=rec_next.stage_begin, staged=rec_next.staged)
+            if tr._installed is not None and tr._installed.wb_done is not None:
+                tl["writeback_done"] = tr._installed.wb_done      # the leg's own boundary: evicted rows back in the master
             full_window["planner_timeline_ms"] = {k: round(e0.elapsed_time(v), 1) for k, v in tl.items()}
             full_window["planner_ms"]["prefetch"] = round(st_ms, 1)
             pcie["prefetch_bytes"] = int(rec_next.stage_bytes)
             pcie["prefetch_ms"] = round(st_ms, 2)
             pcie["prefetch_GB/s"] = round(rec_next.stage_bytes / (st_ms * 1e-3) / 1e9, 2) if st_ms > 0 else None
             pcie["prefetch_frac_of_h2d_peak"] = round(pcie["prefetch_GB/s"] / pcie["h2d_GB/s"], 3) if st_ms > 0 else None
-            pcie["prefetch_how"] = ("SM-driven zero-copy row gathers from the pinned master (32 CTAs), beside the "
-                                    "training steps of the end-to-end leg, all ranks at once")
+            pcie["prefetch_how"] = (("host threads (%d) gather master rows into pinned chunks, cudaMemcpyAsync on the "
+                                     "planner stream (copy engine)" % tr.planner.host_threads)
+                                    if tr.planner.pcie_mode == "ce" else
+                                    "SM-driven zero-copy row gathers from the pinned master (32 CTAs)") + \
+                                   ", beside the training steps of the end-to-end leg, all ranks at once"
         del hosts, hI, hX, hY
     clocks = sampler.stop() if sampler else None
 

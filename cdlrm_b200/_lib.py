@@ -47,6 +47,8 @@ SIGNATURES = {
     "cdlrm_mlp_destroy": (C.c_int, [vp]),
     "cdlrm_mlp_set_option": (C.c_int, [C.c_int, C.c_int]),
     "cdlrm_mlp_set_trace": (C.c_int, [vp]),
+    "cdlrm_mlp_sgd_split": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_float, vp, vp, C.c_int64, vp]),
+    "cdlrm_mlp_invalidate_split": (C.c_int, [vp]),
     "cdlrm_mlp_set_defer_join": (C.c_int, [vp, C.c_int]),
     "cdlrm_mlp_join": (C.c_int, [vp, vp]),
     "cdlrm_mlp_forward": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.POINTER(vp), C.POINTER(vp), vp, C.c_int64, vp]),
@@ -55,6 +57,7 @@ SIGNATURES = {
     "cdlrm_plan_bind_workspace": (C.c_int, [vp, vp, C.c_int64, C.c_int64]),
     "cdlrm_plan_unique": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp, vp]),
     "cdlrm_plan_mark_ids": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp]),
+    "cdlrm_plan_or_peer_bitmaps": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, vp]),
     "cdlrm_synth_ids": (C.c_int, [C.c_int, C.c_int, C.c_int, c_i64p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32,
                                   C.c_int64, C.c_int32, C.c_int, C.c_double, vp, C.c_int64, vp]),
     "cdlrm_plan_phase_a": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_i64p, vp, vp]),
@@ -71,6 +74,9 @@ SIGNATURES = {
     "cdlrm_peer_close": (C.c_int, [C.c_int, vp]),
     "cdlrm_peer_free": (C.c_int, [C.c_int, vp]),
     "cdlrm_ctx_bind_losers_sharded": (C.c_int, [vp, C.POINTER(vp), c_i64p, c_i64p, C.c_int, C.POINTER(vp), vp]),
+    "cdlrm_host_gather_rows": (C.c_int, [vp, C.c_int64, C.c_int, vp, C.c_int64, vp, C.c_int]),
+    "cdlrm_host_scatter_rows": (C.c_int, [vp, C.c_int64, C.c_int, vp, vp, C.c_int64, vp, C.c_int, C.c_int]),
+    "cdlrm_copy_async": (C.c_int, [C.c_int, vp, vp, C.c_int64, C.c_int, vp]),
     "cdlrm_host_register": (C.c_int, [C.c_int, vp, C.c_int64, C.POINTER(vp)]),
     "cdlrm_host_unregister": (C.c_int, [vp]),
     "cdlrm_agg_mark": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp]),

@@ -156,6 +156,15 @@ class WindowPlanner:
         self.collect_losers = False      # also list the window's un-cached ids (for the HBM loser store)
         self._bufs = {}                  # persistent grow-only staging buffers (no cudaMalloc per window)
         self._stage_no = 0
+        # how master rows cross PCIe: "sm" = zero-copy gather / scatter kernels (move.cu), "ce" = host threads gather
+        # into / scatter out of pinned chunks that cudaMemcpyAsync moves (hostio.cu): ~10x gentler on the training
+        # step that runs beside it (bench.py --ce-probe-gb), at the price of host cores
+        self.pcie_mode = "sm"
+        self.host_threads = max(1, min(8, (os.cpu_count() or 2) - 2))
+        self._pin = {}                   # pinned host buffers (grow-only)
+        self._ce_no = 0
+        self._ce_ev = None
+        self._pending_wb = None          # ce: (record, average) of the boundary whose evicted rows are not yet written back
         self._shard = None               # (rank, world, host process group): loser store sharded over the node
         self._peer_bufs = {}             # name -> (capacity rows, [device address of every rank's shard buffer])
         self.plan_tags = None
@@ -180,6 +189,53 @@ class WindowPlanner:
                 gb = min(32.0, max(8.0, ((free + cached) / 1e9 - 70.0) / 2))
             cap = self._loser_cap_rows = int(gb * 1e9 / (4 * self.dim))
         return cap
+
+    # -- window scan sharded over the ranks of a node ------------------------------------------------------
+    def enable_sharded_scan(self, rank, world, group):
+        """Let every rank of a ``world``-GPU node mark only ITS share of a window (``scan_shard``) and OR the other
+        ranks' id bitmaps into its own over NVLink (``merge_marks``) instead of scanning the whole global window on
+        every rank.  The planner workspace moves into a peer-readable allocation (same carve-up on every rank).
+        Collective over ``group`` (host-side, gloo): call it on every rank, from the same point of the program."""
+        if world <= 1:
+            return
+        import torch.distributed as dist
+        dev = self.dev.index
+        nbytes = lib.cdlrm_plan_workspace_bytes(self.ctx, self.window_len)
+        mine, handle = _vp(), ctypes.create_string_buffer(64)
+        check(lib.cdlrm_peer_alloc(dev, nbytes, ctypes.byref(mine), handle))
+        check(lib.cdlrm_plan_bind_workspace(self.ctx, mine, nbytes, self.window_len))
+        self._ws = None                   # the torch-allocated workspace is no longer bound
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        ptrs = []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(mine.value)
+            else:
+                p = _vp()
+                check(lib.cdlrm_peer_open(dev, ctypes.create_string_buffer(handles[r], 64), ctypes.byref(p)))
+                ptrs.append(p.value)
+        self._scan = (int(rank), int(world), group, ptrs)
+
+    @property
+    def scan_shard(self):
+        """(rank, world) of the sharded window scan; (0, 1): this rank marks the whole window."""
+        sc = getattr(self, "_scan", None)
+        return (sc[0], sc[1]) if sc else (0, 1)
+
+    def merge_marks(self):
+        """After this rank's ``mark_ids`` calls: wait until every rank has marked its share, OR the others' bitmaps
+        into this rank's (NVLink reads), and hold every rank until all have done so (phase A clears the bitmaps)."""
+        sc = getattr(self, "_scan", None)
+        if not sc:
+            return
+        import torch.distributed as dist
+        rank, world, group, ptrs = sc
+        self.stream.synchronize()
+        dist.barrier(group=group)
+        check(lib.cdlrm_plan_or_peer_bitmaps(self.ctx, _lib.ptr_array(ptrs), world, rank, _sp(self.stream)))
+        self.stream.synchronize()
+        dist.barrier(group=group)
 
     def _agreed_loser_cap(self):
         """Rows one window's loser store may hold: ``loser_cap_rows`` on one rank; sharded, ``world`` times the
@@ -386,16 +442,124 @@ class WindowPlanner:
             self._bufs[name] = b
         return b
 
+    # -- copy-engine transfers (pcie_mode "ce") -------------------------------------------------
+    CE_CHUNK_BYTES = 128 << 20
+
+    def _pinned(self, name, nbytes):
+        b = self._pin.get(name)
+        if b is None or b.numel() < nbytes:
+            self._pin[name] = None
+            b = self._pin[name] = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, pin_memory=True)
+        return b
+
+    def _ce_chunks(self):
+        """Two pinned staging chunks [rows, dim] that alternate, and the events that tell when the copy engine has
+        finished with each."""
+        rows = max(1, self.CE_CHUNK_BYTES // (4 * self.dim))
+        bufs = [self._pinned("ce%d" % i, rows * 4 * self.dim)[:rows * 4 * self.dim].view(torch.float32).view(rows, self.dim)
+                for i in range(2)]
+        if self._ce_ev is None:
+            self._ce_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        return rows, bufs, self._ce_ev
+
+    def _ids_to_host(self, name, dev_ids, segments):
+        """Copy the id segments [(offset, count)] of a device int64 list into one packed pinned array; returns the
+        host tensor and the packed offsets.  Synchronises the planner's stream."""
+        tot = sum(n for _o, n in segments)
+        h = self._pinned(name, 8 * max(tot, 1))[:8 * max(tot, 1)].view(torch.int64)
+        offs, o = [], 0
+        with torch.cuda.stream(self.stream):
+            for so, n in segments:
+                offs.append(o)
+                if n:
+                    h[o:o + n].copy_(dev_ids[so:so + n], non_blocking=True)
+                o += n
+        self.stream.synchronize()
+        return h, offs
+
+    def _ce_gather(self, segs):
+        """segs: [(table k, host int64 ids, device address of the destination rows)]: rows of the host master gathered
+        by host threads into a pinned chunk while the copy engine moves the previous chunk into HBM."""
+        s, d, dev = self.stream, self.dim, self.dev.index
+        rows_per, bufs, evs = self._ce_chunks()
+        for k, hid, dst in segs:
+            W = self.emb_tables.emb_l[k].weight.data
+            n = int(hid.numel())
+            for a in range(0, n, rows_per):
+                m = min(rows_per, n - a)
+                b = self._ce_no & 1
+                self._ce_no += 1
+                evs[b].synchronize()            # the copy that last read this chunk has finished
+                check(lib.cdlrm_host_gather_rows(_vp(W.data_ptr()), W.shape[0], d, _vp(hid.data_ptr() + 8 * a), m,
+                                                 _vp(bufs[b].data_ptr()), self.host_threads))
+                check(lib.cdlrm_copy_async(dev, _vp(dst + 4 * d * a), _vp(bufs[b].data_ptr()), 4 * d * m, 1, _sp(s)))
+                evs[b].record(s)
+
+    def flush_writeback(self):
+        """ce mode: write the evicted rows of the last installed window back into the host master (device -> pinned
+        chunk by the copy engine, chunk -> master rows by host threads).  Called from the thread that plans the next
+        window, before anything of that window reads the master; a no-op when nothing is pending."""
+        pend, self._pending_wb = self._pending_wb, None
+        if pend is None:
+            return
+        rec, average = pend
+        s, d, dev = self.stream, self.dim, self.dev.index
+        segs = [(rec.off[k], rec.E[k]) for k in range(self.T)]
+        hid, offs = self._ids_to_host("wb_ids", rec.evict_ids, segs)
+        tot = sum(rec.E)
+        hpr = self._pinned("wb_prim", max(tot, 1))[:max(tot, 1)]
+        with torch.cuda.stream(s):
+            for k in range(self.T):
+                if rec.E[k]:
+                    hpr[offs[k]:offs[k] + rec.E[k]].copy_(rec.evict_primary[rec.off[k]:rec.off[k] + rec.E[k]], non_blocking=True)
+        s.synchronize()
+        rows_per, bufs, evs = self._ce_chunks()
+        eoff = [0] * self.T
+        for k in range(1, self.T):
+            eoff[k] = eoff[k - 1] + rec.E[k - 1]
+        jobs = [(k, a, min(rows_per, rec.E[k] - a)) for k in range(self.T) for a in range(0, rec.E[k], rows_per)]
+
+        def scatter(job, b):
+            k, a, m = job
+            W = self.emb_tables.emb_l[k].weight.data
+            evs[b].synchronize()                # the chunk has landed in host memory
+            check(lib.cdlrm_host_scatter_rows(_vp(W.data_ptr()), W.shape[0], d, _vp(hid.data_ptr() + 8 * (offs[k] + a)),
+                                              _vp(hpr.data_ptr() + offs[k] + a), m, _vp(bufs[b].data_ptr()),
+                                              int(average), self.host_threads))
+
+        prev = None
+        for job in jobs:                        # copy of chunk c runs while chunk c-1 is scattered
+            k, a, m = job
+            b = self._ce_no & 1
+            self._ce_no += 1
+            if prev is not None and prev[1] == b:
+                scatter(*prev)
+                prev = None
+            check(lib.cdlrm_copy_async(dev, _vp(bufs[b].data_ptr()), _vp(rec.evict_stage[eoff[k] + a:].data_ptr()),
+                                       4 * d * m, 2, _sp(s)))
+            evs[b].record(s)
+            if prev is not None:
+                scatter(*prev)
+            prev = (job, b)
+        if prev is not None:
+            scatter(*prev)
+        rec.wb_done = torch.cuda.Event(enable_timing=True)
+        rec.wb_done.record(s)
+
     # -- look-ahead staging -------------------------------------------------------------------
     def stage(self, rec):
         """Prefetch, on the planner's stream, everything window w+1 needs from the host master
         while window w still trains: the rows of the fill list and (with ``collect_losers``) the
-        rows of the ids that stay un-cached, gathered zero-copy over PCIe into HBM staging
-        buffers.  Exact under the sequential schedule: none of these ids
-        is cached during window w, so their master rows cannot change before the boundary, and
-        the write-back of the previous boundary precedes these reads in stream order."""
+        rows of the ids that stay un-cached, into HBM staging buffers -- gathered zero-copy over PCIe by a
+        kernel (``pcie_mode`` "sm") or by host threads + cudaMemcpyAsync ("ce").  Exact under the sequential
+        schedule: none of these ids is cached during window w, so their master rows cannot
+        change before the boundary, and the write-back of the previous boundary precedes these reads."""
         s = self.stream
         d = self.dim
+        ce = self.pcie_mode == "ce" and not self.emb_tables.emb_l[0].weight.is_cuda
+        if ce:
+            self.flush_writeback()
+        fill_jobs, loser_jobs = [], []      # (table, offset into the device id list, rows, device address of the rows)
         with torch.cuda.stream(s):
             rec.stage_begin = torch.cuda.Event(enable_timing=True)
             rec.stage_begin.record(s)
@@ -405,11 +569,8 @@ class WindowPlanner:
             rec.fill_stage = self._buf("fill", max(sum(rec.F), 1))
             for k in range(self.T):
                 if rec.F[k]:
-                    ids, _slots = rec.fill_list(k)
-                    check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(ids.data_ptr()), rec.F[k],
-                                                       _vp(rec.fill_stage[rec.fill_soff[k]:].data_ptr()), _sp(s)))
+                    fill_jobs.append((k, rec.off[k], rec.F[k], rec.fill_stage[rec.fill_soff[k]:].data_ptr()))
             rec.loser_shard = rec.loser_peers = None
-            n_loser_rows = 0
             if rec.L is not None and self._shard is not None:
                 # sharded store: this rank pulls rows [rank * shard, (rank + 1) * shard) of every table's list
                 rank, world, _group = self._shard
@@ -426,10 +587,7 @@ class WindowPlanner:
                         lo = r * rec.loser_shard[k]
                         n_k = min(rec.L[k], lo + rec.loser_shard[k]) - lo
                         if n_k > 0:
-                            o = rec.loser_off[k] + lo
-                            check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(rec.loser_ids[o:].data_ptr()), n_k,
-                                                               _vp(rec.loser_peers[k][r]), _sp(s)))
-                            n_loser_rows += n_k
+                            loser_jobs.append((k, rec.loser_off[k] + lo, n_k, rec.loser_peers[k][r]))
             elif rec.L is not None:
                 # two loser stores alternate: the previous window's is read by the forward until the boundary
                 self._stage_no += 1
@@ -439,14 +597,21 @@ class WindowPlanner:
                 rec.loser_stage = self._buf("loser%d" % (self._stage_no & 1), max(sum(rec.L), 1))
                 for k in range(self.T):
                     if rec.L[k]:
-                        o = rec.loser_off[k]
-                        check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(rec.loser_ids[o:].data_ptr()), rec.L[k],
-                                                           _vp(rec.loser_stage[rec.loser_soff[k]:].data_ptr()), _sp(s)))
-                n_loser_rows = sum(rec.L)
+                        loser_jobs.append((k, rec.loser_off[k], rec.L[k], rec.loser_stage[rec.loser_soff[k]:].data_ptr()))
+            if not ce:
+                for ids_dev, jobs in ((rec.fill_ids, fill_jobs), (rec.loser_ids, loser_jobs)):
+                    for k, o, n, dst in jobs:
+                        check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(ids_dev[o:].data_ptr()), n, _vp(dst), _sp(s)))
+        if ce:
+            for name, ids_dev, jobs in (("fill_ids", rec.fill_ids, fill_jobs), ("loser_ids", rec.loser_ids, loser_jobs)):
+                if jobs:
+                    hid, offs = self._ids_to_host(name, ids_dev, [(o, n) for _k, o, n, _dst in jobs])
+                    self._ce_gather([(k, hid[ho:ho + n], dst) for (k, _o, n, dst), ho in zip(jobs, offs)])
+        with torch.cuda.stream(s):
             rec.staged = torch.cuda.Event(enable_timing=True)
             rec.staged.record(s)
-            # host-master rows pulled over PCIe by this prefetch (bench.py: prefetch GB/s = bytes / event time)
-            rec.stage_bytes = 4 * d * (sum(rec.F) + n_loser_rows)
+        # host-master rows pulled over PCIe by this prefetch (bench.py: prefetch GB/s = bytes / event time)
+        rec.stage_bytes = 4 * d * (sum(n for _k, _o, n, _dst in fill_jobs) + sum(n for _k, _o, n, _dst in loser_jobs))
         return rec
 
     def install_staged(self, rec, write_master=True, average_on_writeback=False, stream=None):
@@ -502,7 +667,12 @@ class WindowPlanner:
             moved.record(s)
         ws = self.stream
         ws.wait_event(moved)       # later planner-stream work (next prefetch) may reuse the staging buffers
-        if write_master and sum(rec.E):
+        if write_master and sum(rec.E) and self.pcie_mode == "ce" and not self.emb_tables.emb_l[0].weight.is_cuda:
+            # copy engine + host threads: done by the thread that plans the next window (flush_writeback), before
+            # anything of that window reads the master; callers that read the master themselves call it first
+            rec.evict_stage.record_stream(ws)
+            self._pending_wb = (rec, bool(average_on_writeback))
+        elif write_master and sum(rec.E):
             rec.evict_stage.record_stream(ws)
             with torch.cuda.stream(ws):
                 for k in range(self.T):
@@ -511,7 +681,7 @@ class WindowPlanner:
                         check(lib.cdlrm_move_scatter_master2(self.ctx, k, _vp(ids.data_ptr()), _vp(prim.data_ptr()),
                                                              rec.E[k], _vp(rec.evict_stage[eoff[k]:].data_ptr()),
                                                              int(average_on_writeback), _sp(ws)))
-        rec.wb_done = torch.cuda.Event()
+        rec.wb_done = torch.cuda.Event(enable_timing=True)
         rec.wb_done.record(self.stream)
         return rec
 

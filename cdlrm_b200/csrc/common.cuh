@@ -89,6 +89,7 @@ struct cdlrm_ctx {
     std::vector<PlanTable> ptabs;
     PlanTable* d_ptabs = nullptr;
     int64_t plan_window_len = 0;
+    char* plan_ws = nullptr;             // base of the bound planner workspace (peer copies share its carve-up)
     std::vector<unsigned long long*> pins;  // per table [num_sets] pin masks of the window being planned
     int32_t* p_blocksum2 = nullptr; // second tile-sum array
     int32_t* p_blocksum = nullptr;  // [nblk_max + 1]

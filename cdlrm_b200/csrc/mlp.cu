@@ -512,14 +512,24 @@ struct SplitJob {
     float *hi, *lo; int64_t ld_o;
     float *thi, *tlo; int64_t ld_t;
     int tiles_x, tile0;          // 32 x 32 tiles per row of tiles, first global tile of this job
+    const float* grad;           // SGD fused in front of the split: src <- src - lr * grad (dense, row stride lds); or null
 };
 struct SplitBatch {
     SplitJob job[MAX_LAYERS];
     int n;
+    float lr;
+    // trailing blocks (blockIdx.x >= tiles): plain SGD on a vector that needs no split (the biases)
+    int tiles;
+    float* vec; const float* vec_grad; int64_t vec_n;
 };
 __global__ void __launch_bounds__(256) split_batch_kernel(const __grid_constant__ SplitBatch sb) {
     pdl_enter();
     __shared__ float s_hi[32][33], s_lo[32][33];
+    if (sb.vec && (int)blockIdx.x >= sb.tiles) {
+        const int64_t i = (int64_t)((int)blockIdx.x - sb.tiles) * 256 + threadIdx.x;
+        if (i < sb.vec_n) sb.vec[i] = fmaf(-sb.lr, sb.vec_grad[i], sb.vec[i]);
+        return;
+    }
     int j = 0;
 #pragma unroll 1
     while (j + 1 < sb.n && (int)blockIdx.x >= sb.job[j + 1].tile0) ++j;
@@ -532,7 +542,11 @@ __global__ void __launch_bounds__(256) split_batch_kernel(const __grid_constant_
         const int r = r0 + ty + 8 * i, c = c0 + tx;
         float h = 0.f, l = 0.f;
         if (r < jb.rows && c < jb.cols) {
-            const float v = jb.src[(int64_t)r * jb.lds + c];
+            float v = jb.src[(int64_t)r * jb.lds + c];
+            if (jb.grad) {
+                v = fmaf(-sb.lr, jb.grad[(int64_t)r * jb.lds + c], v);
+                const_cast<float*>(jb.src)[(int64_t)r * jb.lds + c] = v;
+            }
             h = tf32_hi(v);
             l = tf32_lo(v, h);
             jb.hi[(int64_t)r * jb.ld_o + c] = h;
@@ -915,6 +929,7 @@ struct cdlrm_mlp {
     bool last_narrow = false;    // the last forward ran its final layer on the narrow kernels
     const float* last_W = nullptr;   // FP32 weights of that layer (the narrow backward reads them)
     bool ones_set = false;
+    bool w_presplit = false;     // cdlrm_mlp_sgd_split left the splits of the CURRENT weights behind: the next forward skips its own
     int num_sms = 148;
     // weight-gradient GEMMs on a stream of their own beside the data-gradient chain (cdlrm_mlp_backward)
     cudaStream_t s2 = nullptr;
@@ -1069,6 +1084,49 @@ extern "C" int cdlrm_mlp_join(cdlrm_mlp* m, cdlrm_stream stream) {
     return CDLRM_OK;
 }
 
+// SGD step of the weight matrices of up to two MLPs fused with the hi/lo split (row-major and transposed) of the
+// UPDATED weights, plus plain SGD on one extra vector (the biases): ONE launch instead of the optimizer's axpy and one
+// split launch at the head of each forward -- which sat on the critical path of the step (before the bottom MLP's
+// first GEMM, and between the interaction and the top MLP).
+extern "C" int cdlrm_mlp_sgd_split(int n_mlps, cdlrm_mlp* const* mlps, float* const* h_W, const float* const* h_dW, float lr,
+                                   float* vec, const float* vec_grad, int64_t vec_n, cdlrm_stream stream) {
+    ARG_CHECK(n_mlps >= 1 && n_mlps <= 2 && mlps && h_W && h_dW && vec_n >= 0 && (vec_n == 0 || (vec && vec_grad)));
+    cudaStream_t s = (cudaStream_t)stream;
+    SplitBatch sb = {};
+    int tiles = 0, j = 0;
+    for (int a = 0; a < n_mlps; ++a) {
+        cdlrm_mlp* m = mlps[a];
+        ARG_CHECK(m);
+        for (int l = 0; l < m->L; ++l, ++j) {
+            ARG_CHECK(j < MAX_LAYERS && h_W[j] && h_dW[j]);
+            const int K = m->D[l], N = m->D[l + 1];
+            SplitJob& jb = sb.job[j];
+            jb.src = h_W[j]; jb.grad = h_dW[j]; jb.lds = K; jb.rows = N; jb.cols = K;
+            jb.hi = m->w_hi[l]; jb.lo = m->w_lo[l]; jb.ld_o = pad4(K);
+            jb.thi = m->wt_hi[l]; jb.tlo = m->wt_lo[l]; jb.ld_t = pad4(N);
+            jb.tiles_x = (K + 31) / 32; jb.tile0 = tiles;
+            tiles += jb.tiles_x * ((N + 31) / 32);
+        }
+    }
+    CU_CHECK(cudaSetDevice(mlps[0]->device));
+    sb.n = j;
+    sb.lr = lr;
+    sb.tiles = tiles;
+    sb.vec = vec_n ? vec : nullptr; sb.vec_grad = vec_grad; sb.vec_n = vec_n;
+    const int blocks = tiles + (int)((vec_n + 255) / 256);
+    LAUNCH_PDL(K_MLP_SPLIT, s, split_batch_kernel, blocks, 256, 0, sb);
+    CU_CHECK(cudaGetLastError());
+    for (int a = 0; a < n_mlps; ++a) mlps[a]->w_presplit = true;
+    return CDLRM_OK;
+}
+
+// the weights were changed by something else than cdlrm_mlp_sgd_split: the next forward splits them again
+extern "C" int cdlrm_mlp_invalidate_split(cdlrm_mlp* m) {
+    ARG_CHECK(m);
+    m->w_presplit = false;
+    return CDLRM_OK;
+}
+
 extern "C" int cdlrm_mlp_forward(cdlrm_mlp* m, const float* x, int64_t ldx, int32_t batch, const float* const* h_W,
                                  const float* const* h_b, float* y, int64_t ldy, cdlrm_stream stream) {
     ARG_CHECK(m && x && h_W && h_b && y);
@@ -1091,21 +1149,26 @@ extern "C" int cdlrm_mlp_forward(cdlrm_mlp* m, const float* x, int64_t ldx, int3
         CU_CHECK(cudaGetLastError());
         m->ones_set = true;
     }
-    // weights: W [N,K] -> hi/lo K-major and transposed (the dgrad operand), all layers in one launch
-    {
-        SplitBatch sb;
+    // weights: W [N,K] -> hi/lo K-major and transposed (the dgrad operand), all layers in one launch -- unless the
+    // optimizer step that produced these weights already did it (cdlrm_mlp_sgd_split)
+    if (m->w_presplit) {
+        for (int l = 0; l < L; ++l) ARG_CHECK(h_W[l] && h_b[l]);
+        m->w_presplit = false;
+    } else {
+        SplitBatch sb = {};
         int tiles = 0;
         for (int l = 0; l < L; ++l) {
             ARG_CHECK(h_W[l] && h_b[l]);
             const int K = m->D[l], N = m->D[l + 1];
             SplitJob& jb = sb.job[l];
-            jb.src = h_W[l]; jb.lds = K; jb.rows = N; jb.cols = K;
+            jb.src = h_W[l]; jb.grad = nullptr; jb.lds = K; jb.rows = N; jb.cols = K;
             jb.hi = m->w_hi[l]; jb.lo = m->w_lo[l]; jb.ld_o = pad4(K);
             jb.thi = m->wt_hi[l]; jb.tlo = m->wt_lo[l]; jb.ld_t = pad4(N);
             jb.tiles_x = (K + 31) / 32; jb.tile0 = tiles;
             tiles += jb.tiles_x * ((N + 31) / 32);
         }
         sb.n = L;
+        sb.tiles = tiles;
         LAUNCH_PDL(K_MLP_SPLIT, s, split_batch_kernel, tiles, 256, 0, sb);
         CU_CHECK(cudaGetLastError());
     }

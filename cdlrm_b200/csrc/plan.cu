@@ -366,6 +366,7 @@ extern "C" int cdlrm_plan_bind_workspace(cdlrm_ctx* c, void* ws, int64_t bytes, 
     pins.clear();
     carve_workspace(c, window_len, (char*)ws, &c->ptabs, &pins, c);
     c->plan_window_len = window_len;
+    c->plan_ws = (char*)ws;
     // bitmaps start clean (the emit kernel keeps them clean); claims start at -1
     CU_CHECK(cudaDeviceSynchronize());
     for (int k = 0; k < c->T; ++k)
@@ -421,6 +422,49 @@ extern "C" int cdlrm_plan_mark_ids(cdlrm_ctx* c, const int64_t* ids, int64_t ld,
     for (int k = 0; k < c->T; ++k) {
         const int g1 = (int)((n + 1023) / 1024 < 148 * 16 ? (n + 1023) / 1024 : 148 * 16);
         LAUNCH(K_PLAN_BITMAP_SET, s, bitmap_set_kernel<<<g1 > 0 ? g1 : 1, 256, 0, s>>>(ids + k * ld, n, c->ptabs[k].bitmap, c->tabs[k].n_rows, c->d_flags));
+    }
+    CU_CHECK(cudaGetLastError());
+    return CDLRM_OK;
+}
+
+// Window scan sharded over the ranks of a node: every rank marks its own share of the window's steps, then ORs the
+// id bitmaps of all the others into its own, reading them in place over NVLink (peer workspaces mapped with
+// cdlrm_peer_open: same carve-up on every rank, so a table's bitmap sits at the same offset everywhere).
+namespace {
+struct PeerWs { const char* p[CDLRM_MAX_PEERS]; };
+__global__ void __launch_bounds__(256) or_peer_bitmaps_kernel(uint32_t* __restrict__ mine, int64_t off, PeerWs peers, int world,
+                                                              int rank, int64_t words) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {
+        uint32_t v = mine[i];
+        for (int r = 0; r < world; ++r)
+            if (r != rank) v |= __ldcv(reinterpret_cast<const uint32_t*>(peers.p[r] + off) + i);
+        mine[i] = v;
+    }
+}
+}  // namespace
+
+extern "C" int cdlrm_plan_or_peer_bitmaps(cdlrm_ctx* c, const void* const* h_peer_ws, int world, int rank,
+                                          cdlrm_stream stream) {
+    ARG_CHECK(c && h_peer_ws && world >= 1 && world <= CDLRM_MAX_PEERS && rank >= 0 && rank < world);
+    if (c->ptabs.empty() || !c->plan_ws) {
+        cdlrm_set_error("planner workspace not bound");
+        return CDLRM_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(c->device));
+    PeerWs pw;
+    for (int r = 0; r < CDLRM_MAX_PEERS; ++r) pw.p[r] = nullptr;
+    for (int r = 0; r < world; ++r) {
+        ARG_CHECK(r == rank || h_peer_ws[r]);
+        pw.p[r] = (const char*)h_peer_ws[r];
+    }
+    for (int k = 0; k < c->T; ++k) {
+        const int64_t words = (c->tabs[k].n_rows + 31) / 32;
+        const int64_t off = (char*)c->ptabs[k].bitmap - c->plan_ws;
+        int64_t blocks = (words + 255) / 256;
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        LAUNCH(K_PLAN_BITMAP_SET, s, or_peer_bitmaps_kernel<<<(int)blocks, 256, 0, s>>>(c->ptabs[k].bitmap, off, pw, world, rank, words));
     }
     CU_CHECK(cudaGetLastError());
     return CDLRM_OK;

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) synth_ids_kernel(SynthTables tb, int t0, 
         if (uniform || n == 1) {
             r = (int64_t)(u * (double)n);
         } else {
-            r = (int64_t)pow(c0 * u + 1.0, inv_e) - 1;
+            r = (int64_t)exp2(inv_e * log2(c0 * u + 1.0)) - 1;      // x^(1/(1-a)); ~half the cost of pow(), error << 1 rank
         }
         r = r < 0 ? 0 : (r >= n ? n - 1 : r);
         out[(int64_t)blockIdx.z * ld + (int64_t)s * nb + b] = scramble_mod((uint64_t)r, 40503ull * (uint64_t)k, (uint64_t)n, inv_n);

@@ -23,7 +23,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import check, lib
 from .cache_manager import Prefetcher, TorchGlobalRng, VictimRng, VictimRngDevice, WindowPlanner
-from .model_no_ddp import DLRM_Net, Embedding_Table_Cache_Group, Embedding_Table_Group, bce_mean
+from .model_no_ddp import DLRM_Net, Embedding_Table_Cache_Group, Embedding_Table_Group, bce_mean, bce_mean_with_grad
 
 _vp = ctypes.c_void_p
 
@@ -353,6 +353,12 @@ class Trainer:
             check(lib.cdlrm_mlp_set_option(5, int(os.environ.get("CDLRM_WGRAD_SIDE", "1") != "0")))
             if os.environ.get("CDLRM_DEFER_WGRAD", "1") != "0":
                 self.dlrm.defer_wgrad_join(True)     # joined in the step, right before the gradients are used
+        # N > 1: the top MLP's weight gradients (80 % of the dense parameters) are all-reduced as soon as its backward
+        # is enqueued, beside the interaction backward and the bottom MLP; the rest follows at the end of the backward
+        self._ar_stream, self._ar_work = None, None
+        if self.flat and world > 1 and os.environ.get("CDLRM_EARLY_ALLREDUCE", "1") != "0":
+            self._ar_stream = _lib.new_stream(self.dev, priority=-1)
+            self.dlrm._mlp_state["top"].after_backward = self._early_allreduce
         self.optimizer_mlps = torch.optim.SGD(self.dlrm.parameters(), lr=args.learning_rate)
         self.optimizer_embeds = torch.optim.SGD(self.cache_group.parameters(), lr=args.lr_embeds)   # :376
         self.cache_group._ensure_ctx(emb_tables)
@@ -371,6 +377,12 @@ class Trainer:
                                          rng=VictimRngDevice(args.numpy_rand_seed, self.dev), stream=self.side,
                                          lookahead_tags=True)
             self.planner.collect_losers = True     # un-cached ids of a window are served from an HBM loser store
+            # master <-> HBM traffic of the planner: host threads + cudaMemcpyAsync ("ce") when this rank can have at
+            # least 4 host threads to itself, else zero-copy gather / scatter kernels ("sm"); CDLRM_PREFETCH overrides
+            threads = max(1, min(8, (os.cpu_count() or 2) // max(world, 1) - 2))
+            mode = os.environ.get("CDLRM_PREFETCH", "auto")
+            self.planner.host_threads = int(os.environ.get("CDLRM_HOST_THREADS", threads))
+            self.planner.pcie_mode = mode if mode in ("ce", "sm") else ("ce" if self.planner.host_threads >= 4 else "sm")
         self._host_group = dist.new_group(backend="gloo") if world > 1 else None   # plan-thread barrier
         # un-cached ids of a window (the same on every rank): one store sharded over the node's GPUs and read over
         # NVLink instead of a full copy per rank (CDLRM_LOSER_SHARDED=0: one local store per rank)
@@ -378,11 +390,16 @@ class Trainer:
                                and os.environ.get("CDLRM_LOSER_SHARDED", "1") != "0")
         if self.sharded_losers:
             self.planner.enable_sharded_losers(rank, world, self._host_group)
+        # a window handed over as a marker callable (submit_window) is scanned 1/world per rank, bitmaps OR-ed over
+        # NVLink (CDLRM_SCAN_SHARDED=0: every rank scans the whole global window)
+        if world > 1 and self.planner is not None and os.environ.get("CDLRM_SCAN_SHARDED", "1") != "0":
+            self.planner.enable_sharded_scan(rank, world, self._host_group)
         self._installed = None
         self._plan_q = queue.Queue()
         self._plan_thread = None
         self.steps_since_agg = 0
         self.caching_overhead = []
+        self.input_slots = 6             # stage_inputs: device-side input slots (host runs up to 5 steps ahead)
         self.keep_losses = False         # tests: keep every step's loss tensor (no sync) in loss_history
         self.loss_history = []
 
@@ -396,7 +413,9 @@ class Trainer:
         uniq_lists = marker = None
         if callable(win_ids):
             # chunked scan: ``win_ids(planner)`` feeds the window to ``planner.mark_ids`` chunk by chunk (on the
-            # planner's stream, from the plan thread) and returns the number of ids per table it marked
+            # planner's stream, from the plan thread) and returns the number of ids per table of the WHOLE window;
+            # with ``planner.scan_shard == (r, W)``, W > 1, it marks only the r-th of W equal shares of the window
+            # (any partition will do: the ranks' bitmaps are OR-ed afterwards)
             marker = win_ids
         elif isinstance(win_ids, (tuple, list)):
             uniq_lists = [u.to(self.dev, non_blocking=True) for u in win_ids[1]]
@@ -412,9 +431,12 @@ class Trainer:
             torch.cuda.set_device(self.dev)
             self.side.wait_event(ev)
             try:
+                # (copy-engine mode) evicted rows of the window just installed go back to the host master first
+                self.planner.flush_writeback()
                 if marker is not None:
                     with torch.cuda.stream(self.side):
-                        n_marked = marker(self.planner)
+                        n_marked = marker(self.planner)      # this rank's share (planner.scan_shard) or everything
+                    self.planner.merge_marks()
                     rec = self.planner.plan(marked=n_marked)
                 elif uniq_lists is not None:
                     rec = self.planner.plan(uniq_lists=uniq_lists)
@@ -470,6 +492,17 @@ class Trainer:
                                       "aggregate": round(1e3 * (t3 - t2), 2), "install": round(1e3 * (t4 - t3), 2)}
         return rec
 
+    def _early_allreduce(self):
+        """Called from the top MLP's backward (autograd thread, training stream current)."""
+        st = self.dlrm._mlp_state["top"]
+        ars = self._ar_stream
+        ars.wait_stream(torch.cuda.current_stream(self.dev))
+        check(lib.cdlrm_mlp_join(st.handle, ctypes.c_void_p(ars.cuda_stream)))   # its dW are complete on `ars`
+        with torch.cuda.stream(ars):
+            gw = self.dlrm.flat_grads[self.dlrm.flat_top_weight_off:self.dlrm.flat_weight_elems]
+            gw /= self.world
+            self._ar_work = dist.all_reduce(gw, async_op=True)
+
     # -- one training step -------------------------------------------------------------------
     def _step_eager(self, X, lS_o, lS_i, T):
         if self.overlap_update:
@@ -477,22 +510,34 @@ class Trainer:
             self.cache_group.fused_lr = float(self.optimizer_embeds.param_groups[0]["lr"])
         lookups, _idxs = self.cache_group(lS_o, lS_i, self.emb_tables, self.dev.index)
         Z = self.dlrm(X, lookups)
+        dz = None
         if self.args.loss_function == "bce" and os.environ.get("CDLRM_FUSED_LOSS", "1") != "0":
-            E = bce_mean(Z, T)                 # BCELoss(mean) and its derivative in one launch
+            if (self.flat and Z.is_cuda and Z.dtype == torch.float32 and T.dtype == torch.float32
+                    and Z.shape == T.shape and not (0.0 < self.dlrm.loss_threshold < 1.0)):
+                E, dz = bce_mean_with_grad(Z, T)   # loss and d loss / d Z in one launch, outside autograd
+            else:
+                E = bce_mean(Z, T)                 # BCELoss(mean) and its derivative in one launch
         else:
             E = loss_fn_wrap(Z, T, self.loss_fn, self.args, self.loss_ws)
         if self.flat:
             # the MLP backward writes dW / db into the flat bucket; weights (not biases: the reference's
             # aggregate_gradients never reduces them, :234-247) are averaged by ONE in-place all-reduce
-            E.backward()
+            if dz is not None:
+                Z.backward(dz)                     # == E.backward() without the ones seed and the dz * 1 launch
+            else:
+                E.backward()
             work = None
             if self.world > 1:
                 self.dlrm.join_mlp_grads()
-                gw = self.dlrm.flat_grads[:self.dlrm.flat_weight_elems]
+                early, self._ar_work = self._ar_work, None
+                lo = self.dlrm.flat_top_weight_off if early is not None else self.dlrm.flat_weight_elems
+                gw = self.dlrm.flat_grads[:lo]                        # what the early all-reduce did not cover
                 gw /= self.world
                 work = dist.all_reduce(gw, async_op=True)
             self.optimizer_embeds.step()      # applies the fused sparse update (pre-step hook)
             if work is not None:
+                if early is not None:
+                    early.wait()
                 work.wait()
             self.dlrm.join_mlp_grads()        # weight-gradient GEMMs ran beside everything up to here
             self.dlrm.flat_sgd_step(self.optimizer_mlps.param_groups[0]["lr"])
@@ -542,13 +587,14 @@ class Trainer:
 
     def stage_inputs(self, X, lS_i, T):
         """Start the host->device copy of ONE step's inputs (pinned host tensors: dense features, ids [T, lb],
-        labels) on the trainer's copy stream and return a handle for ``step_staged``.  Two device-side slots
-        alternate, so the copy of step i+1 runs beside step i instead of in front of it on the training stream
-        (2.2 MB per step at the Terabyte shape: ~40 us of PCIe time per step otherwise serialised with the step)."""
+        labels) on the trainer's copy stream and return a handle for ``step_staged``.  ``input_slots`` device-side
+        slots rotate, so the copies of the next steps run beside step i instead of in front of it on the training
+        stream (2.2 MB per step at the Terabyte shape: ~40 us of PCIe time per step otherwise serialised with the
+        step), and the host may run ``input_slots - 1`` steps ahead of the device."""
         if getattr(self, "_in_slots", None) is None:
             self._copy_stream = _lib.new_stream(self.dev)
-            self._in_slots, self._in_no = [None, None], 0
-        k = self._in_no & 1
+            self._in_slots, self._in_no = [None] * self.input_slots, 0
+        k = self._in_no % len(self._in_slots)
         self._in_no += 1
         sl = self._in_slots[k]
         shapes = (tuple(X.shape), tuple(lS_i.shape), tuple(T.shape))
@@ -595,11 +641,15 @@ class Trainer:
             work = None
             self.dlrm.join_mlp_grads()
             if self.world > 1:
-                gw = self.dlrm.flat_grads[:self.dlrm.flat_weight_elems]
+                early, self._ar_work = self._ar_work, None
+                lo = self.dlrm.flat_top_weight_off if early is not None else self.dlrm.flat_weight_elems
+                gw = self.dlrm.flat_grads[:lo]
                 gw /= self.world
                 work = dist.all_reduce(gw, async_op=True)
             self.optimizer_embeds.step()
             if work is not None:
+                if early is not None:
+                    early.wait()
                 work.wait()
             self.dlrm.flat_sgd_step(self.optimizer_mlps.param_groups[0]["lr"])
         else:
@@ -613,6 +663,8 @@ class Trainer:
         """Wait for the look-ahead thread and the last asynchronous write-back; raise pending device flags."""
         if self._plan_thread is not None:
             self._plan_thread.join()
+        if self.planner is not None:
+            self.planner.flush_writeback()
         if self._installed is not None and self._installed.wb_done is not None:
             self._installed.wb_done.synchronize()
         torch.cuda.synchronize(self.dev)

@@ -663,6 +663,26 @@ class _BceMeanFn(torch.autograd.Function):
         return dz * g, None
 
 
+def bce_mean_with_grad(Z, T):
+    """(loss, d loss / d Z) of BCELoss(mean) in one launch, outside autograd: a training loop that calls
+    ``Z.backward(dz)`` instead of ``loss.backward()`` saves the two launches autograd spends on seeding the scalar
+    loss with ones and scaling dz by it."""
+    dev = Z.device
+    Zc, Tc = Z.detach(), T
+    n = Zc.numel()
+    ldz = Zc.stride(0) if Zc.dim() == 2 and Zc.shape[1] == 1 else 1
+    ldt = Tc.stride(0) if Tc.dim() == 2 and Tc.shape[1] == 1 else 1
+    if ldz == 1 and not Zc.is_contiguous():
+        Zc = Zc.contiguous()
+    if ldt == 1 and not Tc.is_contiguous():
+        Tc = Tc.contiguous()
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dz = torch.empty(Z.shape, dtype=torch.float32, device=dev)
+    check(lib.cdlrm_bce_mean(dev.index, _vp(Zc.data_ptr()), ldz, _vp(Tc.data_ptr()), ldt, n, _vp(loss.data_ptr()),
+                             _vp(dz.data_ptr()), _stream_ptr(dev)))
+    return loss, dz
+
+
 def bce_mean(Z, T):
     """Fused BCELoss(mean) + derivative for float32 CUDA tensors; anything else goes to torch."""
     if Z.is_cuda and Z.dtype == torch.float32 and T.dtype == torch.float32 and Z.shape == T.shape and Z.numel() > 0:
@@ -690,6 +710,8 @@ class _MlpState:
         self.fwd_id = 0
         self.flat_grads = None     # ([dW views], [db views]) into DLRM_Net's flat gradient bucket, or None
         self.defer_join = False    # cdlrm_mlp_set_defer_join: dW / db complete only after DLRM_Net.join_mlp_grads()
+        self.after_backward = None  # optional callable run right after this MLP's backward was enqueued (Trainer:
+                                    # starts the all-reduce of the top MLP's weight gradients beside the rest)
 
     def ensure(self, batch, dev):
         if self.handle is not None and batch <= self.cap and self.ws.device == dev:
@@ -776,6 +798,8 @@ class _MlpFn(torch.autograd.Function):
         check(lib.cdlrm_mlp_backward(st.handle, _vp(dy.data_ptr()), dy.stride(0), _vp(dx_ptr), lddx,
                                      _lib.ptr_array([t.data_ptr() for t in dWs]),
                                      _lib.ptr_array([t.data_ptr() for t in dbs]), _stream_ptr(dev)))
+        if st.after_backward is not None:
+            st.after_backward()
         if st.flat_grads is not None:      # the bucket already holds them (p.grad is a view of it): nothing for autograd
             return (None, dx, None) + (None,) * ctx.n_params
         grads = []
@@ -809,6 +833,7 @@ class DLRM_Net(nn.Module):
         # "tcgen05": cdlrm_mlp_* (3xTF32 tensor-core GEMMs with fused epilogues, FP32 accuracy);
         # "torch": the stock nn.Sequential (cuBLAS SIMT sgemm)
         self.mlp_impl = os.environ.get("CDLRM_MLP", "tcgen05")
+        self.fused_sgd_split = os.environ.get("CDLRM_SGD_SPLIT", "1") != "0"
         self._mlp_state = {}
 
     def create_mlp(self, ln, sigmoid_layer):
@@ -847,7 +872,10 @@ class DLRM_Net(nn.Module):
         params = [m.weight for m in lin] + [m.bias for m in lin]
         dev = params[0].device
         offs, o = [], 0
+        n_bot = sum(1 for m in self.bot_l if isinstance(m, nn.Linear))
         for q in params:
+            if q is lin[n_bot].weight:
+                self.flat_top_weight_off = o      # [0, off): bottom MLP weights, [off, flat_weight_elems): top MLP weights
             offs.append(o)
             o += (q.numel() + 3) & ~3
             if q is lin[-1].weight:
@@ -886,8 +914,40 @@ class DLRM_Net(nn.Module):
 
     @torch.no_grad()
     def flat_sgd_step(self, lr):
-        """p -= lr * g over the whole flat bucket: one launch for all dense parameters."""
+        """p -= lr * g over the whole flat bucket: one launch for all dense parameters.  On the tensor-core path the
+        same launch also leaves the hi / lo operand copies of the UPDATED weights behind (cdlrm_mlp_sgd_split), so
+        that the next forward of either MLP starts with its first GEMM instead of a split launch.  Dense parameters
+        changed by anything else afterwards (``.data.copy_``) need ``invalidate_weight_splits()``;
+        ``load_state_dict`` and ``.to()`` do it themselves."""
+        sts = [self._mlp_state.get("bot"), self._mlp_state.get("top")]
+        if (self.mlp_impl == "tcgen05" and self.fused_sgd_split
+                and all(st is not None and st.handle is not None for st in sts)):
+            lin = [m for st in sts for m in st.linears]
+            n_w = self.flat_weight_elems
+            check(lib.cdlrm_mlp_sgd_split(
+                2, _lib.ptr_array([st.handle.value for st in sts]),
+                _lib.ptr_array([m.weight.data_ptr() for m in lin]),
+                _lib.ptr_array([g.data_ptr() for st in sts for g in st.flat_grads[0]]), float(lr),   # views of the bucket
+                _vp(self.flat_params.data_ptr() + 4 * n_w), _vp(self.flat_grads.data_ptr() + 4 * n_w),
+                self.flat_params.numel() - n_w, _stream_ptr(self.flat_params.device)))
+            return
         self.flat_params.add_(self.flat_grads, alpha=-float(lr))
+
+    def invalidate_weight_splits(self):
+        for st in self._mlp_state.values():
+            if st.handle is not None:
+                check(lib.cdlrm_mlp_invalidate_split(st.handle))
+
+    def load_state_dict(self, *a, **kw):
+        r = super().load_state_dict(*a, **kw)
+        self.invalidate_weight_splits()
+        return r
+
+    def _apply(self, fn, *a, **kw):
+        r = super()._apply(fn, *a, **kw)
+        if hasattr(self, "_mlp_state"):
+            self.invalidate_weight_splits()
+        return r
 
     def apply_mlp(self, which, x):
         """bot_l / top_l (:306-309).  On CUDA with mlp_impl == "tcgen05" the whole Sequential runs

@@ -54,9 +54,18 @@ class SyntheticStream:
         """int64 [T, n_steps*B] on the device: the whole batch of steps [w*n_steps, (w+1)*n_steps)."""
         return self.ids(w * n_steps, n_steps)
 
-    def dense_and_labels(self, w, n_steps):
+    def dense_and_labels(self, w, n_steps, out=None):
+        """X [N, dense_dim] = log(1 + U{0..100}), T [N, 1] ~ Bernoulli(0.25) for window w.  ``out=(X, T)``: generate
+        in place into float32 buffers of those shapes (no allocation, no int64 temporary: a side stream that
+        allocates gigabytes beside training stalls the host in cudaMalloc)."""
         g = self._gen(10_000_000 + w)
         N = n_steps * self.B
+        if out is not None:
+            X, T = out
+            X.uniform_(0.0, 101.0, generator=g).floor_().clamp_(max=100.0).log1p_()
+            T.uniform_(0.0, 1.0, generator=g)
+            T.copy_(T < 0.25)                      # (a 25 MB bool temporary: small next to X)
+            return X, T
         X = torch.log1p(torch.randint(0, 101, (N, self.dense_dim), generator=g, device=self.dev).float())
         T = (torch.rand(N, 1, generator=g, device=self.dev) < 0.25).float()
         return X, T

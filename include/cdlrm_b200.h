@@ -162,6 +162,15 @@ int cdlrm_mlp_set_option(int key, int value);
  * object: then dW / db are complete on the caller's stream only after cdlrm_mlp_join(mlp, stream) -- which lets
  * the weight gradients of the top MLP run beside the interaction backward and the bottom MLP.  A forward or
  * backward of the same object joins implicitly. */
+/* Optimizer step of the dense parameters (main_no_ddp.py:413, torch.optim.SGD.step on the MLPs) fused with the
+ * operand split of the updated weights: for the n_mlps (1 or 2) objects in turn, layer by layer, W <- W - lr * dW
+ * (h_W / h_dW: host arrays of device pointers, dense [dims[l+1], dims[l]]), written back AND as the hi / lo operand
+ * copies the next forward needs (which then skips its own split launch); vec <- vec - lr * vec_grad (vec_n floats: the
+ * biases) in the same launch.  The weights must not change between this call and the next forward of each object
+ * (cdlrm_mlp_invalidate_split otherwise). */
+int cdlrm_mlp_sgd_split(int n_mlps, cdlrm_mlp* const* mlps, float* const* h_W, const float* const* h_dW, float lr,
+                        float* vec, const float* vec_grad, int64_t vec_n, cdlrm_stream stream);
+int cdlrm_mlp_invalidate_split(cdlrm_mlp* mlp);
 int cdlrm_mlp_set_defer_join(cdlrm_mlp* mlp, int on);
 int cdlrm_mlp_join(cdlrm_mlp* mlp, cdlrm_stream stream);
 /* measurement hook: CTA 0 of every following GEMM writes %globaltimer stamps into d_buf (4 x 128 int64); NULL = off */
@@ -186,6 +195,14 @@ int cdlrm_plan_unique(cdlrm_ctx* ctx, const int64_t* win_ids, int64_t ld, int64_
  * bitmaps.  Any number of calls, in any order, then cdlrm_plan_phase_a with win_ids == NULL and n = the number of
  * ids marked per table (an upper bound of the distinct ids): the window never has to exist as one tensor. */
 int cdlrm_plan_mark_ids(cdlrm_ctx* ctx, const int64_t* ids, int64_t ld, int64_t n, cdlrm_stream stream);
+/* Scan sharded over the `world` ranks of a node (every rank marked its own share of the window with
+ * cdlrm_plan_mark_ids): OR the id bitmaps of the other ranks into this rank's, reading them in place over NVLink.
+ * h_peer_ws[r] = device address on THIS device of rank r's planner workspace (cdlrm_peer_alloc / cdlrm_peer_open;
+ * the entry of `rank` itself is ignored).  The caller orders it between two host barriers: after every rank's marks
+ * are complete, and before any rank's phase A (which clears the bitmaps) starts.  Replaces nothing in the reference
+ * as code: cache_manager.py:27-46 scans the whole window in one worker pool; here the scan of an N-GPU job's global
+ * window would otherwise be repeated on all N ranks. */
+int cdlrm_plan_or_peer_bitmaps(cdlrm_ctx* ctx, const void* const* h_peer_ws, int world, int rank, cdlrm_stream stream);
 /* phase A, all tables: unique ids of the window (ascending), probe against the plan
  * tags, pin hit ways, drop misses whose set is fully pinned, rank the survivors.
  * win_ids of table k at win_ids + k*ld (int64 [n]).  If h_uniq != NULL ids are taken
@@ -292,6 +309,19 @@ int cdlrm_host_unregister(void* h_ptr);
  *      ldz / ldt; dz: n contiguous float32. */
 int cdlrm_bce_mean(int device, const float* z, int64_t ldz, const float* t, int64_t ldt, int32_t n, float* loss,
                    float* dz, cdlrm_stream stream);
+
+/* ---- host side of the copy-engine prefetch / write-back (csrc/hostio.cu) -----------------------------------------
+ * The scattered half of a master <-> GPU transfer on host threads, against a contiguous (pinned) staging chunk that a
+ * plain cudaMemcpyAsync then moves: cache_manager.py:34-43 (`weight[unique_idxs]` of the Prefetcher's workers) and
+ * :58-62 (the eviction manager's `weight[idxs] = rows` / `(weight[idxs] + rows) / 2`).  All pointers are HOST pointers.
+ * gather: dst[i] = master[ids[i]];  scatter: master[ids[i]] = src[i] (mean of the two with `average`) for every i whose
+ * primary[i] != 0 (primary == NULL: all).  `threads` host threads share the rows. */
+int cdlrm_host_gather_rows(const float* master, int64_t n_rows, int dim, const int64_t* ids, int64_t n, float* dst,
+                           int threads);
+int cdlrm_host_scatter_rows(float* master, int64_t n_rows, int dim, const int64_t* ids, const uint8_t* primary,
+                            int64_t n, const float* src, int average, int threads);
+/* cudaMemcpyAsync of a staging chunk on `stream` (copy engine): kind 1 = host to device, 2 = device to host */
+int cdlrm_copy_async(int device, void* dst, const void* src, int64_t bytes, int kind, cdlrm_stream stream);
 
 /* ---- peer-readable device buffers (CUDA IPC over NVLink / NVSwitch) and the SHARDED loser store ----------------
  * No reference counterpart as code: the reference fetches every forward miss from the CPU master table

@@ -49,7 +49,8 @@ def _run_cuda_trace(cfg, mode):
     planner = None
     capped = mode == "staged_capped"      # tiny HBM budget for the loser store: most misses fall back to the host master
     sharded = mode == "staged_sharded"    # loser store cut into 3 per-"rank" shards (all on this device), peer.cu path
-    if capped or sharded:
+    ce = mode == "staged_ce"              # master rows cross PCIe through host threads + cudaMemcpyAsync (hostio.cu)
+    if capped or sharded or ce:
         mode = "staged"
     if mode in ("fast", "fast_devrng", "staged"):
         cg._ensure_ctx(master)
@@ -58,6 +59,9 @@ def _run_cuda_trace(cfg, mode):
         planner.collect_losers = mode == "staged"
         if sharded:
             planner.enable_sharded_losers(1, 3, "local")
+        if ce:
+            planner.pcie_mode, planner.host_threads = "ce", 3
+            planner.CE_CHUNK_BYTES = 64 * 4 * d       # 64-row chunks: many chunk hand-overs even on the tiny traces
     step = 0
     for w in range(cfg["n_windows"]):
         win = torch.from_numpy(ids[:, w * L * B:(w + 1) * L * B])
@@ -76,6 +80,7 @@ def _run_cuda_trace(cfg, mode):
             pr = planner.plan(win_ids=win.to(DEV))
             planner.stage(pr)
             planner.install_staged(pr, write_master=True, average_on_writeback=cfg.get("avg_wb", False))
+            planner.flush_writeback()         # (copy-engine mode: the evicted rows reach the master here)
             torch.cuda.synchronize()
             eo = np.concatenate([[0], np.cumsum(pr.E)])
             ev = [(pr.evict_list(k)[0], pr.evict_stage[eo[k]:eo[k] + pr.E[k]]) for k in range(T)]
@@ -122,7 +127,7 @@ def _run_cuda_trace(cfg, mode):
 
 @pytest.mark.parametrize("name", ["trace_tiny.npz", "trace_pressure.npz", "trace_pressure_avgwb.npz",
                                   "trace_cfg0_small.npz"])
-@pytest.mark.parametrize("mode", ["api", "fast", "fast_devrng", "staged", "staged_capped", "staged_sharded"])
+@pytest.mark.parametrize("mode", ["api", "fast", "fast_devrng", "staged", "staged_capped", "staged_sharded", "staged_ce"])
 def test_trace_matches_reference_golden(name, mode, monkeypatch):
     g = util.load_golden(name)
     cfg = util.golden_cfg(g)

@@ -66,12 +66,7 @@ def _run_trainer(g, use_graph):
             n_miss.append(tr.cache_group.last_n_miss.clone())
             step += 1
     torch.cuda.synchronize()
-    if tr._plan_thread is not None:
-        tr._plan_thread.join()
-    if tr._installed is not None and tr._installed.wb_done is not None:
-        tr._installed.wb_done.synchronize()
-    torch.cuda.synchronize()
-    tr.cache_group.check_device_flags()
+    tr.finish()          # joins the plan thread, completes the last write-back, raises pending device flags
     if use_graph:
         assert tr._graph is not None and tr.graph_launches > 0
     return dict(losses=np.asarray([float(x) for x in losses], dtype=np.float64),

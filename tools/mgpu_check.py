@@ -69,8 +69,23 @@ def main():
         dist.all_gather(out, t.contiguous())
         return out
 
+    use_marker = os.environ.get("MGPU_MARKER", "0") == "1"      # chunked, rank-sharded window scan (bench.py's path)
+
+    def submit(w, g_):
+        if not use_marker:
+            return tr.submit_window(g_)
+
+        def mark(planner):
+            r_, w_ = planner.scan_shard
+            per = (L + w_ - 1) // w_
+            for s0 in range(r_ * per, min(L, (r_ + 1) * per), 2):
+                ns = min(2, min(L, (r_ + 1) * per) - s0)
+                planner.mark_ids(sg.ids(w * L + s0, ns, stream=planner.stream))
+            return L * Bg
+        tr.submit_window(mark)
+
     g = sg.window_ids(0, L)
-    tr.submit_window(g)
+    submit(0, g)
     checked_losers = 0
     j = 0
     losses = []
@@ -99,7 +114,7 @@ def main():
             checked_losers += sum(1 for k in range(T) if rec.L[k])
         dist.barrier()
         nxt = sg.window_ids(w + 1, L)
-        tr.submit_window(nxt)
+        submit(w + 1, nxt)
         loc = g.view(T, L, world, lb)[:, :, rank].reshape(T, L * lb).contiguous()
         X, Y = sl.dense_and_labels(w, L)
         for b in range(L):
@@ -159,6 +174,7 @@ def main():
     if rank == 0:
         print(f"mgpu_check OK: world={world}, {n_windows} windows x {L} steps, loss {losses[0]:.4f} -> {losses[-1]:.4f}; "
               f"loser store {'sharded over the ranks' if tr.sharded_losers else 'per rank'}, {checked_losers} table probes, "
+              f"window scan {'sharded (marker)' if use_marker else 'whole window per rank'}, "
               f"loss digest {hash(tuple(losses)) & 0xffffffff:08x}")
     dist.destroy_process_group()
 

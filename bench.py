@@ -334,7 +334,8 @@ def gpu_run(a, wl, ln_emb):
             master = Embedding_Table_Group(d, np.asarray(ln_emb), init=f"shm:{prefix}:attach")
     log(f"master tables ready ({time.time() - t0:.1f} s)")
     tr = Trainer(args, d, np.asarray(ln_emb), ln_bot, ln_top, master, rank=rank, world=world, device=dev)
-    log(f"trainer ready ({time.time() - t0:.1f} s)")
+    log(f"trainer ready ({time.time() - t0:.1f} s); host cores {os.cpu_count()}, planner PCIe mode "
+        f"{tr.planner.pcie_mode} ({tr.planner.host_threads} host threads)")
     if world > 1:
         dist.barrier()
         if rank == 0:

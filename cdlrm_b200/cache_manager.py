@@ -381,17 +381,21 @@ class WindowPlanner:
             if not dev_rng:
                 q = q_host.to(self.dev, non_blocking=True) if total else torch.empty(0, device=self.dev)
             n = max(total, 1)
-            rec.evict_ids = torch.empty(n, dtype=torch.int64, device=self.dev)
-            rec.evict_slots = torch.empty(n, dtype=torch.int32, device=self.dev)
-            rec.evict_primary = torch.empty(n, dtype=torch.uint8, device=self.dev)
-            rec.fill_ids = torch.empty(n, dtype=torch.int64, device=self.dev)
-            rec.fill_slots = torch.empty(n, dtype=torch.int32, device=self.dev)
+            # the lists of a window live in one of two alternating sets of grow-only buffers (window w's are read
+            # until its write-back, while window w+1 is planned): no per-window allocation beside training
+            self._plan_no = getattr(self, "_plan_no", 0) + 1
+            par = self._plan_no & 1
+            rec.evict_ids = self._list_buf("evict_ids%d" % par, n, torch.int64)
+            rec.evict_slots = self._list_buf("evict_slots%d" % par, n, torch.int32)
+            rec.evict_primary = self._list_buf("evict_primary%d" % par, n, torch.uint8)
+            rec.fill_ids = self._list_buf("fill_ids%d" % par, n, torch.int64)
+            rec.fill_slots = self._list_buf("fill_slots%d" % par, n, torch.int32)
             outs = (_vp(rec.evict_ids.data_ptr()), _vp(rec.evict_slots.data_ptr()),
                     _vp(rec.evict_primary.data_ptr()), _vp(rec.fill_ids.data_ptr()),
                     _vp(rec.fill_slots.data_ptr()), _vp(self._h_counts2.data_ptr()), _sp(s))
             if dev_rng:
                 cap = max(max(rec.rows) * self.ways, 1)          # draws of the largest table
-                raw = torch.empty(2 * cap, dtype=torch.int32, device=self.dev)
+                raw = self._list_buf("rng_raw", 2 * cap, torch.int32)
                 check(lib.cdlrm_plan_phase_b_dev(self.ctx, self.rng._h, _vp(raw.data_ptr()), cap,
                                                  _lib.i64_array(rec.rows), *outs))
             else:
@@ -409,7 +413,7 @@ class WindowPlanner:
                 rec.loser_off = [0] * self.T
                 for k in range(1, self.T):
                     rec.loser_off[k] = rec.loser_off[k - 1] + cap[k - 1]
-                rec.loser_ids = torch.empty(max(sum(cap), 1), dtype=torch.int64, device=self.dev)
+                rec.loser_ids = self._list_buf("loser_ids%d" % par, max(sum(cap), 1), torch.int64)
                 check(lib.cdlrm_plan_losers(self.ctx, _lib.i64_array(rec.uniq), _lib.i64_array(rec.loser_off),
                                             _vp(rec.loser_ids.data_ptr()), _vp(self._h_counts3.data_ptr()), _sp(s)))
                 s.synchronize()
@@ -428,6 +432,14 @@ class WindowPlanner:
         rec.loser_shard = rec.loser_peers = None
         rec.stage_begin, rec.stage_bytes = None, 0
         return rec
+
+    def _list_buf(self, name, n, dtype):
+        """Persistent 1-D device buffer of at least n elements (grown x1.25 when a window needs more)."""
+        b = self._bufs.get(name)
+        if b is None or b.numel() < n or b.dtype != dtype:
+            self._bufs[name] = None
+            b = self._bufs[name] = torch.empty(int(n * 1.25) + 16, dtype=dtype, device=self.dev)
+        return b[:n]
 
     def _buf(self, name, rows):
         """Persistent [rows, dim] fp32 staging buffer, grown (x1.25) only when a window needs more:
@@ -449,7 +461,7 @@ class WindowPlanner:
         b = self._pin.get(name)
         if b is None or b.numel() < nbytes:
             self._pin[name] = None
-            b = self._pin[name] = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, pin_memory=True)
+            b = self._pin[name] = torch.empty(int(nbytes * 1.5) + 256, dtype=torch.uint8, pin_memory=True)
         return b
 
     def _ce_chunks(self):
@@ -561,6 +573,7 @@ class WindowPlanner:
             self.flush_writeback()
         fill_jobs, loser_jobs = [], []      # (table, offset into the device id list, rows, device address of the rows)
         with torch.cuda.stream(s):
+            self._buf("evict", max(sum(rec.F), 1))      # sized now (E <= F): no cudaMalloc at the boundary
             rec.stage_begin = torch.cuda.Event(enable_timing=True)
             rec.stage_begin.record(s)
             rec.fill_soff = [0] * self.T
@@ -603,6 +616,12 @@ class WindowPlanner:
                     for k, o, n, dst in jobs:
                         check(lib.cdlrm_move_gather_master(self.ctx, k, _vp(ids_dev[o:].data_ptr()), n, _vp(dst), _sp(s)))
         if ce:
+            # everything the write-back of this window's boundary will need, sized now (E <= F) with head-room: a
+            # cudaHostAlloc / cudaMalloc in the middle of a window stalls every CUDA call of the process for 10-20 ms
+            n_fill = max(sum(rec.F), 1)
+            self._pinned("wb_ids", 8 * n_fill)
+            self._pinned("wb_prim", n_fill)
+            self._ce_chunks()
             for name, ids_dev, jobs in (("fill_ids", rec.fill_ids, fill_jobs), ("loser_ids", rec.loser_ids, loser_jobs)):
                 if jobs:
                     hid, offs = self._ids_to_host(name, ids_dev, [(o, n) for _k, o, n, _dst in jobs])

@@ -91,7 +91,13 @@ extern "C" int cdlrm_copy_async(int device, void* dst, const void* src, int64_t 
     ARG_CHECK(dst && src && bytes >= 0 && (kind == 1 || kind == 2));
     if (bytes == 0) return CDLRM_OK;
     CU_CHECK(cudaSetDevice(device));
-    CU_CHECK(cudaMemcpyAsync(dst, src, (size_t)bytes, kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
-                             (cudaStream_t)stream));
+    // in pieces: a copy engine does not preempt a copy, and the training step's own small copies (inputs in, loss out)
+    // would otherwise wait for a whole 128 MB chunk (2.3 ms at 55 GB/s, measured as 2.5-3 ms spikes of single steps)
+    constexpr int64_t PIECE = 4 << 20;
+    for (int64_t o = 0; o < bytes; o += PIECE) {
+        const int64_t m = bytes - o < PIECE ? bytes - o : PIECE;
+        CU_CHECK(cudaMemcpyAsync((char*)dst + o, (const char*)src + o, (size_t)m,
+                                 kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    }
     return CDLRM_OK;
 }

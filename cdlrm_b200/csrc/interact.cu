@@ -192,15 +192,13 @@ __global__ void __launch_bounds__(128, 4) interact_fwd_tr_kernel(FeatPtrs fp, in
 // free), then lane L adds up columns 2(L%16), 2(L%16)+1 over the 16 rows of its own half-warp (LDS.64); the tile is
 // double-buffered so that one __syncwarp per block is enough.  Two CTAs of four warps per SM (255 registers).
 template <int F>
-__global__ void __launch_bounds__(128, 2) interact_fwd_h_kernel(FeatPtrs fp, int64_t row_stride, int B,
-                                                                float* __restrict__ out, int64_t ld_out) {
-    pdl_enter();
+__device__ __forceinline__ void fwd_h_pair(const FeatPtrs& fp, int64_t row_stride, int B, float* __restrict__ out,
+                                           int64_t ld_out, int pair, float (*s_part)[32 * 36]) {
     constexpr int DIM = 128, PITCH = 36;
     constexpr int NP = Pairs<F, false>::N;
-    __shared__ __align__(16) float s_part[4][2][32 * PITCH];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int h = lane & 15, half = lane >> 4;
-    const int b = (((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 1) + half;
+    const int b = pair * 2 + half;
     const bool live = b < B;
     const int bb = live ? b : B - 1;                      // a dead half-warp (odd B) recomputes the last sample, stores nothing
     float4 ta[F], tb[F];
@@ -233,13 +231,13 @@ __global__ void __launch_bounds__(128, 2) interact_fwd_h_kernel(FeatPtrs fp, int
             if constexpr ((p + 1) % 8 == 0 || p + 1 == NP) {      // 8 partials (or the tail) -> two STS.128
                 constexpr int c8 = (p % 32) / 8;                  // chunk of 8 within the block
                 constexpr int n8 = p % 8 + 1;                     // valid partials in this chunk
-                float4* wr = reinterpret_cast<float4*>(s_part[wib][blk & 1] + lane * PITCH + c8 * 8);
+                float4* wr = reinterpret_cast<float4*>(s_part[blk & 1] + lane * PITCH + c8 * 8);
                 wr[0] = make_float4(v[0], n8 > 1 ? v[1] : 0.f, n8 > 2 ? v[2] : 0.f, n8 > 3 ? v[3] : 0.f);
                 if constexpr (n8 > 4) wr[1] = make_float4(v[4], n8 > 5 ? v[5] : 0.f, n8 > 6 ? v[6] : 0.f, n8 > 7 ? v[7] : 0.f);
             }
             if constexpr ((p + 1) % 32 == 0 || p + 1 == NP) {
                 constexpr int cnt = p + 1 - blk * 32;
-                const float* buf = s_part[wib][blk & 1];
+                const float* buf = s_part[blk & 1];
                 __syncwarp();
                 const int c0 = 2 * h;
                 if (c0 < cnt) {
@@ -259,6 +257,35 @@ __global__ void __launch_bounds__(128, 2) interact_fwd_h_kernel(FeatPtrs fp, int
             }
         });
     });
+}
+
+template <int F>
+__global__ void __launch_bounds__(128, 2) interact_fwd_h_kernel(FeatPtrs fp, int64_t row_stride, int B,
+                                                                float* __restrict__ out, int64_t ld_out) {
+    pdl_enter();
+    __shared__ __align__(16) float s_part[4][2][32 * 36];
+    fwd_h_pair<F>(fp, row_stride, B, out, ld_out, (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), s_part[threadIdx.x >> 5]);
+}
+
+// The same, persistent: a warp walks sample pairs gw, gw + W, ... (W = warps in the grid: two CTAs per SM).  A grid
+// of one-shot CTAs runs in lock-step waves -- every warp of a wave loads its 27 KB at once (HBM-bound), then every warp
+// computes (issue-bound) -- so neither resource is busy for more than half of the time.  Here the warps of an SM are
+// started `stagger_ns` apart, so that some load while the others compute.
+template <int F>
+__global__ void __launch_bounds__(128, 2) interact_fwd_hp_kernel(FeatPtrs fp, int64_t row_stride, int B,
+                                                                 float* __restrict__ out, int64_t ld_out, int n_pairs,
+                                                                 unsigned stagger_ns) {
+    pdl_enter();
+    __shared__ __align__(16) float s_part[4][2][32 * 36];
+    const int wib = threadIdx.x >> 5;
+    const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), W = (int)((gridDim.x * blockDim.x) >> 5);
+    // warps of the two CTAs that share an SM interleave: slot = (CTA parity, warp) in [0, 8)
+    const unsigned slot = (blockIdx.x & 1u) * 4u + (unsigned)wib;
+    if (stagger_ns && slot) __nanosleep(slot * stagger_ns);
+    for (int pair = gw; pair < n_pairs; pair += W) {
+        fwd_h_pair<F>(fp, row_stride, B, out, ld_out, pair, s_part[wib]);
+        __syncwarp();                                     // the transpose tiles are reused by the next pair
+    }
 }
 
 template <int F, int TPS, bool ITSELF>
@@ -795,10 +822,26 @@ void launch_fwd_tr(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld
     LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_tr_kernel<F, ITSELF>), blocks, 128, 0, fp, rs, B, out, ld_out);
 }
 
+int g_fwd_stagger_ns = [] {
+    const char* e = getenv("CDLRM_INTERACT_STAGGER_NS");
+    return e ? atoi(e) : 800;
+}();
+
 template <int F>
-void launch_fwd_h(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_out, cudaStream_t s) {
+void launch_fwd_h(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_out, cudaStream_t s, bool persistent) {
     const int blocks = (B + 7) / 8;                       // half a warp per sample, 8 samples per block
-    LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_h_kernel<F>), blocks, 128, 0, fp, rs, B, out, ld_out);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    if (persistent && blocks > 2 * sms) {
+        LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_hp_kernel<F>), 2 * sms, 128, 0, fp, rs, B, out, ld_out, (B + 1) / 2,
+                   (unsigned)g_fwd_stagger_ns);
+    } else {
+        LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_h_kernel<F>), blocks, 128, 0, fp, rs, B, out, ld_out);
+    }
 }
 
 template <int F, int TPS, bool ITSELF>
@@ -819,7 +862,7 @@ int g_bwd_pipe = 1;      // cdlrm_interact_set_option(1, .): software-pipelined 
 constexpr int FWD_DEFAULT = 3;
 int g_fwd_pipe = [] {
     const char* e = getenv("CDLRM_INTERACT_FWD");       // A/B switch for whole-step measurements
-    return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : FWD_DEFAULT;
+    return (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : FWD_DEFAULT;
 }();
 int g_variant = 0;       // cdlrm_interact_set_option(0, .): 0 CUDA cores (default), 1 mma.sync 3xTF32, 2 first CUDA-core version
 bool use_simt_only() { return g_variant != 1; }
@@ -910,8 +953,8 @@ bool aligned_for(const FeatPtrs& fp, int n, int64_t rs, int bytes) {
         done = true;                                                                      \
     }
 #define FWD_PIPE_CASE(F_)                                                                                   \
-    if (!done && n_feat == F_ && dim == 128 && !itself && fast16 && g_fwd_pipe == 3 && g_variant == 0) {     \
-        launch_fwd_h<F_>(fp, rs, batch, out, ld_out, s);                                                     \
+    if (!done && n_feat == F_ && dim == 128 && !itself && fast16 && g_fwd_pipe >= 3 && g_variant == 0) {     \
+        launch_fwd_h<F_>(fp, rs, batch, out, ld_out, s, g_fwd_pipe == 4);                                    \
         done = true;                                                                                         \
     }                                                                                                        \
     if (!done && n_feat == F_ && dim == 128 && !itself && fast16 && g_fwd_pipe && g_variant == 0) {          \
@@ -947,8 +990,13 @@ extern "C" int cdlrm_interact_set_option(int key, int value) {
         return CDLRM_OK;
     }
     if (key == 2) {
-        ARG_CHECK(value >= -1 && value <= 3);
+        ARG_CHECK(value >= -1 && value <= 4);
         g_fwd_pipe = value < 0 ? FWD_DEFAULT : value;
+        return CDLRM_OK;
+    }
+    if (key == 3) {                 // start stagger (ns) of the persistent forward's warps (variant 4)
+        ARG_CHECK(value >= 0 && value <= 100000);
+        g_fwd_stagger_ns = value;
         return CDLRM_OK;
     }
     ARG_CHECK(key == 0 && value >= 0 && value <= 2);

@@ -592,7 +592,7 @@ class Trainer:
         stream (2.2 MB per step at the Terabyte shape: ~40 us of PCIe time per step otherwise serialised with the
         step), and the host may run ``input_slots - 1`` steps ahead of the device."""
         if getattr(self, "_in_slots", None) is None:
-            self._copy_stream = _lib.new_stream(self.dev)
+            self._copy_stream = _lib.new_stream(self.dev, priority=-1)   # ahead of the planner's bulk copies
             self._in_slots, self._in_no = [None] * self.input_slots, 0
         k = self._in_no % len(self._in_slots)
         self._in_no += 1

@@ -174,11 +174,12 @@ def test_interaction_other_kernel_variants(shape, variant):
         check(lib.cdlrm_interact_set_option(0, 0))
 
 
-@pytest.mark.parametrize("fwd", [0, 3])
+@pytest.mark.parametrize("fwd", [0, 3, 4])
 @pytest.mark.parametrize("shape", [(8192, 27, 128), (2049, 27, 128), (1, 27, 128), (7, 27, 128), (131, 9, 128)])
 def test_interaction_forward_kernels_dim128(shape, fwd):
     """Both dim-128 forward kernels against the oracle whichever is the default: 0 = interact_fwd_tr_kernel (a warp
-    per sample), 3 = interact_fwd_h_kernel (half a warp per sample; odd batches leave a dead half-warp)."""
+    per sample), 3 = interact_fwd_h_kernel (half a warp per sample; odd batches leave a dead half-warp), 4 = the same
+    with persistent, staggered warps (batches above two CTAs per SM; bit-identical to 3)."""
     from cdlrm_b200._lib import check, lib
     check(lib.cdlrm_interact_set_option(2, fwd))
     try:

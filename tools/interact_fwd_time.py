@@ -20,8 +20,9 @@ NK = lib.cdlrm_prof_num_kernels()
 names = [lib.cdlrm_prof_kernel_name(i).decode() for i in range(NK)]
 sets = [(torch.randn(B, d, device=dev), [torch.randn(B, d, device=dev) for _ in range(F - 1)]) for _ in range(12)]
 s = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-for fwd in (0, 3, 2, 0, 3):
+for fwd, stag in ((0, 0), (3, 0), (4, 0), (4, 400), (4, 800), (4, 1600), (4, 3000), (3, 0), (4, 800)):
     check(lib.cdlrm_interact_set_option(2, fwd))
+    check(lib.cdlrm_interact_set_option(3, stag))
     for rep in range(3):
         if rep == 1:
             lib.cdlrm_prof_enable(1)
@@ -38,6 +39,6 @@ for fwd in (0, 3, 2, 0, 3):
     raw = ms[i] * 1e3 / max(calls[i], 1)
     null = ms[j] * 1e3 / max(calls[j], 1)
     algo = B * (F * 4 * d + (d + F * (F - 1) // 2) * 4)
-    print(f"fwd variant {fwd}: {raw:.1f} us raw, {raw - null:.1f} us net of the event pair ({null:.1f}); "
+    print(f"fwd variant {fwd} stagger {stag} ns: {raw:.1f} us raw, {raw - null:.1f} us net of the event pair ({null:.1f}); "
           f"{algo / (raw - null) / 1e3:.0f} GB/s algorithmic over {calls[i]} launches")
 check(lib.cdlrm_interact_set_option(2, -1))

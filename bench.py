@@ -389,7 +389,7 @@ def gpu_run(a, wl, ln_emb):
                     ns = min(cs, hi_s - s0)
                     planner.mark_ids(stream_g.ids(w * L + s0, ns, out=mark_buf["b"], stream=planner.stream))
                 return L * Bg
-            tr.submit_window(mark)
+            tr.submit_window(mark, own_ids=loc)
         data[w] = (loc, X, Y, ready)
         for old in [x for x in data if x < w - 1]:
             del data[old]
@@ -591,8 +591,6 @@ def gpu_run(a, wl, ln_emb):
         # peers in every step's all-reduce whenever its host thread hiccups): inputs of step i+AHEAD are staged while
         # step i is enqueued, the loss of step i-AHEAD is read while step i runs.
         AHEAD = tr.input_slots - 2
-        loss_pin = torch.zeros(AHEAD + 1, dtype=torch.float32, pin_memory=True)
-        loss_ev = [torch.cuda.Event() for _ in range(AHEAD + 1)]
         loss_host = float("nan")
         e0.record()
         staged = [tr.stage_inputs(hX[q], hI[q], hY[q]) for q in range(min(AHEAD, n_e2e))]
@@ -605,21 +603,16 @@ def gpu_run(a, wl, ln_emb):
                 staged.append(tr.stage_inputs(hX[i + AHEAD], hI[i + AHEAD], hY[i + AHEAD]))
             E, _ = tr.step_staged(staged.pop(0), lS_o)
             aggregate(j)
-            q = i % (AHEAD + 1)
-            loss_pin[q].copy_(E.detach().reshape(()), non_blocking=True)   # device -> host read of the result
-            loss_ev[q].record()
-            if i >= AHEAD:
-                q = (i - AHEAD) % (AHEAD + 1)
-                loss_ev[q].synchronize()
-                loss_host = float(loss_pin[q])
+            tr.push_loss(E)                          # device -> host read of the step's result (asynchronous)
+            if tr.pending_losses() > AHEAD:
+                loss_host = tr.pop_loss()            # the loss of step i - AHEAD
             j += 1
             if ((i + 1) % seg2 == 0 or i < 40) and i + 1 < n_e2e:
                 m = torch.cuda.Event(enable_timing=True)
                 m.record()
                 marks2.append((i + 1, m))
-        for i in range(max(n_e2e - AHEAD, 0), n_e2e):          # the last AHEAD losses
-            loss_ev[i % (AHEAD + 1)].synchronize()
-            loss_host = float(loss_pin[i % (AHEAD + 1)])
+        while tr.pending_losses():                   # the last AHEAD losses
+            loss_host = tr.pop_loss()
         e1.record()
         torch.cuda.synchronize(dev)
         wall_ms = 1000 * (time.perf_counter() - t0)
@@ -686,6 +679,11 @@ def gpu_run(a, wl, ln_emb):
     clocks = sampler.stop() if sampler else None
 
     res = None
+    cache_gb = sum(int(e.weight.numel()) for e in tr.cache_group.emb_l) * 4 / 1e9
+    l2_policy = (f"inputs larger than L2: every step reads a fresh {T}x{lb}-row slice of a {cache_gb:.1f} GB cache and a "
+                 "new batch of the window's inputs") if cache_gb > 0.5 else \
+                (f"NOT flushed: the whole {cache_gb * 1e3:.0f} MB cache fits the 126 MB L2 (a parity-test configuration of "
+                 "BASELINE.json, not the bench line)")
     if rank == 0:
         peak, _src = measured_peak()
         res = {
@@ -696,8 +694,7 @@ def gpu_run(a, wl, ln_emb):
             "config": {"workload": workload_string(a, wl, T, world),
                        "global_batch": Bg, "local_batch": lb, "parallelism": f"dp{world} (replicated cache)",
                        "window_boundaries_in_timed_region": n_boundaries,
-                       "l2_policy": "inputs larger than L2: every step reads a fresh 26x8192-row slice of a "
-                                    "10+ GB cache and a new batch of the 5 GB window",
+                       "l2_policy": l2_policy,
                        "lookahead_plan": "planned inside the timed region" if plan_inside else
                                          "next window planned before the timed region (steps < lookahead); the e2e leg "
                                          "is a whole window with its boundary, plan, prefetch and aggregations inside",

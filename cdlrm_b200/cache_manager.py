@@ -160,7 +160,7 @@ class WindowPlanner:
         # into / scatter out of pinned chunks that cudaMemcpyAsync moves (hostio.cu): ~10x gentler on the training
         # step that runs beside it (bench.py --ce-probe-gb), at the price of host cores
         self.pcie_mode = "sm"
-        self.host_threads = max(1, min(8, (os.cpu_count() or 2) - 2))
+        self.host_threads = max(1, min(4, (os.cpu_count() or 2) - 2))
         self._pin = {}                   # pinned host buffers (grow-only)
         self._ce_no = 0
         self._ce_ev = None
@@ -329,6 +329,13 @@ class WindowPlanner:
         assert ids.is_cuda and ids.dtype == torch.int64 and ids.stride(1) == 1 and ids.shape[0] == self.T
         check(lib.cdlrm_plan_mark_ids(self.ctx, _vp(ids.data_ptr()), ids.stride(0), ids.shape[1], _sp(self.stream)))
 
+    def mark_own_ids(self, ids):
+        """Data-parallel ranks: the ids (int64 device tensor [T, n], any number of chunks) of THIS rank's own batches
+        of the window about to be planned.  With ``collect_losers`` the plan then lists only the un-cached ids among
+        them -- the misses this rank's forwards will actually have -- so the loser store stays as small as on one GPU."""
+        assert ids.is_cuda and ids.dtype == torch.int64 and ids.stride(1) == 1 and ids.shape[0] == self.T
+        check(lib.cdlrm_plan_mark_own_ids(self.ctx, _vp(ids.data_ptr()), ids.stride(0), ids.shape[1], _sp(self.stream)))
+
     def plan(self, win_ids=None, uniq_lists=None, marked=None):
         """win_ids: int64 device tensor [T, n] (raw window ids), or uniq_lists: list of T
         ascending-unique int64 tensors (the reference-API path), or marked: the number of ids per table
@@ -455,7 +462,10 @@ class WindowPlanner:
         return b
 
     # -- copy-engine transfers (pcie_mode "ce") -------------------------------------------------
-    CE_CHUNK_BYTES = 128 << 20
+    # staging chunk: small, because a copy engine does not interleave a chunk with the training step's own copies
+    # (inputs in, loss out): with 128 MB chunks single steps stalled 2.5-3 ms behind a chunk, and cutting the chunk into
+    # 4 MB cudaMemcpyAsync pieces within one stream did not change that; 8 MB = 0.15 ms of link time
+    CE_CHUNK_BYTES = 8 << 20
 
     def _pinned(self, name, nbytes):
         b = self._pin.get(name)

@@ -49,6 +49,7 @@ struct TableDesc {
 // Planner workspace carve-up (device pointers into the caller's buffer).
 struct PlanTable {
     uint32_t* bitmap;   // n_rows bits
+    uint32_t* own;      // n_rows bits: ids of THIS rank's own batches (cdlrm_plan_mark_own_ids), kept clean between windows
     int64_t* uniq;      // [umax]
     int32_t* surv;      // [umax] survivor r -> index into uniq
     uint8_t* state;     // [umax] per-unique state: hit way, 255 = miss (not cached), 254 = miss that won a slot
@@ -89,6 +90,7 @@ struct cdlrm_ctx {
     std::vector<PlanTable> ptabs;
     PlanTable* d_ptabs = nullptr;
     int64_t plan_window_len = 0;
+    bool own_marked = false;             // own-id bitmaps hold a window: cdlrm_plan_losers keeps this rank's own ids only
     char* plan_ws = nullptr;             // base of the bound planner workspace (peer copies share its carve-up)
     std::vector<unsigned long long*> pins;  // per table [num_sets] pin masks of the window being planned
     int32_t* p_blocksum2 = nullptr; // second tile-sum array

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) lists_kernel(int64_t R, const int64_t* __
 // ---- losers: unique ids of the window that stay un-cached (state 255), ascending ------------------
 template <bool EMIT>
 __global__ void __launch_bounds__(256) losers_kernel(const int64_t* __restrict__ uniq, int64_t U,
-                                                     const uint8_t* __restrict__ state,
+                                                     const uint8_t* __restrict__ state, const uint32_t* __restrict__ own,
                                                      int32_t* __restrict__ blocksum, int64_t* __restrict__ out) {
     __shared__ int s_w[33];
     const int64_t u0 = (int64_t)blockIdx.x * TILE + threadIdx.x * 4;
@@ -259,6 +259,10 @@ __global__ void __launch_bounds__(256) losers_kernel(const int64_t* __restrict__
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         lose[q] = (u0 + q < U) && state[u0 + q] == 255;
+        if (lose[q] && own) {          // data-parallel ranks: only the ids this rank's own batches contain
+            const int64_t id = uniq[u0 + q];
+            lose[q] = (own[id >> 5] >> (id & 31)) & 1u;
+        }
         c += lose[q];
     }
     int total;
@@ -309,6 +313,7 @@ size_t carve_workspace(const cdlrm_ctx* c, int64_t N, char* base, std::vector<Pl
         const int64_t words = (t.n_rows + 31) / 32;
         PlanTable p;
         p.bitmap = cv.take<uint32_t>(words);
+        p.own = cv.take<uint32_t>(words);
         p.uniq = cv.take<int64_t>(umax);
         p.surv = cv.take<int32_t>(umax);
         p.state = cv.take<uint8_t>(umax);
@@ -369,8 +374,11 @@ extern "C" int cdlrm_plan_bind_workspace(cdlrm_ctx* c, void* ws, int64_t bytes, 
     c->plan_ws = (char*)ws;
     // bitmaps start clean (the emit kernel keeps them clean); claims start at -1
     CU_CHECK(cudaDeviceSynchronize());
-    for (int k = 0; k < c->T; ++k)
+    for (int k = 0; k < c->T; ++k) {
         CU_CHECK(cudaMemset(c->ptabs[k].bitmap, 0, sizeof(uint32_t) * ((c->tabs[k].n_rows + 31) / 32)));
+        CU_CHECK(cudaMemset(c->ptabs[k].own, 0, sizeof(uint32_t) * ((c->tabs[k].n_rows + 31) / 32)));
+    }
+    c->own_marked = false;
     fill_i32_kernel<<<1184, 256>>>(c->p_claim, c->rows_max, -1);
     CU_CHECK(cudaGetLastError());
     CU_CHECK(cudaDeviceSynchronize());
@@ -424,6 +432,28 @@ extern "C" int cdlrm_plan_mark_ids(cdlrm_ctx* c, const int64_t* ids, int64_t ld,
         LAUNCH(K_PLAN_BITMAP_SET, s, bitmap_set_kernel<<<g1 > 0 ? g1 : 1, 256, 0, s>>>(ids + k * ld, n, c->ptabs[k].bitmap, c->tabs[k].n_rows, c->d_flags));
     }
     CU_CHECK(cudaGetLastError());
+    return CDLRM_OK;
+}
+
+// Own-id bitmaps: the ids of the window that THIS rank's own batches contain (a data-parallel rank trains on its slice of
+// every global batch).  With them marked, cdlrm_plan_losers lists only the un-cached ids this rank itself will look up:
+// a rank-private loser store of the size of a one-GPU run instead of the union over all ranks (42 GB at 8 GPUs).
+extern "C" int cdlrm_plan_mark_own_ids(cdlrm_ctx* c, const int64_t* ids, int64_t ld, int64_t n, cdlrm_stream stream) {
+    ARG_CHECK(c && n >= 0);
+    if (n == 0) return CDLRM_OK;
+    ARG_CHECK(ids);
+    if (c->ptabs.empty()) {
+        cdlrm_set_error("planner workspace not bound");
+        return CDLRM_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaSetDevice(c->device));
+    for (int k = 0; k < c->T; ++k) {
+        const int g1 = (int)((n + 1023) / 1024 < 148 * 16 ? (n + 1023) / 1024 : 148 * 16);
+        LAUNCH(K_PLAN_BITMAP_SET, s, bitmap_set_kernel<<<g1 > 0 ? g1 : 1, 256, 0, s>>>(ids + k * ld, n, c->ptabs[k].own, c->tabs[k].n_rows, c->d_flags));
+    }
+    CU_CHECK(cudaGetLastError());
+    c->own_marked = true;
     return CDLRM_OK;
 }
 
@@ -651,9 +681,15 @@ extern "C" int cdlrm_plan_losers(cdlrm_ctx* c, const int64_t* h_uniq, const int6
         }
         ARG_CHECK(loser_ids);
         const int nblk = (int)((U + TILE - 1) / TILE);
-        LAUNCH(K_PLAN_LISTS, s, losers_kernel<false><<<nblk, 256, 0, s>>>(p.uniq, U, p.state, c->p_blocksum, nullptr));
+        const uint32_t* own = c->own_marked ? p.own : nullptr;
+        LAUNCH(K_PLAN_LISTS, s, losers_kernel<false><<<nblk, 256, 0, s>>>(p.uniq, U, p.state, own, c->p_blocksum, nullptr));
         LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(c->p_blocksum, nblk, ck));
-        LAUNCH(K_PLAN_LISTS, s, losers_kernel<true><<<nblk, 256, 0, s>>>(p.uniq, U, p.state, c->p_blocksum, loser_ids + h_off[k]));
+        LAUNCH(K_PLAN_LISTS, s, losers_kernel<true><<<nblk, 256, 0, s>>>(p.uniq, U, p.state, own, c->p_blocksum, loser_ids + h_off[k]));
+    }
+    if (c->own_marked) {        // the own-id bitmaps are clean again for the next window
+        for (int k = 0; k < c->T; ++k)
+            CU_CHECK(cudaMemsetAsync(c->ptabs[k].own, 0, sizeof(uint32_t) * ((c->tabs[k].n_rows + 31) / 32), s));
+        c->own_marked = false;
     }
     CU_CHECK(cudaGetLastError());
     for (int k = 0; k < c->T; ++k)

@@ -377,17 +377,24 @@ class Trainer:
                                          rng=VictimRngDevice(args.numpy_rand_seed, self.dev), stream=self.side,
                                          lookahead_tags=True)
             self.planner.collect_losers = True     # un-cached ids of a window are served from an HBM loser store
-            # master <-> HBM traffic of the planner: host threads + cudaMemcpyAsync ("ce") when this rank can have at
-            # least 4 host threads to itself, else zero-copy gather / scatter kernels ("sm"); CDLRM_PREFETCH overrides
-            threads = max(1, min(8, (os.cpu_count() or 2) // max(world, 1) - 2))
+            # master <-> HBM traffic of the planner: zero-copy gather / scatter kernels ("sm", default: no dependence
+            # on the host) or host threads + cudaMemcpyAsync (CDLRM_PREFETCH=ce: gentler on the step while it runs,
+            # but only as good as the host cores it gets -- see DESIGN.md section 4)
+            threads = max(1, min(4, (os.cpu_count() or 2) // max(world, 1) - 2))     # more than 4 starve the host thread that enqueues the steps (16-core box)
             mode = os.environ.get("CDLRM_PREFETCH", "auto")
             self.planner.host_threads = int(os.environ.get("CDLRM_HOST_THREADS", threads))
-            self.planner.pcie_mode = mode if mode in ("ce", "sm") else ("ce" if self.planner.host_threads >= 4 else "sm")
+            self.planner.pcie_mode = mode if mode in ("ce", "sm") else "sm"
         self._host_group = dist.new_group(backend="gloo") if world > 1 else None   # plan-thread barrier
         # un-cached ids of a window (the same on every rank): one store sharded over the node's GPUs and read over
         # NVLink instead of a full copy per rank (CDLRM_LOSER_SHARDED=0: one local store per rank)
+        # un-cached ids of a window at N > 1: "own" (default) = every rank stages only the ones its own batches contain
+        # (a rank-private store, as small as on one GPU); CDLRM_LOSER_SHARDED=1 = one store of ALL ranks' un-cached ids
+        # sharded over the node's GPUs and read over NVLink (measured at 8 GPUs: 34 k scattered 512-byte peer reads per
+        # step took 410 us, the private store's local reads 25-60 us); CDLRM_LOSER_OWN=0 = the whole list on every rank
         self.sharded_losers = (world > 1 and self.planner is not None
-                               and os.environ.get("CDLRM_LOSER_SHARDED", "1") != "0")
+                               and os.environ.get("CDLRM_LOSER_SHARDED", "0") == "1")
+        self.own_losers = (world > 1 and self.planner is not None and not self.sharded_losers
+                           and os.environ.get("CDLRM_LOSER_OWN", "1") != "0")
         if self.sharded_losers:
             self.planner.enable_sharded_losers(rank, world, self._host_group)
         # a window handed over as a marker callable (submit_window) is scanned 1/world per rank, bitmaps OR-ed over
@@ -404,8 +411,10 @@ class Trainer:
         self.loss_history = []
 
     # -- look-ahead -------------------------------------------------------------------------
-    def submit_window(self, win_ids):
+    def submit_window(self, win_ids, own_ids=None):
         """Start planning a window in the background; windows must be submitted in training order.
+        ``own_ids`` (N > 1): int64 device tensor [T, m] of the ids of THIS rank's own batches of the window; derived
+        from ``win_ids`` when that is the global id tensor (rank r owns samples [r lb, (r+1) lb) of every step).
         ``win_ids``: int64 [T, n] tensor of the GLOBAL batch ids of the window, or the reference's FIFO entry
         ``(rows, uniq, maps)`` (cache_manager.py:102-104), of which the ascending unique id lists are what the
         plan needs (the rows are read from the master at install time: sequential schedule)."""
@@ -421,6 +430,13 @@ class Trainer:
             uniq_lists = [u.to(self.dev, non_blocking=True) for u in win_ids[1]]
         else:
             win_ids = win_ids.to(self.dev, non_blocking=True)
+            lb, W_ = self.local_batch, self.world
+            if own_ids is None and self.own_losers and win_ids.shape[1] % (lb * W_) == 0:
+                own_ids = win_ids.view(win_ids.shape[0], -1, W_, lb)[:, :, self.rank].reshape(win_ids.shape[0], -1)
+        if own_ids is not None and self.own_losers:
+            own_ids = own_ids.to(self.dev, non_blocking=True).contiguous()
+        else:
+            own_ids = None
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))   # ids produced on the current stream are ready
         prev = self._plan_thread
@@ -433,6 +449,8 @@ class Trainer:
             try:
                 # (copy-engine mode) evicted rows of the window just installed go back to the host master first
                 self.planner.flush_writeback()
+                if own_ids is not None:
+                    self.planner.mark_own_ids(own_ids)
                 if marker is not None:
                     with torch.cuda.stream(self.side):
                         n_marked = marker(self.planner)      # this rank's share (planner.scan_shard) or everything
@@ -617,6 +635,44 @@ class Trainer:
             st.T.copy_(T, non_blocking=True)
             st.ready.record(cs)
         return st
+
+    # -- per-step scalar read-back that never makes the training stream wait for PCIe ---------------
+    def push_loss(self, E):
+        """Queue the device scalar ``E`` (a step's loss) for an asynchronous read-back: a device-to-device copy into a
+        ring slot on the training stream (E is a CUDA-graph output buffer that the next replay overwrites), then the
+        4-byte device-to-host copy on a stream of its own -- so that the next step is never queued behind a PCIe
+        transfer (the copy engine serves the planner's write-back chunks in front of it)."""
+        if getattr(self, "_loss_ring", None) is None:
+            n = self.input_slots
+            self._loss_ring = (torch.zeros(n, dtype=torch.float32, device=self.dev),
+                               torch.zeros(n, dtype=torch.float32, pin_memory=True),
+                               [torch.cuda.Event() for _ in range(n)], [torch.cuda.Event() for _ in range(n)],
+                               _lib.new_stream(self.dev, priority=-1))
+            self._loss_head = self._loss_tail = 0
+        ring, pin, ev_d, ev_h, ls = self._loss_ring
+        n = ring.numel()
+        if self._loss_head - self._loss_tail >= n:
+            raise _lib.CdlrmError("push_loss: ring full, pop_loss first")
+        q = self._loss_head % n
+        self._loss_head += 1
+        cur = torch.cuda.current_stream(self.dev)
+        ring[q].copy_(E.detach().reshape(()))
+        ev_d[q].record(cur)
+        ls.wait_event(ev_d[q])
+        with torch.cuda.stream(ls):
+            pin[q].copy_(ring[q], non_blocking=True)
+            ev_h[q].record(ls)
+
+    def pending_losses(self):
+        return 0 if getattr(self, "_loss_ring", None) is None else self._loss_head - self._loss_tail
+
+    def pop_loss(self):
+        """The oldest queued loss as a Python float (waits for its copy)."""
+        _ring, pin, _ev_d, ev_h, _ls = self._loss_ring
+        q = self._loss_tail % pin.numel()
+        self._loss_tail += 1
+        ev_h[q].synchronize()
+        return float(pin[q])
 
     def step_staged(self, st, lS_o):
         """``step`` on inputs staged by ``stage_inputs``."""

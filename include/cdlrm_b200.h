@@ -195,6 +195,10 @@ int cdlrm_plan_unique(cdlrm_ctx* ctx, const int64_t* win_ids, int64_t ld, int64_
  * bitmaps.  Any number of calls, in any order, then cdlrm_plan_phase_a with win_ids == NULL and n = the number of
  * ids marked per table (an upper bound of the distinct ids): the window never has to exist as one tensor. */
 int cdlrm_plan_mark_ids(cdlrm_ctx* ctx, const int64_t* ids, int64_t ld, int64_t n, cdlrm_stream stream);
+/* Data-parallel ranks: mark the ids of the window that THIS rank's own batches contain (any number of chunks, int64
+ * [num_tables][n]).  The next cdlrm_plan_losers then lists only those un-cached ids -- the ones this rank's forwards will
+ * miss on (model_no_ddp.py:176-179) -- instead of the union over all ranks, and clears the marks. */
+int cdlrm_plan_mark_own_ids(cdlrm_ctx* ctx, const int64_t* ids, int64_t ld, int64_t n, cdlrm_stream stream);
 /* Scan sharded over the `world` ranks of a node (every rank marked its own share of the window with
  * cdlrm_plan_mark_ids): OR the id bitmaps of the other ranks into this rank's, reading them in place over NVLink.
  * h_peer_ws[r] = device address on THIS device of rank r's planner workspace (cdlrm_peer_alloc / cdlrm_peer_open;

@@ -106,3 +106,52 @@ def test_module_attribute_surface_matches_reference():
     d = DLRM_Net(np.asarray([13, 8, 4]), np.asarray([10, 8, 1]), "dot", sigmoid_top=1)
     assert len(d.bot_l) == 4 and len(d.top_l) == 4 and hasattr(d, "interact_features")
     assert isPrime(10006) and isPrime(9) and not isPrime(15)   # the reference quirks
+
+
+def test_host_gather_scatter_rows_match_numpy():
+    """hostio.cu: the host half of the copy-engine prefetch / write-back (cache_manager.py:34-43 `weight[unique_idxs]`,
+    :58-62 `weight[idxs] = rows` and its averaged variant) against numpy, single- and multi-threaded."""
+    from cdlrm_b200._lib import check, lib
+    vp = ctypes.c_void_p
+    rng = np.random.default_rng(0)
+    n_rows, d = 50_000, 16
+    M = rng.standard_normal((n_rows, d)).astype(np.float32)
+    ids = rng.integers(0, n_rows, 30_000).astype(np.int64)
+    for threads in (1, 5):
+        dst = np.empty((ids.size, d), np.float32)
+        check(lib.cdlrm_host_gather_rows(vp(M.ctypes.data), n_rows, d, vp(ids.ctypes.data), ids.size, vp(dst.ctypes.data), threads))
+        assert np.array_equal(dst, M[ids])
+        u = np.unique(ids)
+        rows = rng.standard_normal((u.size, d)).astype(np.float32)
+        prim = (rng.random(u.size) < 0.6).astype(np.uint8)
+        for average in (0, 1):
+            got = M.copy()
+            check(lib.cdlrm_host_scatter_rows(vp(got.ctypes.data), n_rows, d, vp(u.ctypes.data), vp(prim.ctypes.data), u.size,
+                                              vp(rows.ctypes.data), average, threads))
+            want = M.copy()
+            sel = prim == 1
+            want[u[sel]] = (want[u[sel]] + rows[sel]) / 2 if average else rows[sel]
+            assert np.array_equal(got, want)
+    bad = np.asarray([0, n_rows], dtype=np.int64)      # an id outside its table is an error, not a wild access
+    dst = np.zeros((2, d), np.float32)
+    assert lib.cdlrm_host_gather_rows(vp(M.ctypes.data), n_rows, d, vp(bad.ctypes.data), 2, vp(dst.ctypes.data), 1) != 0
+
+
+def test_flat_bucket_layout_for_the_early_allreduce():
+    """DLRM_Net.flatten_parameters: bottom-MLP weights, top-MLP weights, then the biases; the top MLP's weights are the
+    contiguous range [flat_top_weight_off, flat_weight_elems) that Trainer all-reduces as soon as its backward is
+    enqueued (biases are never reduced: main_no_ddp.py:234-247)."""
+    import torch
+    from cdlrm_b200.model_no_ddp import DLRM_Net
+    np.random.seed(1)
+    net = DLRM_Net(np.asarray([13, 7, 5]), np.asarray([9, 6, 1]), "cat", sigmoid_top=1)
+    flat_p, flat_g = net.flatten_parameters()
+    pad = lambda n: (n + 3) & ~3
+    bot = pad(13 * 7) + pad(7 * 5)
+    top = pad(9 * 6) + pad(6 * 1)
+    assert net.flat_top_weight_off == bot and net.flat_weight_elems == bot + top
+    assert flat_p.numel() == bot + top + pad(7) + pad(5) + pad(6) + pad(1)
+    lin = [m for seq in (net.bot_l, net.top_l) for m in seq if isinstance(m, torch.nn.Linear)]
+    assert lin[2].weight.data_ptr() == flat_p.data_ptr() + 4 * bot              # first top-MLP weight
+    assert lin[0].bias.data_ptr() == flat_p.data_ptr() + 4 * (bot + top)        # first bias right behind the weights
+    assert all(m.weight.grad.data_ptr() - flat_g.data_ptr() == m.weight.data_ptr() - flat_p.data_ptr() for m in lin)

@@ -1,18 +1,20 @@
 #!/bin/bash
-# N-GPU visit: multi-rank consistency check with the rank-sharded window scan, then the bench at N.
+# N-GPU visit: multi-rank checks (own-id loser store, whole-window and sharded scan; the NVLink-sharded store too), then the bench at N.
 N=${1:-2}
 mkdir -p gpurun_out
-MGPU_MARKER=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 \
-    tools/mgpu_check.py > gpurun_out/mgpu_check_marker.log 2>&1; echo "mgpu_check marker rc=$?"
-grep -E "mgpu_check OK|Error|error|assert" gpurun_out/mgpu_check_marker.log | head -5
-grep -q "mgpu_check OK" gpurun_out/mgpu_check_marker.log || { tail -30 gpurun_out/mgpu_check_marker.log; echo "multi-rank check failed: no bench"; exit 1; }
+chk() {
+  env $1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $2 \
+    tools/mgpu_check.py > gpurun_out/mgpu_check_$3.log 2>&1; echo "mgpu_check $3 rc=$?"
+  grep -E "mgpu_check OK|Error|error|assert" gpurun_out/mgpu_check_$3.log | head -4
+  grep -q "mgpu_check OK" gpurun_out/mgpu_check_$3.log || { tail -30 gpurun_out/mgpu_check_$3.log; echo "multi-rank check failed: no bench"; exit 1; }
+}
+chk "MGPU_MARKER=1" 29541 own_marker
+chk "MGPU_MARKER=0" 29542 own_tensor
+chk "MGPU_MARKER=1 CDLRM_LOSER_SHARDED=1" 29543 sharded
 T0=$(date +%s)
-( while true; do nvidia-smi --query-gpu=memory.used --format=csv,noheader,nounits | tr '\n' ' '; echo; sleep 5; done ) > gpurun_out/hbm_n$N.txt &
-MON=$!
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 \
   bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench N=$N rc=$? $(( $(date +%s) - T0 )) s"
-kill $MON
-grep -v -i "warn" gpurun_out/bench_n$N.err | grep "rank 0" | tail -8
+grep -v -i "warn" gpurun_out/bench_n$N.err | grep "rank 0" | tail -7
 python - <<PY
 import json
 d=json.loads(open('gpurun_out/bench_n$N.json').read().strip().splitlines()[-1])
@@ -20,7 +22,7 @@ print('N', d['n_gpus'], 'ms/step', round(d['ms_per_step'],4), 'value', round(d['
 fw=d['full_window']; print({k:fw[k] for k in fw if k!='ms_per_step_series'})
 s=fw['ms_per_step_series']; print(s['first_40_steps_ms'][:20]); print(s['ms_per_step'][:60])
 print({n:(k['us_per_launch'],k.get('frac_of_peak'),k.get('misses_per_step')) for n,k in (d['kernels'] or {}).items()})
-print('max memory.used MiB', max(int(x) for line in open('gpurun_out/hbm_n$N.txt') for x in line.split() if x.isdigit()))
+print(d['pcie'])
 PY
 sleep 3
 timeout 60 python -c "import torch; x=torch.zeros(8,device='cuda:0'); torch.cuda.synchronize(); print('gpu alive')"

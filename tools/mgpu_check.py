@@ -82,7 +82,7 @@ def main():
                 ns = min(2, min(L, (r_ + 1) * per) - s0)
                 planner.mark_ids(sg.ids(w * L + s0, ns, stream=planner.stream))
             return L * Bg
-        tr.submit_window(mark)
+        tr.submit_window(mark, own_ids=g_.view(T, L, world, lb)[:, :, rank].reshape(T, L * lb))
 
     g = sg.window_ids(0, L)
     submit(0, g)
@@ -97,6 +97,14 @@ def main():
                 assert torch.equal(other, cg.occupancy_tables[k]), f"tags of table {k} differ across ranks"
         # (1b) the loser store (sharded over the ranks, read over NVLink): a forward over un-cached ids of this window
         # returns exactly their master rows, whichever rank holds them
+        if rec.L is not None and tr.own_losers:
+            # the rank-private loser list is exactly: ids of this rank's own batches of the window that are not cached
+            loc_w = g.view(T, L, world, lb)[:, :, rank].reshape(T, L * lb)
+            for k in range(T):
+                u = torch.unique(loc_w[k])
+                tags = cg.occupancy_tables[k]
+                cached = (tags[u % tags.shape[0]] == u[:, None]).any(1)
+                assert torch.equal(rec.loser_list(k), u[~cached]), f"window {w}: own loser list of table {k} is wrong"
         if rec.L is not None:
             probe = torch.zeros(T, lb, dtype=torch.int64, device=dev)
             for k in range(T):
@@ -173,7 +181,7 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"mgpu_check OK: world={world}, {n_windows} windows x {L} steps, loss {losses[0]:.4f} -> {losses[-1]:.4f}; "
-              f"loser store {'sharded over the ranks' if tr.sharded_losers else 'per rank'}, {checked_losers} table probes, "
+              f"loser store {'sharded over the ranks' if tr.sharded_losers else ('own ids per rank' if tr.own_losers else 'all ids per rank')}, {checked_losers} table probes, "
               f"window scan {'sharded (marker)' if use_marker else 'whole window per rank'}, "
               f"loss digest {hash(tuple(losses)) & 0xffffffff:08x}")
     dist.destroy_process_group()

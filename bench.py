@@ -594,7 +594,10 @@ def gpu_run(a, wl, ln_emb):
         loss_host = float("nan")
         e0.record()
         staged = [tr.stage_inputs(hX[q], hI[q], hY[q]) for q in range(min(AHEAD, n_e2e))]
+        host_t = []                                  # host clock at the top of the first 41 iterations
         for i in range(n_e2e):
+            if i <= 40:
+                host_t.append(time.perf_counter())
             # (one_step indexes the host block by the step's position in its window)
             w_, b_ = divmod(j, L)
             if b_ == 0 and j > 0:
@@ -650,6 +653,9 @@ def gpu_run(a, wl, ln_emb):
             "agg_device_ms_per_call": round(float(np.mean([b0.elapsed_time(b1) for _, b0, b1 in agg_log])), 4) if agg_log else None,
             "agg_ms_per_step_amortised": round(float(np.sum([b0.elapsed_time(b1) for _, b0, b1 in agg_log])) / n_e2e, 5) if agg_log else 0.0,
             "ms_per_step_series": {"steps_per_segment": seg2, "first_40_steps_ms": series2[:40],
+                                   # how long the HOST spent in each of those iterations (a stall here that the device
+                                   # series repeats AHEAD steps later is the host thread's, not the GPU's)
+                                   "first_40_host_iter_ms": [round(1e3 * (y - x), 3) for x, y in zip(host_t, host_t[1:])],
                                    "ms_per_step": series2[40:]},
             "boundary_host_breakdown_ms": [b for _, b in prep_log],
             "next_window_input_generation_host_ms": [p_ for p_, _ in prep_log],

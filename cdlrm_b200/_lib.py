@@ -78,6 +78,10 @@ SIGNATURES = {
     "cdlrm_host_gather_rows": (C.c_int, [vp, C.c_int64, C.c_int, vp, C.c_int64, vp, C.c_int]),
     "cdlrm_host_scatter_rows": (C.c_int, [vp, C.c_int64, C.c_int, vp, vp, C.c_int64, vp, C.c_int, C.c_int]),
     "cdlrm_copy_async": (C.c_int, [C.c_int, vp, vp, C.c_int64, C.c_int, vp]),
+    "cdlrm_host_prefetch_rows": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp), c_i64p, C.c_int, C.POINTER(vp), c_i64p,
+                                           C.POINTER(vp), vp, vp, C.c_int64, C.c_int, vp]),
+    "cdlrm_host_writeback_rows": (C.c_int, [C.c_int, C.c_int, C.POINTER(vp), c_i64p, C.c_int, C.POINTER(vp), C.POINTER(vp),
+                                            c_i64p, C.POINTER(vp), vp, vp, C.c_int64, C.c_int, C.c_int, vp]),
     "cdlrm_host_register": (C.c_int, [C.c_int, vp, C.c_int64, C.POINTER(vp)]),
     "cdlrm_host_unregister": (C.c_int, [vp]),
     "cdlrm_agg_mark": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp]),

@@ -501,21 +501,18 @@ class WindowPlanner:
 
     def _ce_gather(self, segs):
         """segs: [(table k, host int64 ids, device address of the destination rows)]: rows of the host master gathered
-        by host threads into a pinned chunk while the copy engine moves the previous chunk into HBM."""
-        s, d, dev = self.stream, self.dim, self.dev.index
-        rows_per, bufs, evs = self._ce_chunks()
-        for k, hid, dst in segs:
-            W = self.emb_tables.emb_l[k].weight.data
-            n = int(hid.numel())
-            for a in range(0, n, rows_per):
-                m = min(rows_per, n - a)
-                b = self._ce_no & 1
-                self._ce_no += 1
-                evs[b].synchronize()            # the copy that last read this chunk has finished
-                check(lib.cdlrm_host_gather_rows(_vp(W.data_ptr()), W.shape[0], d, _vp(hid.data_ptr() + 8 * a), m,
-                                                 _vp(bufs[b].data_ptr()), self.host_threads))
-                check(lib.cdlrm_copy_async(dev, _vp(dst + 4 * d * a), _vp(bufs[b].data_ptr()), 4 * d * m, 1, _sp(s)))
-                evs[b].record(s)
+        by host threads into a pinned chunk while the copy engine moves the previous chunk into HBM -- the whole list in
+        ONE native call (cdlrm_host_prefetch_rows: no interpreter lock between chunks)."""
+        segs = [(k, hid, dst) for k, hid, dst in segs if int(hid.numel())]
+        if not segs:
+            return
+        rows_per, bufs, _evs = self._ce_chunks()
+        Ws = [self.emb_tables.emb_l[k].weight.data for k, _h, _d in segs]
+        check(lib.cdlrm_host_prefetch_rows(
+            self.dev.index, len(segs), _lib.ptr_array([W.data_ptr() for W in Ws]), _lib.i64_array([W.shape[0] for W in Ws]),
+            self.dim, _lib.ptr_array([hid.data_ptr() for _k, hid, _d in segs]),
+            _lib.i64_array([int(hid.numel()) for _k, hid, _d in segs]), _lib.ptr_array([dst for _k, _h, dst in segs]),
+            _vp(bufs[0].data_ptr()), _vp(bufs[1].data_ptr()), rows_per, self.host_threads, _sp(self.stream)))
 
     def flush_writeback(self):
         """ce mode: write the evicted rows of the last installed window back into the host master (device -> pinned
@@ -535,36 +532,21 @@ class WindowPlanner:
                 if rec.E[k]:
                     hpr[offs[k]:offs[k] + rec.E[k]].copy_(rec.evict_primary[rec.off[k]:rec.off[k] + rec.E[k]], non_blocking=True)
         s.synchronize()
-        rows_per, bufs, evs = self._ce_chunks()
+        rows_per, bufs, _evs = self._ce_chunks()
         eoff = [0] * self.T
         for k in range(1, self.T):
             eoff[k] = eoff[k - 1] + rec.E[k - 1]
-        jobs = [(k, a, min(rows_per, rec.E[k] - a)) for k in range(self.T) for a in range(0, rec.E[k], rows_per)]
-
-        def scatter(job, b):
-            k, a, m = job
-            W = self.emb_tables.emb_l[k].weight.data
-            evs[b].synchronize()                # the chunk has landed in host memory
-            check(lib.cdlrm_host_scatter_rows(_vp(W.data_ptr()), W.shape[0], d, _vp(hid.data_ptr() + 8 * (offs[k] + a)),
-                                              _vp(hpr.data_ptr() + offs[k] + a), m, _vp(bufs[b].data_ptr()),
-                                              int(average), self.host_threads))
-
-        prev = None
-        for job in jobs:                        # copy of chunk c runs while chunk c-1 is scattered
-            k, a, m = job
-            b = self._ce_no & 1
-            self._ce_no += 1
-            if prev is not None and prev[1] == b:
-                scatter(*prev)
-                prev = None
-            check(lib.cdlrm_copy_async(dev, _vp(bufs[b].data_ptr()), _vp(rec.evict_stage[eoff[k] + a:].data_ptr()),
-                                       4 * d * m, 2, _sp(s)))
-            evs[b].record(s)
-            if prev is not None:
-                scatter(*prev)
-            prev = (job, b)
-        if prev is not None:
-            scatter(*prev)
+        ks = [k for k in range(self.T) if rec.E[k]]
+        if ks:
+            Ws = [self.emb_tables.emb_l[k].weight.data for k in ks]
+            # device -> pinned chunk by the copy engine, chunk -> master rows by the pooled host threads, the copy of
+            # chunk c beside the scatter of chunk c-1: one native call for the whole write-back
+            check(lib.cdlrm_host_writeback_rows(
+                dev, len(ks), _lib.ptr_array([W.data_ptr() for W in Ws]), _lib.i64_array([W.shape[0] for W in Ws]), d,
+                _lib.ptr_array([hid.data_ptr() + 8 * offs[k] for k in ks]),
+                _lib.ptr_array([hpr.data_ptr() + offs[k] for k in ks]), _lib.i64_array([rec.E[k] for k in ks]),
+                _lib.ptr_array([rec.evict_stage[eoff[k]:].data_ptr() for k in ks]),
+                _vp(bufs[0].data_ptr()), _vp(bufs[1].data_ptr()), rows_per, int(average), self.host_threads, _sp(s)))
         rec.wb_done = torch.cuda.Event(enable_timing=True)
         rec.wb_done.record(s)
 

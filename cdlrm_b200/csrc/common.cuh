@@ -68,6 +68,12 @@ struct LoserDesc {
     int64_t n;
     int64_t shard;                       // 0: the whole store is local (rows)
     const float* peer[CDLRM_MAX_PEERS];
+    // bucket index over the ascending ids (built by the bind call): bucket[b] = first index whose id >= b << shift, so the
+    // forward's search for an id starts inside [bucket[id >> shift], bucket[(id >> shift) + 1]) -- a handful of entries
+    // in one or two cache lines instead of log2(n) dependent DRAM round trips.  NULL: search the whole list.
+    const int32_t* bucket;
+    int32_t shift;
+    int32_t nb;
 };
 
 struct cdlrm_ctx {
@@ -85,6 +91,8 @@ struct cdlrm_ctx {
     uint32_t* d_flags = nullptr;    // sticky error flags
     LoserDesc* d_losers = nullptr;  // [T] (device), updated in stream order by cdlrm_ctx_bind_losers
     LoserDesc* h_losers = nullptr;  // [2][T] pinned staging for the async update
+    int32_t* d_lbucket = nullptr;   // bucket indices of the bound loser store (all tables, grow-only)
+    int64_t lbucket_cap = 0;
     int losers_flip = 0;
     // planner
     std::vector<PlanTable> ptabs;

@@ -114,6 +114,7 @@ extern "C" int cdlrm_ctx_destroy(cdlrm_ctx* c) {
     cudaFree(c->d_flags);
     cudaFree(c->d_missmap);
     cudaFree(c->d_losers);
+    cudaFree(c->d_lbucket);
     if (c->h_losers) cudaFreeHost(c->h_losers);
     cudaFree(c->p_counts);
     cudaFree(c->d_ptabs);

@@ -185,9 +185,12 @@ __global__ void __launch_bounds__(MISS_NT) fwd_miss_kernel(const TableDesc* __re
     const float* __restrict__ l_rows = nullptr;
     const LoserDesc* __restrict__ l_desc = nullptr;
     int64_t l_n = 0, l_shard = 0;
+    const int32_t* __restrict__ l_bucket = nullptr;
+    int l_shift = 0;
     if (losers) {
         l_desc = losers + tb + t;
         l_ids = l_desc->ids; l_rows = l_desc->rows; l_n = l_desc->n; l_shard = l_desc->shard;
+        l_bucket = l_desc->bucket; l_shift = l_desc->shift;
     }
     // warp `warp` owns words w_lo + warp, w_lo + warp + NW, ... ; its running ordinal starts at the
     // popcount of the range's words that precede each of them, recomputed per word (ranges are short)
@@ -216,6 +219,11 @@ __global__ void __launch_bounds__(MISS_NT) fwd_miss_kernel(const TableDesc* __re
             } else {
                 aux_l = aux_base + ord;
                 int64_t lo = 0, hi = l_n;              // first index with l_ids[idx] >= id
+                if (l_bucket) {                        // bucket index: the answer lies in [bucket[b], bucket[b + 1]]
+                    const int64_t bk = id >> l_shift;
+                    lo = __ldg(l_bucket + bk);
+                    hi = __ldg(l_bucket + bk + 1);
+                }
                 while (lo < hi) {
                     const int64_t mid = (lo + hi) >> 1;
                     if (__ldg(l_ids + mid) < id) lo = mid + 1; else hi = mid;

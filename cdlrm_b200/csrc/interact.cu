@@ -191,24 +191,15 @@ __global__ void __launch_bounds__(128, 4) interact_fwd_tr_kernel(FeatPtrs fp, in
 // Blocks of 32 pairs: every lane stores its 32 partials as one row of a [32 lanes][36] tile (STS.128, conflict
 // free), then lane L adds up columns 2(L%16), 2(L%16)+1 over the 16 rows of its own half-warp (LDS.64); the tile is
 // double-buffered so that one __syncwarp per block is enough.  Two CTAs of four warps per SM (255 registers).
-template <int F>
-__device__ __forceinline__ void fwd_h_pair(const FeatPtrs& fp, int64_t row_stride, int B, float* __restrict__ out,
-                                           int64_t ld_out, int pair, float (*s_part)[32 * 36]) {
+// The arithmetic of a half-warp on the rows it holds in registers (ta / tb: column slices h and h + 16 of the F rows of
+// its sample).  PB transpose tiles per warp: 2 = one __syncwarp per block of 32 pairs, 1 = two (half the shared memory).
+template <int F, int PB>
+__device__ __forceinline__ void fwd_h_math(const float4 (&ta)[F], const float4 (&tb)[F], float* __restrict__ orow, bool live,
+                                           float* __restrict__ s_part) {
     constexpr int DIM = 128, PITCH = 36;
     constexpr int NP = Pairs<F, false>::N;
     const int lane = threadIdx.x & 31;
     const int h = lane & 15, half = lane >> 4;
-    const int b = pair * 2 + half;
-    const bool live = b < B;
-    const int bb = live ? b : B - 1;                      // a dead half-warp (odd B) recomputes the last sample, stores nothing
-    float4 ta[F], tb[F];
-    static_for<F>([&](auto I) {
-        constexpr int i = decltype(I)::value;
-        const float4* row = reinterpret_cast<const float4*>(fp.p[i] + (int64_t)bb * row_stride);
-        ta[i] = __ldg(row + h);
-        tb[i] = __ldg(row + 16 + h);
-    });
-    float* orow = out + (int64_t)bb * ld_out;
     if (live) {                                           // dense features pass through (model_no_ddp.py:293)
         orow[h * 4 + 0] = ta[0].x; orow[h * 4 + 1] = ta[0].y; orow[h * 4 + 2] = ta[0].z; orow[h * 4 + 3] = ta[0].w;
         orow[64 + h * 4 + 0] = tb[0].x; orow[64 + h * 4 + 1] = tb[0].y; orow[64 + h * 4 + 2] = tb[0].z; orow[64 + h * 4 + 3] = tb[0].w;
@@ -231,13 +222,13 @@ __device__ __forceinline__ void fwd_h_pair(const FeatPtrs& fp, int64_t row_strid
             if constexpr ((p + 1) % 8 == 0 || p + 1 == NP) {      // 8 partials (or the tail) -> two STS.128
                 constexpr int c8 = (p % 32) / 8;                  // chunk of 8 within the block
                 constexpr int n8 = p % 8 + 1;                     // valid partials in this chunk
-                float4* wr = reinterpret_cast<float4*>(s_part[blk & 1] + lane * PITCH + c8 * 8);
+                float4* wr = reinterpret_cast<float4*>(s_part + (PB == 2 ? (blk & 1) : 0) * 32 * PITCH + lane * PITCH + c8 * 8);
                 wr[0] = make_float4(v[0], n8 > 1 ? v[1] : 0.f, n8 > 2 ? v[2] : 0.f, n8 > 3 ? v[3] : 0.f);
                 if constexpr (n8 > 4) wr[1] = make_float4(v[4], n8 > 5 ? v[5] : 0.f, n8 > 6 ? v[6] : 0.f, n8 > 7 ? v[7] : 0.f);
             }
             if constexpr ((p + 1) % 32 == 0 || p + 1 == NP) {
                 constexpr int cnt = p + 1 - blk * 32;
-                const float* buf = s_part[blk & 1];
+                const float* buf = s_part + (PB == 2 ? (blk & 1) : 0) * 32 * PITCH;
                 __syncwarp();
                 const int c0 = 2 * h;
                 if (c0 < cnt) {
@@ -254,9 +245,28 @@ __device__ __forceinline__ void fwd_h_pair(const FeatPtrs& fp, int64_t row_strid
                         if (c0 + 1 < cnt) orow[DIM + blk * 32 + c0 + 1] = a0.y;
                     }
                 }
+                if constexpr (PB == 1) __syncwarp();              // single tile: read before the next block's partials land
             }
         });
     });
+}
+
+template <int F>
+__device__ __forceinline__ void fwd_h_pair(const FeatPtrs& fp, int64_t row_stride, int B, float* __restrict__ out,
+                                           int64_t ld_out, int pair, float (*s_part)[32 * 36]) {
+    const int lane = threadIdx.x & 31;
+    const int h = lane & 15, half = lane >> 4;
+    const int b = pair * 2 + half;
+    const bool live = b < B;
+    const int bb = live ? b : B - 1;                      // a dead half-warp (odd B) recomputes the last sample, stores nothing
+    float4 ta[F], tb[F];
+    static_for<F>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const float4* row = reinterpret_cast<const float4*>(fp.p[i] + (int64_t)bb * row_stride);
+        ta[i] = __ldg(row + h);
+        tb[i] = __ldg(row + 16 + h);
+    });
+    fwd_h_math<F, 2>(ta, tb, out + (int64_t)bb * ld_out, live, &s_part[0][0]);
 }
 
 template <int F>
@@ -581,6 +591,77 @@ __global__ void __launch_bounds__(32 * WARPS, 3) interact_fwd_pipe_kernel(FeatPt
     }
 }
 
+// ---- forward, dim 128: half-warp arithmetic fed through shared memory ---------------------------------
+// interact_fwd_h_kernel holds a sample pair in 216 registers per lane, so only 8 warps fit on an SM and all of them
+// load (HBM-bound, issue slots idle), then compute (issue-bound, HBM idle), in lock-step waves: 30.6 us where the
+// loads alone take 20 us and the arithmetic 9-16 us.  Here every warp is persistent and owns a one-item staging
+// buffer [F][2 samples][128] in shared memory plus an mbarrier: as soon as the current pair of samples sits in
+// registers (54 LDS.128 per lane), lanes 0 .. F-1 issue the bulk async copies of the warp's NEXT pair into the same
+// buffer, and the 2 300 instructions of arithmetic on the registers hide that load.  One CTA per SM; WARPS warps of
+// 27 KB staging + PB transpose tiles (4.6 KB each).  Arithmetic: fwd_h_math, bit-identical to interact_fwd_h_kernel.
+template <int F, int WARPS_, int PB_>
+struct FwdHs {
+    static constexpr int DIM = 128, WARPS = WARPS_, PB = PB_;
+    static constexpr int STAGE_BYTES = F * 2 * DIM * 4;                // per warp: [F][2][DIM]
+    static constexpr int PART_BYTES = PB * 32 * 36 * 4;                // per warp
+    static constexpr int SMEM_BYTES = WARPS * (STAGE_BYTES + PART_BYTES) + WARPS * 8;
+};
+
+template <int F, int WARPS, int PB>
+__global__ void __launch_bounds__(32 * WARPS, 1) interact_fwd_hs_kernel(FeatPtrs fp, int64_t row_stride, int B,
+                                                                        float* __restrict__ out, int64_t ld_out) {
+    using P = FwdHs<F, WARPS, PB>;
+    constexpr int DIM = P::DIM;
+    extern __shared__ __align__(128) unsigned char pipe_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int h = lane & 15, half = lane >> 4;
+    float* stage = reinterpret_cast<float*>(pipe_smem + wib * P::STAGE_BYTES);                                  // [F][2][DIM]
+    float* part = reinterpret_cast<float*>(pipe_smem + WARPS * P::STAGE_BYTES + wib * P::PART_BYTES);           // [PB][32 * 36]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(pipe_smem + WARPS * (P::STAGE_BYTES + P::PART_BYTES)) + wib;
+    if (lane == 0) {
+        pipe::bar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    pdl_enter();
+    const int items = (B + 1) / 2;
+    const int gw = blockIdx.x * WARPS + wib, nw = gridDim.x * WARPS;
+    // lane i < F moves feature i of the item's samples (one copy when the rows of consecutive samples are adjacent)
+    auto issue = [&](int item) {
+        const int b0 = item * 2;
+        const int ns = min(2, B - b0);
+        if (lane == 0) pipe::bar_expect(bar, (uint32_t)(ns * F * DIM * 4));
+        __syncwarp();
+        if (lane < F) {
+            float* dst = stage + lane * 2 * DIM;
+            const float* src = fp.p[lane] + (int64_t)b0 * row_stride;
+            if (row_stride == DIM) {
+                pipe::bulk_g2s(dst, src, (uint32_t)(ns * DIM * 4), bar);
+            } else {
+                for (int q = 0; q < ns; ++q) pipe::bulk_g2s(dst + q * DIM, src + (int64_t)q * row_stride, DIM * 4, bar);
+            }
+        }
+    };
+    if (gw < items) issue(gw);
+    int it = 0;
+    for (int item = gw; item < items; item += nw, ++it) {
+        pipe::bar_wait(bar, (uint32_t)(it & 1));
+        const int b = item * 2 + half;
+        const bool live = b < B;            // (the dead half-warp of an odd B works on stale shared memory, stores nothing)
+        float4 ta[F], tb[F];
+        static_for<F>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const float4* row = reinterpret_cast<const float4*>(stage + (i * 2 + half) * DIM);
+            ta[i] = row[h];
+            tb[i] = row[16 + h];
+        });
+        __syncwarp();                                          // the item is in registers: refill the buffer right away
+        if (item + nw < items) issue(item + nw);
+        fwd_h_math<F, PB>(ta, tb, out + (int64_t)(live ? b : 0) * ld_out, live, part);
+        __syncwarp();                                          // the transpose tiles are reused by the next item
+    }
+}
+
 // ---- tensor-core path (F <= 32, dim % 32 == 0, no self-interaction) -----------------------------
 // ncu on the CUDA-core kernels above: issue-bound (3048 / 3864 warp instructions per sample, FMA pipe
 // 36 %, DRAM 35 %), because the K reduction costs one shuffle + add per pair on top of the FMAs.
@@ -858,11 +939,13 @@ int g_bwd_pipe = 1;      // cdlrm_interact_set_option(1, .): software-pipelined 
 // neither faster on B200 (tools/interact_pipe_time.py, event-timed: 54 / 47-50 us against 46-48 us): hiding the row
 // loads does not help a kernel whose 2 050 instructions per sample are mostly dependent FADD / LDS chains of the
 // cross-lane reduction; the backward (independent FFMA2s, 2x the bytes per sample) gains 25 % from the same ring.
-// 3 = interact_fwd_h_kernel (half a warp per sample, not bit-identical to the others: 8-column partials); -1 = default
+// 3 = interact_fwd_h_kernel (half a warp per sample, not bit-identical to the others: 8-column partials); 4 = the same,
+// persistent with staggered warps; 5 / 6 = interact_fwd_hs_kernel (the half-warp arithmetic fed through shared memory by
+// bulk async copies: 7 warps + single transpose tile / 6 warps + two tiles; bit-identical to 3); -1 = default
 constexpr int FWD_DEFAULT = 3;
 int g_fwd_pipe = [] {
     const char* e = getenv("CDLRM_INTERACT_FWD");       // A/B switch for whole-step measurements
-    return (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : FWD_DEFAULT;
+    return (e && e[0] >= '0' && e[0] <= '6') ? e[0] - '0' : FWD_DEFAULT;
 }();
 int g_variant = 0;       // cdlrm_interact_set_option(0, .): 0 CUDA cores (default), 1 mma.sync 3xTF32, 2 first CUDA-core version
 bool use_simt_only() { return g_variant != 1; }
@@ -895,6 +978,26 @@ bool launch_fwd_pipe(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t 
     const int need = (B + WARPS - 1) / WARPS;
     const int grid = need < sms * P::CTAS_PER_SM ? need : sms * P::CTAS_PER_SM;      // persistent warps
     LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_pipe_kernel<F, STAGES, WARPS, PB>), grid, 32 * WARPS, P::SMEM_BYTES, fp, rs, B, out, ld_out);
+    return true;
+}
+
+template <int F, int WARPS, int PB>
+bool launch_fwd_hs(const FeatPtrs& fp, int64_t rs, int B, float* out, int64_t ld_out, cudaStream_t s) {
+    using P = FwdHs<F, WARPS, PB>;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    if (cdlrm_smem_optin((const void*)interact_fwd_hs_kernel<F, WARPS, PB>, P::SMEM_BYTES) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const int items = (B + 1) / 2;
+    const int need = (items + WARPS - 1) / WARPS;
+    const int grid = need < sms ? need : sms;                 // persistent: one CTA per SM
+    LAUNCH_PDL(K_INT_FWD, s, (interact_fwd_hs_kernel<F, WARPS, PB>), grid, 32 * WARPS, P::SMEM_BYTES, fp, rs, B, out, ld_out);
     return true;
 }
 
@@ -953,6 +1056,10 @@ bool aligned_for(const FeatPtrs& fp, int n, int64_t rs, int bytes) {
         done = true;                                                                      \
     }
 #define FWD_PIPE_CASE(F_)                                                                                   \
+    if (!done && n_feat == F_ && dim == 128 && !itself && fast16 && g_fwd_pipe >= 5 && g_variant == 0) {     \
+        done = g_fwd_pipe == 5 ? launch_fwd_hs<F_, 7, 1>(fp, rs, batch, out, ld_out, s)                      \
+                               : launch_fwd_hs<F_, 6, 2>(fp, rs, batch, out, ld_out, s);                     \
+    }                                                                                                        \
     if (!done && n_feat == F_ && dim == 128 && !itself && fast16 && g_fwd_pipe >= 3 && g_variant == 0) {     \
         launch_fwd_h<F_>(fp, rs, batch, out, ld_out, s, g_fwd_pipe == 4);                                    \
         done = true;                                                                                         \
@@ -990,7 +1097,7 @@ extern "C" int cdlrm_interact_set_option(int key, int value) {
         return CDLRM_OK;
     }
     if (key == 2) {
-        ARG_CHECK(value >= -1 && value <= 4);
+        ARG_CHECK(value >= -1 && value <= 6);
         g_fwd_pipe = value < 0 ? FWD_DEFAULT : value;
         return CDLRM_OK;
     }

@@ -226,6 +226,69 @@ extern "C" int cdlrm_move_scatter_master2(cdlrm_ctx* c, int k, const int64_t* id
                           (cudaStream_t)stream);
 }
 
+// Bucket index of a loser store (LoserDesc::bucket): thread b finds the first index whose id >= b << shift.
+__global__ void __launch_bounds__(256) loser_bucket_kernel(const LoserDesc* __restrict__ losers) {
+    const LoserDesc& L = losers[blockIdx.y];
+    if (!L.bucket || L.n <= 0) return;
+    int32_t* __restrict__ bucket = const_cast<int32_t*>(L.bucket);
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < L.nb; b += gridDim.x * blockDim.x) {
+        const int64_t target = (int64_t)b << L.shift;
+        int64_t lo = 0, hi = L.n;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(L.ids + mid) < target) lo = mid + 1; else hi = mid;
+        }
+        bucket[b] = (int32_t)lo;
+    }
+}
+
+// Carve the bucket indices of the descriptors in h[0..T) out of c->d_lbucket (grown when a window needs more; the
+// stores are bound at window boundaries, where a cudaMalloc does not hurt) and launch the build behind the
+// descriptor copy.  About 4 ids per bucket: n / 4 + 2 buckets per table.
+static int build_loser_buckets(cdlrm_ctx* c, LoserDesc* h, cudaStream_t s) {
+    int64_t total = 0;
+    for (int k = 0; k < c->T; ++k) {
+        h[k].bucket = nullptr;
+        h[k].shift = 0;
+        h[k].nb = 0;
+        if (h[k].n < 64 || h[k].n >= (1ll << 31)) continue;             // short lists: the plain search is as fast
+        int shift = 0;
+        while (shift < 40 && ((c->tabs[k].n_rows >> shift) > h[k].n / 4 + 1)) ++shift;
+        const int64_t nb = (c->tabs[k].n_rows >> shift) + 2;
+        if (nb >= (1ll << 31)) continue;
+        h[k].shift = shift;
+        h[k].nb = (int32_t)nb;
+        total += nb;
+    }
+    if (total == 0) return CDLRM_OK;
+    if (total > c->lbucket_cap) {
+        if (c->d_lbucket) CU_CHECK(cudaFree(c->d_lbucket));            // (synchronises: no forward still reads it)
+        c->d_lbucket = nullptr;
+        c->lbucket_cap = total + total / 2 + 1024;
+        CU_CHECK(cudaMalloc(&c->d_lbucket, sizeof(int32_t) * (size_t)c->lbucket_cap));
+    }
+    int64_t off = 0;
+    int64_t nb_max = 0;
+    for (int k = 0; k < c->T; ++k) {
+        if (!h[k].nb) continue;
+        h[k].bucket = c->d_lbucket + off;
+        off += h[k].nb;
+        if (h[k].nb > nb_max) nb_max = h[k].nb;
+    }
+    return CDLRM_OK;
+}
+
+static int launch_loser_buckets(cdlrm_ctx* c, const LoserDesc* h, cudaStream_t s) {
+    int64_t nb_max = 0;
+    for (int k = 0; k < c->T; ++k)
+        if (h[k].nb > nb_max) nb_max = h[k].nb;
+    if (nb_max == 0) return CDLRM_OK;
+    const int gx = (int)((nb_max + 255) / 256 < 592 ? (nb_max + 255) / 256 : 592);
+    LAUNCH(K_MOVE_GATHER, s, loser_bucket_kernel<<<dim3(gx, c->T), 256, 0, s>>>(c->d_losers));
+    CU_CHECK(cudaGetLastError());
+    return CDLRM_OK;
+}
+
 // Loser store (see LoserDesc): the descriptors reach the device in stream order, so the forward
 // launched after this call on `stream` sees the new store and the ones before it the old one.
 extern "C" int cdlrm_ctx_bind_losers(cdlrm_ctx* c, const int64_t* const* h_ids, const float* const* h_rows,
@@ -246,8 +309,9 @@ extern "C" int cdlrm_ctx_bind_losers(cdlrm_ctx* c, const int64_t* const* h_ids, 
         h[k].n = (h_ids && h_rows && h_n) ? h_n[k] : 0;
         ARG_CHECK(h[k].n >= 0 && (h[k].n == 0 || (h[k].ids && h[k].rows)));
     }
+    if (int rc = build_loser_buckets(c, h, s)) return rc;
     CU_CHECK(cudaMemcpyAsync(c->d_losers, h, sizeof(LoserDesc) * c->T, cudaMemcpyHostToDevice, s));
-    return CDLRM_OK;
+    return launch_loser_buckets(c, h, s);
 }
 
 extern "C" int cdlrm_ctx_bind_losers_sharded(cdlrm_ctx* c, const int64_t* const* h_ids, const int64_t* h_n,
@@ -274,8 +338,9 @@ extern "C" int cdlrm_ctx_bind_losers_sharded(cdlrm_ctx* c, const int64_t* const*
             ARG_CHECK(h[k].peer[r] || (int64_t)r * h_shard[k] >= h[k].n);     // a rank without rows may pass NULL
         }
     }
+    if (int rc = build_loser_buckets(c, h, s)) return rc;
     CU_CHECK(cudaMemcpyAsync(c->d_losers, h, sizeof(LoserDesc) * c->T, cudaMemcpyHostToDevice, s));
-    return CDLRM_OK;
+    return launch_loser_buckets(c, h, s);
 }
 
 extern "C" int cdlrm_host_register(int device, void* h_ptr, int64_t bytes, void** dev_ptr) {

@@ -377,13 +377,20 @@ class Trainer:
                                          rng=VictimRngDevice(args.numpy_rand_seed, self.dev), stream=self.side,
                                          lookahead_tags=True)
             self.planner.collect_losers = True     # un-cached ids of a window are served from an HBM loser store
-            # master <-> HBM traffic of the planner: zero-copy gather / scatter kernels ("sm", default: no dependence
-            # on the host) or host threads + cudaMemcpyAsync (CDLRM_PREFETCH=ce: gentler on the step while it runs,
-            # but only as good as the host cores it gets -- see DESIGN.md section 4)
-            threads = max(1, min(4, (os.cpu_count() or 2) // max(world, 1) - 2))     # more than 4 starve the host thread that enqueues the steps (16-core box)
+            # master <-> HBM traffic of the planner: host threads + cudaMemcpyAsync ("ce": the chunk loops are native,
+            # hostio.cu; hardly slows the step that runs beside it) when this rank has host cores to spare, else
+            # zero-copy gather / scatter kernels ("sm": no host threads, but every system-memory access the SMs keep
+            # in flight slows the training kernels 1.2-2x while it runs).  CDLRM_PREFETCH=ce|sm and
+            # CDLRM_HOST_THREADS override; see DESIGN.md section 4 for the measurements behind the rule
+            try:
+                cores = len(os.sched_getaffinity(0))
+            except (AttributeError, OSError):
+                cores = os.cpu_count() or 2
+            threads = max(1, min(4, cores // max(world, 1) - 2))     # more than 4 bring nothing at one window per 2 s
             mode = os.environ.get("CDLRM_PREFETCH", "auto")
             self.planner.host_threads = int(os.environ.get("CDLRM_HOST_THREADS", threads))
-            self.planner.pcie_mode = mode if mode in ("ce", "sm") else "sm"
+            auto = "ce" if (world == 1 and self.planner.host_threads >= 3) else "sm"
+            self.planner.pcie_mode = mode if mode in ("ce", "sm") else auto
         self._host_group = dist.new_group(backend="gloo") if world > 1 else None   # plan-thread barrier
         # un-cached ids of a window (the same on every rank): one store sharded over the node's GPUs and read over
         # NVLink instead of a full copy per rank (CDLRM_LOSER_SHARDED=0: one local store per rank)

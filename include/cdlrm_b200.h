@@ -326,6 +326,20 @@ int cdlrm_host_scatter_rows(float* master, int64_t n_rows, int dim, const int64_
                             int64_t n, const float* src, int average, int threads);
 /* cudaMemcpyAsync of a staging chunk on `stream` (copy engine): kind 1 = host to device, 2 = device to host */
 int cdlrm_copy_async(int device, void* dst, const void* src, int64_t bytes, int kind, cdlrm_stream stream);
+/* Whole transfers in one call (the chunk loop is native: the caller's interpreter lock is dropped once; host threads
+ * come from a persistent pool).  n_jobs lists (one per table): HOST ids / primary flags, DEVICE rows.
+ * prefetch (cache_manager.py:34-43): dst_j[i] = masters[j][ids_j[i]] -- host threads gather chunk c into one of the two
+ * pinned staging chunks (chunk_rows x dim floats each) while cudaMemcpyAsync moves chunk c-1 into HBM; returns when the
+ * last copy has finished.  writeback (cache_manager.py:48-64): masters[j][ids_j[i]] = src_j[i] (mean of the two with
+ * `average`) where primary_j[i] != 0 (primary or primary[j] NULL: all) -- cudaMemcpyAsync brings chunk c out of HBM while
+ * the host threads scatter chunk c-1; returns when every row is in the master. */
+int cdlrm_host_prefetch_rows(int device, int n_jobs, const float* const* masters, const int64_t* n_rows, int dim,
+                             const int64_t* const* ids, const int64_t* counts, float* const* dst, float* chunk0,
+                             float* chunk1, int64_t chunk_rows, int threads, cdlrm_stream stream);
+int cdlrm_host_writeback_rows(int device, int n_jobs, float* const* masters, const int64_t* n_rows, int dim,
+                              const int64_t* const* ids, const uint8_t* const* primary, const int64_t* counts,
+                              const float* const* src, float* chunk0, float* chunk1, int64_t chunk_rows, int average,
+                              int threads, cdlrm_stream stream);
 
 /* ---- peer-readable device buffers (CUDA IPC over NVLink / NVSwitch) and the SHARDED loser store ----------------
  * No reference counterpart as code: the reference fetches every forward miss from the CPU master table

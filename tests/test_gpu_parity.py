@@ -241,7 +241,9 @@ def test_interaction_pipelined_kernels(shape, strided_feats):
         return [big[i, :, :d].detach().requires_grad_() for i in range(nf)]
 
     grads, outs = {}, {}
-    for pipe in (1, 0, 2):                                 # forward variants 1 and 2 (two- / one-stage rings), 0 = plain
+    # forward variants: 1 / 2 = two- / one-stage rings, 0 = plain (a warp per sample); 3 = half a warp per sample, 4 = the
+    # same persistent, 5 / 6 = the same fed through shared memory by bulk async copies (interact_fwd_hs_kernel)
+    for pipe in (1, 0, 2, 3, 4, 5, 6):
         check(lib.cdlrm_interact_set_option(1, min(pipe, 1)))      # backward
         check(lib.cdlrm_interact_set_option(2, pipe))              # forward
         try:
@@ -259,6 +261,11 @@ def test_interaction_pipelined_kernels(shape, strided_feats):
     util.assert_close_fp32(grads[1][1:], np.stack(dly))
     assert np.array_equal(outs[1], outs[0]) and np.array_equal(outs[2], outs[0])
     assert np.array_equal(grads[1], grads[0]) and np.array_equal(grads[2], grads[0])
+    # the half-warp family: 8-column partials (not bit-identical to the warp-per-sample family), identical among themselves
+    util.assert_close_fp32(outs[3], O.interact_fwd(x, ly))
+    for v in (4, 5, 6):
+        assert np.array_equal(outs[v], outs[3]), f"forward variant {v} differs from variant 3"
+        assert np.array_equal(grads[v], grads[0])
 
 
 @pytest.mark.parametrize("mlp_impl", ["tcgen05", "torch"])

@@ -13,7 +13,7 @@ CDLRM_BENCH_CUPROF=1 timeout 600 ncu --set full --clock-control none --import-so
   -o gpurun_out/r2_hot_full -f python bench.py --steps 1 $COMMON > gpurun_out/ncu_full_bench.log 2>&1; echo "ncu full (cache path) rc=$? $(( $(date +%s) - T0 )) s"
 T0=$(date +%s)
 CDLRM_BENCH_CUPROF=1 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -k 'regex:gemm3x' -c 8 -o gpurun_out/r2_gemm_full -f python bench.py --steps 1 $COMMON > gpurun_out/ncu_gemm_bench.log 2>&1; echo "ncu full (gemm) rc=$? $(( $(date +%s) - T0 )) s"
+  -k 'regex:gemm3x' -c 6 -o gpurun_out/r2_gemm_full -f python bench.py --steps 1 $COMMON > gpurun_out/ncu_gemm_bench.log 2>&1; echo "ncu full (gemm) rc=$? $(( $(date +%s) - T0 )) s"
 ls -la gpurun_out | grep r2_
 sleep 3
 timeout 60 python -c "import torch; x=torch.zeros(8,device='cuda:0'); torch.cuda.synchronize(); print('gpu alive')"

@@ -1,6 +1,6 @@
 """Device time of the dim-128 interaction forward kernels at the Terabyte shape (B = 8192, 27 x 128):
 0 = interact_fwd_tr_kernel (a warp per sample), 3 = interact_fwd_h_kernel (half a warp per sample), 1 / 2 = the
-software-pipelined ring variants.  CUDA events around every launch (cdlrm_prof_*), 12 input sets (> L2).  Run under gpurun."""
+software-pipelined ring variants, 5 / 6 = interact_fwd_hs_kernel (half-warp arithmetic fed through shared memory).  CUDA events around every launch (cdlrm_prof_*), 12 input sets (> L2).  Run under gpurun."""
 import ctypes as C
 import os
 import sys
@@ -20,7 +20,7 @@ NK = lib.cdlrm_prof_num_kernels()
 names = [lib.cdlrm_prof_kernel_name(i).decode() for i in range(NK)]
 sets = [(torch.randn(B, d, device=dev), [torch.randn(B, d, device=dev) for _ in range(F - 1)]) for _ in range(12)]
 s = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-for fwd, stag in ((0, 0), (3, 0), (4, 0), (4, 400), (4, 800), (4, 1600), (4, 3000), (3, 0), (4, 800)):
+for fwd, stag in ((0, 0), (3, 0), (5, 0), (6, 0), (4, 800), (3, 0), (5, 0), (6, 0)):
     check(lib.cdlrm_interact_set_option(2, fwd))
     check(lib.cdlrm_interact_set_option(3, stag))
     for rep in range(3):

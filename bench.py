@@ -578,6 +578,7 @@ def gpu_run(a, wl, ln_emb):
             torch.cuda.synchronize(dev)
         log(f"end-to-end leg: {n_e2e} steps from pinned host inputs ({(hI.nbytes + hX.nbytes + hY.nbytes) / 1e9:.1f} GB)")
         logging_on[0] = True
+        tr.cache_group._agg_prof = [] if world > 1 else None      # phase events of every table aggregation of the leg
         lib.cdlrm_prof_launches(1)
         seg2 = max(1, n_e2e // 120)
         marks2 = []
@@ -661,6 +662,18 @@ def gpu_run(a, wl, ln_emb):
             "next_window_input_generation_host_ms": [p_ for p_, _ in prep_log],
             "steady_ms_per_step_before": round(filler_ms, 4) if filler_ms else None,
         }
+        ap = getattr(tr.cache_group, "_agg_prof", None)
+        tr.cache_group._agg_prof = None
+        if ap:
+            # [dirty-bitmap all-gather + OR + slot lists | host reads the counts | pack | all-reduce | unpack], device ms
+            names = ("bitmaps_and_lists", "host_sync_gap", "pack", "all_reduce", "unpack")
+            ph = np.asarray([[m[q].elapsed_time(m[q + 1]) for q in range(5)] for _t, m in ap if len(m) == 6])
+            rows_ = float(np.mean([t_ for t_, _m in ap]))
+            full_window["agg_phases_device_ms"] = {n_: round(float(v_), 3) for n_, v_ in zip(names, ph.mean(0))} if len(ph) else None
+            full_window["agg_rows_per_call"] = int(rows_)
+            full_window["agg_row_bytes_per_call"] = int(rows_ * d * 4)
+            if len(ph) and ph.mean(0)[3] > 0:
+                full_window["agg_all_reduce_algbw_GB/s"] = round(rows_ * d * 4 / (ph.mean(0)[3] * 1e-3) / 1e9, 1)
         if rec_next is not None and not isinstance(rec_next, Exception) and getattr(rec_next, "stage_begin", None) is not None:
             st_ms = rec_next.stage_begin.elapsed_time(rec_next.staged)
             full_window["planner_ms"] = {k: round(1000 * v, 1) for k, v in tr.planner.last_timing.items()}

@@ -231,10 +231,22 @@ def broadcast_and_aggregate(cache_group, cache_group_idxs, rank, reduce_op="mean
                 torch.empty(W, dirty.numel(), dtype=torch.int32, device=dev))
         cg._agg_bufs = bufs
     slot_list, d_counts, h_counts, gathered = bufs
+    # optional phase timing (bench.py sets cache_group._agg_prof = []): events at the phase borders of every call
+    prof = getattr(cg, "_agg_prof", None)
+    marks = []
+
+    def mark():
+        if prof is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(dev))
+            marks.append(e)
+
+    mark()
     if W > 1:
         comm.all_gather_into(gathered.view(-1), dirty)
         check(lib.cdlrm_agg_or_bitmaps(ctx, _vp(gathered.data_ptr()), W, dirty.numel(), s))
     check(lib.cdlrm_agg_collect(ctx, _vp(slot_list.data_ptr()), _vp(d_counts.data_ptr()), _vp(h_counts.data_ptr()), s))
+    mark()
     torch.cuda.current_stream(dev).synchronize()
     counts = h_counts.tolist()
     total = int(sum(counts))
@@ -247,10 +259,16 @@ def broadcast_and_aggregate(cache_group, cache_group_idxs, rank, reduce_op="mean
         rows = cg._agg_rows = torch.empty(int(total * 1.25) + 16, cg.dim, dtype=torch.float32, device=dev)
     buf = rows[:total]
     div = float(W) if reduce_op == "mean" else 1.0
+    mark()
     check(lib.cdlrm_agg_pack(ctx, _vp(slot_list.data_ptr()), carr, div, _vp(buf.data_ptr()), s))
+    mark()
     if W > 1:
         comm.all_reduce(buf, reduce_op)
+    mark()
     check(lib.cdlrm_agg_unpack(ctx, _vp(slot_list.data_ptr()), carr, _vp(buf.data_ptr()), 1, s))
+    mark()
+    if prof is not None:
+        prof.append((total, marks))
 
 
 def share_occupancy_tables(cache_group, occupancy_tables_fifos, rank):

@@ -685,6 +685,8 @@ def gpu_run(a, wl, ln_emb):
                 tl["writeback_done"] = tr._installed.wb_done      # the leg's own boundary: evicted rows back in the master
             full_window["planner_timeline_ms"] = {k: round(e0.elapsed_time(v), 1) for k, v in tl.items()}
             full_window["planner_ms"]["prefetch"] = round(st_ms, 1)
+            pcie["prefetch_rows"] = {"fills": int(sum(rec_next.F)), "evictions": int(sum(rec_next.E)),
+                                     "losers_staged": int(sum(rec_next.L)) if rec_next.L is not None else 0}
             pcie["prefetch_bytes"] = int(rec_next.stage_bytes)
             pcie["prefetch_ms"] = round(st_ms, 2)
             pcie["prefetch_GB/s"] = round(rec_next.stage_bytes / (st_ms * 1e-3) / 1e9, 2) if st_ms > 0 else None

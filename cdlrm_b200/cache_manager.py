@@ -109,6 +109,13 @@ class TorchGlobalRng:
 # ------------------------------------------------------------------------------------
 
 
+def wb_share_range(E, r, W):
+    """(first entry, count) of rank r's share of an eviction list of E entries written back by W ranks: contiguous,
+    disjoint, covering [0, E), sizes differing by at most one."""
+    lo, hi = (E * r) // W, (E * (r + 1)) // W
+    return lo, hi - lo
+
+
 class PlanRecord:
     """Decisions for one window (all device tensors are concatenated over tables; the
     lists of table k start at ``off[k]``)."""
@@ -117,7 +124,7 @@ class PlanRecord:
                  # look-ahead staging (WindowPlanner.stage / install_staged)
                  "L", "loser_off", "loser_soff", "loser_ids", "loser_stage", "fill_stage", "fill_soff", "evict_stage",
                  "staged", "wb_done", "stage_begin", "stage_bytes", "loser_shard", "loser_peers",
-                 "marks")
+                 "marks", "wb_lo", "wb_n")
 
     def loser_list(self, k):
         o, n = self.loser_off[k], self.L[k]
@@ -523,20 +530,22 @@ class WindowPlanner:
             return
         rec, average = pend
         s, d, dev = self.stream, self.dim, self.dev.index
-        segs = [(rec.off[k], rec.E[k]) for k in range(self.T)]
+        wlo, wn = rec.wb_lo, rec.wb_n                  # this rank's share of every table's eviction list
+        segs = [(rec.off[k] + wlo[k], wn[k]) for k in range(self.T)]
         hid, offs = self._ids_to_host("wb_ids", rec.evict_ids, segs)
-        tot = sum(rec.E)
+        tot = sum(wn)
         hpr = self._pinned("wb_prim", max(tot, 1))[:max(tot, 1)]
         with torch.cuda.stream(s):
             for k in range(self.T):
-                if rec.E[k]:
-                    hpr[offs[k]:offs[k] + rec.E[k]].copy_(rec.evict_primary[rec.off[k]:rec.off[k] + rec.E[k]], non_blocking=True)
+                if wn[k]:
+                    o = rec.off[k] + wlo[k]
+                    hpr[offs[k]:offs[k] + wn[k]].copy_(rec.evict_primary[o:o + wn[k]], non_blocking=True)
         s.synchronize()
         rows_per, bufs, _evs = self._ce_chunks()
         eoff = [0] * self.T
         for k in range(1, self.T):
             eoff[k] = eoff[k - 1] + rec.E[k - 1]
-        ks = [k for k in range(self.T) if rec.E[k]]
+        ks = [k for k in range(self.T) if wn[k]]
         if ks:
             Ws = [self.emb_tables.emb_l[k].weight.data for k in ks]
             # device -> pinned chunk by the copy engine, chunk -> master rows by the pooled host threads, the copy of
@@ -544,8 +553,8 @@ class WindowPlanner:
             check(lib.cdlrm_host_writeback_rows(
                 dev, len(ks), _lib.ptr_array([W.data_ptr() for W in Ws]), _lib.i64_array([W.shape[0] for W in Ws]), d,
                 _lib.ptr_array([hid.data_ptr() + 8 * offs[k] for k in ks]),
-                _lib.ptr_array([hpr.data_ptr() + offs[k] for k in ks]), _lib.i64_array([rec.E[k] for k in ks]),
-                _lib.ptr_array([rec.evict_stage[eoff[k]:].data_ptr() for k in ks]),
+                _lib.ptr_array([hpr.data_ptr() + offs[k] for k in ks]), _lib.i64_array([wn[k] for k in ks]),
+                _lib.ptr_array([rec.evict_stage[eoff[k] + wlo[k]:].data_ptr() for k in ks]),
                 _vp(bufs[0].data_ptr()), _vp(bufs[1].data_ptr()), rows_per, int(average), self.host_threads, _sp(s)))
         rec.wb_done = torch.cuda.Event(enable_timing=True)
         rec.wb_done.record(s)
@@ -625,13 +634,19 @@ class WindowPlanner:
         rec.stage_bytes = 4 * d * (sum(n for _k, _o, n, _dst in fill_jobs) + sum(n for _k, _o, n, _dst in loser_jobs))
         return rec
 
-    def install_staged(self, rec, write_master=True, average_on_writeback=False, stream=None):
+    def install_staged(self, rec, write_master=True, average_on_writeback=False, stream=None, wb_share=None):
         """Window boundary with staged data: on ``stream`` (default: current) the evicted rows are
         copied HBM->HBM into a write-back buffer, the fills come HBM->HBM from the staging buffer
         and the loser store is switched; the write-back to the host master then runs on the
-        planner's stream beside the next window's training steps."""
+        planner's stream beside the next window's training steps.
+        ``wb_share = (r, W)``: data-parallel replicas whose caches agree at the boundary (they were just aggregated)
+        and that share ONE host master: this rank writes back only the r-th of W equal shares of every table's
+        eviction list -- the write-back takes 1/W of the time instead of loading rank 0 alone."""
         s = stream or torch.cuda.current_stream(self.dev)
         d = self.dim
+        tm = [time.perf_counter()]               # host time of the phases (Trainer.boundary_breakdown_ms)
+        r_, W_ = wb_share if wb_share is not None else (0, 1)
+        rec.wb_lo, rec.wb_n = zip(*[wb_share_range(E, r_, W_) for E in rec.E]) if rec.E else ((), ())
         if rec.staged is None:
             self.stage(rec)
         s.wait_event(rec.staged)
@@ -645,17 +660,20 @@ class WindowPlanner:
                 eoff[k] = eoff[k - 1] + rec.E[k - 1]
             # (the write-back that last read this buffer precedes rec.staged on the planner stream)
             rec.evict_stage = self._buf("evict", max(sum(rec.E), 1))
+            tm.append(time.perf_counter())
             for k in range(self.T):
                 if rec.E[k]:
                     ids, slots, prim = rec.evict_list(k)
                     check(lib.cdlrm_move_evict(self.ctx, k, _vp(ids.data_ptr()), _vp(slots.data_ptr()),
                                                _vp(prim.data_ptr()), rec.E[k],
                                                _vp(rec.evict_stage[eoff[k]:].data_ptr()), 0, 0, _sp(s)))
+            tm.append(time.perf_counter())
             for k in range(self.T):
                 if rec.F[k]:
                     ids, slots = rec.fill_list(k)
                     check(lib.cdlrm_move_fill(self.ctx, k, _vp(ids.data_ptr()), _vp(slots.data_ptr()), rec.F[k],
                                               _vp(rec.fill_stage[rec.fill_soff[k]:].data_ptr()), None, _sp(s)))
+            tm.append(time.perf_counter())
             if rec.L is not None and rec.loser_peers is not None:
                 world = self._shard[1]
                 check(lib.cdlrm_ctx_bind_losers_sharded(
@@ -676,24 +694,30 @@ class WindowPlanner:
                 check(lib.cdlrm_ctx_bind_losers(self.ctx, None, None, None, _sp(s)))
             moved = torch.cuda.Event()
             moved.record(s)
+        tm.append(time.perf_counter())
         ws = self.stream
         ws.wait_event(moved)       # later planner-stream work (next prefetch) may reuse the staging buffers
-        if write_master and sum(rec.E) and self.pcie_mode == "ce" and not self.emb_tables.emb_l[0].weight.is_cuda:
+        if write_master and sum(rec.wb_n) and self.pcie_mode == "ce" and not self.emb_tables.emb_l[0].weight.is_cuda:
             # copy engine + host threads: done by the thread that plans the next window (flush_writeback), before
             # anything of that window reads the master; callers that read the master themselves call it first
             rec.evict_stage.record_stream(ws)
             self._pending_wb = (rec, bool(average_on_writeback))
-        elif write_master and sum(rec.E):
+        elif write_master and sum(rec.wb_n):
             rec.evict_stage.record_stream(ws)
             with torch.cuda.stream(ws):
                 for k in range(self.T):
-                    if rec.E[k]:
+                    lo, n = rec.wb_lo[k], rec.wb_n[k]
+                    if n:
                         ids, _slots, prim = rec.evict_list(k)
-                        check(lib.cdlrm_move_scatter_master2(self.ctx, k, _vp(ids.data_ptr()), _vp(prim.data_ptr()),
-                                                             rec.E[k], _vp(rec.evict_stage[eoff[k]:].data_ptr()),
+                        check(lib.cdlrm_move_scatter_master2(self.ctx, k, _vp(ids[lo:].data_ptr()), _vp(prim[lo:].data_ptr()),
+                                                             n, _vp(rec.evict_stage[eoff[k] + lo:].data_ptr()),
                                                              int(average_on_writeback), _sp(ws)))
         rec.wb_done = torch.cuda.Event(enable_timing=True)
         rec.wb_done.record(self.stream)
+        tm.append(time.perf_counter())
+        self.last_install_ms = {n: round(1e3 * (y - x), 2) for n, x, y in
+                                zip(("wait_and_buffers", "evict_launches", "fill_launches", "bind_losers", "writeback_launches"),
+                                    tm, tm[1:])}
         return rec
 
     # -- install ---------------------------------------------------------------------------

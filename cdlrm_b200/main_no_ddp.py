@@ -410,6 +410,9 @@ class Trainer:
             auto = "ce" if (world == 1 and self.planner.host_threads >= 3) else "sm"
             self.planner.pcie_mode = mode if mode in ("ce", "sm") else auto
         self._host_group = dist.new_group(backend="gloo") if world > 1 else None   # plan-thread barrier
+        # write-back of a boundary's evictions shared by the ranks (they hold identical rows right after the boundary
+        # aggregation and map the same host master): 1/world of every table's list each
+        self.wb_sharded = world > 1 and self.planner is not None and os.environ.get("CDLRM_WB_SHARDED", "1") != "0"
         # un-cached ids of a window (the same on every rank): one store sharded over the node's GPUs and read over
         # NVLink instead of a full copy per rank (CDLRM_LOSER_SHARDED=0: one local store per rank)
         # un-cached ids of a window at N > 1: "own" (default) = every rank stages only the ones its own batches contain
@@ -489,7 +492,7 @@ class Trainer:
                     # the prefetch below reads master rows: rank 0's write-back of the previous
                     # boundary (asynchronous, on its planner stream) must have landed first
                     prev_rec = self._installed
-                    if self.rank == 0 and prev_rec is not None and prev_rec.wb_done is not None:
+                    if (self.rank == 0 or self.wb_sharded) and prev_rec is not None and prev_rec.wb_done is not None:
                         prev_rec.wb_done.synchronize()
                     dist.barrier(group=self._host_group)
                 rec = self.planner.stage(rec)
@@ -524,15 +527,19 @@ class Trainer:
         t3 = time.perf_counter()
         # evict / fill are HBM->HBM against the staging buffers the plan thread filled during the
         # previous window; the host write-back runs on the planner stream beside the next steps
-        self.planner.install_staged(rec, write_master=(self.rank == 0),
-                                    average_on_writeback=self.args.average_on_writeback)
+        # the replicas were just aggregated, so their evicted rows agree: every rank writes 1/world of them back
+        # into the shared host master (CDLRM_WB_SHARDED=0: rank 0 writes all of them, as the reference does)
+        self.planner.install_staged(rec, write_master=(self.rank == 0 or self.wb_sharded),
+                                    average_on_writeback=self.args.average_on_writeback,
+                                    wb_share=(self.rank, self.world) if self.wb_sharded else None)
         self._installed = rec            # keeps the loser store of this window alive
         t4 = time.perf_counter()
         self.caching_overhead.append(t4 - t0)
         # host milliseconds of the boundary: waiting for the plan, draining the stream for the device flags,
         # aggregation, enqueueing evict / fill
         self.boundary_breakdown_ms = {"wait_plan": round(1e3 * (t1 - t0), 2), "flags_sync": round(1e3 * (t2 - t1), 2),
-                                      "aggregate": round(1e3 * (t3 - t2), 2), "install": round(1e3 * (t4 - t3), 2)}
+                                      "aggregate": round(1e3 * (t3 - t2), 2), "install": round(1e3 * (t4 - t3), 2),
+                                      "install_phases": dict(getattr(self.planner, "last_install_ms", {}))}
         return rec
 
     def _early_allreduce(self):

@@ -93,3 +93,16 @@ def test_prefetcher_window_slicing_contract():
         assert int(wins[0][k].min()) >= 0 and int(wins[0][k].max()) < n
     x, o, i, t = next(iter(test_ld))
     assert x.shape == (8, 13) and i.shape == (3, 8) and t.shape == (8, 1) and torch.equal(o[0], torch.arange(8))
+
+
+def test_writeback_shares_partition_the_eviction_list():
+    """Trainer.install_window at N > 1: rank r writes back wb_share_range(E, r, W) of every table's eviction list
+    (cache_manager.py:48-64 is done by the one eviction manager in the reference): the shares must tile [0, E)."""
+    from cdlrm_b200.cache_manager import wb_share_range
+    for E in (0, 1, 7, 8, 1000, 123457):
+        for W in (1, 2, 3, 8):
+            parts = [wb_share_range(E, r, W) for r in range(W)]
+            assert parts[0][0] == 0 and sum(n for _lo, n in parts) == E
+            for (lo, n), (lo2, _n2) in zip(parts, parts[1:]):
+                assert lo + n == lo2
+            assert max(n for _lo, n in parts) - min(n for _lo, n in parts) <= 1

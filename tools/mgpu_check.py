@@ -168,8 +168,9 @@ def main():
         ids, _slots, prim = rec.evict_list(k)
         ids, prim = ids.cpu(), prim.cpu().bool()
         rows = rec.evict_stage[eo[k]:eo[k] + rec.E[k]].cpu()
-        if rank == 0:
-            assert torch.equal(master.emb_l[k].weight.data[ids[prim]], rows[prim]), f"write-back of table {k} missing"
+        # (every rank checks every row: with the write-back shared by the ranks, each row was written by ONE of them
+        # into the host master that all of them map)
+        assert torch.equal(master.emb_l[k].weight.data[ids[prim]], rows[prim]), f"write-back of table {k} missing"
     # (5) dense weights in sync, loss sane
     for seq in (tr.dlrm.bot_l, tr.dlrm.top_l):
         for layer in seq:
@@ -183,6 +184,7 @@ def main():
         print(f"mgpu_check OK: world={world}, {n_windows} windows x {L} steps, loss {losses[0]:.4f} -> {losses[-1]:.4f}; "
               f"loser store {'sharded over the ranks' if tr.sharded_losers else ('own ids per rank' if tr.own_losers else 'all ids per rank')}, {checked_losers} table probes, "
               f"window scan {'sharded (marker)' if use_marker else 'whole window per rank'}, "
+              f"write-back {'shared by the ranks' if tr.wb_sharded else 'by rank 0'}, "
               f"loss digest {hash(tuple(losses)) & 0xffffffff:08x}")
     dist.destroy_process_group()
 

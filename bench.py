@@ -812,7 +812,7 @@ def kernel_profile(a, wl, tr, lib, _lib, torch, one_step, window, master, lS_o, 
     traffic, traffic_src = {}, None
     tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tpath) and a.workload == "terabyte" and not (a.cache_size or a.num_ways or a.batch):
-        tj = json.load(open(tpath))    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full
+        tj = json.load(open(tpath))    # dram__bytes_read.sum + dram__bytes_write.sum per launch (one ncu pass at this configuration)
         traffic, traffic_src = tj["kernels"], tj.get("source", "profiles/r2_traffic.json")
     for i in range(NK):
         if calls[i] and i != i_null:

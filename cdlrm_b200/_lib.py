@@ -58,6 +58,7 @@ SIGNATURES = {
     "cdlrm_plan_unique": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp, vp]),
     "cdlrm_plan_mark_ids": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp]),
     "cdlrm_plan_mark_own_ids": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp]),
+    "cdlrm_plan_set_primary_evictions": (C.c_int, [vp, C.c_int]),
     "cdlrm_plan_or_peer_bitmaps": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, vp]),
     "cdlrm_synth_ids": (C.c_int, [C.c_int, C.c_int, C.c_int, c_i64p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32,
                                   C.c_int64, C.c_int32, C.c_int, C.c_double, vp, C.c_int64, vp]),

@@ -161,6 +161,9 @@ class WindowPlanner:
         self._h_counts2 = torch.zeros(self.T * 2, dtype=torch.int64).pin_memory()
         self._h_counts3 = torch.zeros(self.T, dtype=torch.int64).pin_memory()
         self.collect_losers = False      # also list the window's un-cached ids (for the HBM loser store)
+        # eviction lists with one entry per replaced (set, way) -- its winner -- instead of one per claimant: all the
+        # write-back needs; the reference-shaped callers (CacheEmbeddings: eviction_data) keep the full lists
+        self.primary_evictions_only = False
         self._bufs = {}                  # persistent grow-only staging buffers (no cudaMalloc per window)
         self._stage_no = 0
         # how master rows cross PCIe: "sm" = zero-copy gather / scatter kernels (move.cu), "ce" = host threads gather
@@ -407,6 +410,7 @@ class WindowPlanner:
             outs = (_vp(rec.evict_ids.data_ptr()), _vp(rec.evict_slots.data_ptr()),
                     _vp(rec.evict_primary.data_ptr()), _vp(rec.fill_ids.data_ptr()),
                     _vp(rec.fill_slots.data_ptr()), _vp(self._h_counts2.data_ptr()), _sp(s))
+            check(lib.cdlrm_plan_set_primary_evictions(self.ctx, int(self.primary_evictions_only)))
             if dev_rng:
                 cap = max(max(rec.rows) * self.ways, 1)          # draws of the largest table
                 raw = self._list_buf("rng_raw", 2 * cap, torch.int32)

@@ -98,6 +98,7 @@ struct cdlrm_ctx {
     std::vector<PlanTable> ptabs;
     PlanTable* d_ptabs = nullptr;
     int64_t plan_window_len = 0;
+    bool primary_evictions = false;      // eviction lists hold only the winner of every replaced (set, way)
     bool own_marked = false;             // own-id bitmaps hold a window: cdlrm_plan_losers keeps this rank's own ids only
     char* plan_ws = nullptr;             // base of the bound planner workspace (peer copies share its carve-up)
     std::vector<unsigned long long*> pins;  // per table [num_sets] pin masks of the window being planned

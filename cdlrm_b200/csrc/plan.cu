@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(256) lists_kernel(int64_t R, const int64_t* __
                                                     int64_t* __restrict__ tags, int64_t S, int ways,
                                                     int64_t* __restrict__ evict_ids, int32_t* __restrict__ evict_slots,
                                                     uint8_t* __restrict__ evict_primary,
-                                                    int64_t* __restrict__ fill_ids, int32_t* __restrict__ fill_slots) {
+                                                    int64_t* __restrict__ fill_ids, int32_t* __restrict__ fill_slots,
+                                                    bool primary_only) {
     __shared__ int s_w[33];
     const int64_t r0 = (int64_t)blockIdx.x * TILE + threadIdx.x * 4;
     uint8_t f[4];
@@ -200,8 +201,10 @@ __global__ void __launch_bounds__(256) lists_kernel(int64_t R, const int64_t* __
         f[qq] = 0;
         if (r < R) {
             if (!EMIT) {
-                const bool ev = old[r] != -1;
                 const bool win = claim[slot[r]] == (int32_t)r;
+                // (primary_only: a (set, way) claimed by several ids of the window is listed once, by its winner -- the
+                // entry whose row the write-back uses; the reference lists it once per claimant, main_no_ddp.py:190-199)
+                const bool ev = old[r] != -1 && (win || !primary_only);
                 f[qq] = (uint8_t)((ev ? 1 : 0) | (win ? 2 : 0));
                 flag[r] = f[qq];
             } else {
@@ -435,6 +438,15 @@ extern "C" int cdlrm_plan_mark_ids(cdlrm_ctx* c, const int64_t* ids, int64_t ld,
     return CDLRM_OK;
 }
 
+// Eviction lists of the next plans: every claimant of a replaced (set, way) (0: the reference's lists, main_no_ddp.py:190-199,
+// needed by callers that return its eviction_data) or only the winner of each (1: what the write-back needs -- under cache
+// pressure the full list is several times longer than the fill list: 27 M entries for 6.8 M fills at 2 GPUs).
+extern "C" int cdlrm_plan_set_primary_evictions(cdlrm_ctx* c, int on) {
+    ARG_CHECK(c);
+    c->primary_evictions = on != 0;
+    return CDLRM_OK;
+}
+
 // Own-id bitmaps: the ids of the window that THIS rank's own batches contain (a data-parallel rank trains on its slice of
 // every global batch).  With them marked, cdlrm_plan_losers lists only the un-cached ids this rank itself will look up:
 // a rank-private loser store of the size of a one-GPU run instead of the union over all ranks (42 GB at 8 GPUs).
@@ -624,10 +636,10 @@ static int phase_b_impl(cdlrm_ctx* c, const float* q, cdlrm_rngdev* rng, uint32_
             }
 #undef LAUNCH_SEL
             const int nblk = (int)((R + TILE - 1) / TILE);
-            LAUNCH(K_PLAN_LISTS, s, lists_kernel<false><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, p.state, bsE, bsF, t.plan_tags, t.num_sets, c->ways, nullptr, nullptr, nullptr, nullptr, nullptr));
+            LAUNCH(K_PLAN_LISTS, s, lists_kernel<false><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, p.state, bsE, bsF, t.plan_tags, t.num_sets, c->ways, nullptr, nullptr, nullptr, nullptr, nullptr, c->primary_evictions));
             LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(bsE, nblk, ck + CNT_E));
             LAUNCH(K_PLAN_COMPACT, s, scan_tiles_kernel<<<1, 1024, 0, s>>>(bsF, nblk, ck + CNT_F));
-            LAUNCH(K_PLAN_LISTS, s, lists_kernel<true><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, p.state, bsE, bsF, t.plan_tags, t.num_sets, c->ways, evict_ids + off, evict_slots + off, evict_primary + off, fill_ids + off, fill_slots + off));
+            LAUNCH(K_PLAN_LISTS, s, lists_kernel<true><<<nblk, 256, 0, s>>>(R, p.uniq, p.surv, c->p_slot, c->p_old, c->p_claim, c->p_flag, p.state, bsE, bsF, t.plan_tags, t.num_sets, c->ways, evict_ids + off, evict_slots + off, evict_primary + off, fill_ids + off, fill_slots + off, c->primary_evictions));
             CU_CHECK(cudaGetLastError());
         }
         off += R;

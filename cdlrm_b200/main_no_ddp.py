@@ -395,6 +395,7 @@ class Trainer:
                                          rng=VictimRngDevice(args.numpy_rand_seed, self.dev), stream=self.side,
                                          lookahead_tags=True)
             self.planner.collect_losers = True     # un-cached ids of a window are served from an HBM loser store
+            self.planner.primary_evictions_only = True   # the write-back needs the winner of a replaced slot only
             # master <-> HBM traffic of the planner: host threads + cudaMemcpyAsync ("ce": the chunk loops are native,
             # hostio.cu; hardly slows the step that runs beside it) when this rank has host cores to spare, else
             # zero-copy gather / scatter kernels ("sm": no host threads, but every system-memory access the SMs keep

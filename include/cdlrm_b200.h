@@ -199,6 +199,10 @@ int cdlrm_plan_mark_ids(cdlrm_ctx* ctx, const int64_t* ids, int64_t ld, int64_t 
  * [num_tables][n]).  The next cdlrm_plan_losers then lists only those un-cached ids -- the ones this rank's forwards will
  * miss on (model_no_ddp.py:176-179) -- instead of the union over all ranks, and clears the marks. */
 int cdlrm_plan_mark_own_ids(cdlrm_ctx* ctx, const int64_t* ids, int64_t ld, int64_t n, cdlrm_stream stream);
+/* Eviction lists of the following cdlrm_plan_phase_b* calls: on = 0 (default) one entry per claimant of a replaced
+ * (set, way), flagged primary for the winner -- the reference's lists (main_no_ddp.py:190-199: `evicted` holds every
+ * claimant's old tag); on = 1 only the winners (all primary): the rows the write-back (cache_manager.py:48-64) uses. */
+int cdlrm_plan_set_primary_evictions(cdlrm_ctx* ctx, int on);
 /* Scan sharded over the `world` ranks of a node (every rank marked its own share of the window with
  * cdlrm_plan_mark_ids): OR the id bitmaps of the other ranks into this rank's, reading them in place over NVLink.
  * h_peer_ws[r] = device address on THIS device of rank r's planner workspace (cdlrm_peer_alloc / cdlrm_peer_open;

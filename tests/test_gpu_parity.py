@@ -50,13 +50,15 @@ def _run_cuda_trace(cfg, mode):
     capped = mode == "staged_capped"      # tiny HBM budget for the loser store: most misses fall back to the host master
     sharded = mode == "staged_sharded"    # loser store cut into 3 per-"rank" shards (all on this device), peer.cu path
     ce = mode == "staged_ce"              # master rows cross PCIe through host threads + cudaMemcpyAsync (hostio.cu)
-    if capped or sharded or ce:
+    primary = mode == "staged_primary"    # eviction lists hold the winner of every replaced (set, way) only (Trainer's setting)
+    if capped or sharded or ce or primary:
         mode = "staged"
     if mode in ("fast", "fast_devrng", "staged"):
         cg._ensure_ctx(master)
         rng = C.VictimRng(seed) if mode == "fast" else C.VictimRngDevice(seed, DEV)
         planner = C.WindowPlanner(cg, master, L * B, rng=rng, lookahead_tags=True)
         planner.collect_losers = mode == "staged"
+        planner.primary_evictions_only = primary
         if sharded:
             planner.enable_sharded_losers(1, 3, "local")
         if ce:
@@ -82,6 +84,8 @@ def _run_cuda_trace(cfg, mode):
             planner.install_staged(pr, write_master=True, average_on_writeback=cfg.get("avg_wb", False))
             planner.flush_writeback()         # (copy-engine mode: the evicted rows reach the master here)
             torch.cuda.synchronize()
+            if primary:
+                assert all(bool(pr.evict_list(k)[2].all()) for k in range(T)) and all(e <= f for e, f in zip(pr.E, pr.F))
             eo = np.concatenate([[0], np.cumsum(pr.E)])
             ev = [(pr.evict_list(k)[0], pr.evict_stage[eo[k]:eo[k] + pr.E[k]]) for k in range(T)]
             for k in range(T):   # losers = window ids that are not cached now, ascending
@@ -127,14 +131,17 @@ def _run_cuda_trace(cfg, mode):
 
 @pytest.mark.parametrize("name", ["trace_tiny.npz", "trace_pressure.npz", "trace_pressure_avgwb.npz",
                                   "trace_cfg0_small.npz"])
-@pytest.mark.parametrize("mode", ["api", "fast", "fast_devrng", "staged", "staged_capped", "staged_sharded", "staged_ce"])
+@pytest.mark.parametrize("mode", ["api", "fast", "fast_devrng", "staged", "staged_capped", "staged_sharded", "staged_ce",
+                                  "staged_primary"])
 def test_trace_matches_reference_golden(name, mode, monkeypatch):
     g = util.load_golden(name)
     cfg = util.golden_cfg(g)
     if mode == "staged_capped":           # room for 7 rows in the whole loser store
         monkeypatch.setenv("CDLRM_LOSER_STORE_GB", repr(7 * 4 * cfg["dim"] / 1e9))
     got = _run_cuda_trace(cfg, mode)
-    n = util.compare_trace(g, got, check_rng=(mode == "api"))
+    n = util.compare_trace(g, got, check_rng=(mode == "api"), skip_evict_lists=(mode == "staged_primary"))
+    if mode == "staged_primary":          # everything else (tags, slots, outputs, final cache and MASTER rows) as the reference
+        util.compare_primary_evictions(g, got, cfg["n_windows"])
     assert n > 20
 
 

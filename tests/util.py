@@ -110,12 +110,34 @@ def assert_close_fp32(v, ref, rtol=1e-5, err_msg=""):
     np.testing.assert_allclose(np.asarray(v), ref, rtol=rtol, atol=rtol * max(scale, 1e-30), err_msg=err_msg)
 
 
-def compare_trace(golden, got, rtol=1e-5, check_rng=True):
+def compare_primary_evictions(golden, got, n_windows, rtol=1e-5):
+    """Eviction lists emitted with one entry per replaced (set, way) (WindowPlanner.primary_evictions_only) against the
+    reference's lists, which hold one entry per claimant (main_no_ddp.py:190-199): per window and table the same SET of
+    evicted ids, each once, with the row the reference evicted for it."""
+    for w in range(n_windows):
+        g_len, m_len = golden[f"w{w}_evict_len"], got[f"w{w}_evict_len"]
+        g_ids, m_ids = golden[f"w{w}_evict_ids"], got[f"w{w}_evict_ids"]
+        g_rows, m_rows = golden[f"w{w}_evict_rows"], got[f"w{w}_evict_rows"]
+        go = np.concatenate([[0], np.cumsum(g_len)])
+        mo = np.concatenate([[0], np.cumsum(m_len)])
+        for k in range(len(g_len)):
+            gi, mi = g_ids[go[k]:go[k + 1]], m_ids[mo[k]:mo[k + 1]]
+            u, first = np.unique(gi, return_index=True)
+            assert len(mi) == len(u) and np.array_equal(np.sort(mi), u), f"window {w} table {k}: evicted id set differs"
+            if len(u):
+                order = np.argsort(mi)
+                assert_close_fp32(m_rows[mo[k]:mo[k + 1]][order], g_rows[go[k]:go[k + 1]][first], rtol=rtol,
+                                  err_msg=f"w{w} table {k} evicted rows")
+
+
+def compare_trace(golden, got, rtol=1e-5, check_rng=True, skip_evict_lists=False):
     """Bit-exact for every integer/decision key, ``rtol`` (north_star: 1e-5
     relative, fp32) for floats.  Only keys present in the golden are checked."""
     checked = 0
     for key, ref in golden.items():
         if key in ("cfg_json", "master_init_digest") or key.startswith("master_init_"):
+            continue
+        if skip_evict_lists and "_evict_" in key:
             continue
         if key.endswith("_rng_digest") and not check_rng:
             continue

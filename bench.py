@@ -695,7 +695,9 @@ def gpu_run(a, wl, ln_emb):
                                      "planner stream (copy engine)" % tr.planner.host_threads)
                                     if tr.planner.pcie_mode == "ce" else
                                     "SM-driven zero-copy row gathers from the pinned master (32 CTAs)") + \
-                                   ", beside the training steps of the end-to-end leg, all ranks at once"
+                                   ", beside the training steps of the end-to-end leg, all ranks at once" + \
+                                   ("; fills sharded over the ranks (1/world of them per rank over PCIe, the others over NVLink "
+                                    "at the boundary)" if getattr(tr, "sharded_fills", False) else "")
         del hosts, hI, hX, hY
     clocks = sampler.stop() if sampler else None
 

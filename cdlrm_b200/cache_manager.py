@@ -124,7 +124,7 @@ class PlanRecord:
                  # look-ahead staging (WindowPlanner.stage / install_staged)
                  "L", "loser_off", "loser_soff", "loser_ids", "loser_stage", "fill_stage", "fill_soff", "evict_stage",
                  "staged", "wb_done", "stage_begin", "stage_bytes", "loser_shard", "loser_peers",
-                 "marks", "wb_lo", "wb_n")
+                 "marks", "wb_lo", "wb_n", "fill_peers")
 
     def loser_list(self, k):
         o, n = self.loser_off[k], self.L[k]
@@ -176,6 +176,7 @@ class WindowPlanner:
         self._ce_ev = None
         self._pending_wb = None          # ce: (record, average) of the boundary whose evicted rows are not yet written back
         self._shard = None               # (rank, world, host process group): loser store sharded over the node
+        self._fill_shard = None          # (rank, world, host process group): fill prefetch sharded over the node
         self._peer_bufs = {}             # name -> (capacity rows, [device address of every rank's shard buffer])
         self.plan_tags = None
         if lookahead_tags:
@@ -274,12 +275,24 @@ class WindowPlanner:
                 raise _lib.CdlrmError("the sharded loser store spans the (at most 8) GPUs of one node")
             self._shard = (int(rank), int(world), group)      # group "local": single-process emulation (tests)
 
-    def _peer_buf(self, name, rows):
+    def enable_sharded_fills(self, rank, world, group):
+        """Shard the FILL prefetch over the ``world`` ranks of one node: the replicas run the same plan, so the rows
+        that enter the cache at a boundary are the same everywhere; rank r pulls the r-th of ``world`` equal shares of
+        every table's fill list over its own PCIe link into a peer-readable staging buffer, and at the boundary every
+        rank fills its cache from all ``world`` buffers (its own share from local HBM, the others over NVLink): 1/world
+        of the PCIe traffic and of the host-memory reads per rank for those rows.  ``group`` as in
+        ``enable_sharded_losers`` ("local": single-process emulation for tests)."""
+        if world > 1:
+            if world > 8:
+                raise _lib.CdlrmError("the sharded fill prefetch spans the (at most 8) GPUs of one node")
+            self._fill_shard = (int(rank), int(world), group)
+
+    def _peer_buf(self, name, rows, shard=None):
         """Peer-readable [rows, dim] fp32 buffer ``name`` of this rank plus the addresses of the same-named buffers
         of every other rank (collective over the host group: every rank asks for the same ``rows``).  Grown (x1.25)
         only when a window needs more."""
         import torch.distributed as dist
-        rank, world, group = self._shard
+        rank, world, group = shard if shard is not None else self._shard
         ent = self._peer_bufs.get(name)
         if ent is not None and ent[0] >= rows:
             return ent
@@ -447,7 +460,7 @@ class WindowPlanner:
                                 "phase_b_s": round(time.perf_counter() - t_c, 4)}
         rec.event = None
         rec.staged = rec.wb_done = rec.fill_stage = rec.loser_stage = rec.evict_stage = None
-        rec.loser_shard = rec.loser_peers = None
+        rec.loser_shard = rec.loser_peers = rec.fill_peers = None
         rec.stage_begin, rec.stage_bytes = None, 0
         return rec
 
@@ -584,10 +597,25 @@ class WindowPlanner:
             rec.fill_soff = [0] * self.T
             for k in range(1, self.T):
                 rec.fill_soff[k] = rec.fill_soff[k - 1] + rec.F[k - 1]
-            rec.fill_stage = self._buf("fill", max(sum(rec.F), 1))
-            for k in range(self.T):
-                if rec.F[k]:
-                    fill_jobs.append((k, rec.off[k], rec.F[k], rec.fill_stage[rec.fill_soff[k]:].data_ptr()))
+            rec.fill_peers = None
+            if self._fill_shard is not None:
+                # sharded: this rank pulls its share of every table's fill list into a peer-readable buffer (two
+                # alternate: the peers read the previous one at THEIR boundary); same layout on every rank
+                rank, world, _group = self._fill_shard
+                self._fill_no = getattr(self, "_fill_no", 0) + 1
+                rec.fill_stage = None
+                rec.fill_peers = self._peer_buf("fill%d" % (self._fill_no & 1), max(sum(rec.F), 1), self._fill_shard)[1]
+                row_b = 4 * d
+                for k in range(self.T):
+                    for r in (range(world) if _group == "local" else (rank,)):
+                        lo, n = wb_share_range(rec.F[k], r, world)
+                        if n:
+                            fill_jobs.append((k, rec.off[k] + lo, n, rec.fill_peers[r] + (rec.fill_soff[k] + lo) * row_b))
+            else:
+                rec.fill_stage = self._buf("fill", max(sum(rec.F), 1))
+                for k in range(self.T):
+                    if rec.F[k]:
+                        fill_jobs.append((k, rec.off[k], rec.F[k], rec.fill_stage[rec.fill_soff[k]:].data_ptr()))
             rec.loser_shard = rec.loser_peers = None
             if rec.L is not None and self._shard is not None:
                 # sharded store: this rank pulls rows [rank * shard, (rank + 1) * shard) of every table's list
@@ -673,7 +701,16 @@ class WindowPlanner:
                                                _vp(rec.evict_stage[eoff[k]:].data_ptr()), 0, 0, _sp(s)))
             tm.append(time.perf_counter())
             for k in range(self.T):
-                if rec.F[k]:
+                if rec.F[k] and rec.fill_peers is not None:
+                    # share r of the list comes out of rank r's staging buffer (local HBM or NVLink peer memory)
+                    ids, slots = rec.fill_list(k)
+                    world = len(rec.fill_peers)
+                    for r in range(world):
+                        lo, n = wb_share_range(rec.F[k], r, world)
+                        if n:
+                            check(lib.cdlrm_move_fill(self.ctx, k, _vp(ids[lo:].data_ptr()), _vp(slots[lo:].data_ptr()), n,
+                                                      _vp(rec.fill_peers[r] + (rec.fill_soff[k] + lo) * 4 * d), None, _sp(s)))
+                elif rec.F[k]:
                     ids, slots = rec.fill_list(k)
                     check(lib.cdlrm_move_fill(self.ctx, k, _vp(ids.data_ptr()), _vp(slots.data_ptr()), rec.F[k],
                                               _vp(rec.fill_stage[rec.fill_soff[k]:].data_ptr()), None, _sp(s)))

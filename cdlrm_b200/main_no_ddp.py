@@ -426,6 +426,12 @@ class Trainer:
                            and os.environ.get("CDLRM_LOSER_OWN", "1") != "0")
         if self.sharded_losers:
             self.planner.enable_sharded_losers(rank, world, self._host_group)
+        # fills are the same rows on every replica: each rank pulls 1/world of them over PCIe, the boundary reads the
+        # rest from the peers' staging buffers over NVLink (CDLRM_FILL_SHARDED=0: every rank pulls all of them)
+        self.sharded_fills = (world > 1 and self.planner is not None
+                              and os.environ.get("CDLRM_FILL_SHARDED", "1") != "0")
+        if self.sharded_fills:
+            self.planner.enable_sharded_fills(rank, world, self._host_group)
         # a window handed over as a marker callable (submit_window) is scanned 1/world per rank, bitmaps OR-ed over
         # NVLink (CDLRM_SCAN_SHARDED=0: every rank scans the whole global window)
         if world > 1 and self.planner is not None and os.environ.get("CDLRM_SCAN_SHARDED", "1") != "0":
@@ -497,9 +503,9 @@ class Trainer:
                         prev_rec.wb_done.synchronize()
                     dist.barrier(group=self._host_group)
                 rec = self.planner.stage(rec)
-                if self.sharded_losers:
-                    # a peer's forward reads this rank's shard right after ITS install: every rank's prefetch must
-                    # have landed before any rank is handed the record
+                if self.sharded_losers or self.sharded_fills:
+                    # a peer's forward (install) reads this rank's shard right after (at) ITS boundary: every rank's
+                    # prefetch must have landed before any rank is handed the record
                     rec.staged.synchronize()
                     dist.barrier(group=self._host_group)
                 self._plan_q.put(rec)

@@ -51,7 +51,8 @@ def _run_cuda_trace(cfg, mode):
     sharded = mode == "staged_sharded"    # loser store cut into 3 per-"rank" shards (all on this device), peer.cu path
     ce = mode == "staged_ce"              # master rows cross PCIe through host threads + cudaMemcpyAsync (hostio.cu)
     primary = mode == "staged_primary"    # eviction lists hold the winner of every replaced (set, way) only (Trainer's setting)
-    if capped or sharded or ce or primary:
+    fillshard = mode == "staged_fillshard"  # fill prefetch cut into 3 per-"rank" shares in 3 staging buffers (peer path)
+    if capped or sharded or ce or primary or fillshard:
         mode = "staged"
     if mode in ("fast", "fast_devrng", "staged"):
         cg._ensure_ctx(master)
@@ -61,6 +62,8 @@ def _run_cuda_trace(cfg, mode):
         planner.primary_evictions_only = primary
         if sharded:
             planner.enable_sharded_losers(1, 3, "local")
+        if fillshard:
+            planner.enable_sharded_fills(1, 3, "local")
         if ce:
             planner.pcie_mode, planner.host_threads = "ce", 3
             planner.CE_CHUNK_BYTES = 64 * 4 * d       # 64-row chunks: many chunk hand-overs even on the tiny traces
@@ -132,7 +135,7 @@ def _run_cuda_trace(cfg, mode):
 @pytest.mark.parametrize("name", ["trace_tiny.npz", "trace_pressure.npz", "trace_pressure_avgwb.npz",
                                   "trace_cfg0_small.npz"])
 @pytest.mark.parametrize("mode", ["api", "fast", "fast_devrng", "staged", "staged_capped", "staged_sharded", "staged_ce",
-                                  "staged_primary"])
+                                  "staged_primary", "staged_fillshard"])
 def test_trace_matches_reference_golden(name, mode, monkeypatch):
     g = util.load_golden(name)
     cfg = util.golden_cfg(g)

@@ -117,14 +117,14 @@ def compare_primary_evictions(golden, got, n_windows, rtol=1e-5):
     for w in range(n_windows):
         g_len, m_len = golden[f"w{w}_evict_len"], got[f"w{w}_evict_len"]
         g_ids, m_ids = golden[f"w{w}_evict_ids"], got[f"w{w}_evict_ids"]
-        g_rows, m_rows = golden[f"w{w}_evict_rows"], got[f"w{w}_evict_rows"]
+        g_rows, m_rows = golden.get(f"w{w}_evict_rows"), got[f"w{w}_evict_rows"]    # (large fixtures keep only the sums)
         go = np.concatenate([[0], np.cumsum(g_len)])
         mo = np.concatenate([[0], np.cumsum(m_len)])
         for k in range(len(g_len)):
             gi, mi = g_ids[go[k]:go[k + 1]], m_ids[mo[k]:mo[k + 1]]
             u, first = np.unique(gi, return_index=True)
             assert len(mi) == len(u) and np.array_equal(np.sort(mi), u), f"window {w} table {k}: evicted id set differs"
-            if len(u):
+            if len(u) and g_rows is not None:
                 order = np.argsort(mi)
                 assert_close_fp32(m_rows[mo[k]:mo[k + 1]][order], g_rows[go[k]:go[k + 1]][first], rtol=rtol,
                                   err_msg=f"w{w} table {k} evicted rows")

@@ -185,6 +185,7 @@ def main():
               f"loser store {'sharded over the ranks' if tr.sharded_losers else ('own ids per rank' if tr.own_losers else 'all ids per rank')}, {checked_losers} table probes, "
               f"window scan {'sharded (marker)' if use_marker else 'whole window per rank'}, "
               f"write-back {'shared by the ranks' if tr.wb_sharded else 'by rank 0'}, "
+              f"fill prefetch {'sharded over the ranks' if tr.sharded_fills else 'whole list per rank'}, "
               f"loss digest {hash(tuple(losses)) & 0xffffffff:08x}")
     dist.destroy_process_group()
 

@@ -405,7 +405,9 @@ class Trainer:
                 cores = len(os.sched_getaffinity(0))
             except (AttributeError, OSError):
                 cores = os.cpu_count() or 2
-            threads = max(1, min(4, cores // max(world, 1) - 2))     # more than 4 bring nothing at one window per 2 s
+            # at most half of this rank's cores (minus one) gather, at most 4: more bring nothing at one window per 2 s,
+            # and the thread that enqueues the steps must never wait for a core
+            threads = max(1, min(4, cores // max(world, 1) // 2 - 1))
             mode = os.environ.get("CDLRM_PREFETCH", "auto")
             self.planner.host_threads = int(os.environ.get("CDLRM_HOST_THREADS", threads))
             auto = "ce" if (world == 1 and self.planner.host_threads >= 3) else "sm"

@@ -89,6 +89,22 @@ def test_compute_entry_points_fail_loudly_without_gpu():
     h = ctypes.c_void_p()
     rc = _lib.lib.cdlrm_ctx_create(ctypes.byref(h), 0, 2, 8, 2, 4, _lib.i64_array([100, 20]), 16)
     assert rc != 0 and b"" != _lib.lib.cdlrm_last_error()
+    # the whole-window prefetch / write-back pipelines need the copy engine: an error without a device, and argument
+    # errors (no staging chunks, negative counts) before anything is touched
+    M = np.zeros((10, 8), np.float32)
+    ids = np.arange(4, dtype=np.int64)
+    chunk = np.zeros((4, 8), np.float32)
+    vp = ctypes.c_void_p
+    args = (0, 1, _lib.ptr_array([M.ctypes.data]), _lib.i64_array([10]), 8, _lib.ptr_array([ids.ctypes.data]),
+            _lib.i64_array([4]), _lib.ptr_array([chunk.ctypes.data]))
+    assert _lib.lib.cdlrm_host_prefetch_rows(*args, vp(chunk.ctypes.data), vp(chunk.ctypes.data), 4, 1, None) != 0
+    assert _lib.lib.cdlrm_host_prefetch_rows(*args, None, None, 4, 1, None) != 0
+    assert np.array_equal(chunk, np.zeros((4, 8), np.float32))
+    assert _lib.lib.cdlrm_host_writeback_rows(0, 1, _lib.ptr_array([M.ctypes.data]), _lib.i64_array([10]), 8,
+                                              _lib.ptr_array([ids.ctypes.data]), None, _lib.i64_array([4]),
+                                              _lib.ptr_array([chunk.ctypes.data]), vp(chunk.ctypes.data),
+                                              vp(chunk.ctypes.data), 4, 0, 1, None) != 0
+    assert not M.any()
 
 
 def test_module_attribute_surface_matches_reference():

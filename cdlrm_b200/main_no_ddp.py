@@ -415,7 +415,12 @@ class Trainer:
         self._host_group = dist.new_group(backend="gloo") if world > 1 else None   # plan-thread barrier
         # write-back of a boundary's evictions shared by the ranks (they hold identical rows right after the boundary
         # aggregation and map the same host master): 1/world of every table's list each
-        self.wb_sharded = world > 1 and self.planner is not None and os.environ.get("CDLRM_WB_SHARDED", "1") != "0"
+        # (only when the master visibly IS one shared object -- a /dev/shm mapping or shared-memory tensors; with anything
+        # else rank 0 writes the whole list, as the reference's one eviction manager does)
+        shared_master = bool(getattr(emb_tables, "_mapped_file", False)) or \
+            all(bool(e.weight.is_shared()) for e in getattr(emb_tables, "emb_l", []))
+        self.wb_sharded = (world > 1 and self.planner is not None and shared_master
+                           and os.environ.get("CDLRM_WB_SHARDED", "1") != "0")
         # un-cached ids of a window (the same on every rank): one store sharded over the node's GPUs and read over
         # NVLink instead of a full copy per rank (CDLRM_LOSER_SHARDED=0: one local store per rank)
         # un-cached ids of a window at N > 1: "own" (default) = every rank stages only the ones its own batches contain

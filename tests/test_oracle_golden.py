@@ -127,3 +127,27 @@ def test_trainer_golden_decisions_match_oracle():
             _ly, _slots, nm = O.forward(cache, [off] * T, win[:, b * B:(b + 1) * B], master)
             n_miss.append(nm)
     assert np.array_equal(np.asarray(n_miss, dtype=np.int64), g["n_miss"])
+
+
+@pytest.mark.parametrize("name", ["trace_pressure.npz", "trace_pressure_avgwb.npz", "trace_tiny.npz"])
+def test_reference_eviction_lists_repeat_one_row_per_replaced_slot(name):
+    """What WindowPlanner.primary_evictions_only (cdlrm_plan_set_primary_evictions) relies on, checked on the REFERENCE's
+    own output: when several ids of a window claim the same (set, way), the reference's eviction list repeats the old
+    tag once per claimant (main_no_ddp.py:190-199) and every repeat carries the same cache row -- so writing each
+    evicted id back once (cache_manager.py:48-64, plain or averaged) leaves the master exactly as the reference does."""
+    g = util.load_golden(name)
+    cfg = util.golden_cfg(g)
+    repeats = 0
+    for w in range(cfg["n_windows"]):
+        ln, ids, rows = g[f"w{w}_evict_len"], g[f"w{w}_evict_ids"], g[f"w{w}_evict_rows"]
+        o = np.concatenate([[0], np.cumsum(ln)])
+        for k in range(len(ln)):
+            gi, gr = ids[o[k]:o[k + 1]], rows[o[k]:o[k + 1]]
+            u, inv = np.unique(gi, return_inverse=True)
+            repeats += len(gi) - len(u)
+            first = np.full(len(u), -1, dtype=np.int64)
+            for i in range(len(gi) - 1, -1, -1):
+                first[inv[i]] = i
+            assert np.array_equal(gr, gr[first[inv]]), f"window {w} table {k}: repeats of an evicted id carry different rows"
+    if "pressure" in name:
+        assert repeats > 50             # the undersized cache does produce duplicate claims
